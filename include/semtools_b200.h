@@ -1,0 +1,188 @@
+/*
+ * semtools_b200.h -- C ABI of the B200-native `search` hot path of semtools.
+ *
+ * The reference (run-llama/semtools v3.0.0, paths relative to /root/reference)
+ * has no FFI layer of its own: the seam is a set of Rust calls into two
+ * third-party crates (model2vec-rs, simsimd) plus its own scan/sort loop.  Each
+ * entry point below names the reference interface it replaces; INTEGRATION.md
+ * shows the `extern "C"` block a semtools maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 (STB_OK) or a negative stb_status;
+ *     stb_last_error() returns the message of the calling thread's last failure
+ *   - nothing throws or aborts across this boundary
+ *   - the caller owns every buffer it passes; the library owns everything
+ *     behind the opaque handles; outputs go to caller-allocated arrays with
+ *     explicit capacities
+ *   - one host thread per context at a time (the reference runs the whole
+ *     search path on one blocking thread, src/bin/semtools.rs:134-135)
+ *   - pointers named *_dev are CUDA device pointers on the context's device,
+ *     everything else is host memory
+ *   - there is NO CPU fallback: without a usable sm_100 device every call fails
+ *     with STB_ERR_CUDA
+ *
+ * Vector width is fixed at 256 f32 (LINE_EMBEDDING_SIZE,
+ * src/workspace/store.rs:37); other widths fail with STB_ERR_ARG.
+ */
+#ifndef SEMTOOLS_B200_H
+#define SEMTOOLS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STB_DIM 256u
+
+typedef enum stb_status {
+  STB_OK = 0,
+  STB_ERR_ARG = -1,      /* bad argument (null handle, wrong width, ...)          */
+  STB_ERR_CUDA = -2,     /* CUDA runtime failure / no sm_100 device                */
+  STB_ERR_NOMEM = -3,    /* host or device allocation failed                       */
+  STB_ERR_RANGE = -4,    /* token id / row range outside the table or corpus       */
+  STB_ERR_CAPACITY = -5, /* result does not fit `cap`; *out_n holds the full count */
+  STB_ERR_STATE = -6     /* call not valid in the handle's current state           */
+} stb_status;
+
+typedef struct stb_ctx stb_ctx;       /* one CUDA device + stream + scratch        */
+typedef struct stb_table stb_table;   /* model2vec embedding table resident in HBM */
+typedef struct stb_corpus stb_corpus; /* row-major N x 256 f32 line-vector matrix  */
+
+/* One search hit: (distance, global row) -- 16 bytes, the unit of the
+ * cross-GPU top-k exchange.  `row` is the line's position in (document order,
+ * line order), i.e. the reference's iteration order (src/search/mod.rs:84-85),
+ * so ordering by (distance, row) reproduces its stable sort (:107-111). */
+typedef struct stb_hit {
+  double distance;
+  uint64_t row;
+} stb_hit;
+
+int stb_version(void);
+const char *stb_last_error(void);
+
+/* Device count visible to the library (0 if no driver / no GPU). */
+int stb_device_count(void);
+
+/* ---- context ----------------------------------------------------------------
+ * `cuda_stream` may be NULL (the library creates its own non-blocking stream) or
+ * an existing cudaStream_t that every kernel/copy of this context is issued on
+ * (lets a host framework time the work with its own events). */
+int stb_ctx_create(int device, void *cuda_stream, stb_ctx **out);
+int stb_ctx_destroy(stb_ctx *ctx);
+int stb_ctx_sync(stb_ctx *ctx);
+/* cudaStream_t the context launches on. */
+void *stb_ctx_stream(stb_ctx *ctx);
+
+/* ---- embedding table ---------------------------------------------------------
+ * Replaces the tensors held by StaticModel after
+ * StaticModel::from_pretrained(MODEL_NAME, None, None, None)
+ * (src/cmds/search.rs:123-128, src/search/mod.rs:16): table E[V][256] f32,
+ * optional per-token weights[n_weights], optional token->row mapping[n_mapping],
+ * and the `normalize` flag from config.json.  Uploaded once, read-only after. */
+int stb_table_load(stb_ctx *ctx, const float *E, uint64_t V, uint32_t D,
+                   const float *weights, uint64_t n_weights,
+                   const uint32_t *mapping, uint64_t n_mapping, int normalize,
+                   stb_table **out);
+int stb_table_destroy(stb_table *table);
+
+/* ---- corpus -------------------------------------------------------------------
+ * Replaces Document.embeddings: Vec<Vec<f32>> (src/search/mod.rs:18-22) and the
+ * line_embeddings shard's vectors (src/workspace/store.rs:140-160) with ONE
+ * contiguous matrix in HBM.  `row_base` is the global row id of local row 0
+ * (non-zero when this context holds one row-shard of a larger corpus). */
+int stb_corpus_create(stb_ctx *ctx, uint32_t D, uint64_t capacity_rows,
+                      uint64_t row_base, stb_corpus **out);
+int stb_corpus_destroy(stb_corpus *corpus);
+int stb_corpus_append(stb_corpus *corpus, const float *rows, uint64_t n);
+int stb_corpus_append_dev(stb_corpus *corpus, const float *rows_dev, uint64_t n);
+int stb_corpus_clear(stb_corpus *corpus);
+int stb_corpus_rows(const stb_corpus *corpus, uint64_t *n);
+/* device pointer of local row 0 (for zero-copy producers). */
+int stb_corpus_data_dev(const stb_corpus *corpus, float **rows_dev);
+/* copy rows [first, first+n) back to the host (tests, store write-back). */
+int stb_corpus_read(const stb_corpus *corpus, uint64_t first, uint64_t n,
+                    float *rows);
+
+/* ---- K3: gather + mean-pool + L2-normalise -------------------------------------
+ * Replaces model.encode_with_args(&lines, Some(2048), 16384)
+ * (src/search/mod.rs:69, src/cmds/search.rs:154) and model.encode_single(q)
+ * (src/search/mod.rs:138,153; src/cmds/search.rs:136) MINUS tokenisation, which
+ * stays on the host: the caller passes the token ids of each line as a CSR batch
+ * (offsets[n_lines+1], ids[offsets[n_lines]]), already unk-dropped and truncated
+ * (2048 ids per corpus line, 512 for the query).  Output row i is bit-identical
+ * to pool_ids(ids of line i) of model2vec-rs 0.1.3.
+ * `out` (host, n_lines x 256) and `append_to` may each be NULL; with `append_to`
+ * the rows are written straight into the corpus in HBM and never visit the host.
+ * A token whose table row is out of range fails the call with STB_ERR_RANGE
+ * (upstream panics) and appends nothing. */
+int stb_embed(stb_ctx *ctx, const stb_table *table, const uint64_t *offsets,
+              const uint32_t *ids, uint64_t n_lines, float *out,
+              stb_corpus *append_to);
+
+/* ---- K1 + K4: cosine scan, top-k / threshold, exact re-rank ---------------------
+ * Replaces search_documents' scan/filter/sort/take (src/search/mod.rs:84-119,
+ * one f32::cosine per line at :86) and, with `row_ranges`, the filtered query of
+ * Store::search_line_embeddings (src/workspace/store.rs:481-546).
+ *
+ *   q            256 f32 query vector (host)
+ *   top_k        config.top_k (:118)
+ *   has_max /    config.max_distance (:88): a hit needs distance < max_distance
+ *   max_distance (strict; 100.0 when absent).
+ *   mode         STB_MODE_SEARCH_DOCUMENTS: has_max lifts the top_k cap (:115-119)
+ *                STB_MODE_STORE_QUERY:      top_k always caps (store.rs:517,543)
+ *   row_ranges   NULL, or n_ranges half-open [begin,end) pairs of GLOBAL rows,
+ *                ascending and disjoint: only these rows are scanned
+ *   out_hits     cap entries; on return the first min(*out_n, cap) are filled,
+ *                ordered by (distance asc, row asc); distances are the canonical
+ *                f64 cosine distance (oracle/semtools_oracle.c: orc_cosine_f32)
+ *   out_n        full result count; if it exceeds cap the call returns
+ *                STB_ERR_CAPACITY after filling cap entries
+ * On a sharded corpus (row_base != 0 or several contexts) the result is the
+ * shard-local answer; merge shards with stb_hits_merge*. */
+#define STB_MODE_SEARCH_DOCUMENTS 0
+#define STB_MODE_STORE_QUERY 1
+int stb_search(stb_ctx *ctx, const stb_corpus *corpus, const float *q,
+               uint32_t top_k, int has_max, double max_distance, int mode,
+               const uint64_t *row_ranges, uint32_t n_ranges, stb_hit *out_hits,
+               uint64_t cap, uint64_t *out_n);
+
+/* Asynchronous device-resident form of the top-k search (no threshold, no
+ * ranges): query and results stay in HBM, nothing synchronises.  out_hits_dev
+ * receives top_k entries (unused tail: distance = +inf, row = UINT64_MAX) and
+ * out_status_dev[0] the hit count, out_status_dev[1] a completeness flag
+ * (1 = provably the exact top-k; 0 = the candidate margin check failed and the
+ * caller must fall back to stb_search, which handles it internally). */
+int stb_search_topk_dev(stb_ctx *ctx, const stb_corpus *corpus,
+                        const float *q_dev, uint32_t top_k, stb_hit *out_hits_dev,
+                        uint32_t *out_status_dev);
+
+/* ---- K4: merge per-shard hit lists -----------------------------------------------
+ * The final sort_by + take of src/search/mod.rs:107-119 applied across row
+ * shards: `lists_dev` holds n_lists x per_list hits (e.g. the all-gathered
+ * per-GPU top-k; padding entries have distance = +inf); writes the top_k best by
+ * (distance, row) to out_dev.  Asynchronous on the context's stream. */
+int stb_hits_merge_dev(stb_ctx *ctx, const stb_hit *lists_dev, uint32_t n_lists,
+                       uint32_t per_list, uint32_t top_k, stb_hit *out_dev);
+/* Host-buffer convenience wrapper (copies in, merges on the GPU, copies out). */
+int stb_hits_merge(stb_ctx *ctx, const stb_hit *lists, uint32_t n_lists,
+                   uint32_t per_list, uint32_t top_k, stb_hit *out,
+                   uint32_t *out_n);
+
+/* ---- ids -------------------------------------------------------------------------
+ * fnv1a_hash (src/workspace/store.rs:651-661); DocMeta::id (:75-80) is
+ * stb_fnv1a64(path); LineEmbedding::id (:82-89) is stb_line_id. Pure host code. */
+uint64_t stb_fnv1a64(const uint8_t *bytes, uint64_t len);
+uint64_t stb_line_id(const uint8_t *path, uint64_t path_len, int32_t line_number);
+
+/* ---- introspection (bench / tests) -------------------------------------------------
+ * Counters since context creation: kernels launched by this library on the
+ * context, and how many searches needed the fallback pass. */
+int stb_ctx_counters(const stb_ctx *ctx, uint64_t *kernel_launches,
+                     uint64_t *fallback_searches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEMTOOLS_B200_H */

@@ -1,0 +1,120 @@
+/*
+ * cpu_baseline.c -- the reference's scan as a TIMED CPU BASELINE (not a parity
+ * oracle).  TEST/BENCH INFRASTRUCTURE ONLY: bench.py's cpu_baseline leg and
+ * `--impl reference` are the only callers.
+ *
+ * Restates search_documents (src/search/mod.rs:77-120) the way it executes on
+ * the host: one cosine per row (simsimd-style f32 SIMD lanes, FMA allowed),
+ * the FULL result vector, a stable sort, take(top_k).  Built with
+ * -O3 -march=x86-64-v3 (AVX2+FMA; portable to the GPU box host) -fopenmp.  threads == 1 is the faithful configuration (the
+ * reference loop is single-threaded); threads > 1 is reported separately and
+ * labelled "not reference behaviour".
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#define ORC_OK 0
+#define ORC_ERR_NOMEM -2
+typedef struct { double d; uint64_t row; } orc_hit;
+
+/* Stable bottom-up merge sort on distance only: equal distances keep their
+ * input (row) order, which is what Rust's slice::sort_by guarantees. */
+static int orc_stable_sort_hits(orc_hit *a, uint64_t n) {
+  if (n < 2) return ORC_OK;
+  orc_hit *tmp = (orc_hit *)malloc(sizeof(orc_hit) * n);
+  if (!tmp) return ORC_ERR_NOMEM;
+  orc_hit *src = a, *dst = tmp;
+  for (uint64_t w = 1; w < n; w *= 2) {
+    for (uint64_t lo = 0; lo < n; lo += 2 * w) {
+      uint64_t mid = lo + w < n ? lo + w : n;
+      uint64_t hi = lo + 2 * w < n ? lo + 2 * w : n;
+      uint64_t i = lo, j = mid, k = lo;
+      while (i < mid && j < hi) {
+        if (src[j].d < src[i].d) dst[k++] = src[j++]; /* right only if strictly smaller */
+        else dst[k++] = src[i++];
+      }
+      while (i < mid) dst[k++] = src[i++];
+      while (j < hi) dst[k++] = src[j++];
+    }
+    orc_hit *s = src; src = dst; dst = s;
+  }
+  if (src != a) memcpy(a, src, sizeof(orc_hit) * n);
+  free(tmp);
+  return ORC_OK;
+}
+
+/* ------------------------------------------------- timed CPU baseline ------
+ * The reference's scan as it would run on the host:
+ * contiguous matrix, one cosine per row, FULL result vector, stable sort,
+ * take(top_k) -- single thread, because src/search/mod.rs:84-104 is a plain
+ * nested loop.  The inner product uses f32 lanes (what simsimd's SIMD backends
+ * do) so the compiler can vectorise with -O3 -march=native; the selection logic
+ * is identical to orc_search_documents.  Used ONLY as bench.py's cpu_baseline /
+ * --impl reference timing leg, never for parity. */
+static inline double orc_cosine_simd_like(const float *a, const float *b) {
+  float ab[8] = {0}, a2[8] = {0}, b2[8] = {0};
+  for (int i = 0; i < 256; i += 8)
+    for (int l = 0; l < 8; ++l) {
+      ab[l] += a[i + l] * b[i + l];
+      a2[l] += a[i + l] * a[i + l];
+      b2[l] += b[i + l] * b[i + l];
+    }
+  double sab = 0, sa2 = 0, sb2 = 0;
+  for (int l = 0; l < 8; ++l) { sab += ab[l]; sa2 += a2[l]; sb2 += b2[l]; }
+  if (sa2 == 0.0 && sb2 == 0.0) return 0.0;
+  if (sab == 0.0) return 1.0;
+  double r = 1.0 - sab / (sqrt(sa2) * sqrt(sb2));
+  return r > 0.0 ? r : 0.0;
+}
+
+int orc_baseline_search(const float *rows, uint64_t n_rows, const float *q,
+                        uint64_t top_k, int has_max, double max_distance,
+                        int threads, uint64_t cap, uint64_t *out_row,
+                        double *out_distance, uint64_t *out_n) {
+  double thr = has_max ? max_distance : 100.0;
+  orc_hit *hits = (orc_hit *)malloc(sizeof(orc_hit) * (n_rows ? n_rows : 1));
+  if (!hits) return ORC_ERR_NOMEM;
+  uint64_t m = 0;
+  if (threads <= 1) {
+    for (uint64_t r = 0; r < n_rows; ++r) {
+      double d = orc_cosine_simd_like(q, rows + r * 256);
+      if (d < thr) { hits[m].d = d; hits[m].row = r; m++; }
+    }
+  } else {
+    /* "not reference behaviour": all-cores variant.  Distances in parallel,
+     * then the same sequential filter so row order (stability) is kept. */
+    double *dist = (double *)malloc(sizeof(double) * (n_rows ? n_rows : 1));
+    if (!dist) { free(hits); return ORC_ERR_NOMEM; }
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(threads)
+#endif
+    for (int64_t r = 0; r < (int64_t)n_rows; ++r)
+      dist[r] = orc_cosine_simd_like(q, rows + (uint64_t)r * 256);
+    for (uint64_t r = 0; r < n_rows; ++r)
+      if (dist[r] < thr) { hits[m].d = dist[r]; hits[m].row = r; m++; }
+    free(dist);
+  }
+  int rc = orc_stable_sort_hits(hits, m);
+  if (rc != ORC_OK) { free(hits); return rc; }
+  uint64_t n_out = has_max ? m : (m < top_k ? m : top_k);
+  *out_n = n_out;
+  for (uint64_t i = 0; i < n_out && i < cap; ++i) {
+    if (out_row) out_row[i] = hits[i].row;
+    if (out_distance) out_distance[i] = hits[i].d;
+  }
+  free(hits);
+  return ORC_OK;
+}
+
+
+int orc_baseline_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}

@@ -1,0 +1,271 @@
+"""ctypes binding of include/semtools_b200.h -- one Python callable per C entry
+point, same names, same argument meaning.  Raises StbError on any negative
+status; never substitutes a CPU computation."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsemtools_b200.so")
+
+STB_DIM = 256
+STB_OK, STB_ERR_ARG, STB_ERR_CUDA, STB_ERR_NOMEM = 0, -1, -2, -3
+STB_ERR_RANGE, STB_ERR_CAPACITY, STB_ERR_STATE = -4, -5, -6
+STB_MODE_SEARCH_DOCUMENTS, STB_MODE_STORE_QUERY = 0, 1
+
+# every symbol include/semtools_b200.h declares (tests check the .so exports all)
+SYMBOLS = [
+    "stb_version", "stb_last_error", "stb_device_count", "stb_ctx_create", "stb_ctx_destroy",
+    "stb_ctx_sync", "stb_ctx_stream", "stb_table_load", "stb_table_destroy", "stb_corpus_create",
+    "stb_corpus_destroy", "stb_corpus_append", "stb_corpus_append_dev", "stb_corpus_clear",
+    "stb_corpus_rows", "stb_corpus_data_dev", "stb_corpus_read", "stb_embed", "stb_search",
+    "stb_search_topk_dev", "stb_hits_merge_dev", "stb_hits_merge", "stb_fnv1a64", "stb_line_id",
+    "stb_ctx_counters",
+]
+
+
+class StbHit(C.Structure):
+    _fields_ = [("distance", C.c_double), ("row", C.c_uint64)]
+
+
+HIT_DTYPE = np.dtype([("distance", np.float64), ("row", np.uint64)])
+
+
+class StbError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"stb status {status}: {message}")
+        self.status = status
+
+
+_lib = None
+vp = C.c_void_p
+u64, u32, i32, f64 = C.c_uint64, C.c_uint32, C.c_int, C.c_double
+
+
+def lib() -> C.CDLL:
+    """Load libsemtools_b200.so; fails loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(scripts/build_lib.sh).  semtools_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.stb_version.restype = i32
+    L.stb_last_error.restype = C.c_char_p
+    L.stb_device_count.restype = i32
+    L.stb_ctx_create.argtypes = [i32, vp, C.POINTER(vp)]
+    L.stb_ctx_destroy.argtypes = [vp]
+    L.stb_ctx_sync.argtypes = [vp]
+    L.stb_ctx_stream.argtypes = [vp]
+    L.stb_ctx_stream.restype = vp
+    L.stb_table_load.argtypes = [vp, vp, u64, u32, vp, u64, vp, u64, i32, C.POINTER(vp)]
+    L.stb_table_destroy.argtypes = [vp]
+    L.stb_corpus_create.argtypes = [vp, u32, u64, u64, C.POINTER(vp)]
+    L.stb_corpus_destroy.argtypes = [vp]
+    L.stb_corpus_append.argtypes = [vp, vp, u64]
+    L.stb_corpus_append_dev.argtypes = [vp, vp, u64]
+    L.stb_corpus_clear.argtypes = [vp]
+    L.stb_corpus_rows.argtypes = [vp, C.POINTER(u64)]
+    L.stb_corpus_data_dev.argtypes = [vp, C.POINTER(vp)]
+    L.stb_corpus_read.argtypes = [vp, u64, u64, vp]
+    L.stb_embed.argtypes = [vp, vp, vp, vp, u64, vp, vp]
+    L.stb_search.argtypes = [vp, vp, vp, u32, i32, f64, i32, vp, u32, vp, u64, C.POINTER(u64)]
+    L.stb_search_topk_dev.argtypes = [vp, vp, vp, u32, vp, vp]
+    L.stb_hits_merge_dev.argtypes = [vp, vp, u32, u32, u32, vp]
+    L.stb_hits_merge.argtypes = [vp, vp, u32, u32, u32, vp, C.POINTER(u32)]
+    L.stb_fnv1a64.argtypes = [C.c_char_p, u64]
+    L.stb_fnv1a64.restype = u64
+    L.stb_line_id.argtypes = [C.c_char_p, u64, C.c_int32]
+    L.stb_line_id.restype = u64
+    L.stb_ctx_counters.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    for name in SYMBOLS:
+        fn = getattr(L, name)
+        if fn.restype is C.c_int and name not in ("stb_version", "stb_device_count"):
+            fn.restype = i32
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> int:
+    if rc < 0 and rc != STB_ERR_CAPACITY:
+        raise StbError(rc, lib().stb_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+def _np_ptr(a):
+    return None if a is None else a.ctypes.data_as(vp)
+
+
+def device_count() -> int:
+    return int(lib().stb_device_count())
+
+
+def fnv1a64(data: bytes) -> int:
+    """fnv1a_hash / DocMeta::id (reference src/workspace/store.rs:651-661, :75-80)."""
+    return int(lib().stb_fnv1a64(data, len(data)))
+
+
+def line_id(path: str, line_number: int) -> int:
+    """LineEmbedding::id (reference src/workspace/store.rs:82-89)."""
+    b = path.encode("utf-8")
+    return int(lib().stb_line_id(b, len(b), line_number))
+
+
+class Context:
+    """stb_ctx: one CUDA device + stream.  `stream` is an optional raw cudaStream_t."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._h = vp()
+        _check(lib().stb_ctx_create(device, vp(stream) if stream else None, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().stb_ctx_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def sync(self):
+        _check(lib().stb_ctx_sync(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(lib().stb_ctx_stream(self._h) or 0)
+
+    def counters(self):
+        a, b = u64(0), u64(0)
+        _check(lib().stb_ctx_counters(self._h, C.byref(a), C.byref(b)))
+        return {"kernel_launches": int(a.value), "fallback_searches": int(b.value)}
+
+    # -- K4 ------------------------------------------------------------------
+    def hits_merge(self, lists: np.ndarray, top_k: int) -> np.ndarray:
+        """lists: (n_lists, per_list) array of HIT_DTYPE; returns the merged top_k."""
+        lists = np.ascontiguousarray(lists, dtype=HIT_DTYPE)
+        n_lists, per_list = lists.shape
+        out = np.zeros(max(top_k, 1), dtype=HIT_DTYPE)
+        n = u32(0)
+        _check(lib().stb_hits_merge(self._h, _np_ptr(lists), n_lists, per_list, top_k, _np_ptr(out),
+                                    C.byref(n)))
+        return out[: n.value]
+
+    def hits_merge_dev(self, lists_dev: int, n_lists: int, per_list: int, top_k: int, out_dev: int):
+        _check(lib().stb_hits_merge_dev(self._h, vp(lists_dev), n_lists, per_list, top_k, vp(out_dev)))
+
+
+class Table:
+    """stb_table: the StaticModel tensors resident in HBM."""
+
+    def __init__(self, ctx: Context, E, weights=None, mapping=None, normalize=True):
+        E = np.ascontiguousarray(E, dtype=np.float32)
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float32)
+        m = None if mapping is None else np.ascontiguousarray(mapping, dtype=np.uint32)
+        self.ctx = ctx
+        self._h = vp()
+        _check(lib().stb_table_load(ctx._h, _np_ptr(E), E.shape[0], E.shape[1], _np_ptr(w),
+                                    0 if w is None else w.size, _np_ptr(m), 0 if m is None else m.size,
+                                    int(normalize), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().stb_table_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+class Corpus:
+    """stb_corpus: contiguous N x 256 f32 line-vector matrix in HBM."""
+
+    def __init__(self, ctx: Context, capacity_rows: int = 1024, row_base: int = 0):
+        self.ctx = ctx
+        self.row_base = row_base
+        self._h = vp()
+        _check(lib().stb_corpus_create(ctx._h, STB_DIM, capacity_rows, row_base, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().stb_corpus_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def append(self, rows: np.ndarray):
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        if rows.size == 0:
+            return
+        if rows.ndim != 2 or rows.shape[1] != STB_DIM:
+            raise StbError(STB_ERR_ARG, f"rows must be (n,{STB_DIM}) f32")
+        _check(lib().stb_corpus_append(self._h, _np_ptr(rows), rows.shape[0]))
+
+    def append_dev(self, rows_dev: int, n: int):
+        _check(lib().stb_corpus_append_dev(self._h, vp(rows_dev), n))
+
+    def clear(self):
+        _check(lib().stb_corpus_clear(self._h))
+
+    def __len__(self) -> int:
+        n = u64(0)
+        _check(lib().stb_corpus_rows(self._h, C.byref(n)))
+        return int(n.value)
+
+    @property
+    def data_dev(self) -> int:
+        p = vp()
+        _check(lib().stb_corpus_data_dev(self._h, C.byref(p)))
+        return int(p.value or 0)
+
+    def read(self, first: int = 0, n: int | None = None) -> np.ndarray:
+        n = len(self) - first if n is None else n
+        out = np.empty((n, STB_DIM), dtype=np.float32)
+        _check(lib().stb_corpus_read(self._h, first, n, _np_ptr(out)))
+        return out
+
+    # -- K1 + K4 -------------------------------------------------------------
+    def search(self, q, top_k: int = 3, max_distance: float | None = None,
+               mode: int = STB_MODE_SEARCH_DOCUMENTS, row_ranges=None, cap: int | None = None):
+        """stb_search.  Returns a HIT_DTYPE array ordered by (distance,row)."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        if q.size != STB_DIM:
+            raise StbError(STB_ERR_ARG, f"query must have {STB_DIM} floats")
+        rr, n_rr = None, 0
+        if row_ranges is not None:
+            rr = np.ascontiguousarray(row_ranges, dtype=np.uint64).reshape(-1, 2)
+            n_rr = rr.shape[0]
+            if n_rr == 0:
+                rr = np.zeros((1, 2), dtype=np.uint64)   # non-null pointer, zero ranges
+        if cap is None:
+            cap = max(top_k, 1) if (max_distance is None or mode == STB_MODE_STORE_QUERY) else max(top_k, 4096)
+        while True:
+            out = np.zeros(max(cap, 1), dtype=HIT_DTYPE)
+            n = u64(0)
+            rc = _check(lib().stb_search(self.ctx._h, self._h, _np_ptr(q), top_k,
+                                         int(max_distance is not None), float(max_distance or 0.0), mode,
+                                         _np_ptr(rr), n_rr, _np_ptr(out), cap, C.byref(n)))
+            if rc == STB_ERR_CAPACITY:
+                cap = int(n.value)
+                continue
+            return out[: int(n.value)]
+
+    def search_topk_dev(self, q_dev: int, top_k: int, out_hits_dev: int, out_status_dev: int):
+        """stb_search_topk_dev: asynchronous, everything stays in HBM."""
+        _check(lib().stb_search_topk_dev(self.ctx._h, self._h, vp(q_dev), top_k, vp(out_hits_dev),
+                                         vp(out_status_dev)))
+
+
+def embed(ctx: Context, table: Table, offsets, ids, out: bool = True, append_to: Corpus | None = None):
+    """stb_embed (K3).  offsets: (n_lines+1,) u64 CSR; ids: u32 token ids."""
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    ids = np.ascontiguousarray(ids, dtype=np.uint32)
+    n_lines = offsets.size - 1
+    res = np.empty((n_lines, STB_DIM), dtype=np.float32) if out else None
+    if ids.size == 0:
+        ids = np.zeros(1, dtype=np.uint32)
+    _check(lib().stb_embed(ctx._h, table._h, _np_ptr(offsets), _np_ptr(ids), n_lines, _np_ptr(res),
+                           append_to._h if append_to is not None else None))
+    return res

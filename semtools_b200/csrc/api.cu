@@ -1,0 +1,534 @@
+// C ABI of libsemtools_b200.so (include/semtools_b200.h).  Host-side orchestration
+// only: argument checking, HBM residency, staging copies, and the exact
+// fallback ladder around the scan kernel.  No CPU implementation of any kernel
+// exists in this library: without an sm_100 device every entry point fails.
+#include <stdarg.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void stb_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------- context ---
+static int ctx_use(const stb_ctx *ctx) {
+  if (!ctx) { stb_set_error("null context"); return STB_ERR_ARG; }
+  STB_CUDA(cudaSetDevice(ctx->device));
+  return STB_OK;
+}
+
+template <class T>
+static int dev_reserve(T **p, size_t *cap, size_t need, size_t floor_cap = 0) {
+  if (need <= *cap && *p) return STB_OK;
+  size_t ncap = std::max(std::max(need, floor_cap), *cap + *cap / 2);
+  T *np = nullptr;
+  cudaError_t e = cudaMalloc((void **)&np, ncap * sizeof(T));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    stb_set_error("cudaMalloc(%zu bytes) failed: %s", ncap * sizeof(T), cudaGetErrorString(e));
+    return STB_ERR_NOMEM;
+  }
+  if (*p) cudaFree(*p);
+  *p = np;
+  *cap = ncap;
+  return STB_OK;
+}
+
+extern "C" {
+
+int stb_version(void) { return 100; }
+const char *stb_last_error(void) { return g_err; }
+
+int stb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int stb_ctx_create(int device, void *cuda_stream, stb_ctx **out) {
+  if (!out) { stb_set_error("out is null"); return STB_ERR_ARG; }
+  *out = nullptr;
+  int n = stb_device_count();
+  if (n <= 0) { stb_set_error("no CUDA device visible (this library has no CPU path)"); return STB_ERR_CUDA; }
+  if (device < 0 || device >= n) { stb_set_error("device %d out of range (0..%d)", device, n - 1); return STB_ERR_ARG; }
+  STB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  STB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    stb_set_error("device %d is sm_%d%d; libsemtools_b200 ships sm_100a code only", device, prop.major, prop.minor);
+    return STB_ERR_CUDA;
+  }
+  stb_ctx *c = new (std::nothrow) stb_ctx();
+  if (!c) { stb_set_error("out of host memory"); return STB_ERR_NOMEM; }
+  memset(c, 0, sizeof(*c));
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
+  else {
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { stb_set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); delete c; return STB_ERR_CUDA; }
+    c->own_stream = true;
+  }
+  int rc = STB_OK;
+  const size_t max_grid = (size_t)c->sm_count * 8;
+  if ((rc = dev_reserve(&c->block_keys, &c->block_keys_cap, 2 * max_grid * 128 + STB_SORT_CAP)) != STB_OK) goto fail;
+  if ((rc = dev_reserve(&c->counters, &c->counters_cap, max_grid + 64)) != STB_OK) goto fail;
+  {
+    size_t one = 0;
+    if ((rc = dev_reserve(&c->q_dev, &one, STB_D)) != STB_OK) goto fail;
+    one = 0;
+    if ((rc = dev_reserve(&c->status_dev, &one, 8)) != STB_OK) goto fail;
+    one = 0;
+    if ((rc = dev_reserve(&c->collect_count, &one, 2)) != STB_OK) goto fail;
+    one = 0;
+    if ((rc = dev_reserve(&c->err_flag, &one, 1)) != STB_OK) goto fail;
+  }
+  if ((rc = dev_reserve(&c->hits_dev, &c->hits_cap, 1024)) != STB_OK) goto fail;
+  if (cudaMemset(c->counters, 0, c->counters_cap * sizeof(unsigned int)) != cudaSuccess ||
+      cudaMallocHost((void **)&c->q_pin, STB_D * sizeof(float)) != cudaSuccess ||
+      cudaMallocHost((void **)&c->status_pin, 8 * sizeof(uint32_t)) != cudaSuccess ||
+      cudaMallocHost((void **)&c->hits_pin, 1024 * sizeof(stb_hit)) != cudaSuccess) {
+    stb_set_error("context staging allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    rc = STB_ERR_NOMEM;
+    goto fail;
+  }
+  c->hits_pin_cap = 1024;
+  *out = c;
+  return STB_OK;
+fail:
+  stb_ctx_destroy(c);
+  return rc;
+}
+
+int stb_ctx_destroy(stb_ctx *c) {
+  if (!c) return STB_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(c->block_keys); cudaFree(c->counters); cudaFree(c->q_dev); cudaFree(c->hits_dev);
+  cudaFree(c->status_dev); cudaFree(c->collect_rows); cudaFree(c->collect_count);
+  cudaFree(c->collect_hits); cudaFree(c->ranges_dev); cudaFree(c->err_flag);
+  cudaFree(c->embed_off_dev); cudaFree(c->embed_ids_dev); cudaFree(c->embed_out_dev);
+  if (c->q_pin) cudaFreeHost(c->q_pin);
+  if (c->hits_pin) cudaFreeHost(c->hits_pin);
+  if (c->status_pin) cudaFreeHost(c->status_pin);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  cudaGetLastError();
+  delete c;
+  return STB_OK;
+}
+
+int stb_ctx_sync(stb_ctx *ctx) {
+  int rc = ctx_use(ctx);
+  if (rc) return rc;
+  STB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return STB_OK;
+}
+
+void *stb_ctx_stream(stb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int stb_ctx_counters(const stb_ctx *ctx, uint64_t *kernel_launches, uint64_t *fallback_searches) {
+  if (!ctx) { stb_set_error("null context"); return STB_ERR_ARG; }
+  if (kernel_launches) *kernel_launches = ctx->kernel_launches;
+  if (fallback_searches) *fallback_searches = ctx->fallback_searches;
+  return STB_OK;
+}
+
+// --------------------------------------------------------------------- table ---
+int stb_table_load(stb_ctx *ctx, const float *E, uint64_t V, uint32_t D, const float *weights,
+                   uint64_t n_weights, const uint32_t *mapping, uint64_t n_mapping, int normalize,
+                   stb_table **out) {
+  int rc = ctx_use(ctx);
+  if (rc) return rc;
+  if (!out || !E || V == 0) { stb_set_error("table_load: null/empty table"); return STB_ERR_ARG; }
+  if (D != STB_D) { stb_set_error("table_load: D=%u, only %u supported", D, STB_D); return STB_ERR_ARG; }
+  if (V > 0xffffffffull) { stb_set_error("table_load: V exceeds 2^32 rows"); return STB_ERR_ARG; }
+  stb_table *t = new (std::nothrow) stb_table();
+  if (!t) { stb_set_error("out of host memory"); return STB_ERR_NOMEM; }
+  memset(t, 0, sizeof(*t));
+  t->ctx = ctx; t->V = V; t->normalize = normalize ? 1 : 0;
+  t->n_weights = weights ? n_weights : 0;
+  t->n_mapping = mapping ? n_mapping : 0;
+  cudaError_t e = cudaMalloc((void **)&t->E, V * STB_D * sizeof(float));
+  if (e == cudaSuccess && t->n_weights) e = cudaMalloc((void **)&t->weights, t->n_weights * sizeof(float));
+  if (e == cudaSuccess && t->n_mapping) e = cudaMalloc((void **)&t->mapping, t->n_mapping * sizeof(uint32_t));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    stb_set_error("table_load: device allocation failed: %s", cudaGetErrorString(e));
+    stb_table_destroy(t);
+    return STB_ERR_NOMEM;
+  }
+  e = cudaMemcpyAsync(t->E, E, V * STB_D * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && t->n_weights)
+    e = cudaMemcpyAsync(t->weights, weights, t->n_weights * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && t->n_mapping)
+    e = cudaMemcpyAsync(t->mapping, mapping, t->n_mapping * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    stb_set_error("table_load: upload failed: %s", cudaGetErrorString(e));
+    stb_table_destroy(t);
+    return STB_ERR_CUDA;
+  }
+  *out = t;
+  return STB_OK;
+}
+
+int stb_table_destroy(stb_table *t) {
+  if (!t) return STB_OK;
+  if (t->ctx) cudaSetDevice(t->ctx->device);
+  cudaFree(t->E); cudaFree(t->weights); cudaFree(t->mapping);
+  cudaGetLastError();
+  delete t;
+  return STB_OK;
+}
+
+// -------------------------------------------------------------------- corpus ---
+static int corpus_reserve(stb_corpus *c, uint64_t need) {
+  if (need <= c->capacity && c->rows) return STB_OK;
+  if (need > 0xfffffffeull) { stb_set_error("corpus shard exceeds 2^32-2 rows; shard it"); return STB_ERR_ARG; }
+  uint64_t ncap = std::max<uint64_t>(std::max<uint64_t>(need, 1024), c->capacity + c->capacity / 2);
+  float *np = nullptr;
+  cudaError_t e = cudaMalloc((void **)&np, ncap * STB_D * sizeof(float));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    stb_set_error("corpus: cudaMalloc(%llu rows) failed: %s", (unsigned long long)ncap, cudaGetErrorString(e));
+    return STB_ERR_NOMEM;
+  }
+  if (c->rows && c->n) {
+    e = cudaMemcpyAsync(np, c->rows, c->n * STB_D * sizeof(float), cudaMemcpyDeviceToDevice, c->ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->ctx->stream);
+    if (e != cudaSuccess) { cudaFree(np); stb_set_error("corpus grow copy: %s", cudaGetErrorString(e)); return STB_ERR_CUDA; }
+  }
+  if (c->rows) cudaFree(c->rows);
+  c->rows = np;
+  c->capacity = ncap;
+  return STB_OK;
+}
+
+int stb_corpus_create(stb_ctx *ctx, uint32_t D, uint64_t capacity_rows, uint64_t row_base, stb_corpus **out) {
+  int rc = ctx_use(ctx);
+  if (rc) return rc;
+  if (!out) { stb_set_error("out is null"); return STB_ERR_ARG; }
+  if (D != STB_D) { stb_set_error("corpus_create: D=%u, only %u supported", D, STB_D); return STB_ERR_ARG; }
+  stb_corpus *c = new (std::nothrow) stb_corpus();
+  if (!c) { stb_set_error("out of host memory"); return STB_ERR_NOMEM; }
+  memset(c, 0, sizeof(*c));
+  c->ctx = ctx; c->row_base = row_base;
+  rc = corpus_reserve(c, std::max<uint64_t>(capacity_rows, 1));
+  if (rc) { delete c; return rc; }
+  *out = c;
+  return STB_OK;
+}
+
+int stb_corpus_destroy(stb_corpus *c) {
+  if (!c) return STB_OK;
+  if (c->ctx) { cudaSetDevice(c->ctx->device); cudaStreamSynchronize(c->ctx->stream); }
+  cudaFree(c->rows);
+  cudaGetLastError();
+  delete c;
+  return STB_OK;
+}
+
+static int corpus_append_impl(stb_corpus *c, const float *rows, uint64_t n, cudaMemcpyKind kind) {
+  if (!c) { stb_set_error("null corpus"); return STB_ERR_ARG; }
+  int rc = ctx_use(c->ctx);
+  if (rc) return rc;
+  if (n == 0) return STB_OK;
+  if (!rows) { stb_set_error("corpus_append: rows is null"); return STB_ERR_ARG; }
+  if ((rc = corpus_reserve(c, c->n + n)) != STB_OK) return rc;
+  STB_CUDA(cudaMemcpyAsync(c->rows + c->n * STB_D, rows, n * STB_D * sizeof(float), kind, c->ctx->stream));
+  STB_CUDA(cudaStreamSynchronize(c->ctx->stream));
+  c->n += n;
+  return STB_OK;
+}
+
+int stb_corpus_append(stb_corpus *c, const float *rows, uint64_t n) {
+  return corpus_append_impl(c, rows, n, cudaMemcpyHostToDevice);
+}
+int stb_corpus_append_dev(stb_corpus *c, const float *rows_dev, uint64_t n) {
+  return corpus_append_impl(c, rows_dev, n, cudaMemcpyDeviceToDevice);
+}
+int stb_corpus_clear(stb_corpus *c) {
+  if (!c) { stb_set_error("null corpus"); return STB_ERR_ARG; }
+  c->n = 0;
+  return STB_OK;
+}
+int stb_corpus_rows(const stb_corpus *c, uint64_t *n) {
+  if (!c || !n) { stb_set_error("null argument"); return STB_ERR_ARG; }
+  *n = c->n;
+  return STB_OK;
+}
+int stb_corpus_data_dev(const stb_corpus *c, float **rows_dev) {
+  if (!c || !rows_dev) { stb_set_error("null argument"); return STB_ERR_ARG; }
+  *rows_dev = c->rows;
+  return STB_OK;
+}
+int stb_corpus_read(const stb_corpus *c, uint64_t first, uint64_t n, float *rows) {
+  if (!c || (!rows && n)) { stb_set_error("null argument"); return STB_ERR_ARG; }
+  int rc = ctx_use(c->ctx);
+  if (rc) return rc;
+  if (first > c->n || n > c->n - first) { stb_set_error("corpus_read: rows [%llu,+%llu) outside corpus of %llu",
+      (unsigned long long)first, (unsigned long long)n, (unsigned long long)c->n); return STB_ERR_RANGE; }
+  if (n == 0) return STB_OK;
+  STB_CUDA(cudaMemcpyAsync(rows, c->rows + first * STB_D, n * STB_D * sizeof(float), cudaMemcpyDeviceToHost, c->ctx->stream));
+  STB_CUDA(cudaStreamSynchronize(c->ctx->stream));
+  return STB_OK;
+}
+
+// ---------------------------------------------------------------------- embed ---
+int stb_embed(stb_ctx *ctx, const stb_table *table, const uint64_t *offsets, const uint32_t *ids,
+              uint64_t n_lines, float *out, stb_corpus *append_to) {
+  int rc = ctx_use(ctx);
+  if (rc) return rc;
+  if (!table) { stb_set_error("embed: null table"); return STB_ERR_ARG; }
+  if (table->ctx != ctx || (append_to && append_to->ctx != ctx)) { stb_set_error("embed: handles belong to another context"); return STB_ERR_ARG; }
+  if (n_lines == 0) return STB_OK;
+  if (!offsets) { stb_set_error("embed: offsets is null"); return STB_ERR_ARG; }
+  if (offsets[0] != 0) { stb_set_error("embed: offsets[0] must be 0"); return STB_ERR_ARG; }
+  const uint64_t total = offsets[n_lines];
+  for (uint64_t i = 0; i < n_lines; ++i)
+    if (offsets[i + 1] < offsets[i]) { stb_set_error("embed: offsets not monotone at line %llu", (unsigned long long)i); return STB_ERR_ARG; }
+  if (total && !ids) { stb_set_error("embed: ids is null"); return STB_ERR_ARG; }
+  if ((rc = dev_reserve(&ctx->embed_off_dev, &ctx->embed_off_cap, n_lines + 1, 4096)) != STB_OK) return rc;
+  if ((rc = dev_reserve(&ctx->embed_ids_dev, &ctx->embed_ids_cap, std::max<uint64_t>(total, 1), 65536)) != STB_OK) return rc;
+  float *dst = nullptr;
+  if (append_to) {
+    if ((rc = corpus_reserve(append_to, append_to->n + n_lines)) != STB_OK) return rc;
+    dst = append_to->rows + append_to->n * STB_D;
+  } else {
+    if ((rc = dev_reserve(&ctx->embed_out_dev, &ctx->embed_out_cap, n_lines * STB_D, 4096 * STB_D)) != STB_OK) return rc;
+    dst = ctx->embed_out_dev;
+  }
+  STB_CUDA(cudaMemcpyAsync(ctx->embed_off_dev, offsets, (n_lines + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (total) STB_CUDA(cudaMemcpyAsync(ctx->embed_ids_dev, ids, total * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  STB_CUDA(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), ctx->stream));
+  if ((rc = stb_launch_embed(ctx, table, ctx->embed_off_dev, ctx->embed_ids_dev, n_lines, dst, ctx->err_flag)) != STB_OK) return rc;
+  int flag = 0;
+  STB_CUDA(cudaMemcpyAsync(&flag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (out) STB_CUDA(cudaMemcpyAsync(out, dst, n_lines * STB_D * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  STB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (flag) { stb_set_error("embed: a token id maps outside the %llu-row table", (unsigned long long)table->V); return STB_ERR_RANGE; }
+  if (append_to) append_to->n += n_lines;
+  return STB_OK;
+}
+
+// --------------------------------------------------------------------- search ---
+static int ensure_hits_pin(stb_ctx *ctx, size_t need) {
+  if (need <= ctx->hits_pin_cap) return STB_OK;
+  stb_hit *np = nullptr;
+  size_t ncap = std::max(need, ctx->hits_pin_cap * 2);
+  if (cudaMallocHost((void **)&np, ncap * sizeof(stb_hit)) != cudaSuccess) {
+    cudaGetLastError();
+    stb_set_error("pinned staging allocation failed");
+    return STB_ERR_NOMEM;
+  }
+  cudaFreeHost(ctx->hits_pin);
+  ctx->hits_pin = np;
+  ctx->hits_pin_cap = ncap;
+  return STB_OK;
+}
+
+// Exact path for any input: collect rows whose approximate cosine >= cos_floor,
+// score them canonically, keep distance < limit, sort by (distance,row).
+// On return ctx->collect_hits holds the sorted hits and *n_pass their count.
+static int collect_exact_sorted(stb_ctx *ctx, const stb_corpus *c, float cos_floor, double limit,
+                                const uint64_t *ranges_dev, uint32_t n_ranges, uint64_t n_virtual,
+                                uint64_t *n_pass) {
+  int rc;
+  unsigned long long count = 0;
+  if ((rc = dev_reserve(&ctx->collect_rows, &ctx->collect_cap, 1, 1u << 20)) != STB_OK) return rc;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    if ((rc = stb_launch_scan_collect(ctx, c->rows, c->n, ctx->q_dev, cos_floor, ranges_dev, n_ranges, n_virtual)) != STB_OK) return rc;
+    STB_CUDA(cudaMemcpyAsync(&count, ctx->collect_count, sizeof(count), cudaMemcpyDeviceToHost, ctx->stream));
+    STB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (count <= ctx->collect_cap) break;
+    if ((rc = dev_reserve(&ctx->collect_rows, &ctx->collect_cap, (size_t)count)) != STB_OK) return rc;
+  }
+  if (count > ctx->collect_cap) { stb_set_error("collect buffer could not be sized"); return STB_ERR_STATE; }
+  uint64_t m = count, m_padded = 1024;
+  while (m_padded < m) m_padded <<= 1;
+  if ((rc = dev_reserve(&ctx->collect_hits, &ctx->collect_hits_cap, (size_t)m_padded)) != STB_OK) return rc;
+  if ((rc = stb_launch_exact(ctx, c->rows, c->row_base, ctx->q_dev, ctx->collect_rows, m, limit,
+                             ctx->collect_hits, m_padded, ctx->collect_count + 1)) != STB_OK) return rc;
+  if ((rc = stb_launch_sort_hits(ctx, ctx->collect_hits, m_padded)) != STB_OK) return rc;
+  unsigned long long pass = 0;
+  STB_CUDA(cudaMemcpyAsync(&pass, ctx->collect_count + 1, sizeof(pass), cudaMemcpyDeviceToHost, ctx->stream));
+  STB_CUDA(cudaStreamSynchronize(ctx->stream));
+  *n_pass = pass;
+  return STB_OK;
+}
+
+int stb_search(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint32_t top_k, int has_max,
+               double max_distance, int mode, const uint64_t *row_ranges, uint32_t n_ranges,
+               stb_hit *out_hits, uint64_t cap, uint64_t *out_n) {
+  int rc = ctx_use(ctx);
+  if (rc) return rc;
+  if (!corpus || !q || !out_n) { stb_set_error("search: null argument"); return STB_ERR_ARG; }
+  if (corpus->ctx != ctx) { stb_set_error("search: corpus belongs to another context"); return STB_ERR_ARG; }
+  if (mode != STB_MODE_SEARCH_DOCUMENTS && mode != STB_MODE_STORE_QUERY) { stb_set_error("search: bad mode %d", mode); return STB_ERR_ARG; }
+  if (n_ranges && !row_ranges) { stb_set_error("search: row_ranges is null"); return STB_ERR_ARG; }
+  if (cap && !out_hits) { stb_set_error("search: out_hits is null"); return STB_ERR_ARG; }
+  *out_n = 0;
+  const bool threshold_all = (mode == STB_MODE_SEARCH_DOCUMENTS) && has_max;   // src/search/mod.rs:115-116
+  if (!threshold_all && top_k == 0) return STB_OK;                             // take(0) / store.rs:489-491
+  if (mode == STB_MODE_STORE_QUERY && row_ranges && n_ranges == 0) return STB_OK;  // empty subset, store.rs:489
+  if (corpus->n == 0) return STB_OK;
+
+  // ---- row ranges: global -> local, clipped to this shard ----------------------
+  const uint64_t *ranges_dev = nullptr;
+  uint32_t n_loc = 0;
+  uint64_t n_virtual = corpus->n;
+  if (row_ranges) {
+    std::vector<uint64_t> vstart, rbegin;
+    vstart.reserve(n_ranges + 1); rbegin.reserve(n_ranges);
+    uint64_t acc = 0, prev_end = 0;
+    const uint64_t lo = corpus->row_base, hi = corpus->row_base + corpus->n;
+    for (uint32_t i = 0; i < n_ranges; ++i) {
+      uint64_t b = row_ranges[2 * i], e = row_ranges[2 * i + 1];
+      if (e < b || (i > 0 && b < prev_end)) { stb_set_error("search: row_ranges must be ascending, disjoint, half-open"); return STB_ERR_RANGE; }
+      prev_end = e;
+      b = std::max(b, lo); e = std::min(e, hi);
+      if (b >= e) continue;
+      vstart.push_back(acc); rbegin.push_back(b - lo);
+      acc += e - b;
+    }
+    if (acc == 0) return STB_OK;
+    vstart.push_back(acc);
+    n_loc = (uint32_t)rbegin.size();
+    n_virtual = acc;
+    std::vector<uint64_t> packed(vstart);
+    packed.insert(packed.end(), rbegin.begin(), rbegin.end());
+    if ((rc = dev_reserve(&ctx->ranges_dev, &ctx->ranges_cap, packed.size(), 4096)) != STB_OK) return rc;
+    STB_CUDA(cudaMemcpyAsync(ctx->ranges_dev, packed.data(), packed.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    STB_CUDA(cudaStreamSynchronize(ctx->stream));   // `packed` dies at scope end
+    ranges_dev = ctx->ranges_dev;
+  }
+
+  memcpy(ctx->q_pin, q, STB_D * sizeof(float));
+  STB_CUDA(cudaMemcpyAsync(ctx->q_dev, ctx->q_pin, STB_D * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+
+  uint64_t total = 0;
+  const stb_hit *src_dev = nullptr;   // sorted device hits to copy out (collect path)
+  if (!threshold_all && top_k <= stb_scan_topk_max_k()) {
+    // ---- fast path: one kernel, k*16+16 bytes back -----------------------------
+    if ((rc = stb_launch_scan_topk(ctx, corpus->rows, corpus->n, corpus->row_base, ctx->q_dev, top_k,
+                                   ranges_dev, n_loc, n_virtual, ctx->hits_dev, ctx->status_dev)) != STB_OK) return rc;
+    STB_CUDA(cudaMemcpyAsync(ctx->status_pin, ctx->status_dev, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    STB_CUDA(cudaMemcpyAsync(ctx->hits_pin, ctx->hits_dev, top_k * sizeof(stb_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    STB_CUDA(cudaStreamSynchronize(ctx->stream));
+    const uint32_t n_hits = ctx->status_pin[0];
+    if (ctx->status_pin[1]) {
+      uint64_t n = 0;
+      for (uint32_t i = 0; i < n_hits; ++i) {
+        if (has_max && !(ctx->hits_pin[i].distance < max_distance)) break;   // strict, sorted ascending
+        if (n < cap) out_hits[n] = ctx->hits_pin[i];
+        ++n;
+      }
+      *out_n = n;
+      if (n > cap) { stb_set_error("search: %llu hits, capacity %llu", (unsigned long long)n, (unsigned long long)cap); return STB_ERR_CAPACITY; }
+      return STB_OK;
+    }
+    // ---- candidate margin not provable: exact collect pass --------------------
+    ctx->fallback_searches++;
+    float floor_cos = -INFINITY;
+    if (n_hits == top_k) floor_cos = (float)(1.0 - ctx->hits_pin[top_k - 1].distance - 2.0 * STB_SCORE_EPS);
+    uint64_t n_pass = 0;
+    if ((rc = collect_exact_sorted(ctx, corpus, floor_cos, has_max ? std::min(max_distance, 100.0) : 100.0,
+                                   ranges_dev, n_loc, n_virtual, &n_pass)) != STB_OK) return rc;
+    total = std::min<uint64_t>(n_pass, top_k);
+    src_dev = ctx->collect_hits;
+  } else {
+    float floor_cos = -INFINITY;
+    double limit = 100.0;
+    if (threshold_all) {
+      limit = max_distance;
+      floor_cos = (float)(1.0 - max_distance - STB_SCORE_EPS);
+      if (!(max_distance == max_distance)) floor_cos = INFINITY;   // NaN threshold: nothing passes
+    } else if (has_max) {
+      limit = std::min(max_distance, 100.0);
+      if (!(max_distance == max_distance)) limit = -1.0;
+    }
+    uint64_t n_pass = 0;
+    if ((rc = collect_exact_sorted(ctx, corpus, floor_cos, limit, ranges_dev, n_loc, n_virtual, &n_pass)) != STB_OK) return rc;
+    total = threshold_all ? n_pass : std::min<uint64_t>(n_pass, top_k);
+    src_dev = ctx->collect_hits;
+  }
+  *out_n = total;
+  uint64_t ncopy = std::min(total, cap);
+  if (ncopy) {
+    STB_CUDA(cudaMemcpyAsync(out_hits, src_dev, ncopy * sizeof(stb_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    STB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  if (total > cap) { stb_set_error("search: %llu hits, capacity %llu", (unsigned long long)total, (unsigned long long)cap); return STB_ERR_CAPACITY; }
+  return STB_OK;
+}
+
+int stb_search_topk_dev(stb_ctx *ctx, const stb_corpus *corpus, const float *q_dev, uint32_t top_k,
+                        stb_hit *out_hits_dev, uint32_t *out_status_dev) {
+  int rc = ctx_use(ctx);
+  if (rc) return rc;
+  if (!corpus || !q_dev || !out_hits_dev || !out_status_dev) { stb_set_error("search_topk_dev: null argument"); return STB_ERR_ARG; }
+  if (corpus->ctx != ctx) { stb_set_error("search_topk_dev: corpus belongs to another context"); return STB_ERR_ARG; }
+  if (top_k == 0 || top_k > stb_scan_topk_max_k()) { stb_set_error("search_topk_dev: top_k must be 1..%u", stb_scan_topk_max_k()); return STB_ERR_ARG; }
+  if (corpus->n == 0) { stb_set_error("search_topk_dev: empty corpus"); return STB_ERR_STATE; }
+  return stb_launch_scan_topk(ctx, corpus->rows, corpus->n, corpus->row_base, q_dev, top_k, nullptr, 0,
+                              corpus->n, out_hits_dev, out_status_dev);
+}
+
+// ---------------------------------------------------------------------- merge ---
+int stb_hits_merge_dev(stb_ctx *ctx, const stb_hit *lists_dev, uint32_t n_lists, uint32_t per_list,
+                       uint32_t top_k, stb_hit *out_dev) {
+  int rc = ctx_use(ctx);
+  if (rc) return rc;
+  if (!lists_dev || !out_dev || n_lists == 0 || per_list == 0 || top_k == 0) { stb_set_error("hits_merge: bad argument"); return STB_ERR_ARG; }
+  return stb_launch_hits_merge(ctx, lists_dev, n_lists, per_list, top_k, out_dev);
+}
+
+int stb_hits_merge(stb_ctx *ctx, const stb_hit *lists, uint32_t n_lists, uint32_t per_list,
+                   uint32_t top_k, stb_hit *out, uint32_t *out_n) {
+  int rc = ctx_use(ctx);
+  if (rc) return rc;
+  if (!lists || !out || !out_n || n_lists == 0 || per_list == 0) { stb_set_error("hits_merge: bad argument"); return STB_ERR_ARG; }
+  *out_n = 0;
+  if (top_k == 0) return STB_OK;
+  const size_t total = (size_t)n_lists * per_list;
+  if ((rc = dev_reserve(&ctx->hits_dev, &ctx->hits_cap, total + top_k)) != STB_OK) return rc;
+  if ((rc = ensure_hits_pin(ctx, std::max<size_t>(total, top_k))) != STB_OK) return rc;
+  memcpy(ctx->hits_pin, lists, total * sizeof(stb_hit));
+  STB_CUDA(cudaMemcpyAsync(ctx->hits_dev, ctx->hits_pin, total * sizeof(stb_hit), cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = stb_launch_hits_merge(ctx, ctx->hits_dev, n_lists, per_list, top_k, ctx->hits_dev + total)) != STB_OK) return rc;
+  STB_CUDA(cudaMemcpyAsync(ctx->hits_pin, ctx->hits_dev + total, top_k * sizeof(stb_hit), cudaMemcpyDeviceToHost, ctx->stream));
+  STB_CUDA(cudaStreamSynchronize(ctx->stream));
+  uint32_t n = 0;
+  for (uint32_t i = 0; i < top_k; ++i) {
+    if (ctx->hits_pin[i].row == 0xffffffffffffffffull) break;
+    out[n++] = ctx->hits_pin[i];
+  }
+  *out_n = n;
+  return STB_OK;
+}
+
+// ------------------------------------------------------------------------ ids ---
+uint64_t stb_fnv1a64(const uint8_t *bytes, uint64_t len) {
+  uint64_t h = 0xcbf29ce484222325ull;
+  for (uint64_t i = 0; i < len; ++i) { h ^= bytes[i]; h *= 0x100000001b3ull; }
+  return h;
+}
+
+uint64_t stb_line_id(const uint8_t *path, uint64_t path_len, int32_t line_number) {
+  uint64_t h = 0xcbf29ce484222325ull;
+  for (uint64_t i = 0; i < path_len; ++i) { h ^= path[i]; h *= 0x100000001b3ull; }
+  const uint32_t u = (uint32_t)line_number;
+  for (int b = 0; b < 4; ++b) { h ^= (u >> (8 * b)) & 0xffu; h *= 0x100000001b3ull; }
+  return h;
+}
+
+}  // extern "C"

@@ -1,0 +1,154 @@
+// Internal declarations shared by the translation units of libsemtools_b200.so.
+// Everything here is sm_100a-only product code; nothing in this directory may
+// include, link or call anything under oracle/.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/semtools_b200.h"
+
+#define STB_D 256           // floats per row
+#define STB_ROW_F4 64       // float4 per row
+#define STB_SCAN_THREADS 256
+#define STB_SCAN_WARPS (STB_SCAN_THREADS / 32)
+#define STB_SORT_CAP 1024   // keys one CTA sorts in shared memory
+// Rigorous bound (with ~4x slack) on |approx cosine - exact cosine| for the fp32
+// scan arithmetic on rows whose squared norm is a normal fp32 number; derivation
+// in DESIGN.md "Candidate completeness".  Rows outside that range are forced
+// into the candidate set instead of being scored.
+#define STB_SCORE_EPS 1.0e-5
+
+void stb_set_error(const char *fmt, ...);
+
+#define STB_CUDA(call)                                                             \
+  do {                                                                             \
+    cudaError_t _e = (call);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      stb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,                  \
+                    cudaGetErrorString(_e));                                       \
+      return STB_ERR_CUDA;                                                         \
+    }                                                                              \
+  } while (0)
+
+struct stb_ctx {
+  int device;
+  int sm_count;
+  cudaStream_t stream;
+  bool own_stream;
+  // --- scan scratch (device) ---
+  uint64_t *block_keys;     // candidate keys of every tree level
+  size_t block_keys_cap;    // in keys
+  unsigned int *counters;   // tree arrival counters (zeroed; kernels re-zero)
+  size_t counters_cap;
+  float *q_dev;             // 256 f32 staging for host queries
+  stb_hit *hits_dev;        // result hits (top-k path)
+  size_t hits_cap;
+  uint32_t *status_dev;     // [0]=n hits, [1]=complete flag, [2..] debug
+  uint32_t *collect_rows;   // threshold/fallback compaction: local row ids
+  size_t collect_cap;
+  unsigned long long *collect_count;
+  stb_hit *collect_hits;    // exact hits of collected rows (sorted in place)
+  size_t collect_hits_cap;
+  uint64_t *ranges_dev;     // [3 * n] : begin(local), end(local), vstart
+  size_t ranges_cap;
+  int *err_flag;            // device int for K3 range errors
+  uint64_t *embed_off_dev;  // K3 staging: CSR offsets
+  size_t embed_off_cap;
+  uint32_t *embed_ids_dev;  // K3 staging: token ids
+  size_t embed_ids_cap;
+  float *embed_out_dev;     // K3 output when not appending to a corpus
+  size_t embed_out_cap;
+  // --- pinned host staging ---
+  float *q_pin;
+  stb_hit *hits_pin;
+  size_t hits_pin_cap;
+  uint32_t *status_pin;
+  // --- counters ---
+  uint64_t kernel_launches;
+  uint64_t fallback_searches;
+};
+
+struct stb_table {
+  stb_ctx *ctx;
+  float *E;            // V x 256
+  uint64_t V;
+  float *weights;      // or nullptr
+  uint64_t n_weights;
+  uint32_t *mapping;   // or nullptr
+  uint64_t n_mapping;
+  int normalize;
+};
+
+struct stb_corpus {
+  stb_ctx *ctx;
+  float *rows;         // capacity x 256
+  uint64_t n;
+  uint64_t capacity;
+  uint64_t row_base;
+};
+
+// ---- scan_topk.cu -------------------------------------------------------------
+// Fast path: one kernel = scan + per-warp running top-K' + CTA/tree merge +
+// exact f64 re-rank + completeness check.  q_dev: 256 f32 on device.
+// n_ranges > 0: ranges_dev holds local [begin,end,vstart] triples.
+int stb_launch_scan_topk(stb_ctx *ctx, const float *rows, uint64_t n_rows,
+                         uint64_t row_base, const float *q_dev, uint32_t top_k,
+                         const uint64_t *ranges_dev, uint32_t n_ranges,
+                         uint64_t n_virtual, stb_hit *out_hits_dev,
+                         uint32_t *out_status_dev);
+// Largest top_k the fast path serves.
+uint32_t stb_scan_topk_max_k(void);
+// Collect path: every row whose approximate cosine >= cos_floor (or that cannot be
+// scored safely) is appended to ctx->collect_rows; total count -> collect_count.
+int stb_launch_scan_collect(stb_ctx *ctx, const float *rows, uint64_t n_rows,
+                            const float *q_dev, float cos_floor,
+                            const uint64_t *ranges_dev, uint32_t n_ranges,
+                            uint64_t n_virtual);
+// Exact canonical distances of m collected rows -> hits (invalid/failing rows get
+// distance=+inf,row=UINT64_MAX); counts passing rows into pass_count.
+int stb_launch_exact(stb_ctx *ctx, const float *rows, uint64_t row_base,
+                     const float *q_dev, const uint32_t *row_ids, uint64_t m,
+                     double limit, stb_hit *hits, uint64_t m_padded,
+                     unsigned long long *pass_count);
+// In-place ascending sort by (distance,row) of m_padded (power of two) hits.
+int stb_launch_sort_hits(stb_ctx *ctx, stb_hit *hits, uint64_t m_padded);
+
+// ---- hits_merge.cu --------------------------------------------------------------
+int stb_launch_hits_merge(stb_ctx *ctx, const stb_hit *lists_dev, uint32_t n_lists,
+                          uint32_t per_list, uint32_t top_k, stb_hit *out_dev);
+
+// ---- embed_pool.cu --------------------------------------------------------------
+int stb_launch_embed(stb_ctx *ctx, const stb_table *t, const uint64_t *offsets_dev,
+                     const uint32_t *ids_dev, uint64_t n_lines, float *out_dev,
+                     int *err_flag_dev);
+
+// ---- device helpers ---------------------------------------------------------------
+#ifdef __CUDACC__
+// Monotone map float -> uint32 (larger float -> larger uint), total order with
+// -inf lowest; NaN never reaches it.
+__device__ __forceinline__ uint32_t stb_f2ord(float f) {
+  uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float stb_ord2f(uint32_t o) {
+  uint32_t b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+  return __uint_as_float(b);
+}
+// Candidate key: ascending key order == (score descending, row ascending).
+__device__ __forceinline__ uint64_t stb_make_key(float score, uint32_t row) {
+  return ((uint64_t)(~stb_f2ord(score)) << 32) | (uint64_t)row;
+}
+#define STB_KEY_INVALID 0xffffffffffffffffull
+__device__ __forceinline__ float stb_key_score(uint64_t k) {
+  return stb_ord2f(~(uint32_t)(k >> 32));
+}
+__device__ __forceinline__ uint32_t stb_key_row(uint64_t k) { return (uint32_t)k; }
+
+__device__ __forceinline__ bool stb_hit_less(double da, uint64_t ra, double db,
+                                             uint64_t rb) {
+  return (da < db) || (da == db && ra < rb);
+}
+#endif
