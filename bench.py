@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- queries/sec of the semtools `search` scan on B200 (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 200 --warmup 10
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference            # the reference's CPU scan on the host cores
+
+A "step" is one query: one pass of the hot path (K1 cosine scan + running top-k +
+exact re-rank [+ NCCL all-gather + K4 merge when sharded]) over the whole corpus.
+Workload: the 10M-line x 256 f32 corpus BASELINE.json's metric is quoted on, top-k 10,
+single query (the HBM-bound brute-force scan; corpus = 10.24 GB >> 126 MB L2, so every
+step streams from HBM and no L2 flush is needed).  N > 1 shards the SAME corpus
+row-wise across ranks ("strong" scaling), one process per GPU.
+
+PyTorch is used here for plumbing only: device allocation of the synthetic corpus,
+CUDA events on the launching stream, torch.distributed (NCCL) for the 160-byte
+per-rank top-k exchange.  All compute is libsemtools_b200.so via its C ABI.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CHUNK = 1_000_000
+SEED = 0x5E117003
+METRIC = "queries/sec over 10M-line corpus, top-k=10"
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=200)
+    p.add_argument("--warmup", type=int, default=10)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--rows", type=int, default=10_000_000)
+    p.add_argument("--topk", type=int, default=10)
+    p.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def workload_name(rows, topk):
+    return (f"{rows}-line corpus x 256 f32 (N(0,1) rows L2-normalised, 0.1% duplicate + 0.01% zero rows), "
+            f"single query, top-k={topk}, brute-force cosine scan (BASELINE configs[1] kernel at the "
+            f"metric's corpus size)")
+
+
+# ------------------------------------------------------------------ synthetic data ---
+def gen_chunk_torch(torch, dev, chunk_id, rows):
+    """Chunk `chunk_id` of the global corpus: identical whatever the rank count."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(SEED + chunk_id)
+    x = torch.randn((rows, 256), generator=g, device=dev, dtype=torch.float32)
+    x /= x.norm(dim=1, keepdim=True)
+    n_dup, n_zero = max(rows // 1000, 1), max(rows // 10000, 1)
+    idx = torch.randint(0, rows, (2 * n_dup + n_zero,), generator=g, device=dev)
+    x[idx[:n_dup]] = x[idx[n_dup:2 * n_dup]]
+    x[idx[2 * n_dup:]] = 0.0
+    return x
+
+
+def gen_chunk_numpy(chunk_id, rows):
+    rng = np.random.default_rng(SEED + chunk_id)
+    x = rng.standard_normal((rows, 256), dtype=np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    n_dup, n_zero = max(rows // 1000, 1), max(rows // 10000, 1)
+    idx = rng.integers(0, rows, 2 * n_dup + n_zero)
+    x[idx[:n_dup]] = x[idx[n_dup:2 * n_dup]]
+    x[idx[2 * n_dup:]] = 0.0
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+def gen_queries(n):
+    rng = np.random.default_rng(SEED - 1)
+    q = rng.standard_normal((n, 256)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    return np.ascontiguousarray(q, dtype=np.float32)
+
+
+# ------------------------------------------------------------------ clock sampling ---
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------ CPU baseline -----
+def cpu_baseline(sample_rows_arr, queries, rows_total, topk, threads):
+    """Times oracle/cpu_baseline.c (the reference's scan restated) on a bounded sample
+    and scales linearly in rows (optimistic for the CPU: its sort is N log N)."""
+    import oracle
+    n = sample_rows_arr.shape[0]
+    oracle.baseline_search(sample_rows_arr[:1000], queries[0], topk, threads=threads)   # load lib
+    times = []
+    for i in range(3):
+        t0 = time.perf_counter()
+        oracle.baseline_search(sample_rows_arr, queries[i % len(queries)], topk, threads=threads)
+        times.append(time.perf_counter() - t0)
+    t = float(np.median(times))
+    scale = rows_total / n
+    return 1.0 / (t * scale), t
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path.  The Rust reference cannot be
+    built here (no cargo/rustc; model2vec-rs / simsimd not vendored), so this is the
+    oracle port of search_documents (oracle/cpu_baseline.c), single-threaded like the
+    reference's loop (src/search/mod.rs:84-104)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    sample = min(args.cpu_sample_rows, args.rows)
+    rows = gen_chunk_numpy(0, sample)
+    queries = gen_queries(8)
+    steps = max(1, min(args.steps, 5))
+    for i in range(min(args.warmup, 1)):
+        oracle.baseline_search(rows, queries[i], args.topk, threads=1)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        oracle.baseline_search(rows, queries[i % 8], args.topk, threads=1)
+    dt = (time.perf_counter() - t0) / steps
+    scale = args.rows / sample
+    qps = 1.0 / (dt * scale)
+    omp_threads = oracle.baseline_threads()
+    t1 = time.perf_counter()
+    oracle.baseline_search(rows, queries[0], args.topk, threads=omp_threads)
+    dt_omp = time.perf_counter() - t1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": 0,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * scale * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args.rows, args.topk), "rows": args.rows, "top_k": args.topk},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": 1, "kind": "port",
+                         "sample": f"{sample} of {args.rows} rows per step, time scaled x{scale:g} (linear; "
+                                   f"the reference's full sort is N log N so this favours the CPU)",
+                         "host_cores": os.cpu_count(),
+                         "all_cores_not_reference_behaviour": {"threads": omp_threads,
+                                                               "value": 1.0 / (dt_omp * scale)}},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ our arm ----------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from semtools_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    # a dedicated non-default stream shared by torch (events, NCCL ordering) and the library
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ctx = capi.Context(local_rank, stream.cuda_stream)
+    assert ctx.stream == stream.cuda_stream
+    k = args.topk
+
+    # ---- corpus shard of this rank (strong scaling: the SAME global corpus) --------
+    per = (args.rows + world - 1) // world
+    lo, hi = min(rank * per, args.rows), min((rank + 1) * per, args.rows)
+    corpus = capi.Corpus(ctx, max(hi - lo, 1), row_base=lo)
+    for c in range(lo // CHUNK, (max(hi, lo + 1) - 1) // CHUNK + 1):
+        c_lo, c_hi = c * CHUNK, min((c + 1) * CHUNK, args.rows)
+        a, b = max(lo, c_lo), min(hi, c_hi)
+        if a >= b:
+            continue
+        x = gen_chunk_torch(torch, dev, c, c_hi - c_lo)
+        torch.cuda.synchronize(dev)
+        sl = x[a - c_lo:b - c_lo]
+        corpus.append_dev(sl.data_ptr(), b - a)
+        del x, sl
+    torch.cuda.empty_cache()
+    assert len(corpus) == hi - lo
+
+    n_q = 64
+    queries_h = gen_queries(n_q)
+    q_dev = torch.from_numpy(queries_h).to(dev)
+    n_slots = args.steps + args.warmup
+    local_hits = torch.zeros((n_slots, k, 2), dtype=torch.float64, device=dev)   # stb_hit = (f64, u64)
+    status = torch.zeros((n_slots, 4), dtype=torch.int32, device=dev)
+    gathered = torch.zeros((world, k, 2), dtype=torch.float64, device=dev) if world > 1 else None
+    final_hits = torch.zeros((n_slots, k, 2), dtype=torch.float64, device=dev)
+
+    def step(i):
+        corpus.search_topk_dev(q_dev[i % n_q].data_ptr(), k, local_hits[i].data_ptr(), status[i].data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, local_hits[i])
+            ctx.hits_merge_dev(gathered.data_ptr(), world, k, k, final_hits[i].data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- value: inputs resident in HBM, device-timed ---------------------------------
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    launches0 = ctx.counters()["kernel_launches"]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for i in range(args.warmup, args.warmup + args.steps):
+        step(i)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.counters()["kernel_launches"] - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    st = status[args.warmup:].cpu().numpy()
+    all_complete = bool((st[:, 1] == 1).all() and (st[:, 0] == min(k, hi - lo)).all())
+
+    # ---- e2e: host query in, host hits out, every step synchronous -------------------
+    q_pin = torch.from_numpy(queries_h).pin_memory()
+    out_pin = torch.zeros((k, 2), dtype=torch.float64).pin_memory()
+    e2e_steps = max(10, min(args.steps, 100))
+
+    def e2e_step(i):
+        if world == 1:
+            return corpus.search(queries_h[i % n_q], top_k=k)        # the C-ABI call a host makes
+        q_dev[i % n_q].copy_(q_pin[i % n_q], non_blocking=True)
+        step(i % n_slots)
+        out_pin.copy_(final_hits[i % n_slots], non_blocking=True)
+        torch.cuda.synchronize(dev)
+        return out_pin
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+
+    # ---- parity spot-check of the benchmarked configuration (not timed) ----------------
+    check = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+        n_s = min(args.cpu_sample_rows, hi - lo)
+        sample = corpus.read(0, n_s)
+        cs = capi.Corpus(ctx, n_s)
+        cs.append(sample)
+        got = cs.search(queries_h[0], top_k=k)
+        r, d = oracle.search_rows(sample, queries_h[0], top_k=k)
+        check = bool(got["row"].tolist() == [int(x) for x in r] and np.array_equal(got["distance"], d))
+        cs.close()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy, burst)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        ms_step = ms_max / args.steps
+        rows_per_gpu = hi - lo
+        # the dominant kernel is stb_scan_topk_kernel: algorithmic bytes = 1024 * rows it scans
+        # (SURVEY 8d K1); its launch duration = step time when it is the only kernel (N=1).
+        kernel_ms = ms_step
+        achieved = rows_per_gpu * 1024 / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": args.steps / (ms_max * 1e-3), "unit": "queries/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args.rows, k), "rows": args.rows, "rows_per_gpu": rows_per_gpu,
+                       "top_k": k, "parallelism": f"row-shard x{world}",
+                       "l2": "corpus shard >> 126 MB L2, no flush needed" if rows_per_gpu * 1024 > 4 * 126e6
+                             else "WARNING shard fits partly in L2",
+                       "distinct_queries": n_q},
+            "clocks": clocks,
+            "e2e": {"value": e2e_steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": 1024,
+                    "d2h_bytes_per_step": 16 * k + 16, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
+                    "timing": "wall clock around synchronous host calls (stb_search: pinned H2D of the query, "
+                              "kernel, D2H of hits, stream sync)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "stb_scan_topk_kernel<E=1,U=2>", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": rows_per_gpu * 1024,
+                         "note": "duration = CUDA-event step time / steps on the launching stream"
+                                 + ("" if world == 1 else " (includes all-gather + merge, so a lower bound on the kernel)")},
+            "all_results_proven_exact": all_complete,
+            "parity_spot_check": check,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            n_s = min(args.cpu_sample_rows, rows_per_gpu)
+            sample = corpus.read(0, n_s)
+            v1, t1 = cpu_baseline(sample, queries_h, args.rows, k, 1)
+            import oracle
+            nt = oracle.baseline_threads()
+            vN, tN = cpu_baseline(sample, queries_h, args.rows, k, nt)
+            line["cpu_baseline"] = {
+                "value": v1, "unit": "queries/s", "cores": 1, "kind": "port",
+                "sample": f"first {n_s} of {args.rows} rows, 3 queries, median {t1:.3f} s, scaled x{args.rows / n_s:g} "
+                          f"(linear in rows; favours the CPU, whose full-result sort is N log N)",
+                "host_cores": os.cpu_count(),
+                "all_cores_not_reference_behaviour": {"threads": nt, "value": vN}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -68,7 +68,9 @@ int stb_device_count(void);
 /* ---- context ----------------------------------------------------------------
  * `cuda_stream` may be NULL (the library creates its own non-blocking stream) or
  * an existing cudaStream_t that every kernel/copy of this context is issued on
- * (lets a host framework time the work with its own events). */
+ * (lets a host framework time the work with its own events).  NULL never means
+ * "the default stream": pass cudaStreamLegacy / cudaStreamPerThread for those.
+ * Tables and corpora may be destroyed after their context (any order is safe). */
 int stb_ctx_create(int device, void *cuda_stream, stb_ctx **out);
 int stb_ctx_destroy(stb_ctx *ctx);
 int stb_ctx_sync(stb_ctx *ctx);

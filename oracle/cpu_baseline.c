@@ -55,16 +55,22 @@ static int orc_stable_sort_hits(orc_hit *a, uint64_t n) {
  * do) so the compiler can vectorise with -O3 -march=native; the selection logic
  * is identical to orc_search_documents.  Used ONLY as bench.py's cpu_baseline /
  * --impl reference timing leg, never for parity. */
+#include <immintrin.h>
+/* simsimd-style Haswell kernel: three 8-lane f32 FMA accumulators over the 256
+ * dims, horizontal reduce, then the normalisation in f64. */
 static inline double orc_cosine_simd_like(const float *a, const float *b) {
-  float ab[8] = {0}, a2[8] = {0}, b2[8] = {0};
-  for (int i = 0; i < 256; i += 8)
-    for (int l = 0; l < 8; ++l) {
-      ab[l] += a[i + l] * b[i + l];
-      a2[l] += a[i + l] * a[i + l];
-      b2[l] += b[i + l] * b[i + l];
-    }
+  __m256 ab = _mm256_setzero_ps(), a2 = _mm256_setzero_ps(), b2 = _mm256_setzero_ps();
+  for (int i = 0; i < 256; i += 8) {
+    __m256 x = _mm256_loadu_ps(a + i), y = _mm256_loadu_ps(b + i);
+    ab = _mm256_fmadd_ps(x, y, ab);
+    a2 = _mm256_fmadd_ps(x, x, a2);
+    b2 = _mm256_fmadd_ps(y, y, b2);
+  }
+  float t[8];
   double sab = 0, sa2 = 0, sb2 = 0;
-  for (int l = 0; l < 8; ++l) { sab += ab[l]; sa2 += a2[l]; sb2 += b2[l]; }
+  _mm256_storeu_ps(t, ab); for (int l = 0; l < 8; ++l) sab += t[l];
+  _mm256_storeu_ps(t, a2); for (int l = 0; l < 8; ++l) sa2 += t[l];
+  _mm256_storeu_ps(t, b2); for (int l = 0; l < 8; ++l) sb2 += t[l];
   if (sa2 == 0.0 && sb2 == 0.0) return 0.0;
   if (sab == 0.0) return 1.0;
   double r = 1.0 - sab / (sqrt(sa2) * sqrt(sb2));

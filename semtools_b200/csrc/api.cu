@@ -5,7 +5,9 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <mutex>
 #include <new>
+#include <unordered_set>
 #include <vector>
 
 #include "common.cuh"
@@ -20,8 +22,18 @@ void stb_set_error(const char *fmt, ...) {
 }
 
 // ------------------------------------------------------------------- context ---
+// Live-context registry: tables/corpora may outlive their context (garbage-collected
+// host languages destroy in any order); their destructors must not touch a dead one.
+static std::mutex g_ctx_mu;
+static std::unordered_set<const stb_ctx *> g_ctx_live;
+static bool ctx_alive(const stb_ctx *ctx) {
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  return g_ctx_live.count(ctx) != 0;
+}
+
 static int ctx_use(const stb_ctx *ctx) {
   if (!ctx) { stb_set_error("null context"); return STB_ERR_ARG; }
+  if (!ctx_alive(ctx)) { stb_set_error("context was destroyed"); return STB_ERR_STATE; }
   STB_CUDA(cudaSetDevice(ctx->device));
   return STB_OK;
 }
@@ -102,6 +114,7 @@ int stb_ctx_create(int device, void *cuda_stream, stb_ctx **out) {
     goto fail;
   }
   c->hits_pin_cap = 1024;
+  { std::lock_guard<std::mutex> lk(g_ctx_mu); g_ctx_live.insert(c); }
   *out = c;
   return STB_OK;
 fail:
@@ -111,6 +124,7 @@ fail:
 
 int stb_ctx_destroy(stb_ctx *c) {
   if (!c) return STB_OK;
+  { std::lock_guard<std::mutex> lk(g_ctx_mu); g_ctx_live.erase(c); }
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   cudaFree(c->block_keys); cudaFree(c->counters); cudaFree(c->q_dev); cudaFree(c->hits_dev);
@@ -183,7 +197,8 @@ int stb_table_load(stb_ctx *ctx, const float *E, uint64_t V, uint32_t D, const f
 
 int stb_table_destroy(stb_table *t) {
   if (!t) return STB_OK;
-  if (t->ctx) cudaSetDevice(t->ctx->device);
+  if (t->ctx && ctx_alive(t->ctx)) { cudaSetDevice(t->ctx->device); cudaStreamSynchronize(t->ctx->stream); }
+  else cudaDeviceSynchronize();
   cudaFree(t->E); cudaFree(t->weights); cudaFree(t->mapping);
   cudaGetLastError();
   delete t;
@@ -230,7 +245,8 @@ int stb_corpus_create(stb_ctx *ctx, uint32_t D, uint64_t capacity_rows, uint64_t
 
 int stb_corpus_destroy(stb_corpus *c) {
   if (!c) return STB_OK;
-  if (c->ctx) { cudaSetDevice(c->ctx->device); cudaStreamSynchronize(c->ctx->stream); }
+  if (c->ctx && ctx_alive(c->ctx)) { cudaSetDevice(c->ctx->device); cudaStreamSynchronize(c->ctx->stream); }
+  else cudaDeviceSynchronize();
   cudaFree(c->rows);
   cudaGetLastError();
   delete c;
@@ -258,6 +274,7 @@ int stb_corpus_append_dev(stb_corpus *c, const float *rows_dev, uint64_t n) {
 }
 int stb_corpus_clear(stb_corpus *c) {
   if (!c) { stb_set_error("null corpus"); return STB_ERR_ARG; }
+  if (!ctx_alive(c->ctx)) { stb_set_error("context was destroyed"); return STB_ERR_STATE; }
   c->n = 0;
   return STB_OK;
 }

@@ -418,7 +418,7 @@ struct CollectSink {
   unsigned long long *count;
   uint64_t cap;
   __device__ __forceinline__ void operator()(float s, uint32_t r) {
-    bool hit = s >= floor_;
+    bool hit = (s >= floor_) && (s > -CUDART_INF_F);   // -inf marks lanes that carry no row
     unsigned mask = __ballot_sync(0xffffffffu, hit);
     if (mask == 0) return;
     int lane = threadIdx.x & 31;

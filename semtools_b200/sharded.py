@@ -1,0 +1,69 @@
+"""Row-sharded search across ranks: one process per GPU, contiguous
+row blocks, ONE exchange per query -- an all-gather of k stb_hit (16 B) per rank --
+then K4 (stb_hits_merge) on every rank.
+
+The collective is whatever `torch.distributed` backend the host initialised (NCCL
+over NVLink on GPUs).  The shard-local search and the merge are injected callables
+so the partition / padding / ordering logic can be exercised on CPU with `gloo`
+(tests/test_sharded_gloo.py injects the oracle there -- tests only).  The product
+wiring, `ShardedCorpus.on_gpu`, uses libsemtools_b200 for both.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable
+
+import numpy as np
+
+from . import capi
+
+PAD_ROW = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def shard_bounds(n_rows: int, world: int, rank: int):
+    """GPU g owns rows [g*ceil(N/G), min(N,(g+1)*ceil(N/G)))  (SURVEY 8e)."""
+    per = (n_rows + world - 1) // world
+    return min(rank * per, n_rows), min((rank + 1) * per, n_rows)
+
+
+def pad_hits(hits: np.ndarray, k: int) -> np.ndarray:
+    out = np.zeros(k, dtype=capi.HIT_DTYPE)
+    out["distance"] = np.inf
+    out["row"] = PAD_ROW
+    out[: len(hits)] = hits[:k]
+    return out
+
+
+@dataclass
+class ShardedCorpus:
+    rank: int
+    world: int
+    local_search: Callable      # (q, top_k, max_distance, mode) -> HIT_DTYPE array, global rows
+    merge: Callable             # ((world, k) HIT_DTYPE, top_k) -> HIT_DTYPE array
+    all_gather: Callable        # (k,) HIT_DTYPE -> (world, k) HIT_DTYPE
+
+    def search(self, q, top_k: int, max_distance=None, mode=capi.STB_MODE_STORE_QUERY):
+        """Global top_k.  (Threshold-lifts-top_k mode is shard-local by nature: its
+        result size is unbounded; callers concatenate shard results instead.)"""
+        if top_k == 0:
+            return np.zeros(0, dtype=capi.HIT_DTYPE)
+        local = pad_hits(self.local_search(q, top_k, max_distance, mode), top_k)
+        lists = self.all_gather(local)
+        return self.merge(lists, top_k)
+
+    @classmethod
+    def on_gpu(cls, ctx: capi.Context, corpus: capi.Corpus, dist, device):
+        """Product wiring: CUDA kernels for search + merge, NCCL all-gather."""
+        import torch
+        rank, world = dist.get_rank(), dist.get_world_size()
+
+        def local_search(q, top_k, max_distance, mode):
+            return corpus.search(q, top_k, max_distance, mode)
+
+        def all_gather(local):
+            t = torch.from_numpy(local.view(np.float64).reshape(-1, 2).copy()).to(device)
+            out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=device)
+            dist.all_gather_into_tensor(out, t)
+            return np.ascontiguousarray(out.cpu().numpy()).view(capi.HIT_DTYPE).reshape(world, -1)
+
+        return cls(rank, world, local_search, ctx.hits_merge, all_gather)

@@ -1,0 +1,338 @@
+"""GPU parity tests proper: K1 (+K4) through the C ABI vs the CPU oracle.
+
+Bar: top-k row indices and order bit-identical to the
+oracle; distances within 1e-5 (they are in fact bit-identical: the GPU re-ranks
+in the oracle's canonical arithmetic, so == is asserted and 1e-5 is the stated
+tolerance)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import unit_rows
+from semtools_b200 import capi, SearchConfig, Searcher
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-5
+
+
+def check(hits, rows_exp, d_exp):
+    assert hits["row"].tolist() == [int(r) for r in rows_exp]
+    assert np.all(np.abs(hits["distance"] - np.asarray(d_exp)) <= TOL)
+    assert np.array_equal(hits["distance"], np.asarray(d_exp, dtype=np.float64))
+
+
+def make_corpus(ctx, rows, row_base=0):
+    c = capi.Corpus(ctx, max(len(rows), 1), row_base)
+    c.append(rows)
+    return c
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 8, 9, 31, 32, 33, 255, 1000, 4099, 50_000])
+@pytest.mark.parametrize("k", [1, 3, 10])
+def test_topk_matches_oracle(ctx, n, k):
+    rng = np.random.default_rng(n * 31 + k)
+    rows = unit_rows(rng, n)
+    q = unit_rows(rng, 1)[0]
+    c = make_corpus(ctx, rows)
+    r, d = oracle.search_rows(rows, q, top_k=k)
+    check(c.search(q, top_k=k), r, d)
+    assert ctx.counters()["fallback_searches"] == 0 or n < 64
+
+
+@pytest.mark.parametrize("k", [16, 17, 40, 41, 64, 96])
+def test_topk_candidate_width_classes(ctx, k):
+    rng = np.random.default_rng(k)
+    rows = unit_rows(rng, 20_000)
+    q = unit_rows(rng, 1)[0]
+    c = make_corpus(ctx, rows)
+    r, d = oracle.search_rows(rows, q, top_k=k)
+    check(c.search(q, top_k=k), r, d)
+
+
+@pytest.mark.parametrize("k", [97, 500, 3000])
+def test_topk_large_k_exact_path(ctx, k):
+    rng = np.random.default_rng(k)
+    rows = unit_rows(rng, 2500)
+    q = unit_rows(rng, 1)[0]
+    c = make_corpus(ctx, rows)
+    r, d = oracle.search_rows(rows, q, top_k=k)
+    check(c.search(q, top_k=k), r, d)
+
+
+def test_config1_1k_lines_top3(ctx):
+    """BASELINE configs[0]: 1k lines, top-k=3."""
+    rng = np.random.default_rng(0x5E117001)
+    rows = unit_rows(rng, 1000)
+    q = unit_rows(rng, 1)[0]
+    c = make_corpus(ctx, rows)
+    r, d = oracle.search_rows(rows, q, top_k=3)
+    check(c.search(q, top_k=3), r, d)
+
+
+def test_golden_cases_through_searcher(ctx):
+    z = np.load(os.path.join(G, "search_small.npz"))
+    cases = json.load(open(os.path.join(G, "search_small.json")))
+    offs = z["doc_offsets"].astype(int)
+    s = Searcher(ctx, capi.Corpus(ctx, 1024))
+    for d in range(len(offs) - 1):
+        lines = [f"doc{d} line{i}" for i in range(offs[d + 1] - offs[d])]
+        doc = s.add_document_embeddings(f"doc{d}.txt", lines, z["rows"][offs[d]:offs[d + 1]])
+        assert (doc is None) == (len(lines) == 0)       # empty content -> None (mod.rs:57-59)
+    names = [f"doc{d}.txt" for d in range(len(offs) - 1)]
+    for name, case in cases.items():
+        kw = case["kw"]
+        res = s.search_documents(z["q"], SearchConfig(kw["n_lines"], kw["top_k"], kw.get("max_distance")))
+        assert len(res) == len(case["res"]), name
+        for got, (dist, row, doc, idx, start, end) in zip(res, case["res"]):
+            assert (got.filename, got.match_line, got.start, got.end) == (names[doc], idx, start, end), name
+            assert got.distance == dist, name
+            assert got.lines == [f"doc{doc} line{i}" for i in range(start, end)]
+
+
+def test_duplicates_zero_rows_and_ties(ctx):
+    """0.1 % duplicates + zero rows: ties resolve by row order."""
+    rng = np.random.default_rng(77)
+    rows = unit_rows(rng, 30_000)
+    dup_src = rng.integers(0, 30_000, 30)
+    dup_dst = rng.integers(0, 30_000, 30)
+    rows[dup_dst] = rows[dup_src]
+    rows[rng.integers(0, 30_000, 5)] = 0.0
+    q = rows[dup_src[0]].copy()
+    c = make_corpus(ctx, rows)
+    for k in (1, 5, 10, 32):
+        r, d = oracle.search_rows(rows, q, top_k=k)
+        check(c.search(q, top_k=k), r, d)
+
+
+def test_heavy_duplication_forces_exact_fallback(ctx):
+    """500 exact copies of the best line: the K' candidate list cannot prove
+    completeness, the exact collect pass must kick in and still match."""
+    rng = np.random.default_rng(5)
+    rows = unit_rows(rng, 40_000)
+    q = unit_rows(rng, 1)[0]
+    where = rng.choice(40_000, 500, replace=False)
+    rows[where] = (q + 0.01 * unit_rows(rng, 1)[0]).astype(np.float32)
+    c = make_corpus(ctx, rows)
+    before = ctx.counters()["fallback_searches"]
+    r, d = oracle.search_rows(rows, q, top_k=10)
+    check(c.search(q, top_k=10), r, d)
+    assert sorted(where)[:10] == [int(x) for x in r]
+    assert ctx.counters()["fallback_searches"] == before + 1
+
+
+def test_zero_query_and_all_zero_corpus(ctx):
+    rng = np.random.default_rng(6)
+    rows = unit_rows(rng, 300)
+    rows[[4, 100, 299]] = 0.0
+    zq = np.zeros(256, dtype=np.float32)
+    c = make_corpus(ctx, rows)
+    r, d = oracle.search_rows(rows, zq, top_k=5)        # zero rows -> 0.0, others 1.0
+    check(c.search(zq, top_k=5), r, d)
+    assert d[:3].tolist() == [0.0, 0.0, 0.0]
+    z = np.zeros((40, 256), dtype=np.float32)
+    c2 = make_corpus(ctx, z)
+    r, d = oracle.search_rows(z, rows[0], top_k=3)
+    check(c2.search(rows[0], top_k=3), r, d)
+    assert d.tolist() == [1.0, 1.0, 1.0]
+
+
+def test_unnormalised_and_scaled_rows(ctx):
+    rng = np.random.default_rng(8)
+    rows = (unit_rows(rng, 5000) * rng.uniform(1e-3, 1e3, (5000, 1))).astype(np.float32)
+    q = (unit_rows(rng, 1)[0] * 37.5).astype(np.float32)
+    c = make_corpus(ctx, rows)
+    r, d = oracle.search_rows(rows, q, top_k=10)
+    check(c.search(q, top_k=10), r, d)
+
+
+def test_extreme_magnitude_rows_are_forced_candidates(ctx):
+    rng = np.random.default_rng(12)
+    rows = unit_rows(rng, 3000)
+    rows[7] *= np.float32(1e-25)       # fp32 squared norm underflows
+    rows[9] *= np.float32(1e22)        # fp32 squared norm overflows
+    q = rows[7] * np.float32(1e25)
+    c = make_corpus(ctx, rows)
+    r, d = oracle.search_rows(rows, q, top_k=4)
+    check(c.search(q, top_k=4), r, d)
+    assert int(r[0]) == 7
+
+
+@pytest.mark.parametrize("thr", [0.0, 0.5, 0.8, 0.93, 1.0, 1.0000001, 2.5])
+def test_threshold_mode_returns_all_under_threshold(ctx, thr):
+    """src/search/mod.rs:88-89 strict <, :115-116 threshold lifts top_k."""
+    rng = np.random.default_rng(int(thr * 1000))
+    rows = unit_rows(rng, 6000)
+    rows[[5, 77]] = 0.0
+    q = unit_rows(rng, 1)[0]
+    rows[123] = q
+    c = make_corpus(ctx, rows)
+    r, d = oracle.search_rows(rows, q, top_k=3, max_distance=thr)
+    hits = c.search(q, top_k=3, max_distance=thr)
+    check(hits, r, d)
+    assert np.all(hits["distance"] < thr)
+
+
+def test_threshold_capacity_protocol(ctx):
+    rng = np.random.default_rng(2)
+    rows = unit_rows(rng, 3000)
+    q = unit_rows(rng, 1)[0]
+    c = make_corpus(ctx, rows)
+    import ctypes as C
+    out = np.zeros(4, dtype=capi.HIT_DTYPE)
+    n = C.c_uint64(0)
+    rc = capi.lib().stb_search(ctx._h, c._h, q.ctypes.data_as(C.c_void_p), 3, 1, 5.0, 0, None, 0,
+                               out.ctypes.data_as(C.c_void_p), 4, C.byref(n))
+    assert rc == capi.STB_ERR_CAPACITY and n.value == 3000
+    r, d = oracle.search_rows(rows, q, top_k=3, max_distance=5.0)
+    assert out["row"].tolist() == [int(x) for x in r[:4]]
+
+
+def test_store_query_mode_and_row_ranges(ctx):
+    """Store::search_line_embeddings semantics (store.rs:481-546): path filter ==
+    row ranges; threshold does NOT lift top_k; distance reported as f32."""
+    rng = np.random.default_rng(14)
+    rows = unit_rows(rng, 9000)
+    q = unit_rows(rng, 1)[0]
+    c = make_corpus(ctx, rows)
+    ranges = [[0, 10], [10, 11], [500, 1500], [4000, 4001], [8990, 9000]]
+    for k, thr in [(1, None), (5, None), (20, 0.9), (7, 0.0), (64, None)]:
+        r, d32 = oracle.store_search(rows, ranges, q, k, thr)
+        hits = c.search(q, top_k=k, max_distance=thr, mode=capi.STB_MODE_STORE_QUERY, row_ranges=ranges)
+        assert hits["row"].tolist() == [int(x) for x in r]
+        assert np.array_equal(hits["distance"].astype(np.float32), d32)
+    assert len(c.search(q, top_k=3, mode=capi.STB_MODE_STORE_QUERY, row_ranges=[])) == 0
+
+
+def test_many_small_ranges(ctx):
+    rng = np.random.default_rng(15)
+    rows = unit_rows(rng, 20_000)
+    q = unit_rows(rng, 1)[0]
+    c = make_corpus(ctx, rows)
+    starts = np.sort(rng.choice(np.arange(0, 20_000, 10), 700, replace=False))
+    ranges = [[int(s), int(s + rng.integers(1, 10))] for s in starts]
+    r, d32 = oracle.store_search(rows, ranges, q, 10)
+    hits = c.search(q, top_k=10, mode=capi.STB_MODE_STORE_QUERY, row_ranges=ranges)
+    assert hits["row"].tolist() == [int(x) for x in r]
+
+
+def test_reference_store_fixture(ctx):
+    """src/workspace/store.rs:753-757,814-850."""
+    s = Searcher(ctx, capi.Corpus(ctx, 16))
+    for i, v in enumerate((0.1, 0.5, 0.75)):
+        s.add_document_embeddings(f"/test/doc{i + 1}.txt", ["line"], np.full((1, 256), v, dtype=np.float32))
+    q = np.full(256, 0.1, dtype=np.float32)
+    res = s.search_line_embeddings(q, ["/test/doc1.txt"], 1, 0.1)
+    assert len(res) == 1 and res[0].line_number == 0 and res[0].path == "/test/doc1.txt"
+    assert res[0].distance < 0.1
+    assert s.search_line_embeddings(q, [], 1, 0.1) == []
+    assert s.search_line_embeddings(q, ["/test/doc1.txt"], 0, 0.1) == []
+
+
+def test_sharded_row_base_and_merge(ctx):
+    """Row-sharding contract: shard-local searches with row_base, then
+    K4 merge == unsharded oracle."""
+    rng = np.random.default_rng(16)
+    rows = unit_rows(rng, 12_000)
+    rows[11_000] = rows[100]                    # cross-shard exact tie
+    q = rows[100].copy()
+    bounds = [0, 3000, 3001, 9000, 12_000]
+    lists = []
+    k = 10
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        c = make_corpus(ctx, rows[a:b], row_base=a)
+        h = c.search(q, top_k=k)
+        pad = np.zeros(k, dtype=capi.HIT_DTYPE)
+        pad["distance"] = np.inf
+        pad["row"] = np.uint64(0xFFFFFFFFFFFFFFFF)
+        pad[: len(h)] = h
+        lists.append(pad)
+    merged = ctx.hits_merge(np.stack(lists), k)
+    r, d = oracle.search_rows(rows, q, top_k=k)
+    check(merged, r, d)
+    assert merged["row"][:2].tolist() == [100, 11_000]
+
+
+def test_device_resident_async_entry_point(ctx):
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(17)
+    rows = unit_rows(rng, 70_000)
+    qs = unit_rows(rng, 4)
+    c = make_corpus(ctx, rows)
+    dev = torch.device("cuda:0")
+    q_dev = torch.from_numpy(qs).to(dev)
+    hits = torch.zeros((4, 10, 2), dtype=torch.float64, device=dev)
+    status = torch.zeros((4, 4), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    for i in range(4):
+        c.search_topk_dev(q_dev[i].data_ptr(), 10, hits[i].data_ptr(), status[i].data_ptr())
+    ctx.sync()
+    raw = hits.cpu().numpy()
+    st = status.cpu().numpy()
+    for i in range(4):
+        r, d = oracle.search_rows(rows, qs[i], top_k=10)
+        got = np.ascontiguousarray(raw[i]).view(capi.HIT_DTYPE).reshape(-1)
+        assert st[i, 0] == 10 and st[i, 1] == 1
+        check(got, r, d)
+
+
+def test_error_paths(ctx):
+    c = capi.Corpus(ctx, 8)
+    q = np.zeros(256, dtype=np.float32)
+    assert len(c.search(q, top_k=3)) == 0                       # empty corpus -> empty
+    c.append(np.ones((2, 256), dtype=np.float32))
+    assert len(c.search(q, top_k=0)) == 0                       # take(0)
+    with pytest.raises(capi.StbError):
+        c.search(np.zeros(100, dtype=np.float32))               # length mismatch
+    with pytest.raises(capi.StbError):
+        c.search(q, top_k=1, row_ranges=[[5, 2]])               # malformed range
+    with pytest.raises(capi.StbError):
+        c.read(1, 5)
+
+
+@pytest.mark.parametrize("n", [1_000_000])
+def test_full_size_properties_1m(ctx, n):
+    """BASELINE configs[1] size: rows generated on the GPU; parity through
+    size-independent properties + an oracle check on a downloaded slice."""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev); g.manual_seed(0x5E117002)
+    x = torch.randn((n, 256), generator=g, device=dev, dtype=torch.float32)
+    x = x / x.norm(dim=1, keepdim=True)
+    q = torch.randn(256, generator=g, device=dev, dtype=torch.float32)
+    q = (q / q.norm()).cpu().numpy()
+    planted = [3, 499_999, n - 1]
+    for j, p in enumerate(planted):                               # plant near-copies of q
+        x[p] = torch.from_numpy(q).to(dev) + 0.02 * (j + 1) * x[p]
+    x[12345] = x[planted[0]]                                     # exact duplicate -> tie by row
+    torch.cuda.synchronize()
+    c = capi.Corpus(ctx, n)
+    c.append_dev(x.data_ptr(), n)
+    hits = c.search(q, top_k=10)
+    assert hits["row"][:4].tolist() == [3, 12345, 499_999, n - 1]
+    assert np.all(np.diff(hits["distance"]) >= 0)
+    # every reported distance is the canonical one
+    rows_h = x[torch.from_numpy(hits["row"].astype(np.int64)).to(dev)].cpu().numpy()
+    for h, row in zip(hits, rows_h):
+        assert h["distance"] == oracle.cosine(q, row)
+    # idempotence and shard-merge consistency: top-k of the whole == merge of halves
+    again = c.search(q, top_k=10)
+    assert np.array_equal(again, hits)
+    lists = []
+    for a, b in [(0, n // 2), (n // 2, n)]:
+        cs = capi.Corpus(ctx, b - a, row_base=a)
+        cs.append_dev(x[a:b].data_ptr(), b - a)
+        lists.append(cs.search(q, top_k=10))
+        cs.close()
+    assert np.array_equal(ctx.hits_merge(np.stack(lists), 10), hits)
+    # oracle on a 200k-row window containing two planted rows
+    lo, hi = 400_000, 600_000
+    win = x[lo:hi].cpu().numpy()
+    r, d = oracle.search_rows(win, q, top_k=5)
+    cw = capi.Corpus(ctx, hi - lo, row_base=lo)
+    cw.append_dev(x[lo:hi].data_ptr(), hi - lo)
+    got = cw.search(q, top_k=5)
+    check(got, r + lo, d)
