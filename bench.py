@@ -196,6 +196,50 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------ K3 side bench -----
+def bench_embed(torch, dev, ctx, stream, V=500_000, n_lines=1_000_000):
+    """K3 on SURVEY 8d's synthetic ingestion batch: V=500k x 256 table (0.5 GB), line
+    lengths ~ clamp(round(LogNormal(2.5,0.8)),0,2048), ids ~ Zipf(1.1).  Algorithmic
+    bytes = sum_i (1028*T_i + 1024)."""
+    from semtools_b200 import capi
+    rng = np.random.default_rng(SEED + 77)
+    E = (rng.standard_normal((V, 256), dtype=np.float32) * np.float32(0.1))
+    T = np.clip(np.round(rng.lognormal(2.5, 0.8, n_lines)), 0, 2048).astype(np.int64)
+    offsets = np.concatenate([[0], np.cumsum(T)]).astype(np.uint64)
+    ids = ((rng.zipf(1.1, int(T.sum())) - 1) % V).astype(np.uint32)
+    table = capi.Table(ctx, E)
+    off_d = torch.from_numpy(offsets.view(np.int64)).to(dev)
+    ids_d = torch.from_numpy(ids.view(np.int32)).to(dev)
+    out_d = torch.empty((n_lines, 256), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize(dev)
+    for _ in range(3):
+        capi.embed_dev(ctx, table, off_d.data_ptr(), ids_d.data_ptr(), n_lines, out_d.data_ptr())
+    capi.embed_status(ctx)
+    iters = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(iters):
+        capi.embed_dev(ctx, table, off_d.data_ptr(), ids_d.data_ptr(), n_lines, out_d.data_ptr())
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / iters
+    alg_bytes = float((1028 * T + 1024).sum())
+    corpus = capi.Corpus(ctx, n_lines)
+    t0 = time.perf_counter()
+    capi.embed(ctx, table, offsets, ids, out=False, append_to=corpus)       # host CSR in, rows stay in HBM
+    e2e_s = time.perf_counter() - t0
+    import oracle
+    n_chk = 2000
+    exp = oracle.embed_csr(E, offsets[:n_chk + 1], ids[:int(offsets[n_chk])])
+    bit_exact = bool(np.array_equal(corpus.read(0, n_chk).view(np.uint32), exp.view(np.uint32)))
+    corpus.close(); table.close()
+    return {"kernel": "stb_embed_kernel", "lines": n_lines, "tokens": int(T.sum()), "table_rows": V,
+            "ms": ms, "lines_per_s": n_lines / (ms * 1e-3), "achieved_GBps": alg_bytes / (ms * 1e-3) / 1e9,
+            "algorithmic_bytes": alg_bytes, "bound": "hbm/l2 (random 1 KiB gathers, Zipf ids)",
+            "e2e_lines_per_s": n_lines / e2e_s, "e2e_h2d_bytes": int(ids.nbytes + offsets.nbytes),
+            "bit_exact_vs_oracle_first_2000": bit_exact}
+
+
 # ------------------------------------------------------------------ our arm ----------
 def run_ours(args):
     import torch
@@ -324,6 +368,11 @@ def run_ours(args):
         check = bool(got["row"].tolist() == [int(x) for x in r] and np.array_equal(got["distance"], d))
         cs.close()
 
+    # ---- K3 (embed gather/pool/normalise) secondary measurement, N=1 only ---------------
+    k3 = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        k3 = bench_embed(torch, dev, ctx, stream)
+
     if rank == 0:
         peaks = {}
         try:
@@ -338,6 +387,13 @@ def run_ours(args):
         # (SURVEY 8d K1); its launch duration = step time when it is the only kernel (N=1).
         kernel_ms = ms_step
         achieved = rows_per_gpu * 1024 / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["stb_scan_topk_kernel"]
+            if tr["rows"] == rows_per_gpu and tr["top_k"] == k:
+                traffic = tr["traffic_bytes"]     # from the committed ncu --set full capture
+        except (OSError, KeyError, ValueError):
+            pass
         line = {
             "metric": METRIC, "value": args.steps / (ms_max * 1e-3), "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -355,7 +411,7 @@ def run_ours(args):
                               "kernel, D2H of hits, stream sync)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "stb_scan_topk_kernel<E=1,U=2>", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": rows_per_gpu * 1024,
                          "note": "duration = CUDA-event step time / steps on the launching stream"
@@ -363,6 +419,9 @@ def run_ours(args):
             "all_results_proven_exact": all_complete,
             "parity_spot_check": check,
         }
+        if k3 is not None:
+            k3["frac"] = k3["achieved_GBps"] / peak
+            line["k3_embed"] = k3
         if world == 1 and not args.no_cpu_baseline:
             n_s = min(args.cpu_sample_rows, rows_per_gpu)
             sample = corpus.read(0, n_s)

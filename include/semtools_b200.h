@@ -123,6 +123,15 @@ int stb_embed(stb_ctx *ctx, const stb_table *table, const uint64_t *offsets,
               const uint32_t *ids, uint64_t n_lines, float *out,
               stb_corpus *append_to);
 
+/* Asynchronous device-resident form of stb_embed: CSR and output already in HBM
+ * (out_dev: n_lines x 256 f32, e.g. a slice of stb_corpus_data_dev), nothing
+ * synchronises.  A token outside the table sets a sticky flag instead of failing;
+ * stb_embed_status() synchronises the stream, returns STB_ERR_RANGE if the flag was
+ * set since the last call, and clears it. */
+int stb_embed_dev(stb_ctx *ctx, const stb_table *table, const uint64_t *offsets_dev,
+                  const uint32_t *ids_dev, uint64_t n_lines, float *out_dev);
+int stb_embed_status(stb_ctx *ctx);
+
 /* ---- K1 + K4: cosine scan, top-k / threshold, exact re-rank ---------------------
  * Replaces search_documents' scan/filter/sort/take (src/search/mod.rs:84-119,
  * one f32::cosine per line at :86) and, with `row_ranges`, the filtered query of

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsemtools_b200.so")
+LIB_PATH = os.environ.get("STB_LIB_PATH") or os.path.join(_HERE, "lib", "libsemtools_b200.so")
 
 STB_DIM = 256
 STB_OK, STB_ERR_ARG, STB_ERR_CUDA, STB_ERR_NOMEM = 0, -1, -2, -3
@@ -21,7 +21,8 @@ SYMBOLS = [
     "stb_version", "stb_last_error", "stb_device_count", "stb_ctx_create", "stb_ctx_destroy",
     "stb_ctx_sync", "stb_ctx_stream", "stb_table_load", "stb_table_destroy", "stb_corpus_create",
     "stb_corpus_destroy", "stb_corpus_append", "stb_corpus_append_dev", "stb_corpus_clear",
-    "stb_corpus_rows", "stb_corpus_data_dev", "stb_corpus_read", "stb_embed", "stb_search",
+    "stb_corpus_rows", "stb_corpus_data_dev", "stb_corpus_read", "stb_embed", "stb_embed_dev",
+    "stb_embed_status", "stb_search",
     "stb_search_topk_dev", "stb_hits_merge_dev", "stb_hits_merge", "stb_fnv1a64", "stb_line_id",
     "stb_ctx_counters",
 ]
@@ -74,6 +75,8 @@ def lib() -> C.CDLL:
     L.stb_corpus_data_dev.argtypes = [vp, C.POINTER(vp)]
     L.stb_corpus_read.argtypes = [vp, u64, u64, vp]
     L.stb_embed.argtypes = [vp, vp, vp, vp, u64, vp, vp]
+    L.stb_embed_dev.argtypes = [vp, vp, vp, vp, u64, vp]
+    L.stb_embed_status.argtypes = [vp]
     L.stb_search.argtypes = [vp, vp, vp, u32, i32, f64, i32, vp, u32, vp, u64, C.POINTER(u64)]
     L.stb_search_topk_dev.argtypes = [vp, vp, vp, u32, vp, vp]
     L.stb_hits_merge_dev.argtypes = [vp, vp, u32, u32, u32, vp]
@@ -256,6 +259,16 @@ class Corpus:
         """stb_search_topk_dev: asynchronous, everything stays in HBM."""
         _check(lib().stb_search_topk_dev(self.ctx._h, self._h, vp(q_dev), top_k, vp(out_hits_dev),
                                          vp(out_status_dev)))
+
+
+def embed_dev(ctx: Context, table: Table, offsets_dev: int, ids_dev: int, n_lines: int, out_dev: int):
+    """stb_embed_dev: asynchronous, CSR and output already in HBM."""
+    _check(lib().stb_embed_dev(ctx._h, table._h, vp(offsets_dev), vp(ids_dev), n_lines, vp(out_dev)))
+
+
+def embed_status(ctx: Context):
+    """stb_embed_status: sync + raise StbError(STB_ERR_RANGE) if a token was out of range."""
+    _check(lib().stb_embed_status(ctx._h))
 
 
 def embed(ctx: Context, table: Table, offsets, ids, out: bool = True, append_to: Corpus | None = None):

@@ -106,6 +106,7 @@ int stb_ctx_create(int device, void *cuda_stream, stb_ctx **out) {
   }
   if ((rc = dev_reserve(&c->hits_dev, &c->hits_cap, 1024)) != STB_OK) goto fail;
   if (cudaMemset(c->counters, 0, c->counters_cap * sizeof(unsigned int)) != cudaSuccess ||
+      cudaMemset(c->err_flag, 0, sizeof(int)) != cudaSuccess ||
       cudaMallocHost((void **)&c->q_pin, STB_D * sizeof(float)) != cudaSuccess ||
       cudaMallocHost((void **)&c->status_pin, 8 * sizeof(uint32_t)) != cudaSuccess ||
       cudaMallocHost((void **)&c->hits_pin, 1024 * sizeof(stb_hit)) != cudaSuccess) {
@@ -334,6 +335,27 @@ int stb_embed(stb_ctx *ctx, const stb_table *table, const uint64_t *offsets, con
   STB_CUDA(cudaStreamSynchronize(ctx->stream));
   if (flag) { stb_set_error("embed: a token id maps outside the %llu-row table", (unsigned long long)table->V); return STB_ERR_RANGE; }
   if (append_to) append_to->n += n_lines;
+  return STB_OK;
+}
+
+int stb_embed_dev(stb_ctx *ctx, const stb_table *table, const uint64_t *offsets_dev,
+                  const uint32_t *ids_dev, uint64_t n_lines, float *out_dev) {
+  int rc = ctx_use(ctx);
+  if (rc) return rc;
+  if (!table || table->ctx != ctx) { stb_set_error("embed_dev: bad table"); return STB_ERR_ARG; }
+  if (n_lines == 0) return STB_OK;
+  if (!offsets_dev || !ids_dev || !out_dev) { stb_set_error("embed_dev: null device pointer"); return STB_ERR_ARG; }
+  return stb_launch_embed(ctx, table, offsets_dev, ids_dev, n_lines, out_dev, ctx->err_flag);
+}
+
+int stb_embed_status(stb_ctx *ctx) {
+  int rc = ctx_use(ctx);
+  if (rc) return rc;
+  int flag = 0;
+  STB_CUDA(cudaMemcpyAsync(&flag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  STB_CUDA(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), ctx->stream));
+  STB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (flag) { stb_set_error("embed: a token id maps outside the table"); return STB_ERR_RANGE; }
   return STB_OK;
 }
 

@@ -12,7 +12,12 @@
 
 #define STB_D 256           // floats per row
 #define STB_ROW_F4 64       // float4 per row
+#ifndef STB_SCAN_THREADS
 #define STB_SCAN_THREADS 256
+#endif
+#ifndef STB_SCAN_MINB
+#define STB_SCAN_MINB 2     // CTAs per SM the scan kernels are register-budgeted for
+#endif
 #define STB_SCAN_WARPS (STB_SCAN_THREADS / 32)
 #define STB_SORT_CAP 1024   // keys one CTA sorts in shared memory
 // Rigorous bound (with ~4x slack) on |approx cosine - exact cosine| for the fp32

@@ -84,8 +84,14 @@ __device__ __forceinline__ void stb_scan_rows(const ScanArgs &args, Sink &sink) 
   b2 += __shfl_xor_sync(0xffffffffu, b2, 4);
   b2 += __shfl_xor_sync(0xffffffffu, b2, 2);
   b2 += __shfl_xor_sync(0xffffffffu, b2, 1);
-  const bool q_zero = (b2 == 0.f);
-  const bool q_bad = !q_zero && !(b2 >= 1e-30f && b2 <= 1e30f);  // NaN/inf/denormal
+  // b2 == 0 in fp32 is either a true zero vector or an underflowed tiny one
+  bool q_any = false;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    q_any |= (q[i].x != 0.f) | (q[i].y != 0.f) | (q[i].z != 0.f) | (q[i].w != 0.f);
+  q_any = __any_sync(0xffffffffu, q_any);   // all four groups hold the same query
+  const bool q_zero = (b2 == 0.f) && !q_any;
+  const bool q_bad = !q_zero && !(b2 >= 1e-30f && b2 <= 1e30f);  // NaN/inf/denormal/underflow
   const float rq = q_zero ? 0.f : rsqrtf(b2);
 
   const uint64_t tile_rows = 4 * U;
@@ -128,8 +134,17 @@ __device__ __forceinline__ void stb_scan_rows(const ScanArgs &args, Sink &sink) 
       ab += __shfl_xor_sync(0xffffffffu, ab, 1);
       a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
       float s;
-      if (a2 == 0.f) s = q_zero ? 1.f : 0.f;            // simsimd zero rules: d = 0 / d = 1
-      else if (q_bad || !(a2 >= 1e-30f && a2 <= 1e30f)) s = CUDART_INF_F;  // forced candidate
+      if (a2 == 0.f) {
+        // rare: a true zero row (simsimd rules: d = 0 vs a zero query, else d = 1) or a
+        // row so small that its fp32 squared norm underflowed -> forced candidate.
+        // All 8 lanes of the group hold the same a2, so the group votes together.
+        bool nz = false;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          nz |= (a[u][i].x != 0.f) | (a[u][i].y != 0.f) | (a[u][i].z != 0.f) | (a[u][i].w != 0.f);
+        nz = __any_sync(0xffu << (8 * g), nz);
+        s = nz ? CUDART_INF_F : (q_zero ? 1.f : 0.f);
+      } else if (q_bad || !(a2 >= 1e-30f && a2 <= 1e30f)) s = CUDART_INF_F;  // forced candidate
       else s = ab * rsqrtf(a2) * rq;
       sc[u] = valid[u] ? s : -CUDART_INF_F;
     }
@@ -210,111 +225,244 @@ __device__ __forceinline__ void stb_cta_sort_keys(uint64_t *keys, int n) {
 struct TopkArgs {
   ScanArgs scan;
   uint64_t row_base;
-  uint64_t *keys;            // tree levels, level l at key offset lvl_off(l)*KP
-  unsigned int *counters;    // one per tree group, all levels
+  uint64_t *keys;            // [gridDim.x][KP] best keys of every CTA
+  unsigned int *counters;    // [0] arrival ticket
   stb_hit *out_hits;
   uint32_t *out_status;
   uint32_t top_k;
 };
 
+// Sort the first `c` keys of skeys (padded with INVALID to a power of two >= KP).
+__device__ __forceinline__ int stb_pad_and_sort(uint64_t *skeys, int c, int min_n) {
+  int n = min_n;
+  while (n < c) n <<= 1;
+  for (int i = c + threadIdx.x; i < n; i += blockDim.x) skeys[i] = STB_KEY_INVALID;
+  __syncthreads();
+  stb_cta_sort_keys(skeys, n);
+  return n;
+}
+
+#define STB_RR_STRIDE 260   // floats per staged row (1 KiB + 16 B pad: conflict-free LDS.128)
+
 template <int E, int U, bool RANGES>
-__global__ void __launch_bounds__(STB_SCAN_THREADS, 2)
+__global__ void __launch_bounds__(STB_SCAN_THREADS, STB_SCAN_MINB)
 stb_scan_topk_kernel(const TopkArgs args) {
   constexpr int KP = 32 * E;
-  constexpr int F = STB_SORT_CAP / KP;   // tree fan-in
   __shared__ uint64_t skeys[STB_SORT_CAP];
-  __shared__ unsigned int s_ticket;
+  __shared__ unsigned int s_T, s_cnt, s_ticket, s_over;
   __shared__ __align__(16) float sq[STB_D];
+  __shared__ __align__(16) float srows[32 * STB_RR_STRIDE];
   __shared__ double s_d[KP];
   __shared__ uint64_t s_r[KP];
-  __shared__ int s_cnt[2];
+  __shared__ int s_nv[2];
 
   TopSink<E> sink;
   sink.init();
   stb_scan_rows<U, RANGES>(args.scan, sink);
 
-  // ---- CTA merge: 8 warps x KP keys -> sorted, keep best KP -------------------
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // ---- CTA merge ------------------------------------------------------------------
+  // T = max over warps of the warp list minimum is a lower bound of the CTA's KP-th
+  // best score (that warp alone holds KP keys >= its minimum), so only keys >= T can
+  // matter: compact those (typically ~KP..2KP of the 8*KP) and sort the small set.
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { s_T = 0u; s_cnt = 0u; s_over = 0u; }
+  __syncthreads();
+  if (lane == 0) atomicMax(&s_T, stb_f2ord(sink.thr));
+  __syncthreads();
+  {
+    const unsigned T = s_T;
 #pragma unroll
-  for (int e = 0; e < E; ++e) {
-    uint32_t r = sink.lr[e];
-    skeys[warp * KP + e * 32 + lane] =
-        (r == 0xffffffffu) ? STB_KEY_INVALID : stb_make_key(sink.ls[e], r);
+    for (int e = 0; e < E; ++e) {
+      if (sink.lr[e] != 0xffffffffu && stb_f2ord(sink.ls[e]) >= T) {
+        unsigned idx = atomicAdd(&s_cnt, 1u);       // <= 8*KP <= STB_SORT_CAP entries exist
+        skeys[idx] = stb_make_key(sink.ls[e], sink.lr[e]);
+      }
+    }
   }
   __syncthreads();
-  stb_cta_sort_keys(skeys, STB_SCAN_WARPS * KP);
+  int c = (int)s_cnt;
+  stb_pad_and_sort(skeys, c, KP);
 
-  // ---- tree merge across CTAs (last arriver of each group continues) ----------
-  uint32_t lists = gridDim.x, my_id = blockIdx.x, lvl_key_off = 0, lvl_cnt_off = 0;
-  while (lists > 1) {
-    // publish my sorted best-KP as list `my_id` of this level
-    uint64_t *lvl = args.keys + (size_t)lvl_key_off * KP;
-    for (int i = threadIdx.x; i < KP; i += blockDim.x) lvl[(size_t)my_id * KP + i] = skeys[i];
+  // ---- publish the CTA's best KP; last CTA to arrive finishes the query -------------
+  if (gridDim.x > 1) {
+    uint64_t *mine = args.keys + (size_t)blockIdx.x * KP;
+    for (int i = threadIdx.x; i < KP; i += blockDim.x) mine[i] = skeys[i];
     __threadfence();
     __syncthreads();
-    uint32_t group = my_id / F;
-    uint32_t first = group * F;
-    uint32_t n_in = min((uint32_t)F, lists - first);
-    if (threadIdx.x == 0) s_ticket = atomicAdd(args.counters + lvl_cnt_off + group, 1u);
+    if (threadIdx.x == 0) s_ticket = atomicAdd(args.counters, 1u);
     __syncthreads();
-    if (s_ticket != n_in - 1) return;          // not the last of my group: done
+    if (s_ticket != gridDim.x - 1) return;
     __threadfence();
-    if (threadIdx.x == 0) args.counters[lvl_cnt_off + group] = 0;   // re-arm for next launch
-    for (int i = threadIdx.x; i < STB_SORT_CAP; i += blockDim.x) {
-      uint32_t li = i / KP;
-      skeys[i] = (li < n_in) ? __ldcg(lvl + (size_t)(first + li) * KP + (i % KP)) : STB_KEY_INVALID;
+    if (threadIdx.x == 0) args.counters[0] = 0u;   // re-arm for the next launch
+
+    // Exact radix select (12+12+8 bits of the ordered score) of the KP-th best score
+    // among the gridDim.x*KP published keys: distribution-independent, 4 coalesced
+    // passes over <= a few hundred KB that sit in L2.  The histogram aliases the
+    // re-rank staging buffer, which is not live yet.
+    unsigned int *hist = reinterpret_cast<unsigned int *>(srows);
+    const size_t total = (size_t)gridDim.x * KP;
+    // Keys are cached in registers, STB_KPT per thread per round, all loads of a round
+    // issued before any use (one L2 latency per round; one round covers 10240 keys,
+    // i.e. the whole E=1 grid, which is then read exactly once).
+    constexpr int KPT = 40;
+    uint64_t kreg[KPT];
+    const int n_rounds = (int)((total + (size_t)KPT * STB_SCAN_THREADS - 1) / ((size_t)KPT * STB_SCAN_THREADS));
+    auto load_round = [&](int round) {
+#pragma unroll
+      for (int j = 0; j < KPT; ++j) {
+        size_t i = ((size_t)round * KPT + j) * STB_SCAN_THREADS + threadIdx.x;
+        kreg[j] = (i < total) ? __ldcg(args.keys + i) : STB_KEY_INVALID;
+      }
+    };
+    if (n_rounds == 1) load_round(0);
+    unsigned prefix = 0u, pmask = 0u;
+    int need = KP;
+    bool select_all = false;
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+      const int shift = pass == 0 ? 20 : (pass == 1 ? 8 : 0);
+      const int nbins = pass == 2 ? 256 : 4096;
+      for (int i = threadIdx.x; i < nbins; i += blockDim.x) hist[i] = 0u;
+      if (threadIdx.x == 0) { s_T = 0u; s_cnt = 0u; }
+      __syncthreads();
+#pragma unroll 1
+      for (int round = 0; round < n_rounds; ++round) {
+        if (n_rounds > 1) load_round(round);
+#pragma unroll
+        for (int j = 0; j < KPT; ++j) {
+          const uint64_t key = kreg[j];
+          if (key != STB_KEY_INVALID) {
+            unsigned o = ~(unsigned)(key >> 32);
+            if ((o & pmask) == prefix) atomicAdd(&hist[(o >> shift) & (unsigned)(nbins - 1)], 1u);
+          }
+        }
+      }
+      __syncthreads();
+      // largest digit d with  count(digit > d) < need <= count(digit >= d)
+      if (threadIdx.x < 32) {
+        const int per_lane = nbins / 32;               // bins per lane, lane 0 = top digits
+        const int hi = nbins - 1 - lane * per_lane;    // this lane scans hi, hi-1, ...
+        unsigned seg = 0u;
+        for (int b = 0; b < per_lane; ++b) seg += hist[hi - b];
+        unsigned incl = seg;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          unsigned v = __shfl_up_sync(0xffffffffu, incl, off);
+          if (lane >= off) incl += v;
+        }
+        const unsigned before = incl - seg;
+        const unsigned all = __shfl_sync(0xffffffffu, incl, 31);
+        if (all < (unsigned)need) { if (lane == 0) s_T = 0xffffffffu; }    // fewer valid keys than needed
+        else if (before < (unsigned)need && (unsigned)need <= incl) {
+          unsigned acc = before;
+          for (int b = 0; b < per_lane; ++b) {
+            unsigned h = hist[hi - b];
+            if (acc + h >= (unsigned)need) { s_T = (unsigned)(hi - b); s_cnt = acc; break; }
+            acc += h;
+          }
+        }
+      }
+      __syncthreads();
+      if (s_T == 0xffffffffu) { select_all = true; break; }
+      prefix |= s_T << shift;
+      pmask |= (unsigned)(nbins - 1) << shift;
+      need -= (int)s_cnt;
+      __syncthreads();
+    }
+    const unsigned Tg = select_all ? 0u : prefix;   // exact ord of the KP-th best score
+    __syncthreads();
+    if (threadIdx.x == 0) s_cnt = 0u;
+    __syncthreads();
+#pragma unroll 1
+    for (int round = 0; round < n_rounds; ++round) {
+      if (n_rounds > 1) load_round(round);
+#pragma unroll
+      for (int j = 0; j < KPT; ++j) {
+        const uint64_t key = kreg[j];
+        if (key != STB_KEY_INVALID && ~(unsigned)(key >> 32) >= Tg) {
+          unsigned idx = atomicAdd(&s_cnt, 1u);
+          if (idx < STB_SORT_CAP) skeys[idx] = key; else s_over = 1u;
+        }
+      }
     }
     __syncthreads();
-    stb_cta_sort_keys(skeys, STB_SORT_CAP);
-    lvl_key_off += lists;
-    uint32_t groups = (lists + F - 1) / F;
-    lvl_cnt_off += groups;
-    lists = groups;
-    my_id = group;
+    if (s_over) {
+      // > 1024 keys share the KP-th best score (mass duplication): they cannot be
+      // ranked here; the host runs the exact collect pass (status[1] = 0).
+      if (threadIdx.x == 0) {
+        args.out_status[0] = 0u; args.out_status[1] = 0u; args.out_status[2] = 0xffffffffu;
+        args.out_status[3] = (uint32_t)KP;
+      }
+      return;
+    }
+    c = (int)s_cnt;
+    stb_pad_and_sort(skeys, c, KP);
   }
 
-  // ---- survivor: exact re-rank of the best KP in canonical arithmetic ----------
+  // ---- exact re-rank of the best KP in canonical arithmetic --------------------------
+  // Rows are staged through shared memory (coalesced, one DRAM latency), then one
+  // thread per candidate accumulates (ab, q2, r2) with f64 FMAs in index order:
+  // f32 x f32 products are exact in f64, so this equals orc_cosine_f32 bit for bit.
   for (int i = threadIdx.x; i < STB_D; i += blockDim.x) sq[i] = __ldg(args.scan.q + i);
-  if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+  if (threadIdx.x < 2) s_nv[threadIdx.x] = 0;
   __syncthreads();
-  if (threadIdx.x < KP) {
-    uint64_t key = skeys[threadIdx.x];
-    double d = CUDART_INF;
-    uint64_t grow = 0xffffffffffffffffull;
-    if (key != STB_KEY_INVALID) {
-      uint32_t row = stb_key_row(key);
-      const float4 *rp = args.scan.rows + (size_t)row * STB_ROW_F4;
-      const float4 *qp = reinterpret_cast<const float4 *>(sq);
-      double ab = 0.0, q2 = 0.0, r2 = 0.0;
-#pragma unroll 4
-      for (int i = 0; i < STB_ROW_F4; ++i) {
-        float4 v = __ldg(rp + i);
-        float4 w = qp[i];
-        // oracle order (orc_cosine_f32(q,row)): ab, q2 (=a2), r2 (=b2), index order
-        ab = fma((double)w.x, (double)v.x, ab); q2 = fma((double)w.x, (double)w.x, q2); r2 = fma((double)v.x, (double)v.x, r2);
-        ab = fma((double)w.y, (double)v.y, ab); q2 = fma((double)w.y, (double)w.y, q2); r2 = fma((double)v.y, (double)v.y, r2);
-        ab = fma((double)w.z, (double)v.z, ab); q2 = fma((double)w.z, (double)w.z, q2); r2 = fma((double)v.z, (double)v.z, r2);
-        ab = fma((double)w.w, (double)v.w, ab); q2 = fma((double)w.w, (double)w.w, q2); r2 = fma((double)v.w, (double)v.w, r2);
+  for (int chunk = 0; chunk < E; ++chunk) {
+    {
+      constexpr int PER = 32 * STB_ROW_F4 / STB_SCAN_THREADS;   // float4 per thread
+      float4 v[PER];
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const int t = threadIdx.x + u * STB_SCAN_THREADS;
+        const uint64_t key = skeys[chunk * 32 + (t >> 6)];
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (key != STB_KEY_INVALID)
+          v[u] = __ldg(args.scan.rows + (size_t)stb_key_row(key) * STB_ROW_F4 + (t & 63));
       }
-      double dist;
-      if (q2 == 0.0 && r2 == 0.0) dist = 0.0;
-      else if (ab == 0.0) dist = 1.0;
-      else {
-        double t = 1.0 - ab / (sqrt(q2) * sqrt(r2));
-        dist = t > 0.0 ? t : 0.0;
-      }
-      atomicAdd(&s_cnt[0], 1);                      // valid candidates
-      if (dist < 100.0) {                           // max_distance.unwrap_or(100.0), strict
-        d = dist;
-        grow = args.row_base + (uint64_t)row;
-        atomicAdd(&s_cnt[1], 1);                    // passing
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const int t = threadIdx.x + u * STB_SCAN_THREADS;
+        *reinterpret_cast<float4 *>(srows + (t >> 6) * STB_RR_STRIDE + (t & 63) * 4) = v[u];
       }
     }
-    s_d[threadIdx.x] = d;
-    s_r[threadIdx.x] = grow;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int ci = chunk * 32 + threadIdx.x;
+      uint64_t key = skeys[ci];
+      double d = CUDART_INF;
+      uint64_t grow = 0xffffffffffffffffull;
+      if (key != STB_KEY_INVALID) {
+        const float4 *rp = reinterpret_cast<const float4 *>(srows + threadIdx.x * STB_RR_STRIDE);
+        const float4 *qp = reinterpret_cast<const float4 *>(sq);
+        double ab = 0.0, q2 = 0.0, r2 = 0.0;
+#pragma unroll 4
+        for (int i = 0; i < STB_ROW_F4; ++i) {
+          float4 v = rp[i];
+          float4 w = qp[i];
+          ab = fma((double)w.x, (double)v.x, ab); q2 = fma((double)w.x, (double)w.x, q2); r2 = fma((double)v.x, (double)v.x, r2);
+          ab = fma((double)w.y, (double)v.y, ab); q2 = fma((double)w.y, (double)w.y, q2); r2 = fma((double)v.y, (double)v.y, r2);
+          ab = fma((double)w.z, (double)v.z, ab); q2 = fma((double)w.z, (double)w.z, q2); r2 = fma((double)v.z, (double)v.z, r2);
+          ab = fma((double)w.w, (double)v.w, ab); q2 = fma((double)w.w, (double)w.w, q2); r2 = fma((double)v.w, (double)v.w, r2);
+        }
+        double dist;
+        if (q2 == 0.0 && r2 == 0.0) dist = 0.0;
+        else if (ab == 0.0) dist = 1.0;
+        else {
+          double t = 1.0 - ab / (sqrt(q2) * sqrt(r2));
+          dist = t > 0.0 ? t : 0.0;
+        }
+        atomicAdd(&s_nv[0], 1);                     // valid candidates
+        if (dist < 100.0) {                         // max_distance.unwrap_or(100.0), strict
+          d = dist;
+          grow = args.row_base + (uint64_t)stb_key_row(key);
+          atomicAdd(&s_nv[1], 1);                   // passing
+        }
+      }
+      s_d[ci] = d;
+      s_r[ci] = grow;
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  // bitonic sort of KP (distance,row) pairs
+  // bitonic sort of the KP (distance,row) pairs
   for (int k = 2; k <= KP; k <<= 1) {
     for (int jj = k >> 1; jj > 0; jj >>= 1) {
       int i = threadIdx.x;
@@ -331,7 +479,7 @@ stb_scan_topk_kernel(const TopkArgs args) {
       __syncthreads();
     }
   }
-  const int n_valid = s_cnt[0], n_pass = s_cnt[1];
+  const int n_valid = s_nv[0], n_pass = s_nv[1];
   const uint32_t k = args.top_k;
   const uint32_t n_out = min((uint32_t)n_pass, k);
   for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
@@ -442,7 +590,7 @@ struct CollectArgs {
 };
 
 template <int U, bool RANGES>
-__global__ void __launch_bounds__(STB_SCAN_THREADS, 2)
+__global__ void __launch_bounds__(STB_SCAN_THREADS, STB_SCAN_MINB)
 stb_scan_collect_kernel(const CollectArgs args) {
   CollectSink sink{args.cos_floor, args.out, args.count, args.cap};
   stb_scan_rows<U, RANGES>(args.scan, sink);
@@ -467,7 +615,7 @@ int stb_launch_scan_collect(stb_ctx *ctx, const float *rows, uint64_t n_rows,
   STB_CUDA(cudaMemsetAsync(ctx->collect_count, 0, sizeof(unsigned long long), ctx->stream));
   uint64_t tiles = (n_virtual + 4 * STB_SCAN_U - 1) / (4 * STB_SCAN_U);
   uint64_t want = (tiles + STB_SCAN_WARPS - 1) / STB_SCAN_WARPS;
-  uint64_t grid = (uint64_t)ctx->sm_count * 2;
+  uint64_t grid = (uint64_t)ctx->sm_count * STB_SCAN_MINB;
   if (want < grid) grid = want < 1 ? 1 : want;
   if (n_ranges > 0)
     stb_scan_collect_kernel<STB_SCAN_U, true><<<(unsigned)grid, STB_SCAN_THREADS, 0, ctx->stream>>>(a);

@@ -80,3 +80,27 @@ def test_out_of_range_token_fails_and_appends_nothing(ctx):
     assert len(c) == 0
     capi.embed(ctx, t, [0, 2, 3], [1, 9, 2], out=False, append_to=c)
     assert len(c) == 2
+
+
+def test_device_resident_embed_entry_point(ctx):
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(4)
+    V = 4000
+    E = (rng.standard_normal((V, 256)) * 0.1).astype(np.float32)
+    offsets, ids = synth_batch(rng, 3000, V)
+    t = capi.Table(ctx, E)
+    dev = torch.device("cuda:0")
+    off_d = torch.from_numpy(offsets.view(np.int64)).to(dev)
+    ids_d = torch.from_numpy(ids.view(np.int32)).to(dev)
+    out_d = torch.zeros((3000, 256), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    capi.embed_dev(ctx, t, off_d.data_ptr(), ids_d.data_ptr(), 3000, out_d.data_ptr())
+    capi.embed_status(ctx)
+    assert np.array_equal(bits(out_d.cpu().numpy()), bits(oracle.embed_csr(E, offsets, ids)))
+    ids_d[5] = V + 3                                   # out of range -> sticky flag, reported once
+    torch.cuda.synchronize()
+    capi.embed_dev(ctx, t, off_d.data_ptr(), ids_d.data_ptr(), 3000, out_d.data_ptr())
+    with pytest.raises(capi.StbError) as e:
+        capi.embed_status(ctx)
+    assert e.value.status == capi.STB_ERR_RANGE
+    capi.embed_status(ctx)                             # cleared
