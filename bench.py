@@ -48,6 +48,8 @@ def parse_args():
     p.add_argument("--topk", type=int, default=10)
     p.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                   help="N>1: p2p = fused in-kernel exchange over NVLink peer memory; nccl = all-gather + merge kernel")
     return p.parse_args()
 
 
@@ -292,7 +294,28 @@ def run_ours(args):
     gathered = torch.zeros((world, k, 2), dtype=torch.float64, device=dev) if world > 1 else None
     final_hits = torch.zeros((n_slots, k, 2), dtype=torch.float64, device=dev)
 
+    # ---- exchange wiring (N > 1) ---------------------------------------------------------
+    xchg, exchange = None, "none"
+    if world > 1:
+        exchange = args.exchange
+        if exchange == "p2p":
+            try:
+                xchg = capi.Exchange(ctx, world, rank, k)
+                handles = [None] * world
+                dist.all_gather_object(handles, xchg.local_handle())
+                xchg.connect(handles)
+                ok = torch.ones(1, device=dev)
+            except capi.StbError as e:
+                print(f"[rank {rank}] p2p exchange unavailable ({e}); using nccl", file=sys.stderr)
+                ok = torch.zeros(1, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() == 0:
+                xchg, exchange = None, "nccl"
+
     def step(i):
+        if xchg is not None:       # ONE kernel: scan + NVLink peer-memory exchange + global merge
+            xchg.search_topk(corpus, q_dev[i % n_q].data_ptr(), k, final_hits[i].data_ptr(), status[i].data_ptr())
+            return
         corpus.search_topk_dev(q_dev[i % n_q].data_ptr(), k, local_hits[i].data_ptr(), status[i].data_ptr())
         if world > 1:
             dist.all_gather_into_tensor(gathered, local_hits[i])
@@ -326,7 +349,17 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     st = status[args.warmup:].cpu().numpy()
-    all_complete = bool((st[:, 1] == 1).all() and (st[:, 0] == min(k, hi - lo)).all())
+    n_expect = min(k, args.rows) if xchg is not None else min(k, hi - lo)
+    all_complete = bool((st[:, 1] == 1).all() and (st[:, 0] == n_expect).all())
+
+    ranks_agree = None
+    if world > 1:
+        mine = final_hits[args.warmup:args.warmup + min(args.steps, 16)].contiguous().view(torch.int64)
+        ref = mine.clone()
+        dist.broadcast(ref, src=0)
+        agree = torch.tensor([int(torch.equal(ref, mine))], device=dev)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        ranks_agree = bool(agree.item())
 
     # ---- e2e: host query in, host hits out, every step synchronous -------------------
     q_pin = torch.from_numpy(queries_h).pin_memory()
@@ -400,7 +433,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": workload_name(args.rows, k), "rows": args.rows, "rows_per_gpu": rows_per_gpu,
-                       "top_k": k, "parallelism": f"row-shard x{world}",
+                       "top_k": k, "parallelism": f"row-shard x{world}", "exchange": exchange,
                        "l2": "corpus shard >> 126 MB L2, no flush needed" if rows_per_gpu * 1024 > 4 * 126e6
                              else "WARNING shard fits partly in L2",
                        "distinct_queries": n_q},
@@ -417,6 +450,7 @@ def run_ours(args):
                          "note": "duration = CUDA-event step time / steps on the launching stream"
                                  + ("" if world == 1 else " (includes all-gather + merge, so a lower bound on the kernel)")},
             "all_results_proven_exact": all_complete,
+            "ranks_agree": ranks_agree,
             "parity_spot_check": check,
         }
         if k3 is not None:

@@ -169,6 +169,33 @@ int stb_search_topk_dev(stb_ctx *ctx, const stb_corpus *corpus,
                         const float *q_dev, uint32_t top_k, stb_hit *out_hits_dev,
                         uint32_t *out_status_dev);
 
+/* ---- fused multi-GPU search: K1 -> exchange over NVLink peer memory -> K4 -------------
+ * One process (or thread) per GPU, one stb_xchg per rank.  Each rank allocates an
+ * exchange buffer; the ranks trade its 64-byte CUDA IPC handle through whatever channel
+ * the host has (MPI, torch.distributed, a pipe ...) and connect.  After that
+ * stb_search_topk_xchg is ONE kernel per query per rank: the scan's final CTA stores its
+ * k hits directly into every peer's buffer, release-stores a sequence flag, waits for
+ * the peers' flags and merges by (distance,row) -- no NCCL call, no second launch.
+ * All ranks must issue the same sequence of stb_search_topk_xchg calls (same top_k).
+ * Within one process (several contexts), use stb_xchg_connect_local instead of IPC.
+ *   out_status_dev[0] = hits, [1] = 1 iff every rank proved its shard result exact
+ *   (0 -> run the per-shard stb_search + stb_hits_merge path), [2] = 0xfffffffe if a
+ *   peer never arrived (timeout). */
+typedef struct stb_xchg stb_xchg;
+#define STB_IPC_HANDLE_BYTES 64
+#define STB_XCHG_MAX_RANKS 8
+int stb_xchg_create(stb_ctx *ctx, uint32_t world, uint32_t rank, uint32_t max_k,
+                    stb_xchg **out);
+int stb_xchg_destroy(stb_xchg *x);
+int stb_xchg_local_handle(stb_xchg *x, uint8_t handle[STB_IPC_HANDLE_BYTES]);
+/* handles: world x 64 bytes, entry r = rank r's handle (own entry ignored). */
+int stb_xchg_connect(stb_xchg *x, const uint8_t *handles);
+/* same-process variant: peers[r] = the stb_xchg of rank r (peers[rank] == x). */
+int stb_xchg_connect_local(stb_xchg *x, stb_xchg *const *peers);
+int stb_search_topk_xchg(stb_ctx *ctx, const stb_corpus *corpus, const float *q_dev,
+                         uint32_t top_k, stb_xchg *x, stb_hit *out_hits_dev,
+                         uint32_t *out_status_dev);
+
 /* ---- K4: merge per-shard hit lists -----------------------------------------------
  * The final sort_by + take of src/search/mod.rs:107-119 applied across row
  * shards: `lists_dev` holds n_lists x per_list hits (e.g. the all-gathered
@@ -192,6 +219,11 @@ uint64_t stb_line_id(const uint8_t *path, uint64_t path_len, int32_t line_number
  * context, and how many searches needed the fallback pass. */
 int stb_ctx_counters(const stb_ctx *ctx, uint64_t *kernel_launches,
                      uint64_t *fallback_searches);
+/* Tuning aid: phase timestamps (ns, %globaltimer) of the last K1 launch; only filled by
+ * libraries built with -DSTB_TAIL_TIMING.  reset=1 arms, reset=0 reads 8 values:
+ * [0] first CTA start, [1] last scan end, [2] last CTA merge end, [3] final ticket,
+ * [4] select done, [5] re-rank done. */
+int stb_debug_timestamps(stb_ctx *ctx, int reset, uint64_t out[8]);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,24 @@
+"""Small-corpus probe of K1 (fixed overhead / tail).  python scripts/tail_probe.py [rows] [iters]"""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from semtools_b200 import capi
+rows = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+dev = torch.device("cuda:0")
+s = torch.cuda.Stream(dev); torch.cuda.set_stream(s)
+ctx = capi.Context(0, s.cuda_stream)
+g = torch.Generator(device=dev); g.manual_seed(1)
+x = torch.randn((rows, 256), generator=g, device=dev); x /= x.norm(dim=1, keepdim=True)
+c = capi.Corpus(ctx, rows); torch.cuda.synchronize(); c.append_dev(x.data_ptr(), rows)
+q = torch.randn((16, 256), generator=g, device=dev); q /= q.norm(dim=1, keepdim=True)
+hits = torch.zeros((16, 10, 2), dtype=torch.float64, device=dev); st = torch.zeros((16, 4), dtype=torch.int32, device=dev)
+for i in range(iters):
+    c.search_topk_dev(q[i % 16].data_ptr(), 10, hits[i % 16].data_ptr(), st[i % 16].data_ptr())
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(s)
+for i in range(iters):
+    c.search_topk_dev(q[i % 16].data_ptr(), 10, hits[i % 16].data_ptr(), st[i % 16].data_ptr())
+e1.record(s); torch.cuda.synchronize()
+print("rows", rows, "us/query", e0.elapsed_time(e1) / iters * 1e3, "complete", bool((st[:, 1] == 1).all()))

@@ -23,8 +23,9 @@ SYMBOLS = [
     "stb_corpus_destroy", "stb_corpus_append", "stb_corpus_append_dev", "stb_corpus_clear",
     "stb_corpus_rows", "stb_corpus_data_dev", "stb_corpus_read", "stb_embed", "stb_embed_dev",
     "stb_embed_status", "stb_search",
-    "stb_search_topk_dev", "stb_hits_merge_dev", "stb_hits_merge", "stb_fnv1a64", "stb_line_id",
-    "stb_ctx_counters",
+    "stb_search_topk_dev", "stb_xchg_create", "stb_xchg_destroy", "stb_xchg_local_handle",
+    "stb_xchg_connect", "stb_xchg_connect_local", "stb_search_topk_xchg", "stb_hits_merge_dev", "stb_hits_merge", "stb_fnv1a64", "stb_line_id",
+    "stb_ctx_counters", "stb_debug_timestamps",
 ]
 
 
@@ -79,6 +80,12 @@ def lib() -> C.CDLL:
     L.stb_embed_status.argtypes = [vp]
     L.stb_search.argtypes = [vp, vp, vp, u32, i32, f64, i32, vp, u32, vp, u64, C.POINTER(u64)]
     L.stb_search_topk_dev.argtypes = [vp, vp, vp, u32, vp, vp]
+    L.stb_xchg_create.argtypes = [vp, u32, u32, u32, C.POINTER(vp)]
+    L.stb_xchg_destroy.argtypes = [vp]
+    L.stb_xchg_local_handle.argtypes = [vp, vp]
+    L.stb_xchg_connect.argtypes = [vp, vp]
+    L.stb_xchg_connect_local.argtypes = [vp, C.POINTER(vp)]
+    L.stb_search_topk_xchg.argtypes = [vp, vp, vp, u32, vp, vp, vp]
     L.stb_hits_merge_dev.argtypes = [vp, vp, u32, u32, u32, vp]
     L.stb_hits_merge.argtypes = [vp, vp, u32, u32, u32, vp, C.POINTER(u32)]
     L.stb_fnv1a64.argtypes = [C.c_char_p, u64]
@@ -86,6 +93,7 @@ def lib() -> C.CDLL:
     L.stb_line_id.argtypes = [C.c_char_p, u64, C.c_int32]
     L.stb_line_id.restype = u64
     L.stb_ctx_counters.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    L.stb_debug_timestamps.argtypes = [vp, i32, vp]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("stb_version", "stb_device_count"):
@@ -259,6 +267,45 @@ class Corpus:
         """stb_search_topk_dev: asynchronous, everything stays in HBM."""
         _check(lib().stb_search_topk_dev(self.ctx._h, self._h, vp(q_dev), top_k, vp(out_hits_dev),
                                          vp(out_status_dev)))
+
+
+class Exchange:
+    """stb_xchg: peer-memory exchange buffers for the fused multi-GPU search."""
+    HANDLE_BYTES = 64
+
+    def __init__(self, ctx: Context, world: int, rank: int, max_k: int):
+        self.ctx, self.world, self.rank, self.max_k = ctx, world, rank, max_k
+        self._h = vp()
+        _check(lib().stb_xchg_create(ctx._h, world, rank, max_k, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().stb_xchg_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def local_handle(self) -> bytes:
+        buf = (C.c_uint8 * self.HANDLE_BYTES)()
+        _check(lib().stb_xchg_local_handle(self._h, buf))
+        return bytes(buf)
+
+    def connect(self, handles: list):
+        """handles[r] = rank r's 64-byte IPC handle (other processes)."""
+        blob = b"".join(handles)
+        assert len(blob) == self.world * self.HANDLE_BYTES
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        _check(lib().stb_xchg_connect(self._h, buf))
+
+    def connect_local(self, peers: list):
+        """peers[r] = the Exchange of rank r living in this process."""
+        arr = (vp * self.world)(*[p._h for p in peers])
+        _check(lib().stb_xchg_connect_local(self._h, arr))
+
+    def search_topk(self, corpus: "Corpus", q_dev: int, top_k: int, out_hits_dev: int, out_status_dev: int):
+        """stb_search_topk_xchg: one kernel = scan + NVLink exchange + global merge."""
+        _check(lib().stb_search_topk_xchg(self.ctx._h, corpus._h, vp(q_dev), top_k, self._h, vp(out_hits_dev),
+                                          vp(out_status_dev)))
 
 
 def embed_dev(ctx: Context, table: Table, offsets_dev: int, ids_dev: int, n_lines: int, out_dev: int):

@@ -103,6 +103,8 @@ int stb_ctx_create(int device, void *cuda_stream, stb_ctx **out) {
     if ((rc = dev_reserve(&c->collect_count, &one, 2)) != STB_OK) goto fail;
     one = 0;
     if ((rc = dev_reserve(&c->err_flag, &one, 1)) != STB_OK) goto fail;
+    one = 0;
+    if ((rc = dev_reserve(&c->dbg_dev, &one, 8)) != STB_OK) goto fail;
   }
   if ((rc = dev_reserve(&c->hits_dev, &c->hits_cap, 1024)) != STB_OK) goto fail;
   if (cudaMemset(c->counters, 0, c->counters_cap * sizeof(unsigned int)) != cudaSuccess ||
@@ -131,7 +133,7 @@ int stb_ctx_destroy(stb_ctx *c) {
   cudaFree(c->block_keys); cudaFree(c->counters); cudaFree(c->q_dev); cudaFree(c->hits_dev);
   cudaFree(c->status_dev); cudaFree(c->collect_rows); cudaFree(c->collect_count);
   cudaFree(c->collect_hits); cudaFree(c->ranges_dev); cudaFree(c->err_flag);
-  cudaFree(c->embed_off_dev); cudaFree(c->embed_ids_dev); cudaFree(c->embed_out_dev);
+  cudaFree(c->dbg_dev); cudaFree(c->embed_off_dev); cudaFree(c->embed_ids_dev); cudaFree(c->embed_out_dev);
   if (c->q_pin) cudaFreeHost(c->q_pin);
   if (c->hits_pin) cudaFreeHost(c->hits_pin);
   if (c->status_pin) cudaFreeHost(c->status_pin);
@@ -149,6 +151,21 @@ int stb_ctx_sync(stb_ctx *ctx) {
 }
 
 void *stb_ctx_stream(stb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+// Tuning aid (STB_TAIL_TIMING builds): reset=1 arms the timestamps, reset=0 reads them.
+int stb_debug_timestamps(stb_ctx *ctx, int reset, uint64_t out[8]) {
+  int rc = ctx_use(ctx);
+  if (rc) return rc;
+  if (reset) {
+    unsigned long long init[8] = {~0ull, 0, 0, 0, 0, 0, 0, 0};
+    STB_CUDA(cudaMemcpyAsync(ctx->dbg_dev, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    STB_CUDA(cudaStreamSynchronize(ctx->stream));
+  } else {
+    STB_CUDA(cudaMemcpyAsync(out, ctx->dbg_dev, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    STB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return STB_OK;
+}
 
 int stb_ctx_counters(const stb_ctx *ctx, uint64_t *kernel_launches, uint64_t *fallback_searches) {
   if (!ctx) { stb_set_error("null context"); return STB_ERR_ARG; }
@@ -520,6 +537,117 @@ int stb_search_topk_dev(stb_ctx *ctx, const stb_corpus *corpus, const float *q_d
   if (corpus->n == 0) { stb_set_error("search_topk_dev: empty corpus"); return STB_ERR_STATE; }
   return stb_launch_scan_topk(ctx, corpus->rows, corpus->n, corpus->row_base, q_dev, top_k, nullptr, 0,
                               corpus->n, out_hits_dev, out_status_dev);
+}
+
+// ------------------------------------------------------------ peer-memory exchange ---
+static size_t xchg_bytes(uint32_t world, uint32_t max_k) {
+  return (size_t)STB_XCHG_SLOTS * world * 16 + (size_t)STB_XCHG_SLOTS * world * max_k * sizeof(stb_hit);
+}
+
+int stb_xchg_create(stb_ctx *ctx, uint32_t world, uint32_t rank, uint32_t max_k, stb_xchg **out) {
+  int rc = ctx_use(ctx);
+  if (rc) return rc;
+  if (!out) { stb_set_error("xchg_create: out is null"); return STB_ERR_ARG; }
+  if (world < 1 || world > STB_XCHG_MAX_WORLD || rank >= world) { stb_set_error("xchg_create: world must be 1..%d and rank < world", STB_XCHG_MAX_WORLD); return STB_ERR_ARG; }
+  if (max_k < 1 || max_k > stb_scan_topk_max_k()) { stb_set_error("xchg_create: max_k must be 1..%u", stb_scan_topk_max_k()); return STB_ERR_ARG; }
+  stb_xchg *x = new (std::nothrow) stb_xchg();
+  if (!x) { stb_set_error("out of host memory"); return STB_ERR_NOMEM; }
+  memset(x, 0, sizeof(*x));
+  x->ctx = ctx; x->world = world; x->rank = rank; x->max_k = max_k;
+  x->bytes = xchg_bytes(world, max_k);
+  // plain cudaMalloc memory: required for cudaIpcGetMemHandle
+  cudaError_t e = cudaMalloc((void **)&x->local, x->bytes);
+  if (e == cudaSuccess) e = cudaMemset(x->local, 0, x->bytes);
+  if (e != cudaSuccess) { cudaGetLastError(); stb_set_error("xchg_create: %s", cudaGetErrorString(e)); delete x; return STB_ERR_NOMEM; }
+  x->peers[rank] = x->local;
+  x->connected = (world == 1);
+  *out = x;
+  return STB_OK;
+}
+
+int stb_xchg_destroy(stb_xchg *x) {
+  if (!x) return STB_OK;
+  if (x->ctx && ctx_alive(x->ctx)) { cudaSetDevice(x->ctx->device); cudaStreamSynchronize(x->ctx->stream); }
+  else cudaDeviceSynchronize();
+  for (uint32_t r = 0; r < x->world; ++r)
+    if (x->ipc_opened[r] && x->peers[r]) cudaIpcCloseMemHandle(x->peers[r]);
+  cudaFree(x->local);
+  cudaGetLastError();
+  delete x;
+  return STB_OK;
+}
+
+int stb_xchg_local_handle(stb_xchg *x, uint8_t handle[STB_IPC_HANDLE_BYTES]) {
+  if (!x || !handle) { stb_set_error("xchg_local_handle: null argument"); return STB_ERR_ARG; }
+  int rc = ctx_use(x->ctx);
+  if (rc) return rc;
+  static_assert(sizeof(cudaIpcMemHandle_t) == STB_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  STB_CUDA(cudaIpcGetMemHandle(&h, x->local));
+  memcpy(handle, &h, sizeof(h));
+  return STB_OK;
+}
+
+int stb_xchg_connect(stb_xchg *x, const uint8_t *handles) {
+  if (!x || !handles) { stb_set_error("xchg_connect: null argument"); return STB_ERR_ARG; }
+  int rc = ctx_use(x->ctx);
+  if (rc) return rc;
+  for (uint32_t r = 0; r < x->world; ++r) {
+    if (r == x->rank || x->peers[r]) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * STB_IPC_HANDLE_BYTES, sizeof(h));
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      stb_set_error("xchg_connect: cannot map rank %u's buffer (%s); use the NCCL path", r, cudaGetErrorString(e));
+      return STB_ERR_CUDA;
+    }
+    x->peers[r] = (unsigned char *)p;
+    x->ipc_opened[r] = true;
+  }
+  x->connected = true;
+  return STB_OK;
+}
+
+int stb_xchg_connect_local(stb_xchg *x, stb_xchg *const *peers) {
+  if (!x || !peers) { stb_set_error("xchg_connect_local: null argument"); return STB_ERR_ARG; }
+  int rc = ctx_use(x->ctx);
+  if (rc) return rc;
+  for (uint32_t r = 0; r < x->world; ++r) {
+    if (r == x->rank) continue;
+    if (!peers[r] || peers[r]->world != x->world || peers[r]->rank != r || peers[r]->max_k != x->max_k) { stb_set_error("xchg_connect_local: peer %u mismatched", r); return STB_ERR_ARG; }
+    const int pd = peers[r]->ctx->device;
+    if (pd != x->ctx->device) {
+      int can = 0;
+      STB_CUDA(cudaDeviceCanAccessPeer(&can, x->ctx->device, pd));
+      if (!can) { stb_set_error("xchg_connect_local: device %d cannot access device %d", x->ctx->device, pd); return STB_ERR_CUDA; }
+      cudaError_t e = cudaDeviceEnablePeerAccess(pd, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { stb_set_error("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); return STB_ERR_CUDA; }
+      cudaGetLastError();
+    }
+    x->peers[r] = peers[r]->local;
+  }
+  x->connected = true;
+  return STB_OK;
+}
+
+int stb_search_topk_xchg(stb_ctx *ctx, const stb_corpus *corpus, const float *q_dev, uint32_t top_k,
+                         stb_xchg *x, stb_hit *out_hits_dev, uint32_t *out_status_dev) {
+  int rc = ctx_use(ctx);
+  if (rc) return rc;
+  if (!corpus || !q_dev || !x || !out_hits_dev || !out_status_dev) { stb_set_error("search_topk_xchg: null argument"); return STB_ERR_ARG; }
+  if (corpus->ctx != ctx || x->ctx != ctx) { stb_set_error("search_topk_xchg: handles belong to another context"); return STB_ERR_ARG; }
+  if (!x->connected) { stb_set_error("search_topk_xchg: exchange not connected"); return STB_ERR_STATE; }
+  if (top_k == 0 || top_k > x->max_k) { stb_set_error("search_topk_xchg: top_k must be 1..%u", x->max_k); return STB_ERR_ARG; }
+  StbXchgArgs a;
+  memset(&a, 0, sizeof(a));
+  for (uint32_t r = 0; r < x->world; ++r) a.base[r] = x->peers[r];
+  a.world = x->world; a.rank = x->rank; a.max_k = x->max_k;
+  a.seq = ++x->seq;
+  a.slot = (uint32_t)(a.seq % STB_XCHG_SLOTS);
+  return stb_launch_scan_topk(ctx, corpus->rows, corpus->n, corpus->row_base, q_dev, top_k, nullptr, 0,
+                              corpus->n, out_hits_dev, out_status_dev, &a);
 }
 
 // ---------------------------------------------------------------------- merge ---

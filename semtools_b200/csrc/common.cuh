@@ -60,6 +60,7 @@ struct stb_ctx {
   uint64_t *ranges_dev;     // [3 * n] : begin(local), end(local), vstart
   size_t ranges_cap;
   int *err_flag;            // device int for K3 range errors
+  unsigned long long *dbg_dev;  // 8 u64 phase timestamps (STB_TAIL_TIMING builds; else unused)
   uint64_t *embed_off_dev;  // K3 staging: CSR offsets
   size_t embed_off_cap;
   uint32_t *embed_ids_dev;  // K3 staging: token ids
@@ -74,6 +75,25 @@ struct stb_ctx {
   // --- counters ---
   uint64_t kernel_launches;
   uint64_t fallback_searches;
+};
+
+#define STB_XCHG_SLOTS 4
+#define STB_XCHG_MAX_WORLD 8
+struct StbXchgArgs {
+  unsigned char *base[STB_XCHG_MAX_WORLD];   // exchange buffer of every rank (peer-mapped)
+  uint32_t world, rank, max_k, slot;
+  unsigned long long seq;
+};
+
+struct stb_xchg {
+  stb_ctx *ctx;
+  uint32_t world, rank, max_k;
+  unsigned char *local;                      // this rank's buffer (cudaMalloc)
+  size_t bytes;
+  unsigned char *peers[STB_XCHG_MAX_WORLD];  // peers[rank] == local
+  bool ipc_opened[STB_XCHG_MAX_WORLD];
+  bool connected;
+  unsigned long long seq;
 };
 
 struct stb_table {
@@ -103,7 +123,7 @@ int stb_launch_scan_topk(stb_ctx *ctx, const float *rows, uint64_t n_rows,
                          uint64_t row_base, const float *q_dev, uint32_t top_k,
                          const uint64_t *ranges_dev, uint32_t n_ranges,
                          uint64_t n_virtual, stb_hit *out_hits_dev,
-                         uint32_t *out_status_dev);
+                         uint32_t *out_status_dev, const StbXchgArgs *xchg = nullptr);
 // Largest top_k the fast path serves.
 uint32_t stb_scan_topk_max_k(void);
 // Collect path: every row whose approximate cosine >= cos_floor (or that cannot be

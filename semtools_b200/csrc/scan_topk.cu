@@ -153,7 +153,7 @@ __device__ __forceinline__ void stb_scan_rows(const ScanArgs &args, Sink &sink) 
 #pragma unroll
     for (int u = 0; u < U; ++u)
       if (j == u) { s = sc[u]; r = row[u]; }
-    sink(s, r);
+    sink.template consume<4 * U>(s, r);
   }
 }
 
@@ -164,11 +164,13 @@ struct TopSink {
   uint32_t lr[E];
   float thr;   // min score in the list (warp-uniform); -inf while not full
   int lane;
+  int fill;    // slots bulk-filled so far (warp-uniform); 32*E once the fill phase is over
   __device__ __forceinline__ void init() {
 #pragma unroll
     for (int e = 0; e < E; ++e) { ls[e] = -CUDART_INF_F; lr[e] = 0xffffffffu; }
     thr = -CUDART_INF_F;
     lane = threadIdx.x & 31;
+    fill = 0;
   }
   __device__ __forceinline__ float warp_min(float m) const {
 #pragma unroll
@@ -193,6 +195,50 @@ struct TopSink {
     for (int e = 1; e < E; ++e) m = fminf(m, ls[e]);
     thr = warp_min(m);
   }
+  // Bulk fill: while the list has room and tiles are complete, the tile's rows are
+  // gathered straight into the free slots (slot -> lane slot%32, entry slot/32) with two
+  // shuffles, instead of one min-reduction per row.  ROWS = rows a full tile carries,
+  // sitting in lanes g*8+u (g < 4, u < ROWS/4).
+  template <int ROWS>
+  __device__ __forceinline__ bool try_fill(float s, uint32_t r, unsigned vmask) {
+    constexpr int KP = 32 * E;
+    constexpr int UU = ROWS / 4;
+    unsigned full = 0u;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int u = 0; u < UU; ++u) full |= 1u << (g * 8 + u);
+    if (fill >= KP) return false;
+    if (vmask != full || fill + ROWS > KP) {      // ragged tile: leave the fill phase for good
+      fill = KP;
+      return false;
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int d = e * 32 + lane - fill;          // which row of the tile this slot takes
+      const bool want = (d >= 0 && d < ROWS);
+      const int src = want ? ((d / UU) * 8 + (d % UU)) : 0;
+      const float cs = __shfl_sync(0xffffffffu, s, src);
+      const uint32_t cr = __shfl_sync(0xffffffffu, r, src);
+      if (want) { ls[e] = cs; lr[e] = cr; }
+    }
+    fill += ROWS;
+    if (fill >= KP) {
+      float m = ls[0];
+#pragma unroll
+      for (int e = 1; e < E; ++e) m = fminf(m, ls[e]);
+      thr = warp_min(m);
+    }
+    return true;
+  }
+  template <int ROWS>
+  __device__ __forceinline__ void consume(float s, uint32_t r) {
+    if (fill < 32 * E) {
+      const unsigned vmask = __ballot_sync(0xffffffffu, s > -CUDART_INF_F);
+      if (try_fill<ROWS>(s, r, vmask)) return;
+    }
+    (*this)(s, r);
+  }
   __device__ __forceinline__ void operator()(float s, uint32_t r) {
     unsigned mask = __ballot_sync(0xffffffffu, s > thr);
     while (mask) {
@@ -205,38 +251,124 @@ struct TopSink {
   }
 };
 
-// Ascending bitonic sort of n (power of two <= STB_SORT_CAP) keys in shared memory.
-__device__ __forceinline__ void stb_cta_sort_keys(uint64_t *keys, int n) {
-  for (int k = 2; k <= n; k <<= 1) {
-    for (int jj = k >> 1; jj > 0; jj >>= 1) {
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        int ixj = i ^ jj;
-        if (ixj > i) {
-          uint64_t x = keys[i], y = keys[ixj];
-          bool up = ((i & k) == 0);
-          if ((x > y) == up) { keys[i] = y; keys[ixj] = x; }
+// Ascending bitonic sort of n keys (power of two, <= R*256) held in shared memory,
+// done in registers: element i = r*256 + tid lives in register k[r] of thread tid, so a
+// compare-exchange at distance j is a register swap (j >= 256), a shuffle (j < 32) or a
+// shared-memory exchange (32 <= j < 256; the only steps that need __syncthreads).
+// Requires blockDim.x == 256.
+template <int R>
+__device__ __forceinline__ void stb_cta_sort_keys_t(uint64_t *keys, int n) {
+  const int tid = threadIdx.x;
+  uint64_t k[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) k[r] = (r * 256 + tid < n) ? keys[r * 256 + tid] : STB_KEY_INVALID;
+  __syncthreads();
+  for (int kk = 2; kk <= n; kk <<= 1) {
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      if (j >= 256) {
+        // in-thread exchange; dr spelled out so k[] stays in registers
+#pragma unroll
+        for (int dr = 1; dr < R; dr <<= 1) {
+          if (j == dr * 256) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              if ((r & dr) == 0) {
+                const bool up = (((r * 256 + tid) & kk) == 0);
+                uint64_t x = k[r], y = k[r | dr];
+                if ((x > y) == up) { k[r] = y; k[r | dr] = x; }
+              }
+            }
+          }
+        }
+      } else if (j >= 32) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) keys[r * 256 + tid] = k[r];
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int i = r * 256 + tid;
+          const uint64_t other = keys[i ^ j];
+          const bool keep_min = (((i & j) == 0) == ((i & kk) == 0));
+          k[r] = keep_min ? (k[r] < other ? k[r] : other) : (k[r] > other ? k[r] : other);
+        }
+        __syncthreads();
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int i = r * 256 + tid;
+          const uint64_t other = __shfl_xor_sync(0xffffffffu, k[r], j);
+          const bool keep_min = (((i & j) == 0) == ((i & kk) == 0));
+          k[r] = keep_min ? (k[r] < other ? k[r] : other) : (k[r] > other ? k[r] : other);
         }
       }
-      __syncthreads();
     }
   }
+#pragma unroll
+  for (int r = 0; r < R; ++r) keys[r * 256 + tid] = k[r];
+  __syncthreads();
+}
+
+__device__ __forceinline__ void stb_cta_sort_keys(uint64_t *keys, int n) {
+  static_assert(STB_SCAN_THREADS == 256, "register sort assumes 256 threads");
+  if (n <= 256) stb_cta_sort_keys_t<1>(keys, n);
+  else stb_cta_sort_keys_t<4>(keys, n);
 }
 
 struct TopkArgs {
   ScanArgs scan;
   uint64_t row_base;
-  uint64_t *keys;            // [gridDim.x][KP] best keys of every CTA
-  unsigned int *counters;    // [0] arrival ticket
+  uint64_t *keys;            // sorted best-KP lists of every tree level
+  unsigned int *counters;    // one arrival ticket per tree group, all levels
   stb_hit *out_hits;
   uint32_t *out_status;
   uint32_t top_k;
+  StbXchgArgs xchg;          // world == 0: no cross-GPU exchange
+  unsigned long long *dbg;   // STB_TAIL_TIMING builds only: phase timestamps (ns)
 };
+
+__device__ __forceinline__ unsigned long long stb_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#ifdef STB_TAIL_TIMING
+#define STB_T_MIN(i) do { if (threadIdx.x == 0 && args.dbg) atomicMin(args.dbg + (i), stb_globaltimer()); } while (0)
+#define STB_T_MAX(i) do { if (threadIdx.x == 0 && args.dbg) atomicMax(args.dbg + (i), stb_globaltimer()); } while (0)
+#else
+#define STB_T_MIN(i) do { } while (0)
+#define STB_T_MAX(i) do { } while (0)
+#endif
+
+// ---- peer-memory exchange (fused K1 -> all-gather -> K4) ------------------------------
+// Every rank owns one exchange buffer (cudaMalloc, mapped into all peers through CUDA
+// IPC or peer access):  flags[S][world] u64 | status[S][world] u32 | hits[S][world][max_k].
+// The final CTA of rank r stores its k hits into slot (seq % S), lane r of EVERY peer's
+// buffer over NVLink, fences, release-stores seq into the peers' flags, then
+// acquire-spins on its own flags until all `world` lanes carry seq, and merges.
+__device__ __forceinline__ void stb_st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long stb_ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long *stb_x_flags(const StbXchgArgs &x, int peer) {
+  return reinterpret_cast<unsigned long long *>(x.base[peer]);
+}
+__device__ __forceinline__ uint32_t *stb_x_status(const StbXchgArgs &x, int peer) {
+  return reinterpret_cast<uint32_t *>(x.base[peer] + (size_t)STB_XCHG_SLOTS * x.world * 8);
+}
+__device__ __forceinline__ stb_hit *stb_x_hits(const StbXchgArgs &x, int peer) {
+  return reinterpret_cast<stb_hit *>(x.base[peer] + (size_t)STB_XCHG_SLOTS * x.world * 16);
+}
 
 // Sort the first `c` keys of skeys (padded with INVALID to a power of two >= KP).
 __device__ __forceinline__ int stb_pad_and_sort(uint64_t *skeys, int c, int min_n) {
   int n = min_n;
   while (n < c) n <<= 1;
-  for (int i = c + threadIdx.x; i < n; i += blockDim.x) skeys[i] = STB_KEY_INVALID;
+  const int span = n <= 256 ? 256 : STB_SORT_CAP;   // the register sort writes back its whole span
+  for (int i = c + threadIdx.x; i < span; i += blockDim.x) skeys[i] = STB_KEY_INVALID;
   __syncthreads();
   stb_cta_sort_keys(skeys, n);
   return n;
@@ -250,15 +382,21 @@ stb_scan_topk_kernel(const TopkArgs args) {
   constexpr int KP = 32 * E;
   __shared__ uint64_t skeys[STB_SORT_CAP];
   __shared__ unsigned int s_T, s_cnt, s_ticket, s_over;
-  __shared__ __align__(16) float sq[STB_D];
+  __shared__ double sqd[STB_D];                  // query in f64 (exact conversion)
   __shared__ __align__(16) float srows[32 * STB_RR_STRIDE];
-  __shared__ double s_d[KP];
+  __shared__ double s_d[KP], s_r2[KP], s_q2;
   __shared__ uint64_t s_r[KP];
   __shared__ int s_nv[2];
 
+  STB_T_MIN(0);                      // first CTA starts
   TopSink<E> sink;
   sink.init();
   stb_scan_rows<U, RANGES>(args.scan, sink);
+  STB_T_MAX(1);                      // last CTA leaves the scan loop
+  // Programmatic dependent launch: the scan above reads only the corpus and the query,
+  // so the NEXT query's kernel may start streaming as soon as every CTA of this one has
+  // left its scan loop; this kernel's merge / re-rank tail then overlaps with it.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // ---- CTA merge ------------------------------------------------------------------
   // T = max over warps of the warp list minimum is a lower bound of the CTA's KP-th
@@ -273,140 +411,84 @@ stb_scan_topk_kernel(const TopkArgs args) {
     const unsigned T = s_T;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-      if (sink.lr[e] != 0xffffffffu && stb_f2ord(sink.ls[e]) >= T) {
-        unsigned idx = atomicAdd(&s_cnt, 1u);       // <= 8*KP <= STB_SORT_CAP entries exist
-        skeys[idx] = stb_make_key(sink.ls[e], sink.lr[e]);
-      }
+      const bool take = sink.lr[e] != 0xffffffffu && stb_f2ord(sink.ls[e]) >= T;
+      const unsigned m = __ballot_sync(0xffffffffu, take);
+      unsigned base = 0u;
+      if (lane == 0 && m) base = atomicAdd(&s_cnt, (unsigned)__popc(m));   // <= 8*KP <= STB_SORT_CAP
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (take) skeys[base + __popc(m & ((1u << lane) - 1u))] = stb_make_key(sink.ls[e], sink.lr[e]);
     }
   }
   __syncthreads();
   int c = (int)s_cnt;
   stb_pad_and_sort(skeys, c, KP);
+  STB_T_MAX(2);                      // last CTA-level merge done
 
-  // ---- publish the CTA's best KP; last CTA to arrive finishes the query -------------
-  if (gridDim.x > 1) {
-    uint64_t *mine = args.keys + (size_t)blockIdx.x * KP;
-    for (int i = threadIdx.x; i < KP; i += blockDim.x) mine[i] = skeys[i];
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_ticket = atomicAdd(args.counters, 1u);
-    __syncthreads();
-    if (s_ticket != gridDim.x - 1) return;
-    __threadfence();
-    if (threadIdx.x == 0) args.counters[0] = 0u;   // re-arm for the next launch
+  // Everything below writes scratch shared with the PREVIOUS launch on this stream
+  // (keys, tickets, exchange slots): wait until that grid has completed and flushed.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    // Exact radix select (12+12+8 bits of the ordered score) of the KP-th best score
-    // among the gridDim.x*KP published keys: distribution-independent, 4 coalesced
-    // passes over <= a few hundred KB that sit in L2.  The histogram aliases the
-    // re-rank staging buffer, which is not live yet.
-    unsigned int *hist = reinterpret_cast<unsigned int *>(srows);
-    const size_t total = (size_t)gridDim.x * KP;
-    // Keys are cached in registers, STB_KPT per thread per round, all loads of a round
-    // issued before any use (one L2 latency per round; one round covers 10240 keys,
-    // i.e. the whole E=1 grid, which is then read exactly once).
-    constexpr int KPT = 40;
-    uint64_t kreg[KPT];
-    const int n_rounds = (int)((total + (size_t)KPT * STB_SCAN_THREADS - 1) / ((size_t)KPT * STB_SCAN_THREADS));
-    auto load_round = [&](int round) {
-#pragma unroll
-      for (int j = 0; j < KPT; ++j) {
-        size_t i = ((size_t)round * KPT + j) * STB_SCAN_THREADS + threadIdx.x;
-        kreg[j] = (i < total) ? __ldcg(args.keys + i) : STB_KEY_INVALID;
-      }
-    };
-    if (n_rounds == 1) load_round(0);
-    unsigned prefix = 0u, pmask = 0u;
-    int need = KP;
-    bool select_all = false;
-#pragma unroll 1
-    for (int pass = 0; pass < 3; ++pass) {
-      const int shift = pass == 0 ? 20 : (pass == 1 ? 8 : 0);
-      const int nbins = pass == 2 ? 256 : 4096;
-      for (int i = threadIdx.x; i < nbins; i += blockDim.x) hist[i] = 0u;
-      if (threadIdx.x == 0) { s_T = 0u; s_cnt = 0u; }
+  // ---- tree merge across CTAs ------------------------------------------------------------
+  // Lists of KP sorted keys are merged F = 1024/KP at a time by the last CTA to arrive in
+  // each group (atomic ticket + fences), level by level: 296 -> 10 -> 1 lists at E = 1.
+  // Each merge is one register/shuffle bitonic sort of <= 1024 keys (~2 us); the groups of
+  // a level run in parallel on different SMs.  Level l's lists live at key offset
+  // lvl_key_off*KP, its tickets at counters[lvl_cnt_off + group].
+  {
+    constexpr int F = STB_SORT_CAP / KP;
+    uint32_t lists = gridDim.x, my_id = blockIdx.x, lvl_key_off = 0, lvl_cnt_off = 0;
+    while (lists > 1) {
+      uint64_t *lvl = args.keys + (size_t)lvl_key_off * KP;
+      for (int i = threadIdx.x; i < KP; i += blockDim.x) lvl[(size_t)my_id * KP + i] = skeys[i];
+      __threadfence();
       __syncthreads();
-#pragma unroll 1
-      for (int round = 0; round < n_rounds; ++round) {
-        if (n_rounds > 1) load_round(round);
+      const uint32_t group = my_id / F, first = group * F;
+      const uint32_t n_in = min((uint32_t)F, lists - first);
+      if (threadIdx.x == 0) s_ticket = atomicAdd(args.counters + lvl_cnt_off + group, 1u);
+      __syncthreads();
+      if (s_ticket != n_in - 1) return;            // not the last of my group: done
+      __threadfence();
+      if (threadIdx.x == 0) args.counters[lvl_cnt_off + group] = 0u;   // re-arm for the next launch
+      {
+        constexpr int PER = STB_SORT_CAP / STB_SCAN_THREADS;
+        uint64_t v[PER];
 #pragma unroll
-        for (int j = 0; j < KPT; ++j) {
-          const uint64_t key = kreg[j];
-          if (key != STB_KEY_INVALID) {
-            unsigned o = ~(unsigned)(key >> 32);
-            if ((o & pmask) == prefix) atomicAdd(&hist[(o >> shift) & (unsigned)(nbins - 1)], 1u);
-          }
+        for (int u = 0; u < PER; ++u) {
+          const int i = threadIdx.x + u * STB_SCAN_THREADS;
+          const uint32_t li = i / KP;
+          v[u] = (li < n_in) ? __ldcg(lvl + (size_t)(first + li) * KP + (i % KP)) : STB_KEY_INVALID;
         }
+#pragma unroll
+        for (int u = 0; u < PER; ++u) skeys[threadIdx.x + u * STB_SCAN_THREADS] = v[u];
       }
       __syncthreads();
-      // largest digit d with  count(digit > d) < need <= count(digit >= d)
-      if (threadIdx.x < 32) {
-        const int per_lane = nbins / 32;               // bins per lane, lane 0 = top digits
-        const int hi = nbins - 1 - lane * per_lane;    // this lane scans hi, hi-1, ...
-        unsigned seg = 0u;
-        for (int b = 0; b < per_lane; ++b) seg += hist[hi - b];
-        unsigned incl = seg;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-          unsigned v = __shfl_up_sync(0xffffffffu, incl, off);
-          if (lane >= off) incl += v;
-        }
-        const unsigned before = incl - seg;
-        const unsigned all = __shfl_sync(0xffffffffu, incl, 31);
-        if (all < (unsigned)need) { if (lane == 0) s_T = 0xffffffffu; }    // fewer valid keys than needed
-        else if (before < (unsigned)need && (unsigned)need <= incl) {
-          unsigned acc = before;
-          for (int b = 0; b < per_lane; ++b) {
-            unsigned h = hist[hi - b];
-            if (acc + h >= (unsigned)need) { s_T = (unsigned)(hi - b); s_cnt = acc; break; }
-            acc += h;
-          }
-        }
-      }
-      __syncthreads();
-      if (s_T == 0xffffffffu) { select_all = true; break; }
-      prefix |= s_T << shift;
-      pmask |= (unsigned)(nbins - 1) << shift;
-      need -= (int)s_cnt;
-      __syncthreads();
+      stb_cta_sort_keys(skeys, (int)(n_in * KP) <= 256 ? 256 : STB_SORT_CAP);
+      lvl_key_off += lists;
+      const uint32_t groups = (lists + F - 1) / F;
+      lvl_cnt_off += groups;
+      lists = groups;
+      my_id = group;
     }
-    const unsigned Tg = select_all ? 0u : prefix;   // exact ord of the KP-th best score
-    __syncthreads();
-    if (threadIdx.x == 0) s_cnt = 0u;
-    __syncthreads();
-#pragma unroll 1
-    for (int round = 0; round < n_rounds; ++round) {
-      if (n_rounds > 1) load_round(round);
-#pragma unroll
-      for (int j = 0; j < KPT; ++j) {
-        const uint64_t key = kreg[j];
-        if (key != STB_KEY_INVALID && ~(unsigned)(key >> 32) >= Tg) {
-          unsigned idx = atomicAdd(&s_cnt, 1u);
-          if (idx < STB_SORT_CAP) skeys[idx] = key; else s_over = 1u;
-        }
-      }
-    }
-    __syncthreads();
-    if (s_over) {
-      // > 1024 keys share the KP-th best score (mass duplication): they cannot be
-      // ranked here; the host runs the exact collect pass (status[1] = 0).
-      if (threadIdx.x == 0) {
-        args.out_status[0] = 0u; args.out_status[1] = 0u; args.out_status[2] = 0xffffffffu;
-        args.out_status[3] = (uint32_t)KP;
-      }
-      return;
-    }
-    c = (int)s_cnt;
-    stb_pad_and_sort(skeys, c, KP);
   }
+  STB_T_MAX(3);                      // survivor holds the global best KP
+  const bool overflow = (s_over != 0u);
+  STB_T_MAX(4);                      // radix select + final key sort done
 
   // ---- exact re-rank of the best KP in canonical arithmetic --------------------------
   // Rows are staged through shared memory (coalesced, one DRAM latency), then one
   // thread per candidate accumulates (ab, q2, r2) with f64 FMAs in index order:
   // f32 x f32 products are exact in f64, so this equals orc_cosine_f32 bit for bit.
-  for (int i = threadIdx.x; i < STB_D; i += blockDim.x) sq[i] = __ldg(args.scan.q + i);
+  for (int i = threadIdx.x; i < STB_D; i += blockDim.x) sqd[i] = (double)__ldg(args.scan.q + i);
   if (threadIdx.x < 2) s_nv[threadIdx.x] = 0;
+  if (threadIdx.x < KP) { s_d[threadIdx.x] = CUDART_INF; s_r[threadIdx.x] = 0xffffffffffffffffull; }
   __syncthreads();
-  for (int chunk = 0; chunk < E; ++chunk) {
+  if (threadIdx.x == 5 * 32) {                       // an otherwise idle warp: ||q||^2 once
+    double q2 = 0.0;
+#pragma unroll 8
+    for (int i = 0; i < STB_D; ++i) q2 = fma(sqd[i], sqd[i], q2);
+    s_q2 = q2;
+  }
+  for (int chunk = 0; chunk < (overflow ? 0 : E); ++chunk) {
     {
       constexpr int PER = 32 * STB_ROW_F4 / STB_SCAN_THREADS;   // float4 per thread
       float4 v[PER];
@@ -425,43 +507,54 @@ stb_scan_topk_kernel(const TopkArgs args) {
       }
     }
     __syncthreads();
-    if (threadIdx.x < 32) {
-      const int ci = chunk * 32 + threadIdx.x;
-      uint64_t key = skeys[ci];
-      double d = CUDART_INF;
-      uint64_t grow = 0xffffffffffffffffull;
-      if (key != STB_KEY_INVALID) {
-        const float4 *rp = reinterpret_cast<const float4 *>(srows + threadIdx.x * STB_RR_STRIDE);
-        const float4 *qp = reinterpret_cast<const float4 *>(sq);
-        double ab = 0.0, q2 = 0.0, r2 = 0.0;
-#pragma unroll 4
+    // 8 candidates per warp on 4 warps (one per SM sub-partition): the f64 chains are
+    // latency-bound, so spreading them quarters the issue time
+    if (threadIdx.x < 128 && lane < 8) {
+      const int cl = (threadIdx.x >> 5) * 8 + lane;          // candidate inside the chunk
+      const int ci = chunk * 32 + cl;
+      if (skeys[ci] != STB_KEY_INVALID) {
+        const float4 *rp = reinterpret_cast<const float4 *>(srows + cl * STB_RR_STRIDE);
+        double ab = 0.0, r2 = 0.0;
+#pragma unroll 8
         for (int i = 0; i < STB_ROW_F4; ++i) {
-          float4 v = rp[i];
-          float4 w = qp[i];
-          ab = fma((double)w.x, (double)v.x, ab); q2 = fma((double)w.x, (double)w.x, q2); r2 = fma((double)v.x, (double)v.x, r2);
-          ab = fma((double)w.y, (double)v.y, ab); q2 = fma((double)w.y, (double)w.y, q2); r2 = fma((double)v.y, (double)v.y, r2);
-          ab = fma((double)w.z, (double)v.z, ab); q2 = fma((double)w.z, (double)w.z, q2); r2 = fma((double)v.z, (double)v.z, r2);
-          ab = fma((double)w.w, (double)v.w, ab); q2 = fma((double)w.w, (double)w.w, q2); r2 = fma((double)v.w, (double)v.w, r2);
+          const float4 v = rp[i];
+          const double vx = (double)v.x, vy = (double)v.y, vz = (double)v.z, vw = (double)v.w;
+          // oracle order (orc_cosine_f32(q,row)): index order, one rounding per step
+          ab = fma(sqd[4 * i + 0], vx, ab); r2 = fma(vx, vx, r2);
+          ab = fma(sqd[4 * i + 1], vy, ab); r2 = fma(vy, vy, r2);
+          ab = fma(sqd[4 * i + 2], vz, ab); r2 = fma(vz, vz, r2);
+          ab = fma(sqd[4 * i + 3], vw, ab); r2 = fma(vw, vw, r2);
         }
-        double dist;
-        if (q2 == 0.0 && r2 == 0.0) dist = 0.0;
-        else if (ab == 0.0) dist = 1.0;
-        else {
-          double t = 1.0 - ab / (sqrt(q2) * sqrt(r2));
-          dist = t > 0.0 ? t : 0.0;
-        }
-        atomicAdd(&s_nv[0], 1);                     // valid candidates
-        if (dist < 100.0) {                         // max_distance.unwrap_or(100.0), strict
-          d = dist;
-          grow = args.row_base + (uint64_t)stb_key_row(key);
-          atomicAdd(&s_nv[1], 1);                   // passing
-        }
+        s_d[ci] = ab;          // finalised below once ||q||^2 is known
+        s_r2[ci] = r2;
       }
-      s_d[ci] = d;
-      s_r[ci] = grow;
     }
     __syncthreads();
   }
+  if (threadIdx.x < KP && !overflow) {
+    const uint64_t key = skeys[threadIdx.x];
+    double d = CUDART_INF;
+    uint64_t grow = 0xffffffffffffffffull;
+    if (key != STB_KEY_INVALID) {
+      const double ab = s_d[threadIdx.x], r2 = s_r2[threadIdx.x], q2 = s_q2;
+      double dist;
+      if (q2 == 0.0 && r2 == 0.0) dist = 0.0;
+      else if (ab == 0.0) dist = 1.0;
+      else {
+        double t = 1.0 - ab / (sqrt(q2) * sqrt(r2));
+        dist = t > 0.0 ? t : 0.0;
+      }
+      atomicAdd(&s_nv[0], 1);                     // valid candidates
+      if (dist < 100.0) {                         // max_distance.unwrap_or(100.0), strict
+        d = dist;
+        grow = args.row_base + (uint64_t)stb_key_row(key);
+        atomicAdd(&s_nv[1], 1);                   // passing
+      }
+    }
+    s_d[threadIdx.x] = d;
+    s_r[threadIdx.x] = grow;
+  }
+  __syncthreads();
   // bitonic sort of the KP (distance,row) pairs
   for (int k = 2; k <= KP; k <<= 1) {
     for (int jj = k >> 1; jj > 0; jj >>= 1) {
@@ -479,25 +572,110 @@ stb_scan_topk_kernel(const TopkArgs args) {
       __syncthreads();
     }
   }
+  STB_T_MAX(5);                      // exact re-rank + hit sort done
   const int n_valid = s_nv[0], n_pass = s_nv[1];
   const uint32_t k = args.top_k;
-  const uint32_t n_out = min((uint32_t)n_pass, k);
+  const uint32_t n_out = overflow ? 0u : min((uint32_t)n_pass, k);
+  bool complete;
+  if (overflow) complete = false;
+  else if (n_valid < KP) complete = true;   // every scorable row is in the candidate set
+  else {
+    float s_min = stb_key_score(skeys[KP - 1]);
+    complete = (n_out == k) && ((1.0 - (double)s_min - STB_SCORE_EPS) > s_d[k - 1]);
+  }
+  if (args.xchg.world <= 1) {
+    for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
+      stb_hit h;
+      h.distance = (i < n_out) ? s_d[i] : CUDART_INF;
+      h.row = (i < n_out) ? s_r[i] : 0xffffffffffffffffull;
+      args.out_hits[i] = h;
+    }
+    if (threadIdx.x == 0) {
+      args.out_status[0] = n_out;
+      args.out_status[1] = complete ? 1u : 0u;
+      args.out_status[2] = overflow ? 0xffffffffu : (uint32_t)n_valid;
+      args.out_status[3] = (uint32_t)KP;
+    }
+    return;
+  }
+
+  // ---- fused exchange over NVLink peer memory + global merge ---------------------------
+  const StbXchgArgs &X = args.xchg;
+  const int world = (int)X.world, me = (int)X.rank;
+  const size_t lane_off = (size_t)X.slot * world + me;
+  for (int idx = threadIdx.x; idx < world * (int)k; idx += blockDim.x) {
+    const int p = idx / (int)k, i = idx % (int)k;
+    stb_hit h;
+    h.distance = ((uint32_t)i < n_out) ? s_d[i] : CUDART_INF;
+    h.row = ((uint32_t)i < n_out) ? s_r[i] : 0xffffffffffffffffull;
+    stb_x_hits(X, p)[lane_off * X.max_k + i] = h;
+  }
+  if (threadIdx.x < world) stb_x_status(X, threadIdx.x)[lane_off] = (complete ? 1u : 0u) | (n_out << 8);
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < world) stb_st_release_sys(stb_x_flags(X, threadIdx.x) + lane_off, X.seq);
+  __shared__ unsigned int s_timeout;
+  if (threadIdx.x == 0) s_timeout = 0u;
+  __syncthreads();
+  if (threadIdx.x < world) {
+    const unsigned long long *f = stb_x_flags(X, me) + (size_t)X.slot * world + threadIdx.x;
+    const long long t0 = clock64();
+    while (stb_ld_acquire_sys(f) != X.seq) {
+      if (clock64() - t0 > 8000000000ll) { s_timeout = 1u; break; }   // ~4 s: a peer is gone
+    }
+  }
+  __syncthreads();
+  // merge world x k hits by (distance,row); buffers alias the re-rank staging area
+  double *md = reinterpret_cast<double *>(srows);
+  uint64_t *mr = reinterpret_cast<uint64_t *>(srows) + 1024;
+  const int n_in = world * (int)k;
+  int n_sort = 2;
+  while (n_sort < n_in) n_sort <<= 1;
+  const stb_hit *lh = stb_x_hits(X, me) + (size_t)X.slot * world * X.max_k;
+  for (int i = threadIdx.x; i < n_sort; i += blockDim.x) {
+    double d = CUDART_INF;
+    uint64_t r = 0xffffffffffffffffull;
+    if (i < n_in) {
+      const stb_hit *src = lh + (size_t)(i / (int)k) * X.max_k + (i % (int)k);
+      d = __ldcv(&src->distance);
+      r = __ldcv(&src->row);
+    }
+    md[i] = d; mr[i] = r;
+  }
+  __syncthreads();
+  for (int kk = 2; kk <= n_sort; kk <<= 1) {
+    for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+      for (int i = threadIdx.x; i < n_sort; i += blockDim.x) {
+        int ixj = i ^ jj;
+        if (ixj > i) {
+          bool up = ((i & kk) == 0);
+          bool gt = stb_hit_less(md[ixj], mr[ixj], md[i], mr[i]);
+          if (gt == up) {
+            double td = md[i]; uint64_t tr = mr[i];
+            md[i] = md[ixj]; mr[i] = mr[ixj]; md[ixj] = td; mr[ixj] = tr;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
   for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
     stb_hit h;
-    h.distance = (i < n_out) ? s_d[i] : CUDART_INF;
-    h.row = (i < n_out) ? s_r[i] : 0xffffffffffffffffull;
+    h.distance = md[i];
+    h.row = mr[i];
     args.out_hits[i] = h;
   }
   if (threadIdx.x == 0) {
-    bool complete;
-    if (n_valid < KP) complete = true;   // every scorable row is in the candidate set
-    else {
-      float s_min = stb_key_score(skeys[KP - 1]);
-      complete = (n_out == k) && ((1.0 - (double)s_min - STB_SCORE_EPS) > s_d[k - 1]);
+    uint32_t all_complete = s_timeout ? 0u : 1u, total = 0u;
+    const uint32_t *st = stb_x_status(X, me) + (size_t)X.slot * world;
+    for (int p = 0; p < world; ++p) {
+      uint32_t v = __ldcv(st + p);
+      all_complete &= (v & 1u);
+      total += v >> 8;
     }
-    args.out_status[0] = n_out;
-    args.out_status[1] = complete ? 1u : 0u;
-    args.out_status[2] = (uint32_t)n_valid;
+    args.out_status[0] = min(total, k);
+    args.out_status[1] = all_complete;
+    args.out_status[2] = s_timeout ? 0xfffffffeu : (uint32_t)n_valid;
     args.out_status[3] = (uint32_t)KP;
   }
 }
@@ -526,7 +704,18 @@ static int stb_launch_topk_t(stb_ctx *ctx, const TopkArgs &a) {
     stb_set_error("scan scratch too small (grid=%llu)", (unsigned long long)grid);
     return STB_ERR_STATE;
   }
-  kern<<<(unsigned)grid, STB_SCAN_THREADS, 0, ctx->stream>>>(a);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(STB_SCAN_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL, see the kernel
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  STB_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
   STB_CUDA(cudaGetLastError());
   ctx->kernel_launches++;
   return STB_OK;
@@ -536,7 +725,7 @@ int stb_launch_scan_topk(stb_ctx *ctx, const float *rows, uint64_t n_rows,
                          uint64_t row_base, const float *q_dev, uint32_t top_k,
                          const uint64_t *ranges_dev, uint32_t n_ranges,
                          uint64_t n_virtual, stb_hit *out_hits_dev,
-                         uint32_t *out_status_dev) {
+                         uint32_t *out_status_dev, const StbXchgArgs *xchg) {
   (void)n_rows;
   TopkArgs a;
   a.scan.rows = reinterpret_cast<const float4 *>(rows);
@@ -551,6 +740,8 @@ int stb_launch_scan_topk(stb_ctx *ctx, const float *rows, uint64_t n_rows,
   a.out_hits = out_hits_dev;
   a.out_status = out_status_dev;
   a.top_k = top_k;
+  if (xchg) a.xchg = *xchg; else memset(&a.xchg, 0, sizeof(a.xchg));
+  a.dbg = ctx->dbg_dev;
   const bool rg = n_ranges > 0;
   switch (stb_pick_e(top_k)) {
     case 1: return rg ? stb_launch_topk_t<1, true>(ctx, a) : stb_launch_topk_t<1, false>(ctx, a);
@@ -565,6 +756,8 @@ struct CollectSink {
   uint32_t *out;
   unsigned long long *count;
   uint64_t cap;
+  template <int ROWS>
+  __device__ __forceinline__ void consume(float s, uint32_t r) { (*this)(s, r); }
   __device__ __forceinline__ void operator()(float s, uint32_t r) {
     bool hit = (s >= floor_) && (s > -CUDART_INF_F);   // -inf marks lanes that carry no row
     unsigned mask = __ballot_sync(0xffffffffu, hit);

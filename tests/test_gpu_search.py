@@ -336,3 +336,61 @@ def test_full_size_properties_1m(ctx, n):
     cw.append_dev(x[lo:hi].data_ptr(), hi - lo)
     got = cw.search(q, top_k=5)
     check(got, r + lo, d)
+
+
+@pytest.mark.parametrize("world,k", [(2, 10), (3, 1), (4, 40), (8, 10)])
+def test_fused_peer_memory_exchange_single_gpu(world, k):
+    """The fused K1 -> exchange -> K4 kernel (stb_search_topk_xchg): `world` contexts
+    on cuda:0 stand in for `world` GPUs (same-process peer buffers); every rank must
+    end up with the global top-k of the unsharded oracle."""
+    torch = pytest.importorskip("torch")
+    from semtools_b200.sharded import shard_bounds
+    rng = np.random.default_rng(world * 100 + k)
+    n = 60_000 + world
+    rows = unit_rows(rng, n)
+    rows[n - 1] = rows[7]                         # cross-shard exact tie
+    qs = np.stack([rows[7], unit_rows(rng, 1)[0], (unit_rows(rng, 1)[0] * 3.5).astype(np.float32)])
+    dev = torch.device("cuda:0")
+    ctxs = [capi.Context(0) for _ in range(world)]
+    corpora, xs = [], []
+    for r in range(world):
+        lo, hi = shard_bounds(n, world, r)
+        c = capi.Corpus(ctxs[r], max(hi - lo, 1), row_base=lo)
+        c.append(rows[lo:hi])
+        corpora.append(c)
+        xs.append(capi.Exchange(ctxs[r], world, r, max(k, 16)))
+    for x in xs:
+        x.connect_local(xs)
+    q_dev = torch.from_numpy(qs).to(dev)
+    hits = torch.zeros((world, len(qs), k, 2), dtype=torch.float64, device=dev)
+    status = torch.zeros((world, len(qs), 4), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    for rep in range(3):                          # several rounds: slot reuse / sequence numbers
+        for qi in range(len(qs)):
+            for r in range(world):
+                xs[r].search_topk(corpora[r], q_dev[qi].data_ptr(), k, hits[r, qi].data_ptr(),
+                                  status[r, qi].data_ptr())
+        for c in ctxs:
+            c.sync()
+        raw, st = hits.cpu().numpy(), status.cpu().numpy()
+        for qi in range(len(qs)):
+            r_exp, d_exp = oracle.search_rows(rows, qs[qi], top_k=k)
+            for r in range(world):
+                got = np.ascontiguousarray(raw[r, qi]).view(capi.HIT_DTYPE).reshape(-1)
+                assert st[r, qi, 1] == 1 and st[r, qi, 0] == k, (world, r, qi, st[r, qi])
+                check(got, r_exp, d_exp)
+    # a zero query ties every row at distance 1.0: no rank can prove its top-k, and the
+    # fused kernel must say so on every rank (status[1] == 0) instead of guessing
+    zq = torch.zeros(256, dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    for r in range(world):
+        xs[r].search_topk(corpora[r], zq.data_ptr(), k, hits[r, 0].data_ptr(), status[r, 0].data_ptr())
+    for c in ctxs:
+        c.sync()
+    assert (status.cpu().numpy()[:, 0, 1] == 0).all()
+    for x in xs:
+        x.close()
+    for c in corpora:
+        c.close()
+    for c in ctxs:
+        c.close()
