@@ -169,6 +169,27 @@ int stb_search_topk_dev(stb_ctx *ctx, const stb_corpus *corpus,
                         const float *q_dev, uint32_t top_k, stb_hit *out_hits_dev,
                         uint32_t *out_status_dev);
 
+/* ---- K2: batched queries on the tensor cores ------------------------------------------
+ * Q independent top-k searches (the semantics of Q calls of search_documents,
+ * src/search/mod.rs:77-120, without max_distance) in one pass over the corpus: an
+ * L2-normalised bf16 copy of the corpus (built lazily, 512 B/row, rebuilt after the
+ * corpus changes; stb_corpus_prepare_batch builds it ahead of time) is multiplied with
+ * the query tile on tcgen05 tensor cores, the 32 most promising 32-row sub-tiles per
+ * query are re-scored exactly (canonical f64 distance on the f32 rows) and the result is
+ * accepted only if the bf16 error bound proves no other row can enter the top-k;
+ * unproven queries are answered by the single-query path (stb_search).  Results are
+ * therefore identical to stb_search.
+ *   q         nq x 256 f32 (host);  out_hits nq x top_k (unused tail: +inf / UINT64_MAX)
+ *   out_n     nq counts */
+int stb_corpus_prepare_batch(stb_corpus *corpus);
+int stb_search_batch(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint32_t nq,
+                     uint32_t top_k, stb_hit *out_hits, uint32_t *out_n);
+/* Asynchronous device-resident form: out_status_dev[2*i] = hits of query i,
+ * [2*i+1] = 1 iff proven exact (0: re-run query i through stb_search). */
+int stb_search_batch_dev(stb_ctx *ctx, const stb_corpus *corpus, const float *q_dev,
+                         uint32_t nq, uint32_t top_k, stb_hit *out_hits_dev,
+                         uint32_t *out_status_dev);
+
 /* ---- fused multi-GPU search: K1 -> exchange over NVLink peer memory -> K4 -------------
  * One process (or thread) per GPU, one stb_xchg per rank.  Each rank allocates an
  * exchange buffer; the ranks trade its 64-byte CUDA IPC handle through whatever channel
@@ -224,6 +245,11 @@ int stb_ctx_counters(const stb_ctx *ctx, uint64_t *kernel_launches,
  * [0] first CTA start, [1] last scan end, [2] last CTA merge end, [3] final ticket,
  * [4] select done, [5] re-rank done. */
 int stb_debug_timestamps(stb_ctx *ctx, int reset, uint64_t out[8]);
+/* Test hook for K2: shadow build + tcgen05 GEMM on host inputs; out_full receives the
+ * approximate cosine matrix [ceil(nq/128)*128][ceil(n/256)*256] (f32), out_submax (may be
+ * NULL) the per-32-row maxima [ceil(n/256)*8][ceil(nq/128)*128]. */
+int stb_debug_batch_gemm(stb_ctx *ctx, const float *q, uint32_t nq, const float *rows,
+                         uint64_t n, float *out_full, float *out_submax);
 
 #ifdef __cplusplus
 }

@@ -23,9 +23,10 @@ SYMBOLS = [
     "stb_corpus_destroy", "stb_corpus_append", "stb_corpus_append_dev", "stb_corpus_clear",
     "stb_corpus_rows", "stb_corpus_data_dev", "stb_corpus_read", "stb_embed", "stb_embed_dev",
     "stb_embed_status", "stb_search",
-    "stb_search_topk_dev", "stb_xchg_create", "stb_xchg_destroy", "stb_xchg_local_handle",
+    "stb_search_topk_dev", "stb_corpus_prepare_batch", "stb_search_batch", "stb_search_batch_dev",
+    "stb_xchg_create", "stb_xchg_destroy", "stb_xchg_local_handle",
     "stb_xchg_connect", "stb_xchg_connect_local", "stb_search_topk_xchg", "stb_hits_merge_dev", "stb_hits_merge", "stb_fnv1a64", "stb_line_id",
-    "stb_ctx_counters", "stb_debug_timestamps",
+    "stb_ctx_counters", "stb_debug_timestamps", "stb_debug_batch_gemm",
 ]
 
 
@@ -80,6 +81,9 @@ def lib() -> C.CDLL:
     L.stb_embed_status.argtypes = [vp]
     L.stb_search.argtypes = [vp, vp, vp, u32, i32, f64, i32, vp, u32, vp, u64, C.POINTER(u64)]
     L.stb_search_topk_dev.argtypes = [vp, vp, vp, u32, vp, vp]
+    L.stb_corpus_prepare_batch.argtypes = [vp]
+    L.stb_search_batch.argtypes = [vp, vp, vp, u32, u32, vp, vp]
+    L.stb_search_batch_dev.argtypes = [vp, vp, vp, u32, u32, vp, vp]
     L.stb_xchg_create.argtypes = [vp, u32, u32, u32, C.POINTER(vp)]
     L.stb_xchg_destroy.argtypes = [vp]
     L.stb_xchg_local_handle.argtypes = [vp, vp]
@@ -94,6 +98,7 @@ def lib() -> C.CDLL:
     L.stb_line_id.restype = u64
     L.stb_ctx_counters.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.stb_debug_timestamps.argtypes = [vp, i32, vp]
+    L.stb_debug_batch_gemm.argtypes = [vp, vp, u32, vp, u64, vp, vp]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("stb_version", "stb_device_count"):
@@ -262,6 +267,27 @@ class Corpus:
                 cap = int(n.value)
                 continue
             return out[: int(n.value)]
+
+    # -- K2 -----------------------------------------------------------------
+    def prepare_batch(self):
+        """stb_corpus_prepare_batch: build the bf16 tensor-core shadow now."""
+        _check(lib().stb_corpus_prepare_batch(self._h))
+
+    def search_batch(self, queries, top_k: int = 10):
+        """stb_search_batch.  Returns a list of HIT_DTYPE arrays, one per query."""
+        queries = np.ascontiguousarray(queries, dtype=np.float32)
+        if queries.ndim != 2 or queries.shape[1] != STB_DIM:
+            raise StbError(STB_ERR_ARG, f"queries must be (nq,{STB_DIM}) f32")
+        nq = queries.shape[0]
+        out = np.zeros((nq, max(top_k, 1)), dtype=HIT_DTYPE)
+        cnt = np.zeros(max(nq, 1), dtype=np.uint32)
+        _check(lib().stb_search_batch(self.ctx._h, self._h, _np_ptr(queries), nq, top_k, _np_ptr(out), _np_ptr(cnt)))
+        return [out[i, : cnt[i]] for i in range(nq)]
+
+    def search_batch_dev(self, q_dev: int, nq: int, top_k: int, out_hits_dev: int, out_status_dev: int):
+        """stb_search_batch_dev: asynchronous, everything stays in HBM."""
+        _check(lib().stb_search_batch_dev(self.ctx._h, self._h, vp(q_dev), nq, top_k, vp(out_hits_dev),
+                                          vp(out_status_dev)))
 
     def search_topk_dev(self, q_dev: int, top_k: int, out_hits_dev: int, out_status_dev: int):
         """stb_search_topk_dev: asynchronous, everything stays in HBM."""

@@ -133,7 +133,8 @@ int stb_ctx_destroy(stb_ctx *c) {
   cudaFree(c->block_keys); cudaFree(c->counters); cudaFree(c->q_dev); cudaFree(c->hits_dev);
   cudaFree(c->status_dev); cudaFree(c->collect_rows); cudaFree(c->collect_count);
   cudaFree(c->collect_hits); cudaFree(c->ranges_dev); cudaFree(c->err_flag);
-  cudaFree(c->dbg_dev); cudaFree(c->embed_off_dev); cudaFree(c->embed_ids_dev); cudaFree(c->embed_out_dev);
+  cudaFree(c->dbg_dev); cudaFree(c->bq_tiles); cudaFree(c->b_submax); cudaFree(c->b_tilemax); cudaFree(c->b_cand);
+  cudaFree(c->bq_dev); cudaFree(c->bh_dev); cudaFree(c->bs_dev); cudaFree(c->embed_off_dev); cudaFree(c->embed_ids_dev); cudaFree(c->embed_out_dev);
   if (c->q_pin) cudaFreeHost(c->q_pin);
   if (c->hits_pin) cudaFreeHost(c->hits_pin);
   if (c->status_pin) cudaFreeHost(c->status_pin);
@@ -265,6 +266,7 @@ int stb_corpus_destroy(stb_corpus *c) {
   if (!c) return STB_OK;
   if (c->ctx && ctx_alive(c->ctx)) { cudaSetDevice(c->ctx->device); cudaStreamSynchronize(c->ctx->stream); }
   else cudaDeviceSynchronize();
+  cudaFree(c->shadow);
   cudaFree(c->rows);
   cudaGetLastError();
   delete c;
@@ -281,6 +283,7 @@ static int corpus_append_impl(stb_corpus *c, const float *rows, uint64_t n, cuda
   STB_CUDA(cudaMemcpyAsync(c->rows + c->n * STB_D, rows, n * STB_D * sizeof(float), kind, c->ctx->stream));
   STB_CUDA(cudaStreamSynchronize(c->ctx->stream));
   c->n += n;
+  c->shadow_rows = 0;     // K2 shadow is rebuilt lazily
   return STB_OK;
 }
 
@@ -294,6 +297,7 @@ int stb_corpus_clear(stb_corpus *c) {
   if (!c) { stb_set_error("null corpus"); return STB_ERR_ARG; }
   if (!ctx_alive(c->ctx)) { stb_set_error("context was destroyed"); return STB_ERR_STATE; }
   c->n = 0;
+  c->shadow_rows = 0;
   return STB_OK;
 }
 int stb_corpus_rows(const stb_corpus *c, uint64_t *n) {
@@ -351,7 +355,7 @@ int stb_embed(stb_ctx *ctx, const stb_table *table, const uint64_t *offsets, con
   if (out) STB_CUDA(cudaMemcpyAsync(out, dst, n_lines * STB_D * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   STB_CUDA(cudaStreamSynchronize(ctx->stream));
   if (flag) { stb_set_error("embed: a token id maps outside the %llu-row table", (unsigned long long)table->V); return STB_ERR_RANGE; }
-  if (append_to) append_to->n += n_lines;
+  if (append_to) { append_to->n += n_lines; append_to->shadow_rows = 0; }
   return STB_OK;
 }
 
@@ -648,6 +652,151 @@ int stb_search_topk_xchg(stb_ctx *ctx, const stb_corpus *corpus, const float *q_
   a.slot = (uint32_t)(a.seq % STB_XCHG_SLOTS);
   return stb_launch_scan_topk(ctx, corpus->rows, corpus->n, corpus->row_base, q_dev, top_k, nullptr, 0,
                               corpus->n, out_hits_dev, out_status_dev, &a);
+}
+
+// ----------------------------------------------------------------- K2 batched search ---
+static int corpus_ensure_shadow(stb_ctx *ctx, stb_corpus *c) {
+  if (c->shadow && c->shadow_rows == c->n) {
+    if (c->shadow_bad) { stb_set_error("search_batch: corpus holds rows whose norm is not a normal fp32 number; use stb_search"); return STB_ERR_STATE; }
+    return STB_OK;
+  }
+  const uint64_t tiles = (c->n + 255) / 256;
+  if (tiles > c->shadow_cap_tiles || !c->shadow) {
+    uint8_t *np = nullptr;
+    cudaError_t e = cudaMalloc((void **)&np, tiles * 131072ull);
+    if (e != cudaSuccess) { cudaGetLastError(); stb_set_error("search_batch: cannot allocate the %llu MiB bf16 shadow", (unsigned long long)(tiles >> 3)); return STB_ERR_NOMEM; }
+    cudaFree(c->shadow);
+    c->shadow = np;
+    c->shadow_cap_tiles = tiles;
+  }
+  int rc;
+  STB_CUDA(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), ctx->stream));
+  if ((rc = stb_launch_shadow_build(ctx, c->rows, c->n, 256, c->shadow, ctx->err_flag)) != STB_OK) return rc;
+  int flag = 0;
+  STB_CUDA(cudaMemcpyAsync(&flag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  STB_CUDA(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), ctx->stream));
+  STB_CUDA(cudaStreamSynchronize(ctx->stream));
+  c->shadow_rows = c->n;
+  c->shadow_bad = flag;
+  if (flag) { stb_set_error("search_batch: corpus holds rows whose norm is not a normal fp32 number; use stb_search"); return STB_ERR_STATE; }
+  return STB_OK;
+}
+
+int stb_corpus_prepare_batch(stb_corpus *corpus) {
+  if (!corpus) { stb_set_error("null corpus"); return STB_ERR_ARG; }
+  int rc = ctx_use(corpus->ctx);
+  if (rc) return rc;
+  if (corpus->n == 0) return STB_OK;
+  return corpus_ensure_shadow(corpus->ctx, corpus);
+}
+
+int stb_search_batch_dev(stb_ctx *ctx, const stb_corpus *corpus_c, const float *q_dev, uint32_t nq,
+                         uint32_t top_k, stb_hit *out_hits_dev, uint32_t *out_status_dev) {
+  int rc = ctx_use(ctx);
+  if (rc) return rc;
+  stb_corpus *corpus = const_cast<stb_corpus *>(corpus_c);
+  if (!corpus || !q_dev || !out_hits_dev || !out_status_dev) { stb_set_error("search_batch_dev: null argument"); return STB_ERR_ARG; }
+  if (corpus->ctx != ctx) { stb_set_error("search_batch_dev: corpus belongs to another context"); return STB_ERR_ARG; }
+  if (nq == 0) return STB_OK;
+  if (top_k == 0 || top_k > 1024) { stb_set_error("search_batch_dev: top_k must be 1..1024"); return STB_ERR_ARG; }
+  if (corpus->n == 0) { stb_set_error("search_batch_dev: empty corpus"); return STB_ERR_STATE; }
+  if ((rc = corpus_ensure_shadow(ctx, corpus)) != STB_OK) return rc;
+  const uint32_t m_tiles = (nq + 127) / 128, q_pad = m_tiles * 128;
+  const uint32_t n_tiles = (uint32_t)((corpus->n + 255) / 256), n_sub = n_tiles * 8;
+  uint32_t n_slices = std::max<uint32_t>(1, std::min<uint32_t>(32, 2048 / (q_pad / 32)));
+  n_slices = std::min<uint32_t>(n_slices, std::max<uint32_t>(1, n_tiles / 64));
+  if ((rc = dev_reserve(&ctx->bq_tiles, &ctx->bq_tiles_cap, (size_t)q_pad * 512)) != STB_OK) return rc;
+  if ((rc = dev_reserve(&ctx->b_submax, &ctx->b_submax_cap, (size_t)n_sub * q_pad)) != STB_OK) return rc;
+  if ((rc = dev_reserve(&ctx->b_tilemax, &ctx->b_tilemax_cap, (size_t)n_tiles * q_pad)) != STB_OK) return rc;
+  if ((rc = dev_reserve(&ctx->b_cand, &ctx->b_cand_cap, (size_t)q_pad * n_slices * 32)) != STB_OK) return rc;
+  // query tiles: padding queries beyond nq are written as zeros by the shadow builder
+  STB_CUDA(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), ctx->stream));
+  if ((rc = stb_launch_shadow_build(ctx, q_dev, nq, 128, ctx->bq_tiles, ctx->err_flag)) != STB_OK) return rc;
+  if ((rc = stb_launch_batch_gemm(ctx, ctx->bq_tiles, m_tiles, corpus->shadow, n_tiles, ctx->b_submax, ctx->b_tilemax, nullptr)) != STB_OK) return rc;
+  // two-level selection: the best tiles by tile maximum (1/8 of the data), refined to
+  // sub-tiles inside the finish kernel
+  if ((rc = stb_launch_batch_select(ctx, ctx->b_tilemax, n_tiles, q_pad, n_slices, ctx->b_cand)) != STB_OK) return rc;
+  return stb_launch_batch_finish(ctx, ctx->b_cand, n_slices, n_sub, nq, top_k, corpus->rows, corpus->n,
+                                 corpus->row_base, q_dev, out_hits_dev, out_status_dev, ctx->b_submax, q_pad);
+}
+
+int stb_search_batch(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint32_t nq, uint32_t top_k,
+                     stb_hit *out_hits, uint32_t *out_n) {
+  int rc = ctx_use(ctx);
+  if (rc) return rc;
+  if (!corpus || !q || !out_hits || !out_n) { stb_set_error("search_batch: null argument"); return STB_ERR_ARG; }
+  if (nq == 0) return STB_OK;
+  for (uint32_t i = 0; i < nq; ++i) out_n[i] = 0;
+  if (top_k == 0 || corpus->n == 0) return STB_OK;
+  bool tensor_ok = top_k <= 1024;
+  std::vector<uint32_t> status((size_t)nq * 2, 0);
+  if (tensor_ok) {
+    if ((rc = dev_reserve(&ctx->bq_dev, &ctx->bq_dev_cap, (size_t)nq * STB_D)) != STB_OK) return rc;
+    if ((rc = dev_reserve(&ctx->bh_dev, &ctx->bh_dev_cap, (size_t)nq * top_k)) != STB_OK) return rc;
+    if ((rc = dev_reserve(&ctx->bs_dev, &ctx->bs_dev_cap, (size_t)nq * 2)) != STB_OK) return rc;
+    STB_CUDA(cudaMemcpyAsync(ctx->bq_dev, q, (size_t)nq * STB_D * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    rc = stb_search_batch_dev(ctx, corpus, ctx->bq_dev, nq, top_k, ctx->bh_dev, ctx->bs_dev);
+    if (rc == STB_ERR_STATE) { tensor_ok = false; }        // un-normalisable rows: K1 handles them
+    else if (rc != STB_OK) return rc;
+    else {
+      int qbad = 0;
+      STB_CUDA(cudaMemcpyAsync(&qbad, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      STB_CUDA(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), ctx->stream));
+      STB_CUDA(cudaMemcpyAsync(out_hits, ctx->bh_dev, (size_t)nq * top_k * sizeof(stb_hit), cudaMemcpyDeviceToHost, ctx->stream));
+      STB_CUDA(cudaMemcpyAsync(status.data(), ctx->bs_dev, (size_t)nq * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      STB_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (qbad) std::fill(status.begin(), status.end(), 0u);   // a query could not be normalised: trust none
+    }
+  }
+  // queries the tensor path could not prove (or could not run): exact single-query path
+  for (uint32_t i = 0; i < nq; ++i) {
+    if (tensor_ok && status[2 * i + 1]) { out_n[i] = status[2 * i]; continue; }
+    ctx->fallback_searches++;
+    uint64_t n = 0;
+    rc = stb_search(ctx, corpus, q + (size_t)i * STB_D, top_k, 0, 0.0, STB_MODE_SEARCH_DOCUMENTS, nullptr, 0,
+                    out_hits + (size_t)i * top_k, top_k, &n);
+    if (rc != STB_OK) return rc;
+    out_n[i] = (uint32_t)n;
+    for (uint64_t j = n; j < top_k; ++j) { out_hits[(size_t)i * top_k + j].distance = INFINITY; out_hits[(size_t)i * top_k + j].row = 0xffffffffffffffffull; }
+  }
+  return STB_OK;
+}
+
+// ------------------------------------------------------------------- K2 debug hook ---
+// Runs shadow build + tcgen05 GEMM on host inputs and returns the FULL approximate score
+// matrix (tests only: validates descriptors / TMEM / epilogue against a reference matmul).
+int stb_debug_batch_gemm(stb_ctx *ctx, const float *q, uint32_t nq, const float *rows, uint64_t n,
+                         float *out_full, float *out_submax) {
+  int rc = ctx_use(ctx);
+  if (rc) return rc;
+  if (!q || !rows || !out_full || nq == 0 || n == 0) { stb_set_error("debug_batch_gemm: bad argument"); return STB_ERR_ARG; }
+  const uint32_t m_tiles = (nq + 127) / 128;
+  const uint32_t n_tiles = (uint32_t)((n + 255) / 256);
+  const size_t q_pad = (size_t)m_tiles * 128, n_pad = (size_t)n_tiles * 256;
+  float *dq = nullptr, *dr = nullptr, *dfull = nullptr, *dsub = nullptr, *dtile = nullptr;
+  uint8_t *da = nullptr, *db = nullptr;
+  int *dbad = nullptr;
+  cudaError_t e = cudaMalloc(&dq, (size_t)nq * 1024);
+  if (e == cudaSuccess) e = cudaMalloc(&dr, n * 1024);
+  if (e == cudaSuccess) e = cudaMalloc(&da, q_pad * 512);
+  if (e == cudaSuccess) e = cudaMalloc(&db, n_pad * 512);
+  if (e == cudaSuccess) e = cudaMalloc(&dfull, q_pad * n_pad * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&dsub, (size_t)n_tiles * 8 * q_pad * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&dtile, (size_t)n_tiles * q_pad * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&dbad, 4);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dbad, 0, 4, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dq, q, (size_t)nq * 1024, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dr, rows, n * 1024, cudaMemcpyHostToDevice, ctx->stream);
+  rc = STB_OK;
+  if (e == cudaSuccess) rc = stb_launch_shadow_build(ctx, dq, nq, 128, da, dbad);
+  if (e == cudaSuccess && rc == STB_OK) rc = stb_launch_shadow_build(ctx, dr, n, 256, db, dbad);
+  if (e == cudaSuccess && rc == STB_OK) rc = stb_launch_batch_gemm(ctx, da, m_tiles, db, n_tiles, dsub, dtile, dfull);
+  if (e == cudaSuccess && rc == STB_OK) e = cudaMemcpyAsync(out_full, dfull, q_pad * n_pad * 4, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess && rc == STB_OK && out_submax) e = cudaMemcpyAsync(out_submax, dsub, (size_t)n_tiles * 8 * q_pad * 4, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess && rc == STB_OK) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dq); cudaFree(dr); cudaFree(da); cudaFree(db); cudaFree(dfull); cudaFree(dsub); cudaFree(dtile); cudaFree(dbad);
+  if (e != cudaSuccess) { stb_set_error("debug_batch_gemm: %s", cudaGetErrorString(e)); cudaGetLastError(); return STB_ERR_CUDA; }
+  return rc;
 }
 
 // ---------------------------------------------------------------------- merge ---

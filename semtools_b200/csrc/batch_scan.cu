@@ -1,0 +1,586 @@
+// K2: batched-query cosine scan on the 5th-gen tensor cores (tcgen05 + TMEM + bulk-TMA).
+//
+// No reference analogue (the reference handles one query per process,
+// src/search/mod.rs:77-120); semantics are those of Q independent search_documents
+// calls.  BASELINE config 3: 10M x 256 corpus, 1024 queries, top-k 10.
+//
+// Pipeline (all on the context's stream):
+//   1. stb_shadow_build_kernel  rows/queries f32 -> L2-normalised bf16, stored in HBM
+//                               ALREADY in the tcgen05 shared-memory tile layout
+//                               (K-major, 128-byte swizzle), so a tile is one
+//                               contiguous block and is fetched with plain bulk-TMA
+//                               copies (cp.async.bulk), no tensor map needed.
+//   2. stb_batch_gemm_kernel    D[128 queries x 256 rows] = A . B^T per (query tile,
+//                               corpus tile) on tcgen05.mma (bf16 in, f32 TMEM
+//                               accumulators, 2 x 256 TMEM columns double-buffered).
+//                               Warp-specialised: TMA producer / MMA issuer / 4 epilogue
+//                               warps.  The corpus tile (128 KB) stays resident in smem
+//                               while the query tiles stream through a 6-slab ring from
+//                               L2 -- the order that keeps L2->SM traffic under the LTS
+//                               cap (64 KB streamed per 8.4 MFLOP... see DESIGN.md).
+//                               Epilogue: thread = TMEM lane = query; max over each
+//                               32-row sub-tile -> submax[subtile][query] (coalesced).
+//   3. stb_batch_select_kernel  per query: the 32 sub-tiles with the largest maxima.
+//   4. stb_batch_finish_kernel  per query: exact canonical f64 re-score of the 32x32
+//                               candidate rows, sort by (distance,row), top-k, and the
+//                               completeness proof: every unselected row has approximate
+//                               cosine <= m* (the smallest selected sub-tile maximum),
+//                               hence exact cosine <= m* + EPS2 (bf16 rounding bound).
+// Tensor-bound: 2*Q*N*256 FLOP per batch; HBM traffic N*512 B (bf16 shadow) once.
+#include <cuda_bf16.h>
+#include <math_constants.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+#define STB_B_TILE 256            // corpus rows per tile  (UMMA N)
+#define STB_A_TILE 128            // queries per tile      (UMMA M)
+#define STB_SLAB_K 64             // bf16 per 128-byte swizzled row
+#define STB_N_SLABS 4             // 256 / 64
+#define STB_B_SLAB_BYTES (STB_B_TILE * 128)     // 32 KiB
+#define STB_A_SLAB_BYTES (STB_A_TILE * 128)     // 16 KiB
+#define STB_A_RING 6
+#define STB_SUB 32                // rows per sub-tile (one tcgen05.ld.x32 chunk)
+#define STB_BATCH_KSEL 32         // sub-tiles kept per query
+// |approx cosine - exact cosine| for bf16-rounded unit vectors: (2u+u^2) with u = 2^-9,
+// plus f32 accumulation of 256 exact products and the rsqrt normalisation: < 0.0040.
+#define STB_BATCH_EPS 0.0045
+
+// ------------------------------------------------------------------ PTX wrappers ---
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  // bounded spin: a protocol bug must trap, never hang the GPU
+  for (uint32_t spins = 0;; ++spins) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 x bf16 -> f32
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle (sm_100 format):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled
+//   K-major, canonical value 1) | [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024)
+//   | [46,48) descriptor version = 1 | [61,64) layout = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor, kind::f16: D f32 (bits 4-5 = 1), A bf16 (bits 7-9 = 1), B bf16
+// (bits 10-12 = 1), both K-major (bits 15,16 = 0), N >> 3 at bits 17-22, M >> 4 at 24-28.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// --------------------------------------------------------------- 1. shadow builder ---
+// One warp per row; lane l owns k = 8l..8l+7 = one 16-byte bf16 chunk (slab l/8, chunk
+// l%8).  Tile layout: tile t -> 4 slabs -> [TILE rows x 128 B], 8-row x 128-B atoms with
+// the 16-byte chunk index XOR-ed by (row % 8)  (the hardware 128B swizzle).
+template <int TILE>
+__global__ void __launch_bounds__(256)
+stb_shadow_build_kernel(const float4 *__restrict__ rows, uint64_t n_rows, uint64_t n_padded,
+                        uint8_t *__restrict__ out, int *bad_flag) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t row = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= n_padded) return;
+  float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+  if (row < n_rows) {
+    v0 = __ldg(rows + row * STB_ROW_F4 + 2 * lane);
+    v1 = __ldg(rows + row * STB_ROW_F4 + 2 * lane + 1);
+  }
+  float ss = v0.x * v0.x + v0.y * v0.y + v0.z * v0.z + v0.w * v0.w + v1.x * v1.x + v1.y * v1.y +
+             v1.z * v1.z + v1.w * v1.w;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  float inv = 0.f;
+  if (ss != 0.f) {
+    if (!(ss >= 1e-30f && ss <= 1e30f)) { if (lane == 0) atomicExch(bad_flag, 1); }   // NaN/inf/extreme
+    else inv = rsqrtf(ss);
+  } else {
+    // fp32 underflow of a tiny non-zero row: cannot be normalised here -> batch path unusable
+    bool nz = (v0.x != 0.f) | (v0.y != 0.f) | (v0.z != 0.f) | (v0.w != 0.f) | (v1.x != 0.f) | (v1.y != 0.f) |
+              (v1.z != 0.f) | (v1.w != 0.f);
+    if (__any_sync(0xffffffffu, nz) && lane == 0) atomicExch(bad_flag, 1);
+  }
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(v0.x * inv, v0.y * inv);
+  __nv_bfloat162 p1 = __floats2bfloat162_rn(v0.z * inv, v0.w * inv);
+  __nv_bfloat162 p2 = __floats2bfloat162_rn(v1.x * inv, v1.y * inv);
+  __nv_bfloat162 p3 = __floats2bfloat162_rn(v1.z * inv, v1.w * inv);
+  uint4 pk;
+  pk.x = *reinterpret_cast<uint32_t *>(&p0); pk.y = *reinterpret_cast<uint32_t *>(&p1);
+  pk.z = *reinterpret_cast<uint32_t *>(&p2); pk.w = *reinterpret_cast<uint32_t *>(&p3);
+  const uint64_t tile = row / TILE;
+  const uint32_t r = (uint32_t)(row % TILE);
+  const uint32_t slab = lane >> 3, chunk = lane & 7;
+  const size_t off = tile * (size_t)(TILE * 512) + (size_t)slab * (TILE * 128) + (size_t)(r >> 3) * 1024 +
+                     (size_t)(r & 7) * 128 + (size_t)((chunk ^ (r & 7)) * 16);
+  *reinterpret_cast<uint4 *>(out + off) = pk;
+}
+
+// ------------------------------------------------------------------ 2. tcgen05 GEMM ---
+struct GemmArgs {
+  const uint8_t *a_tiles;     // query shadow: m_tiles x (4 slabs x 16 KiB)
+  const uint8_t *b_tiles;     // corpus shadow: n_tiles x (4 slabs x 32 KiB)
+  uint32_t m_tiles;           // ceil(Q / 128)
+  uint32_t n_tiles;           // ceil(N / 256)
+  float *submax;              // [n_tiles * 8][m_tiles * 128]  per-32-row maxima
+  float *tilemax;             // [n_tiles][m_tiles * 128]      per-256-row maxima
+  float *full_out;            // debug: full score matrix [m_tiles*128][n_tiles*256] or null
+};
+
+#define STB_GEMM_THREADS 256
+#define STB_GEMM_SMEM (STB_N_SLABS * STB_B_SLAB_BYTES + STB_A_RING * STB_A_SLAB_BYTES + 1024 + 256)
+
+__global__ void __launch_bounds__(STB_GEMM_THREADS, 1)
+stb_batch_gemm_kernel(const GemmArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment required by the 128-byte swizzle atoms
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *sB = smem;
+  uint8_t *sA = smem + STB_N_SLABS * STB_B_SLAB_BYTES;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sA + STB_A_RING * STB_A_SLAB_BYTES);
+  uint64_t *b_full = bars + 0, *b_empty = bars + STB_N_SLABS;      // one pair per K-slab
+  uint64_t *a_full = bars + 2 * STB_N_SLABS, *a_empty = a_full + STB_A_RING;
+  uint64_t *d_full = a_empty + STB_A_RING, *d_empty = d_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STB_N_SLABS; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
+    for (int i = 0; i < STB_A_RING; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(d_full + i, 1); mbar_init(d_empty + i, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {   // TMEM: 512 columns = two 128 x 256 f32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t my_tiles = (args.n_tiles > blockIdx.x) ? (args.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp == 0) {
+    // ===== bulk-TMA producer (one thread) =====
+    if (lane == 0) {
+      uint32_t a_cnt = 0;
+      for (uint32_t it = 0; it < my_tiles; ++it) {
+        const uint64_t t = blockIdx.x + (uint64_t)it * gridDim.x;
+        // corpus tile, slab by slab: slab s of the previous tile is released as soon as the
+        // last query tile's MMAs on it retire, so the refill overlaps the remaining slabs
+        const uint8_t *src = args.b_tiles + t * (size_t)(STB_N_SLABS * STB_B_SLAB_BYTES);
+        for (int s = 0; s < STB_N_SLABS; ++s) {
+          mbar_wait(b_empty + s, (it & 1) ^ 1);
+          mbar_expect_tx(b_full + s, STB_B_SLAB_BYTES);
+          bulk_g2s(sB + s * STB_B_SLAB_BYTES, src + (size_t)s * STB_B_SLAB_BYTES, STB_B_SLAB_BYTES, b_full + s);
+        }
+        for (uint32_t m = 0; m < args.m_tiles; ++m) {
+          for (int s = 0; s < STB_N_SLABS; ++s, ++a_cnt) {
+            const uint32_t slot = a_cnt % STB_A_RING;
+            mbar_wait(a_empty + slot, ((a_cnt / STB_A_RING) & 1) ^ 1);
+            mbar_expect_tx(a_full + slot, STB_A_SLAB_BYTES);
+            bulk_g2s(sA + slot * STB_A_SLAB_BYTES,
+                     args.a_tiles + ((size_t)m * STB_N_SLABS + s) * STB_A_SLAB_BYTES, STB_A_SLAB_BYTES,
+                     a_full + slot);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(STB_A_TILE, STB_B_TILE);
+      uint32_t a_cnt = 0, d_cnt = 0;
+      for (uint32_t it = 0; it < my_tiles; ++it) {
+        for (uint32_t m = 0; m < args.m_tiles; ++m, ++d_cnt) {
+          const uint32_t acc = d_cnt & 1;
+          mbar_wait(d_empty + acc, ((d_cnt >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * STB_B_TILE;
+          for (int s = 0; s < STB_N_SLABS; ++s, ++a_cnt) {
+            const uint32_t slot = a_cnt % STB_A_RING;
+            if (m == 0) mbar_wait(b_full + s, it & 1);
+            mbar_wait(a_full + slot, (a_cnt / STB_A_RING) & 1);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(sA + slot * STB_A_SLAB_BYTES);
+            const uint32_t b_addr = smem_u32(sB + s * STB_B_SLAB_BYTES);
+#pragma unroll
+            for (int k = 0; k < STB_SLAB_K / 16; ++k) {
+              // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle atom
+              tc_mma_bf16(tmem_d, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                          (uint32_t)((s | k) != 0));
+            }
+            tc_commit(a_empty + slot);      // query slab free once these MMAs retire
+            if (m + 1 == args.m_tiles) tc_commit(b_empty + s);   // corpus slab free for the next tile
+          }
+          tc_commit(d_full + acc);          // accumulator ready for the epilogue
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: thread = TMEM lane = query; max over each 32-row sub-tile =====
+    const uint32_t quarter = warp & 3;
+    const uint32_t q_pad = args.m_tiles * STB_A_TILE;
+    uint32_t d_cnt = 0;
+    for (uint32_t it = 0; it < my_tiles; ++it) {
+      const uint64_t t = blockIdx.x + (uint64_t)it * gridDim.x;
+      for (uint32_t m = 0; m < args.m_tiles; ++m, ++d_cnt) {
+        const uint32_t acc = d_cnt & 1;
+        mbar_wait(d_full + acc, (d_cnt >> 1) & 1);
+        tc_fence_after();
+        const uint32_t q = m * STB_A_TILE + quarter * 32 + lane;
+        float tmx = -CUDART_INF_F;
+#pragma unroll 1
+        for (int c = 0; c < STB_B_TILE / STB_SUB; ++c) {
+          uint32_t r[32];
+          tc_ld_32x32b_x32(tmem_base + ((quarter * 32u) << 16) + acc * STB_B_TILE + c * STB_SUB, r);
+          tc_wait_ld();
+          float mx = __uint_as_float(r[0]);
+#pragma unroll
+          for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+          args.submax[(t * (STB_B_TILE / STB_SUB) + c) * (size_t)q_pad + q] = mx;
+          tmx = fmaxf(tmx, mx);
+          if (args.full_out) {
+            float *o = args.full_out + (size_t)q * ((size_t)args.n_tiles * STB_B_TILE) + t * STB_B_TILE + c * STB_SUB;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(r[i]);
+          }
+        }
+        args.tilemax[t * (size_t)q_pad + q] = tmx;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d_empty + acc);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ------------------------------------------------------- host-side: shadow + GEMM ------
+int stb_launch_shadow_build(stb_ctx *ctx, const float *rows_dev, uint64_t n_rows, int tile, uint8_t *out,
+                            int *bad_flag_dev) {
+  const uint64_t n_padded = (n_rows + tile - 1) / tile * tile;
+  if (n_padded == 0) return STB_OK;
+  const unsigned blocks = (unsigned)((n_padded + 7) / 8);
+  if (tile == STB_B_TILE)
+    stb_shadow_build_kernel<STB_B_TILE><<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const float4 *>(rows_dev), n_rows, n_padded, out, bad_flag_dev);
+  else
+    stb_shadow_build_kernel<STB_A_TILE><<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const float4 *>(rows_dev), n_rows, n_padded, out, bad_flag_dev);
+  STB_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  return STB_OK;
+}
+
+int stb_launch_batch_gemm(stb_ctx *ctx, const uint8_t *a_tiles, uint32_t m_tiles, const uint8_t *b_tiles,
+                          uint32_t n_tiles, float *submax, float *tilemax, float *full_out) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    STB_CUDA(cudaFuncSetAttribute(stb_batch_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STB_GEMM_SMEM));
+    attr_set = true;
+  }
+  GemmArgs a;
+  a.a_tiles = a_tiles; a.b_tiles = b_tiles; a.m_tiles = m_tiles; a.n_tiles = n_tiles;
+  a.submax = submax; a.tilemax = tilemax; a.full_out = full_out;
+  unsigned grid = (unsigned)std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count);
+  if (grid == 0) return STB_OK;
+  stb_batch_gemm_kernel<<<grid, STB_GEMM_THREADS, STB_GEMM_SMEM, ctx->stream>>>(a);
+  STB_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  return STB_OK;
+}
+
+
+// ------------------------------------------------------------- 3. sub-tile selection ---
+// grid (q_pad/32, n_slices/4), 128 threads: a warp = 32 consecutive queries x one slice of
+// sub-tiles; lane keeps the KSEL best (value, sub-tile) of its query in shared memory
+// ([entry][lane] layout: conflict-free) with the running minimum in registers.
+struct SelectArgs {
+  const float *submax;      // [n_sub][q_pad]
+  uint32_t n_sub, q_pad, n_slices;
+  uint64_t *cand;           // [q_pad][n_slices][KSEL] keys: (~ord(value) << 32) | sub-tile
+};
+
+__global__ void __launch_bounds__(128)
+stb_batch_select_kernel(const SelectArgs a) {
+  __shared__ float s_val[4][STB_BATCH_KSEL * 32];
+  __shared__ uint32_t s_idx[4][STB_BATCH_KSEL * 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t slice = blockIdx.y * 4 + warp;
+  if (slice >= a.n_slices) return;
+  const uint32_t q = blockIdx.x * 32 + lane;
+  const uint32_t per = (a.n_sub + a.n_slices - 1) / a.n_slices;
+  const uint32_t s0 = slice * per, s1 = min(a.n_sub, s0 + per);
+  float *val = s_val[warp];
+  uint32_t *idx = s_idx[warp];
+  int cnt = 0, minpos = 0;
+  float thr = -CUDART_INF_F;
+  const float *p = a.submax + q;
+  // 16 independent coalesced loads in flight per lane before the (rare) list updates
+  constexpr int UNR = 16;
+  for (uint32_t st0 = s0; st0 < s1; st0 += UNR) {
+    float vbuf[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+      vbuf[u] = (st0 + u < s1) ? __ldcs(p + (size_t)(st0 + u) * a.q_pad) : -CUDART_INF_F;
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const float v = vbuf[u];
+      const uint32_t st = st0 + u;
+      if (st >= s1) break;
+      if (cnt < STB_BATCH_KSEL) {
+        val[cnt * 32 + lane] = v; idx[cnt * 32 + lane] = st;
+        if (++cnt == STB_BATCH_KSEL) {
+          thr = CUDART_INF_F;
+          for (int e = 0; e < STB_BATCH_KSEL; ++e) { float x = val[e * 32 + lane]; if (x < thr) { thr = x; minpos = e; } }
+        }
+      } else if (v > thr) {
+        val[minpos * 32 + lane] = v; idx[minpos * 32 + lane] = st;
+        thr = CUDART_INF_F;
+        for (int e = 0; e < STB_BATCH_KSEL; ++e) { float x = val[e * 32 + lane]; if (x < thr) { thr = x; minpos = e; } }
+      }
+    }
+  }
+  uint64_t *out = a.cand + ((size_t)q * a.n_slices + slice) * STB_BATCH_KSEL;
+  for (int e = 0; e < STB_BATCH_KSEL; ++e)
+    out[e] = (e < cnt) ? stb_make_key(val[e * 32 + lane], idx[e * 32 + lane]) : STB_KEY_INVALID;
+}
+
+// ------------------------------------------------------------------ 4. exact finish ---
+struct FinishArgs {
+  const uint64_t *cand;     // [q_pad][n_slices][KSEL]  keys over TILES (value = tile maximum)
+  const float *submax;      // [n_tiles * 8][q_pad]
+  uint32_t q_pad;
+  uint32_t n_slices, n_sub, nq, top_k;
+  const float4 *rows;       // corpus f32 rows (local)
+  uint64_t n_rows, row_base;
+  const float *queries;     // [nq][256] f32 (device)
+  stb_hit *out_hits;        // [nq][top_k]
+  uint32_t *out_status;     // [nq][2]: hits, complete
+};
+
+__global__ void __launch_bounds__(256, 3)
+stb_batch_finish_kernel(const FinishArgs a) {
+  __shared__ uint64_t skeys[1024];
+  __shared__ double sd[1024];
+  __shared__ uint64_t sr[1024];
+  __shared__ double sqd[STB_D];
+  __shared__ double s_q2;
+  __shared__ int s_pass, s_alltiles;
+  const uint32_t q = blockIdx.x;
+  const int tid = threadIdx.x;
+  // 1. merge the per-slice candidate sub-tiles, keep the KSEL best
+  const uint32_t n_in = a.n_slices * STB_BATCH_KSEL;     // <= 1024
+  const uint64_t *src = a.cand + (size_t)q * n_in;
+  for (int i = tid; i < 1024; i += 256) skeys[i] = ((uint32_t)i < n_in) ? src[i] : STB_KEY_INVALID;
+  for (int i = tid; i < STB_D; i += 256) sqd[i] = (double)__ldg(a.queries + (size_t)q * STB_D + i);
+  if (tid == 0) s_pass = 0;
+  __syncthreads();
+  // in-place ascending sort of 1024 keys (best first)
+  for (int kk = 2; kk <= 1024; kk <<= 1)
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < 1024; i += 256) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          uint64_t x = skeys[i], y = skeys[ixj];
+          bool up = ((i & kk) == 0);
+          if ((x > y) == up) { skeys[i] = y; skeys[ixj] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  // 1b. the KSEL best sub-tiles all lie inside the KSEL best tiles (a tile's maximum is the
+  //     maximum of its 8 sub-tiles): expand those tiles to their 8 sub-tile maxima, sort
+  //     again and keep the KSEL best sub-tiles.
+  {
+    // <= KSEL tile candidates in total means every slice offered ALL its tiles: nothing unselected
+    if (tid == 0) s_alltiles = (skeys[STB_BATCH_KSEL] == STB_KEY_INVALID) ? 1 : 0;
+    uint64_t mykey = STB_KEY_INVALID;
+    const uint64_t tkey = skeys[tid >> 3];                 // tid < 256 -> tile slot tid/8, sub-tile tid%8
+    if (tkey != STB_KEY_INVALID) {
+      const uint32_t st = stb_key_row(tkey) * (STB_B_TILE / STB_SUB) + (tid & 7);
+      if (st < a.n_sub) mykey = stb_make_key(__ldg(a.submax + (size_t)st * a.q_pad + q), st);
+    }
+    __syncthreads();
+    for (int i = tid; i < 1024; i += 256) skeys[i] = (i < 256) ? mykey : STB_KEY_INVALID;
+    __syncthreads();
+    for (int kk = 2; kk <= 256; kk <<= 1)
+      for (int j = kk >> 1; j > 0; j >>= 1) {
+        const int i = tid, ixj = i ^ j;
+        if (ixj > i) {
+          uint64_t x = skeys[i], y = skeys[ixj];
+          bool up = ((i & kk) == 0);
+          if ((x > y) == up) { skeys[i] = y; skeys[ixj] = x; }
+        }
+        __syncthreads();
+      }
+  }
+  if (tid == 0) {
+    double q2 = 0.0;
+    for (int i = 0; i < STB_D; ++i) q2 = fma(sqd[i], sqd[i], q2);
+    s_q2 = q2;
+  }
+  __syncthreads();
+  // 2. exact canonical distance of every row of the selected sub-tiles (one thread per row,
+  //    f64 accumulation in index order == oracle orc_cosine_f32)
+  const double q2 = s_q2;
+  for (int c = tid; c < STB_BATCH_KSEL * STB_SUB; c += 256) {
+    const uint64_t key = skeys[c / STB_SUB];
+    double d = CUDART_INF;
+    uint64_t grow = 0xffffffffffffffffull;
+    if (key != STB_KEY_INVALID) {
+      const uint64_t row = (uint64_t)stb_key_row(key) * STB_SUB + (c % STB_SUB);
+      if (row < a.n_rows) {
+        const float4 *rp = a.rows + row * STB_ROW_F4;
+        double ab = 0.0, r2 = 0.0;
+#pragma unroll 8
+        for (int i = 0; i < STB_ROW_F4; ++i) {
+          const float4 v = __ldg(rp + i);
+          const double vx = (double)v.x, vy = (double)v.y, vz = (double)v.z, vw = (double)v.w;
+          ab = fma(sqd[4 * i + 0], vx, ab); r2 = fma(vx, vx, r2);
+          ab = fma(sqd[4 * i + 1], vy, ab); r2 = fma(vy, vy, r2);
+          ab = fma(sqd[4 * i + 2], vz, ab); r2 = fma(vz, vz, r2);
+          ab = fma(sqd[4 * i + 3], vw, ab); r2 = fma(vw, vw, r2);
+        }
+        double dist;
+        if (q2 == 0.0 && r2 == 0.0) dist = 0.0;
+        else if (ab == 0.0) dist = 1.0;
+        else {
+          double t = 1.0 - ab / (sqrt(q2) * sqrt(r2));
+          dist = t > 0.0 ? t : 0.0;
+        }
+        if (dist < 100.0) { d = dist; grow = a.row_base + row; atomicAdd(&s_pass, 1); }
+      }
+    }
+    sd[c] = d; sr[c] = grow;
+  }
+  __syncthreads();
+  // 3. sort the 1024 (distance,row) pairs
+  for (int kk = 2; kk <= 1024; kk <<= 1)
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < 1024; i += 256) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          bool up = ((i & kk) == 0);
+          bool gt = stb_hit_less(sd[ixj], sr[ixj], sd[i], sr[i]);
+          if (gt == up) {
+            double td = sd[i]; uint64_t tr = sr[i];
+            sd[i] = sd[ixj]; sr[i] = sr[ixj]; sd[ixj] = td; sr[ixj] = tr;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  // 4. hits + completeness proof
+  const uint32_t k = a.top_k;
+  const uint32_t n_out = min((uint32_t)s_pass, k);
+  for (uint32_t i = tid; i < k; i += 256) {
+    stb_hit h;
+    h.distance = (i < n_out) ? sd[i] : CUDART_INF;
+    h.row = (i < n_out) ? sr[i] : 0xffffffffffffffffull;
+    a.out_hits[(size_t)q * k + i] = h;
+  }
+  if (tid == 0) {
+    bool complete;
+    if (s_alltiles && skeys[STB_BATCH_KSEL] == STB_KEY_INVALID) complete = true;   // every sub-tile was re-scored
+    else if (skeys[STB_BATCH_KSEL - 1] == STB_KEY_INVALID) complete = false;        // (cannot happen: < KSEL sub-tiles but tiles left out)
+    else {
+      // m* = KSEL-th best selected sub-tile maximum bounds every unselected row's approximate
+      // cosine: sub-tiles left out inside the selected tiles rank below it, and a left-out
+      // tile's maximum is <= the KSEL-th tile maximum <= m* (each selected tile contributes a
+      // sub-tile equal to its maximum).  Hence exact cosine <= m* + EPS for all of them.
+      const float m_star = stb_key_score(skeys[STB_BATCH_KSEL - 1]);
+      complete = (n_out == k) && ((1.0 - (double)m_star - STB_BATCH_EPS) > sd[k - 1]);
+    }
+    a.out_status[2 * q] = n_out;
+    a.out_status[2 * q + 1] = complete ? 1u : 0u;
+  }
+}
+
+int stb_launch_batch_select(stb_ctx *ctx, const float *submax, uint32_t n_sub, uint32_t q_pad,
+                            uint32_t n_slices, uint64_t *cand) {
+  SelectArgs a;
+  a.submax = submax; a.n_sub = n_sub; a.q_pad = q_pad; a.n_slices = n_slices; a.cand = cand;
+  dim3 grid(q_pad / 32, (n_slices + 3) / 4);
+  stb_batch_select_kernel<<<grid, 128, 0, ctx->stream>>>(a);
+  STB_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  return STB_OK;
+}
+
+int stb_launch_batch_finish(stb_ctx *ctx, const uint64_t *cand, uint32_t n_slices, uint32_t n_sub,
+                            uint32_t nq, uint32_t top_k, const float *rows, uint64_t n_rows,
+                            uint64_t row_base, const float *queries_dev, stb_hit *out_hits,
+                            uint32_t *out_status, const float *submax, uint32_t q_pad) {
+  FinishArgs a;
+  a.cand = cand; a.n_slices = n_slices; a.n_sub = n_sub; a.nq = nq; a.top_k = top_k;
+  a.submax = submax; a.q_pad = q_pad;
+  a.rows = reinterpret_cast<const float4 *>(rows); a.n_rows = n_rows; a.row_base = row_base;
+  a.queries = queries_dev; a.out_hits = out_hits; a.out_status = out_status;
+  stb_batch_finish_kernel<<<nq, 256, 0, ctx->stream>>>(a);
+  STB_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  return STB_OK;
+}

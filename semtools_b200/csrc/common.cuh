@@ -61,6 +61,14 @@ struct stb_ctx {
   size_t ranges_cap;
   int *err_flag;            // device int for K3 range errors
   unsigned long long *dbg_dev;  // 8 u64 phase timestamps (STB_TAIL_TIMING builds; else unused)
+  // --- K2 scratch ---
+  uint8_t *bq_tiles; size_t bq_tiles_cap;     // query shadow tiles
+  float *b_submax; size_t b_submax_cap;       // [n_sub][q_pad]
+  float *b_tilemax; size_t b_tilemax_cap;     // [n_tiles][q_pad]
+  uint64_t *b_cand; size_t b_cand_cap;        // [q_pad][slices][32]
+  float *bq_dev; size_t bq_dev_cap;           // host-call staging: queries
+  stb_hit *bh_dev; size_t bh_dev_cap;         // host-call staging: hits
+  uint32_t *bs_dev; size_t bs_dev_cap;        // host-call staging: status
   uint64_t *embed_off_dev;  // K3 staging: CSR offsets
   size_t embed_off_cap;
   uint32_t *embed_ids_dev;  // K3 staging: token ids
@@ -113,6 +121,11 @@ struct stb_corpus {
   uint64_t n;
   uint64_t capacity;
   uint64_t row_base;
+  // K2: L2-normalised bf16 copy in tcgen05 tile layout (built lazily, rebuilt when n changes)
+  uint8_t *shadow;
+  uint64_t shadow_rows;      // rows covered by `shadow` (== n when valid)
+  uint64_t shadow_cap_tiles;
+  int shadow_bad;            // 1: some row cannot be normalised in fp32 -> tensor path refused
 };
 
 // ---- scan_topk.cu -------------------------------------------------------------
@@ -149,6 +162,19 @@ int stb_launch_hits_merge(stb_ctx *ctx, const stb_hit *lists_dev, uint32_t n_lis
 int stb_launch_embed(stb_ctx *ctx, const stb_table *t, const uint64_t *offsets_dev,
                      const uint32_t *ids_dev, uint64_t n_lines, float *out_dev,
                      int *err_flag_dev);
+
+// ---- batch_scan.cu (K2) ------------------------------------------------------------------
+int stb_launch_shadow_build(stb_ctx *ctx, const float *rows_dev, uint64_t n_rows, int tile,
+                            uint8_t *out, int *bad_flag_dev);
+int stb_launch_batch_gemm(stb_ctx *ctx, const uint8_t *a_tiles, uint32_t m_tiles,
+                          const uint8_t *b_tiles, uint32_t n_tiles, float *submax,
+                          float *tilemax, float *full_out);
+int stb_launch_batch_select(stb_ctx *ctx, const float *submax, uint32_t n_sub, uint32_t q_pad,
+                            uint32_t n_slices, uint64_t *cand);
+int stb_launch_batch_finish(stb_ctx *ctx, const uint64_t *cand, uint32_t n_slices, uint32_t n_sub,
+                            uint32_t nq, uint32_t top_k, const float *rows, uint64_t n_rows,
+                            uint64_t row_base, const float *queries_dev, stb_hit *out_hits,
+                            uint32_t *out_status, const float *submax, uint32_t q_pad);
 
 // ---- device helpers ---------------------------------------------------------------
 #ifdef __CUDACC__

@@ -1,0 +1,118 @@
+"""GPU: K2 (tcgen05 batched scan).  Stage 1: the tensor-core GEMM itself against a
+bf16 reference matmul; stage 2 (stb_search_batch): parity with the oracle per query."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import unit_rows
+from semtools_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+
+def bf16_round(x):
+    torch = pytest.importorskip("torch")
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+@pytest.mark.parametrize("nq,n", [(128, 256), (200, 1000), (1, 5), (384, 40_000)])
+def test_tcgen05_gemm_matches_bf16_reference(ctx, nq, n):
+    rng = np.random.default_rng(nq * 7 + n)
+    rows = (unit_rows(rng, n) * rng.uniform(0.5, 2.0, (n, 1))).astype(np.float32)
+    rows[n // 2] = 0.0
+    q = unit_rows(rng, nq)
+    mt, nt = (nq + 127) // 128, (n + 255) // 256
+    full = np.zeros((mt * 128, nt * 256), dtype=np.float32)
+    sub = np.zeros((nt * 8, mt * 128), dtype=np.float32)
+    vp = C.c_void_p
+    capi._check(capi.lib().stb_debug_batch_gemm(ctx._h, q.ctypes.data_as(vp), nq, rows.ctypes.data_as(vp), n,
+                                                full.ctypes.data_as(vp), sub.ctypes.data_as(vp)))
+    norm = np.linalg.norm(rows, axis=1, keepdims=True)
+    rn = bf16_round(np.divide(rows, norm, out=np.zeros_like(rows), where=norm > 0))
+    qn = bf16_round(q / np.linalg.norm(q, axis=1, keepdims=True))
+    ref = qn @ rn.T
+    got = full[:nq, :n]
+    assert np.max(np.abs(got - ref)) < 2e-3, np.max(np.abs(got - ref))
+    # exact cosine is within the rigorous bf16 bound used by the completeness proof
+    exact = 1.0 - np.stack([oracle.distances(rows, q[i]) for i in range(min(nq, 4))])
+    exact[:, n // 2] = 0.0
+    assert np.max(np.abs(got[: exact.shape[0]] - exact)) < 0.0045
+    # padding rows / queries are zeros; sub-tile maxima agree with the full matrix
+    assert np.all(full[:, n:] == 0.0)
+    exp_sub = full.reshape(mt * 128, nt * 8, 32).max(axis=2).T
+    assert np.array_equal(sub, exp_sub)
+
+
+def check_batch(res, rows, queries, k):
+    for i, q in enumerate(queries):
+        r, d = oracle.search_rows(rows, q, top_k=k)
+        assert res[i]["row"].tolist() == [int(x) for x in r], i
+        assert np.array_equal(res[i]["distance"], d), i
+
+
+@pytest.mark.parametrize("nq,n,k", [(1, 40, 3), (5, 1000, 10), (130, 70_000, 10), (300, 20_000, 1), (64, 50_000, 40)])
+def test_search_batch_matches_oracle(ctx, nq, n, k):
+    rng = np.random.default_rng(nq + n + k)
+    rows = unit_rows(rng, n)
+    queries = unit_rows(rng, nq)
+    c = capi.Corpus(ctx, n)
+    c.append(rows)
+    before = ctx.counters()["fallback_searches"]
+    res = c.search_batch(queries, top_k=k)
+    check_batch(res, rows, queries, k)
+    if n >= 20_000 and k <= 16:
+        # 32 sub-tiles are re-scored per query, enough to PROVE top-k for k <= ~16; larger k is
+        # answered (correctly) through the single-query path
+        assert ctx.counters()["fallback_searches"] == before
+
+
+def test_search_batch_ties_zero_rows_and_unprovable_queries(ctx):
+    rng = np.random.default_rng(42)
+    rows = unit_rows(rng, 30_000)
+    rows[rng.integers(0, 30_000, 20)] = rows[rng.integers(0, 30_000, 20)]      # duplicates
+    rows[[3, 999, 29_999]] = 0.0
+    queries = unit_rows(rng, 40)
+    queries[0] = rows[17]                      # exact hit (distance 0)
+    queries[1] = 0.0                           # zero query: everything ties at 1.0 -> fallback
+    where = rng.choice(30_000, 600, replace=False)
+    rows[where] = (queries[2] + 0.005 * unit_rows(rng, 1)[0]).astype(np.float32)   # 600 near-identical best rows
+    c = capi.Corpus(ctx, 30_000)
+    c.append(rows)
+    before = ctx.counters()["fallback_searches"]
+    res = c.search_batch(queries, top_k=10)
+    check_batch(res, rows, queries, 10)
+    assert ctx.counters()["fallback_searches"] >= before + 2     # queries 1 and 2 cannot be proven
+
+
+def test_search_batch_refuses_unnormalisable_rows_but_still_answers(ctx):
+    rng = np.random.default_rng(43)
+    rows = unit_rows(rng, 5000)
+    rows[11] *= np.float32(1e-25)
+    queries = unit_rows(rng, 3)
+    queries[0] = rows[11] * np.float32(1e25)
+    c = capi.Corpus(ctx, 5000)
+    c.append(rows)
+    res = c.search_batch(queries, top_k=5)     # tensor path refused (STATE) -> K1 for every query
+    check_batch(res, rows, queries, 5)
+    assert int(res[0]["row"][0]) == 11
+
+
+def test_search_batch_sharded_row_base_and_rebuild_after_append(ctx):
+    rng = np.random.default_rng(44)
+    rows = unit_rows(rng, 24_000)
+    queries = unit_rows(rng, 10)
+    c = capi.Corpus(ctx, 16_000, row_base=1_000_000)
+    c.append(rows[:12_000])
+    c.prepare_batch()
+    res = c.search_batch(queries, top_k=5)
+    for i, q in enumerate(queries):
+        r, d = oracle.search_rows(rows[:12_000], q, top_k=5)
+        assert res[i]["row"].tolist() == [int(x) + 1_000_000 for x in r]
+    c.append(rows[12_000:])                    # shadow must be rebuilt
+    res = c.search_batch(queries, top_k=5)
+    for i, q in enumerate(queries):
+        r, d = oracle.search_rows(rows, q, top_k=5)
+        assert res[i]["row"].tolist() == [int(x) + 1_000_000 for x in r]
+        assert np.array_equal(res[i]["distance"], d)
