@@ -1,0 +1,389 @@
+"""Workspace embedding store -- the semantic contract of the reference's
+src/workspace/mod.rs (Workspace, WorkspaceConfig) and src/workspace/store.rs (Store)
+on a flat, GPU-friendly on-disk format.
+
+The reference persists line vectors in two Qdrant Edge shards
+(`documents.qdrant/`, `line_embeddings.qdrant/`, store.rs:113-183).  That segment /
+WAL byte format is third-party and opaque, so BYTE compatibility with existing
+`*.qdrant` directories is NOT provided (parity unpinned).  What is kept,
+name for name:
+
+  Workspace.open / save / active / active_path / root_path       mod.rs:32-101
+  WorkspaceConfig {name, root_dir, in_batch_size, oversample_factor}  mod.rs:8-25
+  DocMeta {path,size_bytes,mtime,_version}, id = fnv1a(path)     store.rs:52-58,75-80
+  LineEmbedding {path,line_number,embedding}, id = fnv1a(path||i32 LE)  :67-73,82-89
+  Store.open / get_existing_docs / analyze_document_states / upsert_line_embeddings /
+        upsert_document_metadata / search_line_embeddings / delete_documents /
+        delete_document_metadata / delete_line_embeddings / get_all_document_paths /
+        get_stats / count_documents / count_line_embeddings      store.rs:111-648
+  CURRENT_EMBEDDING_VERSION = 2, LINE_EMBEDDING_SIZE = 256       store.rs:34,37
+
+On disk (`<root_dir>/flat.b200/`):
+  line_embeddings.f32   row-major N x 256 f32 -- exactly the HBM corpus matrix, so
+                        opening a workspace is one read + one cudaMemcpy into a shard
+  rows.i32              N x 2 int32: (path index, line_number) per row
+  store.json            {"format", "paths": [...], "docs": [DocMeta...]}
+Upserts overwrite the row whose id already exists and append otherwise, which
+reproduces the reference's behaviour that rows of a shrunken file are NOT removed
+(store.rs upsert only overwrites existing ids).
+
+The nearest-neighbour query runs on the GPU (stb_search with row ranges = the path
+filter, STB_MODE_STORE_QUERY); nothing here computes a distance on the CPU.
+"""
+from __future__ import annotations
+
+import json
+import os
+from dataclasses import asdict, dataclass, field
+
+import numpy as np
+
+from . import capi
+from .search import RankedLine
+
+CURRENT_EMBEDDING_VERSION = 2     # store.rs:34
+LINE_EMBEDDING_SIZE = 256         # store.rs:37
+FORMAT = "semtools_b200.flat.v1"
+
+
+# ------------------------------------------------------------------ mod.rs ------------
+@dataclass
+class WorkspaceConfig:
+    """mod.rs:8-25 (in_batch_size / oversample_factor are unused vestiges upstream too)."""
+    name: str = "default"
+    root_dir: str = ""
+    in_batch_size: int = 5_000
+    oversample_factor: int = 3
+
+
+def _home() -> str:
+    home = os.environ.get("HOME") or os.path.expanduser("~")
+    if not home:
+        raise RuntimeError("No home dir found?")          # mod.rs:83
+    return home
+
+
+@dataclass
+class Workspace:
+    config: WorkspaceConfig
+
+    @staticmethod
+    def root_path(name: str) -> str:                       # mod.rs:82-91
+        return os.path.join(_home(), ".semtools", "workspaces", name)
+
+    @staticmethod
+    def _config_path_for(name: str) -> str:                # mod.rs:93-101
+        return os.path.join(_home(), ".semtools", "workspaces", name, "config.json")
+
+    @staticmethod
+    def active(workspace_name: str | None = None) -> str:  # mod.rs:69-79
+        active = os.environ.get("SEMTOOLS_WORKSPACE", "") if workspace_name is None else workspace_name
+        if not active:
+            raise RuntimeError("No active workspace. Run: workspace use <name>")
+        return active
+
+    @staticmethod
+    def active_path(workspace_name: str | None = None) -> str:   # mod.rs:58-67
+        return Workspace.root_path(Workspace.active(workspace_name))
+
+    @classmethod
+    def open(cls, workspace_name: str | None = None) -> "Workspace":   # mod.rs:32-47
+        active = cls.active(workspace_name)
+        cfg = None
+        try:
+            with open(cls._config_path_for(active)) as f:
+                d = json.load(f)
+            cfg = WorkspaceConfig(**{k: d[k] for k in ("name", "root_dir", "in_batch_size", "oversample_factor")})
+        except (OSError, ValueError, KeyError, TypeError):
+            cfg = None
+        config = cfg or WorkspaceConfig()
+        if not config.root_dir:
+            config.root_dir = cls.root_path(active)
+        if not config.name or config.name == "default":
+            config.name = active
+        return cls(config)
+
+    def save(self) -> None:                                # mod.rs:49-56
+        p = self._config_path_for(self.config.name)
+        os.makedirs(os.path.dirname(p), exist_ok=True)
+        with open(p, "w") as f:
+            json.dump(asdict(self.config), f, indent=2)    # serde_json::to_string_pretty
+
+
+# ------------------------------------------------------------------ store.rs ----------
+@dataclass
+class DocMeta:
+    path: str
+    size_bytes: int
+    mtime: int
+    _version: int = CURRENT_EMBEDDING_VERSION
+
+    def id(self) -> int:
+        return capi.fnv1a64(self.path.encode("utf-8"))
+
+
+@dataclass
+class LineEmbedding:
+    path: str
+    line_number: int
+    embedding: np.ndarray = field(repr=False, default=None)
+
+    def id(self) -> int:
+        return capi.line_id(self.path, self.line_number)
+
+
+@dataclass
+class DocumentInfo:                                        # search/mod.rs:26-30
+    filename: str
+    content: str
+    meta: DocMeta
+
+
+@dataclass
+class DocumentState:                                       # store.rs:60-65
+    kind: str                  # "Unchanged" | "Changed" | "New"
+    filename: str
+    info: DocumentInfo | None = None
+
+
+@dataclass
+class WorkspaceStats:                                      # store.rs:98-103
+    total_documents: int
+    has_index: bool
+    index_type: str | None
+
+
+class Store:
+    """Flat-file restatement of store.rs `Store`."""
+
+    def __init__(self, workspace_dir: str, ctx: capi.Context | None = None):
+        self.dir = os.path.join(workspace_dir, "flat.b200")
+        self.ctx = ctx
+        self._paths: list = []                 # path table
+        self._path_idx: dict = {}
+        self._docs: dict = {}                  # path -> DocMeta
+        self._rows = np.zeros((0, 2), dtype=np.int32)          # (path idx, line_number)
+        self._emb = np.zeros((0, LINE_EMBEDDING_SIZE), dtype=np.float32)
+        self._id_row: dict = {}                # LineEmbedding id -> row
+        self._corpus = None                    # capi.Corpus mirror of self._emb (lazy)
+
+    # -- Store::open, store.rs:113-183 (creates the directories on first use)
+    @classmethod
+    def open(cls, workspace_dir: str, ctx: capi.Context | None = None) -> "Store":
+        s = cls(workspace_dir, ctx)
+        os.makedirs(s.dir, exist_ok=True)
+        meta_p = os.path.join(s.dir, "store.json")
+        if os.path.exists(meta_p):
+            with open(meta_p) as f:
+                d = json.load(f)
+            if d.get("format") != FORMAT:
+                raise RuntimeError(f"unknown store format {d.get('format')!r}")
+            s._paths = list(d["paths"])
+            s._path_idx = {p: i for i, p in enumerate(s._paths)}
+            s._docs = {m["path"]: DocMeta(**m) for m in d["docs"]}
+            s._rows = np.fromfile(os.path.join(s.dir, "rows.i32"), dtype=np.int32).reshape(-1, 2)
+            s._emb = np.fromfile(os.path.join(s.dir, "line_embeddings.f32"), dtype=np.float32).reshape(
+                -1, LINE_EMBEDDING_SIZE)
+            if len(s._rows) != len(s._emb):
+                raise RuntimeError("store files disagree on the row count")
+            for r, (pi, ln) in enumerate(s._rows):
+                s._id_row[capi.line_id(s._paths[pi], int(ln))] = r
+        return s
+
+    # -- flush_documents / flush_line_embeddings, store.rs:639-648
+    def _flush(self) -> None:
+        tmp = os.path.join(self.dir, "store.json.tmp")
+        with open(tmp, "w") as f:
+            json.dump({"format": FORMAT, "dim": LINE_EMBEDDING_SIZE, "rows": int(len(self._rows)),
+                       "paths": self._paths, "docs": [asdict(m) for m in self._docs.values()]}, f)
+        self._rows.astype(np.int32).tofile(os.path.join(self.dir, "rows.i32"))
+        self._emb.astype(np.float32).tofile(os.path.join(self.dir, "line_embeddings.f32"))
+        os.replace(tmp, os.path.join(self.dir, "store.json"))
+
+    def flush_documents(self) -> None:
+        self._flush()
+
+    def flush_line_embeddings(self) -> None:
+        self._flush()
+
+    # -- store.rs:185-233
+    def get_existing_docs(self, paths) -> dict:
+        return {p: self._docs[p] for p in paths if p in self._docs}
+
+    # -- store.rs:549-611
+    def analyze_document_states(self, file_paths) -> list:
+        existing = self.get_existing_docs(file_paths)
+        states = []
+        for fp in file_paths:
+            try:
+                st = os.stat(fp)
+            except OSError:
+                continue                                             # :578-581 missing file: skipped
+            cur = DocMeta(fp, st.st_size, int(st.st_mtime), CURRENT_EMBEDDING_VERSION)
+            old = existing.get(fp)
+            if old is not None and old.size_bytes == cur.size_bytes and old.mtime == cur.mtime \
+                    and old._version == CURRENT_EMBEDDING_VERSION:
+                states.append(DocumentState("Unchanged", fp))
+                continue
+            with open(fp, encoding="utf-8") as f:                    # read_to_string: invalid UTF-8 is an error
+                content = f.read()
+            states.append(DocumentState("Changed" if old is not None else "New", fp, DocumentInfo(fp, content, cur)))
+        return states
+
+    # -- store.rs:373-399
+    def upsert_document_metadata(self, metas) -> None:
+        if not metas:
+            return
+        for m in metas:
+            self._docs[m.path] = m                                   # same id (fnv1a(path)) -> replaced
+        self._flush()
+
+    # -- store.rs:402-434
+    def upsert_line_embeddings(self, line_embeddings) -> None:
+        if not line_embeddings:
+            return
+        new_rows, new_emb = [], []
+        for le in line_embeddings:
+            emb = np.asarray(le.embedding, dtype=np.float32)
+            if emb.shape != (LINE_EMBEDDING_SIZE,):
+                raise ValueError("embedding must have 256 floats")
+            pi = self._path_idx.get(le.path)
+            if pi is None:
+                pi = len(self._paths)
+                self._paths.append(le.path)
+                self._path_idx[le.path] = pi
+            rid = le.id()
+            row = self._id_row.get(rid)
+            if row is not None and row < len(self._emb):
+                self._emb[row] = emb                                  # upsert replaces by id
+                self._rows[row] = (pi, le.line_number)
+            elif row is not None:                                     # replaced inside this same batch
+                new_emb[row - len(self._emb)] = emb
+            else:
+                self._id_row[rid] = len(self._emb) + len(new_emb)
+                new_rows.append((pi, le.line_number))
+                new_emb.append(emb)
+        if new_emb:
+            self._emb = np.concatenate([self._emb, np.stack(new_emb)]) if len(self._emb) else np.stack(new_emb)
+            self._rows = np.concatenate([self._rows, np.asarray(new_rows, dtype=np.int32).reshape(-1, 2)])
+        self._corpus = None
+        self._flush()
+
+    # -- store.rs:235-296: only metadata of the CURRENT embedding version is deleted
+    def delete_document_metadata(self, paths) -> None:
+        for p in paths:
+            m = self._docs.get(p)
+            if m is not None and m._version == CURRENT_EMBEDDING_VERSION:
+                del self._docs[p]
+        if paths:
+            self._flush()
+
+    # -- store.rs:298-357
+    def delete_line_embeddings(self, paths) -> None:
+        if not paths:
+            return
+        kill = {self._path_idx[p] for p in paths if p in self._path_idx}
+        if kill:
+            keep = ~np.isin(self._rows[:, 0], list(kill))
+            self._rows = self._rows[keep]
+            self._emb = np.ascontiguousarray(self._emb[keep])
+            self._id_row = {capi.line_id(self._paths[pi], int(ln)): r for r, (pi, ln) in enumerate(self._rows)}
+            self._corpus = None
+        self._flush()
+
+    # -- store.rs:360-370
+    def delete_documents(self, paths) -> None:
+        if not paths:
+            return
+        self.delete_document_metadata(paths)
+        self.delete_line_embeddings(paths)
+
+    # -- store.rs:436-479
+    def get_stats(self) -> WorkspaceStats:
+        # the reference hard-codes "HNSW" (store.rs:440-444) although its shards use the
+        # default plain index; this store really is an exact flat scan
+        return WorkspaceStats(self.count_documents(), True, "FLAT")
+
+    def get_all_document_paths(self) -> list:
+        return [m.path for m in self._docs.values()]
+
+    def count_documents(self) -> int:                                # store.rs:613-625
+        return len(self._docs)
+
+    def count_line_embeddings(self) -> int:                          # store.rs:627-637
+        return int(len(self._emb))
+
+    # -- GPU residency ---------------------------------------------------------------------
+    def _gpu_corpus(self) -> capi.Corpus:
+        if self.ctx is None:
+            self.ctx = capi.Context(0)                               # no GPU -> StbError, never a CPU scan
+        if self._corpus is None:
+            c = capi.Corpus(self.ctx, max(len(self._emb), 1))
+            c.append(self._emb)
+            self._corpus = c
+        return self._corpus
+
+    def _ranges_for(self, subset_paths) -> np.ndarray:
+        sel = [self._path_idx[p] for p in subset_paths if p in self._path_idx]
+        if not sel or not len(self._rows):
+            return np.zeros((0, 2), dtype=np.uint64)
+        mask = np.isin(self._rows[:, 0], sel).astype(np.int8)
+        edges = np.flatnonzero(np.diff(np.concatenate([[0], mask, [0]])))
+        return edges.reshape(-1, 2).astype(np.uint64)
+
+    # -- store.rs:481-546
+    def search_line_embeddings(self, query_vec, subset_paths, top_k: int, max_distance=None) -> list:
+        if len(subset_paths) == 0 or top_k == 0:                     # :489-491
+            return []
+        ranges = self._ranges_for(subset_paths)
+        if len(ranges) == 0:
+            return []
+        hits = self._gpu_corpus().search(query_vec, top_k, max_distance, capi.STB_MODE_STORE_QUERY,
+                                         row_ranges=ranges)
+        out = []
+        for h in hits:
+            pi, ln = self._rows[int(h["row"])]
+            out.append(RankedLine(self._paths[pi], int(ln), float(np.float32(h["distance"]))))   # :531 f32
+        return out
+
+
+# ------------------------------------------------------------------ search/mod.rs:146-216 ---
+def search_with_workspace(files, query_embedding, embed_lines, config, workspace_name=None, ctx=None,
+                          log=None) -> list:
+    """search_with_workspace: diff `files` against the store, embed only New/Changed
+    documents (`embed_lines(list[str]) -> (n,256) f32`, i.e. create_document_from_content's
+    encode_with_args on the caller's tokenizer + K3), upsert, then the filtered query."""
+    ws = Workspace.open(workspace_name)
+    store = Store.open(ws.config.root_dir, ctx)
+    to_upsert, docs = [], []
+    for st in store.analyze_document_states(files):
+        if st.kind == "Unchanged":
+            continue
+        lines = _rust_lines(st.info.content)
+        if not lines:
+            continue                                                  # create_document_from_content -> None
+        emb = embed_lines([l.lower() for l in lines] if config.ignore_case else lines)
+        for i in range(len(lines)):
+            to_upsert.append(LineEmbedding(st.filename, i, emb[i]))   # 0-based line numbers (:178)
+        docs.append(st.info.meta)
+    if to_upsert:
+        if log:
+            log(f"Updating workspace with {len(to_upsert)} lines from new/changed docs...")
+        store.upsert_line_embeddings(to_upsert)
+    if docs:
+        if log:
+            log(f"Updating workspace with {len(docs)} new/changed documents...")
+        store.upsert_document_metadata(docs)
+    max_d = None if config.max_distance is None else float(np.float32(config.max_distance))   # :211 `as f32`
+    return store.search_line_embeddings(query_embedding, files, config.top_k, max_d)
+
+
+def _rust_lines(content: str) -> list:
+    """str::lines(): split on '\\n', strip one trailing '\\r' per line, no trailing empty
+    line (search/mod.rs:55)."""
+    if not content:
+        return []
+    parts = content.split("\n")
+    if parts and parts[-1] == "":
+        parts.pop()
+    return [p[:-1] if p.endswith("\r") else p for p in parts]
