@@ -217,6 +217,24 @@ int stb_search_topk_xchg(stb_ctx *ctx, const stb_corpus *corpus, const float *q_
                          uint32_t top_k, stb_xchg *x, stb_hit *out_hits_dev,
                          uint32_t *out_status_dev);
 
+/* ---- K5: IVF-PQ index (approximate) ------------------------------------------------------
+ * NOT a replacement of any reference code: this snapshot of semtools has no IVF_PQ (the
+ * store is qdrant-edge with a plain index, src/workspace/store.rs:129-130,156-157; the
+ * string survives only in README.md:125).  Self-specified for BASELINE config 5 and
+ * measured by recall against stb_search: coarse spherical k-means (nlist lists), 32 x 8-bit
+ * product quantiser on the residual, ADC lookup-table scan of the nprobe best lists,
+ * exact re-rank of the `rerank` best candidates.  Returned distances are exact canonical
+ * distances; only the candidate set is approximate.  The index refers to the corpus it
+ * was built on (rows [0, n) at build time) and must be destroyed before it. */
+typedef struct stb_ivfpq stb_ivfpq;
+int stb_ivfpq_build(stb_ctx *ctx, const stb_corpus *corpus, uint32_t nlist, uint32_t train_rows,
+                    uint32_t iters, stb_ivfpq **out);
+int stb_ivfpq_destroy(stb_ivfpq *index);
+int stb_ivfpq_stats(const stb_ivfpq *index, uint64_t *rows, uint32_t *nlist, uint32_t *max_list,
+                    uint64_t *index_bytes);
+int stb_ivfpq_search(stb_ivfpq *index, const float *q, uint32_t nprobe, uint32_t top_k,
+                     uint32_t rerank, stb_hit *out_hits, uint32_t *out_n, uint64_t *out_scanned);
+
 /* ---- K4: merge per-shard hit lists -----------------------------------------------
  * The final sort_by + take of src/search/mod.rs:107-119 applied across row
  * shards: `lists_dev` holds n_lists x per_list hits (e.g. the all-gathered

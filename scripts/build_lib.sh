@@ -9,4 +9,4 @@ $NVCC -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
   -o semtools_b200/lib/libsemtools_b200.so \
   semtools_b200/csrc/api.cu semtools_b200/csrc/scan_topk.cu \
   semtools_b200/csrc/hits_merge.cu semtools_b200/csrc/embed_pool.cu \
-  semtools_b200/csrc/batch_scan.cu "$@"
+  semtools_b200/csrc/batch_scan.cu semtools_b200/csrc/ivfpq.cu "$@"

@@ -25,7 +25,8 @@ SYMBOLS = [
     "stb_embed_status", "stb_search",
     "stb_search_topk_dev", "stb_corpus_prepare_batch", "stb_search_batch", "stb_search_batch_dev",
     "stb_xchg_create", "stb_xchg_destroy", "stb_xchg_local_handle",
-    "stb_xchg_connect", "stb_xchg_connect_local", "stb_search_topk_xchg", "stb_hits_merge_dev", "stb_hits_merge", "stb_fnv1a64", "stb_line_id",
+    "stb_xchg_connect", "stb_xchg_connect_local", "stb_search_topk_xchg", "stb_ivfpq_build",
+    "stb_ivfpq_destroy", "stb_ivfpq_stats", "stb_ivfpq_search", "stb_hits_merge_dev", "stb_hits_merge", "stb_fnv1a64", "stb_line_id",
     "stb_ctx_counters", "stb_debug_timestamps", "stb_debug_batch_gemm",
 ]
 
@@ -90,6 +91,10 @@ def lib() -> C.CDLL:
     L.stb_xchg_connect.argtypes = [vp, vp]
     L.stb_xchg_connect_local.argtypes = [vp, C.POINTER(vp)]
     L.stb_search_topk_xchg.argtypes = [vp, vp, vp, u32, vp, vp, vp]
+    L.stb_ivfpq_build.argtypes = [vp, vp, u32, u32, u32, C.POINTER(vp)]
+    L.stb_ivfpq_destroy.argtypes = [vp]
+    L.stb_ivfpq_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)]
+    L.stb_ivfpq_search.argtypes = [vp, vp, u32, u32, u32, vp, C.POINTER(u32), C.POINTER(u64)]
     L.stb_hits_merge_dev.argtypes = [vp, vp, u32, u32, u32, vp]
     L.stb_hits_merge.argtypes = [vp, vp, u32, u32, u32, vp, C.POINTER(u32)]
     L.stb_fnv1a64.argtypes = [C.c_char_p, u64]
@@ -141,8 +146,8 @@ class Context:
         self.device = device
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h:
-            lib().stb_ctx_destroy(self._h)
+        if getattr(self, "_h", None) is not None and self._h and _lib is not None:
+            _lib.stb_ctx_destroy(self._h)
             self._h = None
 
     __del__ = close
@@ -188,8 +193,8 @@ class Table:
                                     int(normalize), C.byref(self._h)))
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h:
-            lib().stb_table_destroy(self._h)
+        if getattr(self, "_h", None) is not None and self._h and _lib is not None:
+            _lib.stb_table_destroy(self._h)
             self._h = None
 
     __del__ = close
@@ -205,8 +210,8 @@ class Corpus:
         _check(lib().stb_corpus_create(ctx._h, STB_DIM, capacity_rows, row_base, C.byref(self._h)))
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h:
-            lib().stb_corpus_destroy(self._h)
+        if getattr(self, "_h", None) is not None and self._h and _lib is not None:
+            _lib.stb_corpus_destroy(self._h)
             self._h = None
 
     __del__ = close
@@ -295,6 +300,36 @@ class Corpus:
                                          vp(out_status_dev)))
 
 
+class IvfPq:
+    """stb_ivfpq: approximate IVF-PQ index over a corpus (K5; self-specified, see header)."""
+
+    def __init__(self, corpus: "Corpus", nlist: int = 4096, train_rows: int = 262144, iters: int = 8):
+        self.corpus = corpus
+        self._h = vp()
+        _check(lib().stb_ivfpq_build(corpus.ctx._h, corpus._h, nlist, train_rows, iters, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h and _lib is not None:
+            _lib.stb_ivfpq_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def stats(self):
+        rows, nbytes, nlist, mx = u64(0), u64(0), u32(0), u32(0)
+        _check(lib().stb_ivfpq_stats(self._h, C.byref(rows), C.byref(nlist), C.byref(mx), C.byref(nbytes)))
+        return {"rows": int(rows.value), "nlist": int(nlist.value), "max_list": int(mx.value),
+                "index_bytes": int(nbytes.value)}
+
+    def search(self, q, nprobe: int = 64, top_k: int = 10, rerank: int = 256):
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        out = np.zeros(max(top_k, 1), dtype=HIT_DTYPE)
+        n, scanned = u32(0), u64(0)
+        _check(lib().stb_ivfpq_search(self._h, _np_ptr(q), nprobe, top_k, rerank, _np_ptr(out), C.byref(n),
+                                      C.byref(scanned)))
+        return out[: n.value], int(scanned.value)
+
+
 class Exchange:
     """stb_xchg: peer-memory exchange buffers for the fused multi-GPU search."""
     HANDLE_BYTES = 64
@@ -305,8 +340,8 @@ class Exchange:
         _check(lib().stb_xchg_create(ctx._h, world, rank, max_k, C.byref(self._h)))
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h:
-            lib().stb_xchg_destroy(self._h)
+        if getattr(self, "_h", None) is not None and self._h and _lib is not None:
+            _lib.stb_xchg_destroy(self._h)
             self._h = None
 
     __del__ = close

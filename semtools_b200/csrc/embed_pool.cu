@@ -18,7 +18,12 @@
 
 #define STB_EMBED_THREADS 256
 #define STB_EMBED_WARPS (STB_EMBED_THREADS / 32)
-#define STB_EMBED_DEPTH 8
+#ifndef STB_EMBED_DEPTH
+#define STB_EMBED_DEPTH 4     // tokens (2 x 512-byte warp loads each) in flight per warp
+#endif
+#ifndef STB_EMBED_MINB
+#define STB_EMBED_MINB 3      // CTAs per SM the register budget is sized for
+#endif
 
 struct EmbedArgs {
   const float4 *E;
@@ -35,7 +40,7 @@ struct EmbedArgs {
   int *err_flag;
 };
 
-__global__ void __launch_bounds__(STB_EMBED_THREADS)
+__global__ void __launch_bounds__(STB_EMBED_THREADS, STB_EMBED_MINB)
 stb_embed_kernel(const EmbedArgs a) {
   __shared__ __align__(16) float s_sq[STB_EMBED_WARPS][STB_D];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

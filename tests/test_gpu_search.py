@@ -39,8 +39,9 @@ def test_topk_matches_oracle(ctx, n, k):
     q = unit_rows(rng, 1)[0]
     c = make_corpus(ctx, rows)
     r, d = oracle.search_rows(rows, q, top_k=k)
+    before = ctx.counters()["fallback_searches"]
     check(c.search(q, top_k=k), r, d)
-    assert ctx.counters()["fallback_searches"] == 0 or n < 64
+    assert ctx.counters()["fallback_searches"] == before      # random data: fast path proves it
 
 
 @pytest.mark.parametrize("k", [16, 17, 40, 41, 64, 96])
