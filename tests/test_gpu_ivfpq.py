@@ -10,10 +10,13 @@ from semtools_b200 import capi
 pytestmark = pytest.mark.gpu
 
 
-def clustered(rng, n, n_centers=4000, spread=0.6):
+def make_centers(rng, n_centers=4000):
     centers = rng.standard_normal((n_centers, 256)).astype(np.float32)
-    centers /= np.linalg.norm(centers, axis=1, keepdims=True)
-    x = centers[rng.integers(0, n_centers, n)] + spread * rng.standard_normal((n, 256)).astype(np.float32) / 16.0
+    return centers / np.linalg.norm(centers, axis=1, keepdims=True)
+
+
+def clustered(rng, centers, n, spread=0.6):
+    x = centers[rng.integers(0, len(centers), n)] + spread * rng.standard_normal((n, 256)).astype(np.float32) / 16.0
     x /= np.linalg.norm(x, axis=1, keepdims=True)
     return np.ascontiguousarray(x, dtype=np.float32)
 
@@ -21,13 +24,14 @@ def clustered(rng, n, n_centers=4000, spread=0.6):
 def test_ivfpq_recall_and_exact_distances(ctx):
     rng = np.random.default_rng(5)
     n = 200_000
-    rows = clustered(rng, n)
+    centers = make_centers(rng)
+    rows = clustered(rng, centers, n)
     c = capi.Corpus(ctx, n)
     c.append(rows)
     idx = capi.IvfPq(c, nlist=256, train_rows=65536, iters=6)
     st = idx.stats()
     assert st["rows"] == n and st["nlist"] == 256 and st["max_list"] < n // 8
-    queries = clustered(rng, 30)
+    queries = clustered(rng, centers, 30)          # queries come from the corpus' own clusters
     recalls, scanned = [], []
     for q in queries:
         got, n_scan = idx.search(q, nprobe=32, top_k=10, rerank=512)
