@@ -530,8 +530,9 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": 1024,
                     "d2h_bytes_per_step": 16 * k + 16, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
-                    "timing": "wall clock around synchronous host calls (stb_search: pinned H2D of the query, "
-                              "kernel, D2H of hits, stream sync)"},
+                    "timing": "wall clock around synchronous per-query host calls: pinned H2D of the query, kernel(s), "
+                              "D2H of the hits, stream sync (N=1: stb_search; N>1: pinned copy + stb_search_topk_xchg "
+                              "or NCCL path + pinned copy back, every rank)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "stb_scan_topk_kernel<E=1,U=2>", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -235,6 +235,13 @@ int stb_ivfpq_stats(const stb_ivfpq *index, uint64_t *rows, uint32_t *nlist, uin
 int stb_ivfpq_search(stb_ivfpq *index, const float *q, uint32_t nprobe, uint32_t top_k,
                      uint32_t rerank, stb_hit *out_hits, uint32_t *out_n, uint64_t *out_scanned);
 
+/* Host-buffer form of the fused multi-GPU search (the call a sharded host makes per query):
+ * pinned H2D of the query, ONE kernel (scan + NVLink exchange + merge), D2H of the merged
+ * hits, stream sync.  *out_complete = 0 means some rank could not prove its shard result
+ * (all ranks see the same flag): run stb_search per shard + stb_hits_merge instead. */
+int stb_search_xchg(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint32_t top_k,
+                    stb_xchg *x, stb_hit *out_hits, uint32_t *out_n, int *out_complete);
+
 /* ---- K4: merge per-shard hit lists -----------------------------------------------
  * The final sort_by + take of src/search/mod.rs:107-119 applied across row
  * shards: `lists_dev` holds n_lists x per_list hits (e.g. the all-gathered

@@ -25,7 +25,7 @@ SYMBOLS = [
     "stb_embed_status", "stb_search",
     "stb_search_topk_dev", "stb_corpus_prepare_batch", "stb_search_batch", "stb_search_batch_dev",
     "stb_xchg_create", "stb_xchg_destroy", "stb_xchg_local_handle",
-    "stb_xchg_connect", "stb_xchg_connect_local", "stb_search_topk_xchg", "stb_ivfpq_build",
+    "stb_xchg_connect", "stb_xchg_connect_local", "stb_search_topk_xchg", "stb_search_xchg", "stb_ivfpq_build",
     "stb_ivfpq_destroy", "stb_ivfpq_stats", "stb_ivfpq_search", "stb_hits_merge_dev", "stb_hits_merge", "stb_fnv1a64", "stb_line_id",
     "stb_ctx_counters", "stb_debug_timestamps", "stb_debug_batch_gemm",
 ]
@@ -91,6 +91,7 @@ def lib() -> C.CDLL:
     L.stb_xchg_connect.argtypes = [vp, vp]
     L.stb_xchg_connect_local.argtypes = [vp, C.POINTER(vp)]
     L.stb_search_topk_xchg.argtypes = [vp, vp, vp, u32, vp, vp, vp]
+    L.stb_search_xchg.argtypes = [vp, vp, vp, u32, vp, vp, C.POINTER(u32), C.POINTER(i32)]
     L.stb_ivfpq_build.argtypes = [vp, vp, u32, u32, u32, C.POINTER(vp)]
     L.stb_ivfpq_destroy.argtypes = [vp]
     L.stb_ivfpq_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)]
@@ -362,6 +363,15 @@ class Exchange:
         """peers[r] = the Exchange of rank r living in this process."""
         arr = (vp * self.world)(*[p._h for p in peers])
         _check(lib().stb_xchg_connect_local(self._h, arr))
+
+    def search(self, corpus: "Corpus", q, top_k: int):
+        """stb_search_xchg: host query in, merged global hits out; returns (hits, complete)."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        out = np.zeros(max(top_k, 1), dtype=HIT_DTYPE)
+        n, ok = u32(0), i32(0)
+        _check(lib().stb_search_xchg(self.ctx._h, corpus._h, _np_ptr(q), top_k, self._h, _np_ptr(out), C.byref(n),
+                                     C.byref(ok)))
+        return out[: n.value], bool(ok.value)
 
     def search_topk(self, corpus: "Corpus", q_dev: int, top_k: int, out_hits_dev: int, out_status_dev: int):
         """stb_search_topk_xchg: one kernel = scan + NVLink exchange + global merge."""

@@ -799,6 +799,25 @@ int stb_debug_batch_gemm(stb_ctx *ctx, const float *q, uint32_t nq, const float 
   return rc;
 }
 
+int stb_search_xchg(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint32_t top_k, stb_xchg *x,
+                    stb_hit *out_hits, uint32_t *out_n, int *out_complete) {
+  int rc = ctx_use(ctx);
+  if (rc) return rc;
+  if (!q || !out_hits || !out_n || !out_complete) { stb_set_error("search_xchg: null argument"); return STB_ERR_ARG; }
+  memcpy(ctx->q_pin, q, STB_D * sizeof(float));
+  STB_CUDA(cudaMemcpyAsync(ctx->q_dev, ctx->q_pin, STB_D * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = stb_search_topk_xchg(ctx, corpus, ctx->q_dev, top_k, x, ctx->hits_dev, ctx->status_dev)) != STB_OK) return rc;
+  STB_CUDA(cudaMemcpyAsync(ctx->status_pin, ctx->status_dev, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  STB_CUDA(cudaMemcpyAsync(ctx->hits_pin, ctx->hits_dev, top_k * sizeof(stb_hit), cudaMemcpyDeviceToHost, ctx->stream));
+  STB_CUDA(cudaStreamSynchronize(ctx->stream));
+  const uint32_t n = std::min<uint32_t>(ctx->status_pin[0], top_k);
+  memcpy(out_hits, ctx->hits_pin, n * sizeof(stb_hit));
+  *out_n = n;
+  *out_complete = ctx->status_pin[1] ? 1 : 0;
+  if (ctx->status_pin[2] == 0xfffffffeu) { stb_set_error("search_xchg: a peer rank never arrived (timeout)"); return STB_ERR_STATE; }
+  return STB_OK;
+}
+
 // ---------------------------------------------------------------------- merge ---
 int stb_hits_merge_dev(stb_ctx *ctx, const stb_hit *lists_dev, uint32_t n_lists, uint32_t per_list,
                        uint32_t top_k, stb_hit *out_dev) {

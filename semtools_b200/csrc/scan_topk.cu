@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(STB_SCAN_THREADS, STB_SCAN_MINB)
 stb_scan_topk_kernel(const TopkArgs args) {
   constexpr int KP = 32 * E;
   __shared__ uint64_t skeys[STB_SORT_CAP];
-  __shared__ unsigned int s_T, s_cnt, s_ticket, s_over;
+  __shared__ unsigned int s_T, s_cnt, s_ticket;
   __shared__ double sqd[STB_D];                  // query in f64 (exact conversion)
   __shared__ __align__(16) float srows[32 * STB_RR_STRIDE];
   __shared__ double s_d[KP], s_r2[KP], s_q2;
@@ -403,7 +403,7 @@ stb_scan_topk_kernel(const TopkArgs args) {
   // best score (that warp alone holds KP keys >= its minimum), so only keys >= T can
   // matter: compact those (typically ~KP..2KP of the 8*KP) and sort the small set.
   const int lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) { s_T = 0u; s_cnt = 0u; s_over = 0u; }
+  if (threadIdx.x == 0) { s_T = 0u; s_cnt = 0u; }
   __syncthreads();
   if (lane == 0) atomicMax(&s_T, stb_f2ord(sink.thr));
   __syncthreads();
@@ -471,8 +471,7 @@ stb_scan_topk_kernel(const TopkArgs args) {
     }
   }
   STB_T_MAX(3);                      // survivor holds the global best KP
-  const bool overflow = (s_over != 0u);
-  STB_T_MAX(4);                      // radix select + final key sort done
+  STB_T_MAX(4);
 
   // ---- exact re-rank of the best KP in canonical arithmetic --------------------------
   // Rows are staged through shared memory (coalesced, one DRAM latency), then one
@@ -488,7 +487,7 @@ stb_scan_topk_kernel(const TopkArgs args) {
     for (int i = 0; i < STB_D; ++i) q2 = fma(sqd[i], sqd[i], q2);
     s_q2 = q2;
   }
-  for (int chunk = 0; chunk < (overflow ? 0 : E); ++chunk) {
+  for (int chunk = 0; chunk < E; ++chunk) {
     {
       constexpr int PER = 32 * STB_ROW_F4 / STB_SCAN_THREADS;   // float4 per thread
       float4 v[PER];
@@ -531,7 +530,7 @@ stb_scan_topk_kernel(const TopkArgs args) {
     }
     __syncthreads();
   }
-  if (threadIdx.x < KP && !overflow) {
+  if (threadIdx.x < KP) {
     const uint64_t key = skeys[threadIdx.x];
     double d = CUDART_INF;
     uint64_t grow = 0xffffffffffffffffull;
@@ -575,10 +574,9 @@ stb_scan_topk_kernel(const TopkArgs args) {
   STB_T_MAX(5);                      // exact re-rank + hit sort done
   const int n_valid = s_nv[0], n_pass = s_nv[1];
   const uint32_t k = args.top_k;
-  const uint32_t n_out = overflow ? 0u : min((uint32_t)n_pass, k);
+  const uint32_t n_out = min((uint32_t)n_pass, k);
   bool complete;
-  if (overflow) complete = false;
-  else if (n_valid < KP) complete = true;   // every scorable row is in the candidate set
+  if (n_valid < KP) complete = true;   // every scorable row is in the candidate set
   else {
     float s_min = stb_key_score(skeys[KP - 1]);
     complete = (n_out == k) && ((1.0 - (double)s_min - STB_SCORE_EPS) > s_d[k - 1]);
@@ -593,7 +591,7 @@ stb_scan_topk_kernel(const TopkArgs args) {
     if (threadIdx.x == 0) {
       args.out_status[0] = n_out;
       args.out_status[1] = complete ? 1u : 0u;
-      args.out_status[2] = overflow ? 0xffffffffu : (uint32_t)n_valid;
+      args.out_status[2] = (uint32_t)n_valid;
       args.out_status[3] = (uint32_t)KP;
     }
     return;

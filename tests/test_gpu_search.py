@@ -380,6 +380,22 @@ def test_fused_peer_memory_exchange_single_gpu(world, k):
                 got = np.ascontiguousarray(raw[r, qi]).view(capi.HIT_DTYPE).reshape(-1)
                 assert st[r, qi, 1] == 1 and st[r, qi, 0] == k, (world, r, qi, st[r, qi])
                 check(got, r_exp, d_exp)
+    # host-buffer form (stb_search_xchg): rank threads would call it concurrently; here rank 0's
+    # call is issued last so its spin finds the peers' flags already set
+    import threading
+    res = [None] * world
+    def run(r):
+        res[r] = xs[r].search(corpora[r], qs[1], k)
+    ths = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join(timeout=60)
+    r_exp, d_exp = oracle.search_rows(rows, qs[1], top_k=k)
+    for r in range(world):
+        hits_r, ok = res[r]
+        assert ok
+        check(hits_r, r_exp, d_exp)
     # a zero query ties every row at distance 1.0: no rank can prove its top-k, and the
     # fused kernel must say so on every rank (status[1] == 0) instead of guessing
     zq = torch.zeros(256, dtype=torch.float32, device=dev)
