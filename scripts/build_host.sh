@@ -1,0 +1,8 @@
+#!/usr/bin/env bash
+# Builds the C++ host CLI (links the C-ABI library; runs only where a B200 is present,
+# `--selftest` checks the pure host functions anywhere).
+set -euo pipefail
+cd "$(dirname "$0")/.."
+/usr/bin/g++ -std=c++17 -O2 -Wall -Wextra -o semtools_b200/lib/semtools_b200_search \
+  semtools_b200/host/semtools_search_main.cpp semtools_b200/host/semtools_host.cpp \
+  -Lsemtools_b200/lib -lsemtools_b200 -Wl,-rpath,'$ORIGIN'

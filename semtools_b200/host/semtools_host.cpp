@@ -1,0 +1,260 @@
+#include "semtools_host.hpp"
+
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <sstream>
+
+namespace semtools {
+
+static void check(int rc) {
+  if (rc < 0) throw StbError(rc, stb_last_error());
+}
+
+std::vector<std::string> rust_lines(const std::string &content) {
+  std::vector<std::string> out;
+  if (content.empty()) return out;
+  size_t pos = 0;
+  while (pos <= content.size()) {
+    size_t nl = content.find('\n', pos);
+    if (nl == std::string::npos) {
+      if (pos < content.size()) out.emplace_back(content.substr(pos));
+      break;
+    }
+    out.emplace_back(content.substr(pos, nl - pos));
+    pos = nl + 1;
+  }
+  for (auto &l : out)
+    if (!l.empty() && l.back() == '\r') l.pop_back();
+  return out;
+}
+
+std::string to_lowercase_ascii(const std::string &s) {
+  std::string r = s;
+  for (auto &c : r)
+    if (c >= 'A' && c <= 'Z') c = (char)(c - 'A' + 'a');
+  return r;
+}
+
+// shortest round-trip decimal digits and exponent: value = 0.d1d2... x 10^exp10
+static void shortest_digits(double x, std::string &digits, int &exp10) {
+  char buf[64];
+  auto r = std::to_chars(buf, buf + sizeof(buf), x, std::chars_format::scientific);
+  std::string s(buf, r.ptr);                       // d.ddddde[+-]XX
+  size_t e = s.find('e');
+  std::string mant = s.substr(0, e);
+  int ex = std::stoi(s.substr(e + 1));
+  digits.clear();
+  for (char c : mant)
+    if (c >= '0' && c <= '9') digits.push_back(c);
+  while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+  exp10 = ex + 1;                                  // digits as 0.DDDD x 10^exp10
+}
+
+static std::string positional(double x, bool keep_point_zero) {
+  if (x == 0.0) return keep_point_zero ? (std::signbit(x) ? "-0.0" : "0.0") : (std::signbit(x) ? "-0" : "0");
+  std::string d;
+  int e;
+  shortest_digits(std::fabs(x), d, e);
+  std::string s;
+  if (e <= 0) s = "0." + std::string((size_t)(-e), '0') + d;
+  else if ((size_t)e >= d.size()) { s = d + std::string((size_t)e - d.size(), '0'); if (keep_point_zero) s += ".0"; }
+  else s = d.substr(0, (size_t)e) + "." + d.substr((size_t)e);
+  return (x < 0 ? "-" : "") + s;
+}
+
+std::string rust_display_f64(double x) {
+  if (std::isnan(x)) return "NaN";
+  if (std::isinf(x)) return x > 0 ? "inf" : "-inf";
+  return positional(x, false);
+}
+
+std::string json_f64(double x) {
+  if (std::isnan(x) || std::isinf(x)) return "null";
+  const double a = std::fabs(x);
+  if (x == 0.0 || (a >= 1e-5 && a < 1e21)) return positional(x, true);
+  std::string d;
+  int e;
+  shortest_digits(a, d, e);
+  std::string m = d.substr(0, 1);
+  if (d.size() > 1) m += "." + d.substr(1);
+  return (x < 0 ? "-" : "") + m + "e" + std::to_string(e - 1);
+}
+
+std::string json_string(const std::string &s) {
+  std::string o = "\"";
+  for (unsigned char c : s) {
+    switch (c) {
+      case '"': o += "\\\""; break;
+      case '\\': o += "\\\\"; break;
+      case '\n': o += "\\n"; break;
+      case '\r': o += "\\r"; break;
+      case '\t': o += "\\t"; break;
+      case 8: o += "\\b"; break;
+      case 12: o += "\\f"; break;
+      default:
+        if (c < 0x20) { char b[8]; snprintf(b, sizeof(b), "\\u%04x", c); o += b; }
+        else o.push_back((char)c);
+    }
+  }
+  return o + "\"";
+}
+
+WordLevelTokenizer::WordLevelTokenizer(const std::string &vocab_path) {
+  std::ifstream f(vocab_path);
+  if (!f) throw std::runtime_error("cannot open vocabulary " + vocab_path);
+  std::string tok;
+  uint32_t id = 0;
+  while (std::getline(f, tok)) vocab.emplace_back(tok, id++);
+  std::sort(vocab.begin(), vocab.end());
+}
+
+std::vector<uint32_t> WordLevelTokenizer::encode(const std::string &text) const {
+  std::vector<uint32_t> ids;
+  std::istringstream ss(text);
+  std::string w;
+  while (ss >> w) {
+    auto it = std::lower_bound(vocab.begin(), vocab.end(), std::make_pair(w, (uint32_t)0));
+    if (it != vocab.end() && it->first == w) ids.push_back(it->second);   // unknown words: dropped (unk removal)
+  }
+  return ids;
+}
+
+Searcher::Searcher(int device) {
+  check(stb_ctx_create(device, nullptr, &ctx_));
+  check(stb_corpus_create(ctx_, STB_DIM, 1024, 0, &corpus_));
+}
+
+Searcher::~Searcher() {
+  stb_corpus_destroy(corpus_);
+  stb_table_destroy(table_);
+  stb_ctx_destroy(ctx_);
+}
+
+void Searcher::load_table(const float *E, uint64_t V, bool normalize) {
+  if (table_) { stb_table_destroy(table_); table_ = nullptr; }
+  check(stb_table_load(ctx_, E, V, STB_DIM, nullptr, 0, nullptr, 0, normalize ? 1 : 0, &table_));
+}
+
+uint64_t Searcher::rows() const {
+  uint64_t n = 0;
+  check(stb_corpus_rows(corpus_, &n));
+  return n;
+}
+
+static void to_csr(const std::vector<std::string> &lines, const Tokenizer &tok, size_t max_len,
+                   std::vector<uint64_t> &offsets, std::vector<uint32_t> &ids) {
+  offsets.assign(1, 0);
+  ids.clear();
+  for (const auto &l : lines) {
+    auto t = tok.encode(l);
+    if (t.size() > max_len) t.resize(max_len);                 // truncate(max_length)
+    ids.insert(ids.end(), t.begin(), t.end());
+    offsets.push_back(ids.size());
+  }
+}
+
+bool Searcher::add_document(const std::string &filename, const std::string &content, const Tokenizer &tok, bool ignore_case) {
+  auto lines = rust_lines(content);
+  if (lines.empty()) return false;                             // mod.rs:57-59
+  if (!table_) throw std::runtime_error("load_table first");
+  std::vector<std::string> emb_lines = lines;
+  if (ignore_case) for (auto &l : emb_lines) l = to_lowercase_ascii(l);
+  std::vector<uint64_t> offsets;
+  std::vector<uint32_t> ids;
+  to_csr(emb_lines, tok, 2048, offsets, ids);                  // encode_with_args(.., Some(2048), 16384), mod.rs:69
+  Document d{filename, std::move(lines), rows()};
+  uint32_t dummy = 0;
+  check(stb_embed(ctx_, table_, offsets.data(), ids.empty() ? &dummy : ids.data(), d.lines.size(), nullptr, corpus_));
+  docs_.push_back(std::move(d));
+  return true;
+}
+
+bool Searcher::add_document_embeddings(const std::string &filename, const std::vector<std::string> &lines, const float *emb) {
+  if (lines.empty()) return false;
+  Document d{filename, lines, rows()};
+  check(stb_corpus_append(corpus_, emb, lines.size()));
+  docs_.push_back(std::move(d));
+  return true;
+}
+
+std::vector<float> Searcher::encode_single(const std::string &query, const Tokenizer &tok) const {
+  if (!table_) throw std::runtime_error("load_table first");
+  std::vector<uint64_t> offsets;
+  std::vector<uint32_t> ids;
+  to_csr({query}, tok, 512, offsets, ids);                     // encode -> max_length 512
+  std::vector<float> out(STB_DIM);
+  uint32_t dummy = 0;
+  check(stb_embed(ctx_, table_, offsets.data(), ids.empty() ? &dummy : ids.data(), 1, out.data(), nullptr));
+  return out;
+}
+
+std::vector<SearchResult> Searcher::search_documents(const std::vector<float> &q, const SearchConfig &cfg) const {
+  if (q.size() != STB_DIM) return {};                          // cosine -> None: every line skipped (mod.rs:87)
+  uint64_t cap = std::max<uint64_t>(cfg.top_k, 1), n = 0;
+  if (cfg.max_distance) cap = std::max<uint64_t>(cap, 4096);
+  std::vector<stb_hit> hits(cap);
+  for (;;) {
+    int rc = stb_search(ctx_, corpus_, q.data(), (uint32_t)cfg.top_k, cfg.max_distance ? 1 : 0,
+                        cfg.max_distance.value_or(0.0), STB_MODE_SEARCH_DOCUMENTS, nullptr, 0, hits.data(), cap, &n);
+    if (rc == STB_ERR_CAPACITY) { cap = n; hits.resize(cap); continue; }
+    check(rc);
+    break;
+  }
+  std::vector<SearchResult> out;
+  for (uint64_t i = 0; i < n; ++i) {
+    // locate (document, line): last document with row_start <= row
+    auto it = std::upper_bound(docs_.begin(), docs_.end(), hits[i].row,
+                               [](uint64_t r, const Document &d) { return r < d.row_start; });
+    const Document &d = *(it - 1);
+    const size_t idx = (size_t)(hits[i].row - d.row_start);
+    const size_t start = idx > cfg.n_lines ? idx - cfg.n_lines : 0;            // mod.rs:90
+    const size_t end = std::min(d.lines.size(), idx + cfg.n_lines + 1);        // mod.rs:91
+    SearchResult r;
+    r.filename = d.filename;
+    r.lines.assign(d.lines.begin() + start, d.lines.begin() + end);
+    r.start = start; r.end = end; r.match_line = idx; r.distance = hits[i].distance;
+    out.push_back(std::move(r));
+  }
+  return out;
+}
+
+std::string format_search_results(const std::vector<SearchResult> &results, bool is_tty) {
+  std::string out;
+  char num[32];
+  for (const auto &r : results) {
+    out += r.filename + ":" + std::to_string(r.start) + "::" + std::to_string(r.end) + " (" + rust_display_f64(r.distance) + ")\n";
+    for (size_t i = 0; i < r.lines.size(); ++i) {
+      const size_t n = r.start + i;
+      snprintf(num, sizeof(num), "%4zu", n + 1);
+      if (n == r.match_line && is_tty) out += std::string("\x1b[43m\x1b[30m") + num + ": " + r.lines[i] + "\x1b[0m\n";
+      else out += std::string(num) + ": " + r.lines[i] + "\n";
+    }
+    out += "\n";
+  }
+  return out;
+}
+
+std::string search_output_json(const std::vector<SearchResult> &results) {
+  if (results.empty()) return "{\n  \"results\": []\n}";
+  std::string o = "{\n  \"results\": [\n";
+  for (size_t i = 0; i < results.size(); ++i) {
+    const auto &r = results[i];
+    std::string content;
+    for (size_t j = 0; j < r.lines.size(); ++j) { if (j) content += "\n"; content += r.lines[j]; }
+    o += "    {\n";
+    o += "      \"filename\": " + json_string(r.filename) + ",\n";
+    o += "      \"start_line_number\": " + std::to_string(r.start) + ",\n";
+    o += "      \"end_line_number\": " + std::to_string(r.end) + ",\n";
+    o += "      \"match_line_number\": " + std::to_string(r.match_line) + ",\n";
+    o += "      \"distance\": " + json_f64(r.distance) + ",\n";
+    o += "      \"content\": " + json_string(content) + "\n";
+    o += i + 1 < results.size() ? "    },\n" : "    }\n";
+  }
+  o += "  ]\n}";
+  return o;
+}
+
+}  // namespace semtools

@@ -1,0 +1,104 @@
+// semtools_b200_search: `semtools search` (reference src/bin/semtools.rs:52-83,
+// src/cmds/search.rs:113-276, non-workspace path) on the C++ host layer.
+//   semtools_b200_search --vocab vocab.txt --table table.f32 QUERY [FILES...]
+//       [-n N|--n-lines N|--context N] [--top-k K] [-m D|--max-distance D|--threshold D]
+//       [-i|--ignore-case] [-j|--json]
+// The model comes as a WordLevel vocabulary (one token per line) + a raw V x 256 f32 table;
+// real model2vec checkpoints are tokenised by the Python host (semtools_b200/model.py).
+// `--selftest` exercises the pure host functions without a GPU.
+#include <unistd.h>
+
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <iterator>
+
+#include "semtools_host.hpp"
+
+using namespace semtools;
+
+static int selftest() {
+  int bad = 0;
+  auto expect = [&](const std::string &got, const std::string &want) {
+    if (got != want) { fprintf(stderr, "selftest: got '%s' want '%s'\n", got.c_str(), want.c_str()); ++bad; }
+  };
+  expect(rust_display_f64(0.0), "0");
+  expect(rust_display_f64(1.0), "1");
+  expect(rust_display_f64(0.25), "0.25");
+  expect(rust_display_f64(0.1 + 0.2), "0.30000000000000004");
+  expect(rust_display_f64(1e-7), "0.0000001");
+  expect(rust_display_f64(1e21), "1000000000000000000000");
+  expect(json_f64(1.0), "1.0");
+  expect(json_f64(0.00001), "0.00001");
+  expect(json_f64(0.000001), "1e-6");
+  expect(json_f64(2.220446049250313e-16), "2.220446049250313e-16");
+  expect(json_string("a\"b\n\t\x01"), "\"a\\\"b\\n\\t\\u0001\"");
+  auto l = rust_lines("a\r\nb\n\nc");
+  if (l.size() != 4 || l[0] != "a" || l[2] != "" || l[3] != "c") { fprintf(stderr, "selftest: rust_lines\n"); ++bad; }
+  if (!rust_lines("").empty() || rust_lines("\n").size() != 1) { fprintf(stderr, "selftest: rust_lines edge\n"); ++bad; }
+  SearchResult r{"f.txt", {"x", "y", "z"}, 4, 7, 5, 0.5};
+  expect(format_search_results({r}, false), "f.txt:4::7 (0.5)\n   5: x\n   6: y\n   7: z\n\n");
+  expect(search_output_json({}), "{\n  \"results\": []\n}");
+  printf(bad ? "selftest FAILED\n" : "selftest ok\n");
+  return bad ? 1 : 0;
+}
+
+int main(int argc, char **argv) {
+  std::string vocab, table, query;
+  std::vector<std::string> files;
+  SearchConfig cfg;
+  bool json = false, have_query = false;
+  for (int i = 1; i < argc; ++i) {
+    std::string a = argv[i];
+    auto next = [&]() -> std::string { if (i + 1 >= argc) { fprintf(stderr, "error: %s needs a value\n", a.c_str()); exit(2); } return argv[++i]; };
+    if (a == "--selftest") return selftest();
+    else if (a == "--vocab") vocab = next();
+    else if (a == "--table") table = next();
+    else if (a == "-n" || a == "--n-lines" || a == "--context") cfg.n_lines = std::stoul(next());
+    else if (a == "--top-k") cfg.top_k = std::stoul(next());
+    else if (a == "-m" || a == "--max-distance" || a == "--threshold") cfg.max_distance = std::stod(next());
+    else if (a == "-i" || a == "--ignore-case") cfg.ignore_case = true;
+    else if (a == "-j" || a == "--json") json = true;
+    else if (!have_query) { query = a; have_query = true; }
+    else files.push_back(a);
+  }
+  if (!have_query || vocab.empty() || table.empty()) {
+    fprintf(stderr, "usage: semtools_b200_search --vocab V --table T QUERY [FILES...] [-n N] [--top-k K] [-m D] [-i] [-j]\n");
+    return 2;
+  }
+  try {
+    if (cfg.ignore_case) query = to_lowercase_ascii(query);
+    const bool stdin_tty = isatty(0);
+    std::vector<std::pair<std::string, std::string>> inputs;      // (filename, content)
+    if (files.empty() && !stdin_tty) {
+      std::string content((std::istreambuf_iterator<char>(std::cin)), std::istreambuf_iterator<char>());
+      if (!content.empty()) inputs.emplace_back("<stdin>", content);
+    }
+    if (files.empty() && inputs.empty()) {
+      const char *msg = "No input provided. Either specify files as arguments or pipe input to stdin.";
+      if (json) fprintf(stderr, "{\n  \"error\": %s,\n  \"error_type\": \"NoInput\"\n}\n", json_string(msg).c_str());
+      else fprintf(stderr, "Error: %s\n", msg);
+      return 1;
+    }
+    for (const auto &f : files) {
+      std::ifstream in(f, std::ios::binary);
+      if (!in) { fprintf(stderr, "Error: %s: No such file or directory (os error 2)\n", f.c_str()); return 1; }
+      inputs.emplace_back(f, std::string((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>()));
+    }
+    WordLevelTokenizer tok(vocab);
+    std::ifstream tf(table, std::ios::binary);
+    std::vector<char> raw((std::istreambuf_iterator<char>(tf)), std::istreambuf_iterator<char>());
+    if (raw.empty() || raw.size() % (STB_DIM * sizeof(float))) { fprintf(stderr, "Error: bad table file\n"); return 1; }
+    Searcher s(0);
+    s.load_table(reinterpret_cast<const float *>(raw.data()), raw.size() / (STB_DIM * sizeof(float)), true);
+    for (const auto &in : inputs) s.add_document(in.first, in.second, tok, cfg.ignore_case);
+    auto results = s.search_documents(s.encode_single(query, tok), cfg);
+    if (json) printf("%s\n", search_output_json(results).c_str());
+    else fputs(format_search_results(results, isatty(1)).c_str(), stdout);
+  } catch (const std::exception &e) {
+    fprintf(stderr, "Error: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}
