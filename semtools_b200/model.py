@@ -106,13 +106,36 @@ class StaticModel:
 
     # -- encode_with_args(&sentences, max_length, batch_size) -> Vec<Vec<f32>> -------------------------
     def encode_with_args(self, sentences, max_length=512, batch_size=1024, append_to: capi.Corpus | None = None):
+        """Batches are tokenised on a producer thread (HF tokenizers releases the GIL and is
+        itself multi-threaded) while the previous batch is pooled on the GPU: host
+        tokenisation, the remaining CPU cost of ingestion, overlaps K3."""
+        import queue
+        import threading
         out = [] if append_to is None else None
-        for b in range(0, len(sentences), batch_size):
-            offsets, ids = self.tokenize(sentences[b:b + batch_size], max_length)
-            res = capi.embed(self.ctx or self.table().ctx, self.table(), offsets, ids, out=append_to is None,
-                             append_to=append_to)
+        table = self.table()
+        starts = list(range(0, len(sentences), batch_size))
+        if not starts:
+            return None if append_to is not None else np.zeros((0, capi.STB_DIM), dtype=np.float32)
+        q: "queue.Queue" = queue.Queue(maxsize=2)
+
+        def producer():
+            try:
+                for b in starts:
+                    q.put(self.tokenize(sentences[b:b + batch_size], max_length))
+            except BaseException as e:          # surface tokenizer failures on the consumer side
+                q.put(e)
+
+        t = threading.Thread(target=producer, daemon=True)
+        t.start()
+        for _ in starts:
+            item = q.get()
+            if isinstance(item, BaseException):
+                raise item
+            offsets, ids = item
+            res = capi.embed(self.ctx, table, offsets, ids, out=append_to is None, append_to=append_to)
             if out is not None:
                 out.append(res)
+        t.join()
         if append_to is not None:
             return None
         return np.concatenate(out) if out else np.zeros((0, capi.STB_DIM), dtype=np.float32)

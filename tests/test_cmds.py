@@ -183,3 +183,20 @@ def test_search_cmd_files_text_and_json(model_dir, tmp_path, ctx, monkeypatch):
     cmds.search_cmd("apple fruit", [], 0, 1, 1.5, False, True, None, model, stdin_lines=flat, stdin_is_tty=False, out=out)
     js = json.loads(out.getvalue())["results"]
     assert all(r["filename"] == "<stdin>" and r["distance"] < 1.5 for r in js) and len(js) > 1
+
+
+@pytest.mark.gpu
+def test_pipelined_ingestion_matches_oracle_and_preserves_order(model_dir, ctx):
+    """encode_with_args tokenises batch i+1 on a producer thread while K3 pools batch i:
+    row order and bits must be those of the sequential oracle path."""
+    d, E, vocab = model_dir
+    model = StaticModel.from_pretrained(d, ctx=ctx)
+    rng = np.random.default_rng(3)
+    lines = [" ".join(rng.choice(WORDS + ["zzz"], rng.integers(0, 12))) for _ in range(5000)]
+    got = model.encode_with_args(lines, 2048, 700)          # 8 batches through the queue
+    off, ids = model.tokenize(lines, 2048)
+    assert np.array_equal(got.view(np.uint32), oracle.embed_csr(E, off, ids).view(np.uint32))
+    from semtools_b200 import capi
+    c = capi.Corpus(ctx, 16)
+    model.encode_with_args(lines, 2048, 512, append_to=c)
+    assert len(c) == 5000 and np.array_equal(c.read().view(np.uint32), got.view(np.uint32))

@@ -294,10 +294,30 @@ def test_error_paths(ctx):
         c.read(1, 5)
 
 
-@pytest.mark.parametrize("n", [1_000_000])
-def test_full_size_properties_1m(ctx, n):
-    """BASELINE configs[1] size: rows generated on the GPU; parity through
-    size-independent properties + an oracle check on a downloaded slice."""
+@pytest.mark.parametrize("n", [1_000_000, 10_000_000])
+def cs_batch(corpus, queries):
+    return corpus.search_batch(queries, top_k=10)
+
+
+def test_nan_and_inf_rows_follow_the_simsimd_rules(ctx):
+    """simsimd's `result > 0 ? result : 0` turns a NaN distance into 0.0 (restated in the
+    oracle), so NaN/inf rows rank FIRST; the scan must force them into the candidate set."""
+    rng = np.random.default_rng(31)
+    rows = unit_rows(rng, 4000)
+    rows[100, 7] = np.nan
+    rows[2000, 0] = np.inf
+    rows[3999, 255] = -np.inf
+    q = unit_rows(rng, 1)[0]
+    c = make_corpus(ctx, rows)
+    for k in (2, 5):
+        r, d = oracle.search_rows(rows, q, top_k=k)
+        check(c.search(q, top_k=k), r, d)
+    assert [int(x) for x in r[:3]] == [100, 2000, 3999]
+
+
+def test_full_size_properties(ctx, n):
+    """BASELINE configs[1] (1M) and the metric's corpus size (10M): rows generated on the
+    GPU; parity through size-independent properties + an oracle check on a downloaded slice."""
     torch = pytest.importorskip("torch")
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev); g.manual_seed(0x5E117002)
@@ -305,7 +325,7 @@ def test_full_size_properties_1m(ctx, n):
     x = x / x.norm(dim=1, keepdim=True)
     q = torch.randn(256, generator=g, device=dev, dtype=torch.float32)
     q = (q / q.norm()).cpu().numpy()
-    planted = [3, 499_999, n - 1]
+    planted = [3, n // 2 - 1, n - 1]
     for j, p in enumerate(planted):                               # plant near-copies of q
         x[p] = torch.from_numpy(q).to(dev) + 0.02 * (j + 1) * x[p]
     x[12345] = x[planted[0]]                                     # exact duplicate -> tie by row
@@ -313,7 +333,7 @@ def test_full_size_properties_1m(ctx, n):
     c = capi.Corpus(ctx, n)
     c.append_dev(x.data_ptr(), n)
     hits = c.search(q, top_k=10)
-    assert hits["row"][:4].tolist() == [3, 12345, 499_999, n - 1]
+    assert hits["row"][:4].tolist() == [3, 12345, n // 2 - 1, n - 1]
     assert np.all(np.diff(hits["distance"]) >= 0)
     # every reported distance is the canonical one
     rows_h = x[torch.from_numpy(hits["row"].astype(np.int64)).to(dev)].cpu().numpy()
@@ -329,8 +349,12 @@ def test_full_size_properties_1m(ctx, n):
         lists.append(cs.search(q, top_k=10))
         cs.close()
     assert np.array_equal(ctx.hits_merge(np.stack(lists), 10), hits)
-    # oracle on a 200k-row window containing two planted rows
-    lo, hi = 400_000, 600_000
+    # the batched tensor-core path (K2) must return the same hits as the single-query path
+    qs = np.stack([q, q * np.float32(2.0)])      # x2 is exact in binary fp: identical canonical distances
+    for got_b in cs_batch(c, qs):
+        assert np.array_equal(got_b, hits)
+    # oracle on a 200k-row window containing a planted row
+    lo, hi = n // 2 - 100_000, n // 2 + 100_000
     win = x[lo:hi].cpu().numpy()
     r, d = oracle.search_rows(win, q, top_k=5)
     cw = capi.Corpus(ctx, hi - lo, row_base=lo)
