@@ -294,7 +294,6 @@ def test_error_paths(ctx):
         c.read(1, 5)
 
 
-@pytest.mark.parametrize("n", [1_000_000, 10_000_000])
 def cs_batch(corpus, queries):
     return corpus.search_batch(queries, top_k=10)
 
@@ -315,6 +314,7 @@ def test_nan_and_inf_rows_follow_the_simsimd_rules(ctx):
     assert [int(x) for x in r[:3]] == [100, 2000, 3999]
 
 
+@pytest.mark.parametrize("n", [1_000_000, 10_000_000])
 def test_full_size_properties(ctx, n):
     """BASELINE configs[1] (1M) and the metric's corpus size (10M): rows generated on the
     GPU; parity through size-independent properties + an oracle check on a downloaded slice."""
