@@ -105,6 +105,8 @@ int stb_ctx_create(int device, void *cuda_stream, stb_ctx **out) {
     if ((rc = dev_reserve(&c->err_flag, &one, 1)) != STB_OK) goto fail;
     one = 0;
     if ((rc = dev_reserve(&c->dbg_dev, &one, 8)) != STB_OK) goto fail;
+    one = 0;
+    if ((rc = dev_reserve(&c->hist_dev, &one, 4096)) != STB_OK) goto fail;
   }
   if ((rc = dev_reserve(&c->hits_dev, &c->hits_cap, 1024)) != STB_OK) goto fail;
   if (cudaMemset(c->counters, 0, c->counters_cap * sizeof(unsigned int)) != cudaSuccess ||
@@ -133,7 +135,7 @@ int stb_ctx_destroy(stb_ctx *c) {
   cudaFree(c->block_keys); cudaFree(c->counters); cudaFree(c->q_dev); cudaFree(c->hits_dev);
   cudaFree(c->status_dev); cudaFree(c->collect_rows); cudaFree(c->collect_count);
   cudaFree(c->collect_hits); cudaFree(c->ranges_dev); cudaFree(c->err_flag);
-  cudaFree(c->dbg_dev); cudaFree(c->bq_tiles); cudaFree(c->b_submax); cudaFree(c->b_tilemax); cudaFree(c->b_cand);
+  cudaFree(c->dbg_dev); cudaFree(c->hist_dev); cudaFree(c->bq_tiles); cudaFree(c->b_submax); cudaFree(c->b_tilemax); cudaFree(c->b_cand);
   cudaFree(c->bq_dev); cudaFree(c->bh_dev); cudaFree(c->bs_dev); cudaFree(c->embed_off_dev); cudaFree(c->embed_ids_dev); cudaFree(c->embed_out_dev);
   if (c->q_pin) cudaFreeHost(c->q_pin);
   if (c->hits_pin) cudaFreeHost(c->hits_pin);
@@ -512,9 +514,21 @@ int stb_search(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint32_t 
       limit = max_distance;
       floor_cos = (float)(1.0 - max_distance - STB_SCORE_EPS);
       if (!(max_distance == max_distance)) floor_cos = INFINITY;   // NaN threshold: nothing passes
-    } else if (has_max) {
-      limit = std::min(max_distance, 100.0);
-      if (!(max_distance == max_distance)) limit = -1.0;
+    } else {
+      if (has_max) {
+        limit = std::min(max_distance, 100.0);
+        if (!(max_distance == max_distance)) limit = -1.0;
+      }
+      // top_k beyond the register lists: histogram pass to find the score bin of the k-th
+      // best, then collect only rows at or above that bin (instead of the whole shard)
+      if ((rc = stb_launch_scan_hist(ctx, corpus->rows, ctx->q_dev, ranges_dev, n_loc, n_virtual, ctx->hist_dev)) != STB_OK) return rc;
+      std::vector<unsigned int> hist(4096);
+      STB_CUDA(cudaMemcpyAsync(hist.data(), ctx->hist_dev, 4096 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+      STB_CUDA(cudaStreamSynchronize(ctx->stream));
+      uint64_t cum = 0;
+      int b = 0;
+      for (; b < 4096; ++b) { cum += hist[b]; if (cum >= top_k) break; }
+      if (b < 4095) floor_cos = (float)(1.0 - (double)(b + 1) / 2048.0 - 2.0 * STB_SCORE_EPS);   // else: fewer than k rows, take all
     }
     uint64_t n_pass = 0;
     if ((rc = collect_exact_sorted(ctx, corpus, floor_cos, limit, ranges_dev, n_loc, n_virtual, &n_pass)) != STB_OK) return rc;

@@ -60,6 +60,7 @@ struct stb_ctx {
   uint64_t *ranges_dev;     // [3 * n] : begin(local), end(local), vstart
   size_t ranges_cap;
   int *err_flag;            // device int for K3 range errors
+  unsigned int *hist_dev;       // 4096-bin score histogram (large-k path)
   unsigned long long *dbg_dev;  // 8 u64 phase timestamps (STB_TAIL_TIMING builds; else unused)
   // --- K2 scratch ---
   uint8_t *bq_tiles; size_t bq_tiles_cap;     // query shadow tiles
@@ -145,6 +146,10 @@ int stb_launch_scan_collect(stb_ctx *ctx, const float *rows, uint64_t n_rows,
                             const float *q_dev, float cos_floor,
                             const uint64_t *ranges_dev, uint32_t n_ranges,
                             uint64_t n_virtual);
+// Large-k support: 4096-bin histogram of the approximate cosine over the scanned rows
+// (bin b: cos in (1-(b+1)/2048, 1-b/2048]).  hist_dev: 4096 u32 on device.
+int stb_launch_scan_hist(stb_ctx *ctx, const float *rows, const float *q_dev, const uint64_t *ranges_dev,
+                         uint32_t n_ranges, uint64_t n_virtual, unsigned int *hist_dev);
 // Exact canonical distances of m collected rows -> hits (invalid/failing rows get
 // distance=+inf,row=UINT64_MAX); counts passing rows into pass_count.
 int stb_launch_exact(stb_ctx *ctx, const float *rows, uint64_t row_base,

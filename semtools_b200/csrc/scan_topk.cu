@@ -817,6 +817,60 @@ int stb_launch_scan_collect(stb_ctx *ctx, const float *rows, uint64_t n_rows,
   return STB_OK;
 }
 
+// ------------------------------------------------------------ histogram pass (large k) ---
+// For top_k beyond the register lists: one scan builds a 4096-bin histogram of the
+// approximate cosine (bin b covers cos in (1-(b+1)/2048, 1-b/2048]; forced candidates fall
+// in bin 0), the host picks the bin that contains the k-th best, and the collect pass
+// gathers everything at or above that bin's lower edge (minus the score error bound).
+#define STB_HIST_BINS 4096
+struct HistSink {
+  unsigned int *hist;   // shared-memory histogram of this CTA
+  template <int ROWS>
+  __device__ __forceinline__ void consume(float s, uint32_t) {
+    if (s > -CUDART_INF_F) {
+      float b = floorf((1.0f - s) * (STB_HIST_BINS / 2.0f));
+      int bin = b < 0.f ? 0 : (b > (float)(STB_HIST_BINS - 1) ? STB_HIST_BINS - 1 : (int)b);   // +inf -> 0, NaN cannot occur
+      atomicAdd(hist + bin, 1u);
+    }
+  }
+};
+
+template <int U, bool RANGES>
+__global__ void __launch_bounds__(STB_SCAN_THREADS, STB_SCAN_MINB)
+stb_scan_hist_kernel(const ScanArgs scan, unsigned int *global_hist) {
+  __shared__ unsigned int s_hist[STB_HIST_BINS];
+  for (int i = threadIdx.x; i < STB_HIST_BINS; i += blockDim.x) s_hist[i] = 0u;
+  __syncthreads();
+  HistSink sink{s_hist};
+  stb_scan_rows<U, RANGES>(scan, sink);
+  __syncthreads();
+  for (int i = threadIdx.x; i < STB_HIST_BINS; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(global_hist + i, s_hist[i]);
+}
+
+int stb_launch_scan_hist(stb_ctx *ctx, const float *rows, const float *q_dev, const uint64_t *ranges_dev,
+                         uint32_t n_ranges, uint64_t n_virtual, unsigned int *hist_dev) {
+  ScanArgs a;
+  a.rows = reinterpret_cast<const float4 *>(rows);
+  a.n_virtual = n_virtual;
+  a.q = q_dev;
+  a.vstart = ranges_dev;
+  a.rbegin = ranges_dev ? ranges_dev + (n_ranges + 1) : nullptr;
+  a.n_ranges = n_ranges;
+  STB_CUDA(cudaMemsetAsync(hist_dev, 0, STB_HIST_BINS * sizeof(unsigned int), ctx->stream));
+  uint64_t tiles = (n_virtual + 4 * STB_SCAN_U - 1) / (4 * STB_SCAN_U);
+  uint64_t want = (tiles + STB_SCAN_WARPS - 1) / STB_SCAN_WARPS;
+  uint64_t grid = (uint64_t)ctx->sm_count * STB_SCAN_MINB;
+  if (want < grid) grid = want < 1 ? 1 : want;
+  if (n_ranges > 0)
+    stb_scan_hist_kernel<STB_SCAN_U, true><<<(unsigned)grid, STB_SCAN_THREADS, 0, ctx->stream>>>(a, hist_dev);
+  else
+    stb_scan_hist_kernel<STB_SCAN_U, false><<<(unsigned)grid, STB_SCAN_THREADS, 0, ctx->stream>>>(a, hist_dev);
+  STB_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  return STB_OK;
+}
+
 // Exact canonical distance of each collected row; one thread per row.
 __global__ void stb_exact_kernel(const float4 *rows, uint64_t row_base, const float *q,
                                  const uint32_t *row_ids, uint64_t m, double limit,

@@ -435,3 +435,22 @@ def test_fused_peer_memory_exchange_single_gpu(world, k):
         c.close()
     for c in ctxs:
         c.close()
+
+
+@pytest.mark.parametrize("n,k", [(200_000, 1000), (50_000, 97), (30_000, 30_000)])
+def test_large_k_histogram_path(ctx, n, k):
+    """top_k beyond the register lists: histogram pass + collect pass, still bit-identical;
+    duplicates, zero rows and forced candidates included."""
+    rng = np.random.default_rng(n + k)
+    rows = unit_rows(rng, n)
+    rows[rng.integers(0, n, 50)] = rows[rng.integers(0, n, 50)]
+    rows[[1, n // 3]] = 0.0
+    rows[7] *= np.float32(1e-25)
+    q = unit_rows(rng, 1)[0]
+    c = make_corpus(ctx, rows)
+    r, d = oracle.search_rows(rows, q, top_k=k)
+    check(c.search(q, top_k=k), r, d)
+    ranges = [[10, n // 2], [n // 2 + 5, n - 3]]
+    r2, d2 = oracle.store_search(rows, ranges, q, k)
+    got = c.search(q, top_k=k, mode=capi.STB_MODE_STORE_QUERY, row_ranges=ranges)
+    assert got["row"].tolist() == [int(x) for x in r2]
