@@ -272,7 +272,7 @@ int stb_ctx_counters(const stb_ctx *ctx, uint64_t *kernel_launches,
 int stb_debug_timestamps(stb_ctx *ctx, int reset, uint64_t out[8]);
 /* Test hook for K2: shadow build + tcgen05 GEMM on host inputs; out_full receives the
  * approximate cosine matrix [ceil(nq/128)*128][ceil(n/256)*256] (f32), out_submax (may be
- * NULL) the per-32-row maxima [ceil(n/256)*8][ceil(nq/128)*128]. */
+ * NULL) the per-32-row maxima [ceil(nq/128)][ceil(n/256)*8][128]. */
 int stb_debug_batch_gemm(stb_ctx *ctx, const float *q, uint32_t nq, const float *rows,
                          uint64_t n, float *out_full, float *out_submax);
 

@@ -717,8 +717,10 @@ int stb_search_batch_dev(stb_ctx *ctx, const stb_corpus *corpus_c, const float *
   if ((rc = corpus_ensure_shadow(ctx, corpus)) != STB_OK) return rc;
   const uint32_t m_tiles = (nq + 127) / 128, q_pad = m_tiles * 128;
   const uint32_t n_tiles = (uint32_t)((corpus->n + 255) / 256), n_sub = n_tiles * 8;
-  uint32_t n_slices = std::max<uint32_t>(1, std::min<uint32_t>(32, 2048 / (q_pad / 32)));
-  n_slices = std::min<uint32_t>(n_slices, std::max<uint32_t>(1, n_tiles / 64));
+  // selection slices: enough CTAs (m_tiles x n_slices) to hide the latency of the streaming
+  // read; the finish kernel merges n_slices x 32 <= 4096 candidate tiles per query
+  uint32_t n_slices = std::max<uint32_t>(1, std::min<uint32_t>(128, 1536 / m_tiles));
+  n_slices = std::min<uint32_t>(n_slices, std::max<uint32_t>(1, n_tiles / 48));
   if ((rc = dev_reserve(&ctx->bq_tiles, &ctx->bq_tiles_cap, (size_t)q_pad * 512)) != STB_OK) return rc;
   if ((rc = dev_reserve(&ctx->b_submax, &ctx->b_submax_cap, (size_t)n_sub * q_pad)) != STB_OK) return rc;
   if ((rc = dev_reserve(&ctx->b_tilemax, &ctx->b_tilemax_cap, (size_t)n_tiles * q_pad)) != STB_OK) return rc;

@@ -179,8 +179,10 @@ struct GemmArgs {
   const uint8_t *b_tiles;     // corpus shadow: n_tiles x (4 slabs x 32 KiB)
   uint32_t m_tiles;           // ceil(Q / 128)
   uint32_t n_tiles;           // ceil(N / 256)
-  float *submax;              // [n_tiles * 8][m_tiles * 128]  per-32-row maxima
-  float *tilemax;             // [n_tiles][m_tiles * 128]      per-256-row maxima
+  // maxima are stored [query tile][sub-tile or tile][128 queries]: the epilogue writes 512 B
+  // contiguous per (query tile, tile) and the selection pass streams contiguously
+  float *submax;              // [m_tiles][n_tiles * 8][128]  per-32-row maxima
+  float *tilemax;             // [m_tiles][n_tiles][128]      per-256-row maxima
   float *full_out;            // debug: full score matrix [m_tiles*128][n_tiles*256] or null
 };
 
@@ -278,7 +280,7 @@ stb_batch_gemm_kernel(const GemmArgs args) {
   } else if (warp >= 4) {
     // ===== epilogue: thread = TMEM lane = query; max over each 32-row sub-tile =====
     const uint32_t quarter = warp & 3;
-    const uint32_t q_pad = args.m_tiles * STB_A_TILE;
+    const uint64_t n_sub = (uint64_t)args.n_tiles * (STB_B_TILE / STB_SUB);
     uint32_t d_cnt = 0;
     for (uint32_t it = 0; it < my_tiles; ++it) {
       const uint64_t t = blockIdx.x + (uint64_t)it * gridDim.x;
@@ -296,7 +298,7 @@ stb_batch_gemm_kernel(const GemmArgs args) {
           float mx = __uint_as_float(r[0]);
 #pragma unroll
           for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-          args.submax[(t * (STB_B_TILE / STB_SUB) + c) * (size_t)q_pad + q] = mx;
+          args.submax[((size_t)m * n_sub + t * (STB_B_TILE / STB_SUB) + c) * STB_A_TILE + quarter * 32 + lane] = mx;
           tmx = fmaxf(tmx, mx);
           if (args.full_out) {
             float *o = args.full_out + (size_t)q * ((size_t)args.n_tiles * STB_B_TILE) + t * STB_B_TILE + c * STB_SUB;
@@ -304,7 +306,7 @@ stb_batch_gemm_kernel(const GemmArgs args) {
             for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(r[i]);
           }
         }
-        args.tilemax[t * (size_t)q_pad + q] = tmx;
+        args.tilemax[((size_t)m * args.n_tiles + t) * STB_A_TILE + quarter * 32 + lane] = tmx;
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(d_empty + acc);
@@ -354,11 +356,11 @@ int stb_launch_batch_gemm(stb_ctx *ctx, const uint8_t *a_tiles, uint32_t m_tiles
 
 
 // ------------------------------------------------------------- 3. sub-tile selection ---
-// grid (q_pad/32, n_slices/4), 128 threads: a warp = 32 consecutive queries x one slice of
+// grid (m_tiles, n_slices), 128 threads = the 128 queries of one query tile x one slice of
 // sub-tiles; lane keeps the KSEL best (value, sub-tile) of its query in shared memory
 // ([entry][lane] layout: conflict-free) with the running minimum in registers.
 struct SelectArgs {
-  const float *submax;      // [n_sub][q_pad]
+  const float *submax;      // [m_tiles][n_sub][128]  (tile maxima when called on tilemax)
   uint32_t n_sub, q_pad, n_slices;
   uint64_t *cand;           // [q_pad][n_slices][KSEL] keys: (~ord(value) << 32) | sub-tile
 };
@@ -368,16 +370,15 @@ stb_batch_select_kernel(const SelectArgs a) {
   __shared__ float s_val[4][STB_BATCH_KSEL * 32];
   __shared__ uint32_t s_idx[4][STB_BATCH_KSEL * 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t slice = blockIdx.y * 4 + warp;
-  if (slice >= a.n_slices) return;
-  const uint32_t q = blockIdx.x * 32 + lane;
+  const uint32_t slice = blockIdx.y;
+  const uint32_t q = blockIdx.x * 128 + threadIdx.x;
   const uint32_t per = (a.n_sub + a.n_slices - 1) / a.n_slices;
   const uint32_t s0 = slice * per, s1 = min(a.n_sub, s0 + per);
   float *val = s_val[warp];
   uint32_t *idx = s_idx[warp];
   int cnt = 0, minpos = 0;
   float thr = -CUDART_INF_F;
-  const float *p = a.submax + q;
+  const float *p = a.submax + (size_t)blockIdx.x * a.n_sub * 128 + threadIdx.x;   // CTA reads 512 B rows
   // 16 independent coalesced loads in flight per lane before the (rare) list updates
   // (measured: 64 is slower -- 151 registers, longer serial tail per batch)
   constexpr int UNR = 16;
@@ -385,7 +386,7 @@ stb_batch_select_kernel(const SelectArgs a) {
     float vbuf[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; ++u)
-      vbuf[u] = (st0 + u < s1) ? __ldcs(p + (size_t)(st0 + u) * a.q_pad) : -CUDART_INF_F;
+      vbuf[u] = (st0 + u < s1) ? __ldcs(p + (size_t)(st0 + u) * 128) : -CUDART_INF_F;
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const float v = vbuf[u];
@@ -412,7 +413,7 @@ stb_batch_select_kernel(const SelectArgs a) {
 // ------------------------------------------------------------------ 4. exact finish ---
 struct FinishArgs {
   const uint64_t *cand;     // [q_pad][n_slices][KSEL]  keys over TILES (value = tile maximum)
-  const float *submax;      // [n_tiles * 8][q_pad]
+  const float *submax;      // [m_tiles][n_tiles * 8][128]
   uint32_t q_pad;
   uint32_t n_slices, n_sub, nq, top_k;
   const float4 *rows;       // corpus f32 rows (local)
@@ -422,27 +423,34 @@ struct FinishArgs {
   uint32_t *out_status;     // [nq][2]: hits, complete
 };
 
+#define STB_FINISH_KEYS 4096     // candidate tile keys one query can bring (128 slices x 32)
+
 __global__ void __launch_bounds__(256, 3)
 stb_batch_finish_kernel(const FinishArgs a) {
-  __shared__ uint64_t skeys[1024];
-  __shared__ double sd[1024];
-  __shared__ uint64_t sr[1024];
+  // one 32 KB buffer, reused: [0,4096) tile keys -> [0,256) sub-tile keys, then
+  // sd = buf[1024..2048) as doubles and sr = buf[2048..3072) for the (distance,row) pairs
+  __shared__ uint64_t buf[STB_FINISH_KEYS];
+  uint64_t *skeys = buf;
+  double *sd = reinterpret_cast<double *>(buf + 1024);
+  uint64_t *sr = buf + 2048;
   __shared__ double sqd[STB_D];
   __shared__ double s_q2;
   __shared__ int s_pass, s_alltiles;
   const uint32_t q = blockIdx.x;
   const int tid = threadIdx.x;
-  // 1. merge the per-slice candidate sub-tiles, keep the KSEL best
-  const uint32_t n_in = a.n_slices * STB_BATCH_KSEL;     // <= 1024
+  // 1. merge the per-slice candidate tiles, keep the KSEL best
+  const uint32_t n_in = a.n_slices * STB_BATCH_KSEL;     // <= STB_FINISH_KEYS
+  int n_sort = 64;
+  while ((uint32_t)n_sort < n_in) n_sort <<= 1;
   const uint64_t *src = a.cand + (size_t)q * n_in;
-  for (int i = tid; i < 1024; i += 256) skeys[i] = ((uint32_t)i < n_in) ? src[i] : STB_KEY_INVALID;
+  for (int i = tid; i < n_sort; i += 256) skeys[i] = ((uint32_t)i < n_in) ? src[i] : STB_KEY_INVALID;
   for (int i = tid; i < STB_D; i += 256) sqd[i] = (double)__ldg(a.queries + (size_t)q * STB_D + i);
   if (tid == 0) s_pass = 0;
   __syncthreads();
-  // in-place ascending sort of 1024 keys (best first)
-  for (int kk = 2; kk <= 1024; kk <<= 1)
+  // in-place ascending sort (best first)
+  for (int kk = 2; kk <= n_sort; kk <<= 1)
     for (int j = kk >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < 1024; i += 256) {
+      for (int i = tid; i < n_sort; i += 256) {
         int ixj = i ^ j;
         if (ixj > i) {
           uint64_t x = skeys[i], y = skeys[ixj];
@@ -462,10 +470,10 @@ stb_batch_finish_kernel(const FinishArgs a) {
     const uint64_t tkey = skeys[tid >> 3];                 // tid < 256 -> tile slot tid/8, sub-tile tid%8
     if (tkey != STB_KEY_INVALID) {
       const uint32_t st = stb_key_row(tkey) * (STB_B_TILE / STB_SUB) + (tid & 7);
-      if (st < a.n_sub) mykey = stb_make_key(__ldg(a.submax + (size_t)st * a.q_pad + q), st);
+      if (st < a.n_sub) mykey = stb_make_key(__ldg(a.submax + ((size_t)(q >> 7) * a.n_sub + st) * 128 + (q & 127)), st);
     }
     __syncthreads();
-    for (int i = tid; i < 1024; i += 256) skeys[i] = (i < 256) ? mykey : STB_KEY_INVALID;
+    skeys[tid] = mykey;                                   // 256 threads -> 256 sub-tile keys
     __syncthreads();
     for (int kk = 2; kk <= 256; kk <<= 1)
       for (int j = kk >> 1; j > 0; j >>= 1) {
@@ -564,7 +572,7 @@ int stb_launch_batch_select(stb_ctx *ctx, const float *submax, uint32_t n_sub, u
                             uint32_t n_slices, uint64_t *cand) {
   SelectArgs a;
   a.submax = submax; a.n_sub = n_sub; a.q_pad = q_pad; a.n_slices = n_slices; a.cand = cand;
-  dim3 grid(q_pad / 32, (n_slices + 3) / 4);
+  dim3 grid(q_pad / 128, n_slices);
   stb_batch_select_kernel<<<grid, 128, 0, ctx->stream>>>(a);
   STB_CUDA(cudaGetLastError());
   ctx->kernel_launches++;

@@ -25,7 +25,7 @@ def test_tcgen05_gemm_matches_bf16_reference(ctx, nq, n):
     q = unit_rows(rng, nq)
     mt, nt = (nq + 127) // 128, (n + 255) // 256
     full = np.zeros((mt * 128, nt * 256), dtype=np.float32)
-    sub = np.zeros((nt * 8, mt * 128), dtype=np.float32)
+    sub = np.zeros((mt, nt * 8, 128), dtype=np.float32)
     vp = C.c_void_p
     capi._check(capi.lib().stb_debug_batch_gemm(ctx._h, q.ctypes.data_as(vp), nq, rows.ctypes.data_as(vp), n,
                                                 full.ctypes.data_as(vp), sub.ctypes.data_as(vp)))
@@ -41,7 +41,7 @@ def test_tcgen05_gemm_matches_bf16_reference(ctx, nq, n):
     assert np.max(np.abs(got[: exact.shape[0]] - exact)) < 0.0045
     # padding rows / queries are zeros; sub-tile maxima agree with the full matrix
     assert np.all(full[:, n:] == 0.0)
-    exp_sub = full.reshape(mt * 128, nt * 8, 32).max(axis=2).T
+    exp_sub = full.reshape(mt, 128, nt * 8, 32).max(axis=3).transpose(0, 2, 1)
     assert np.array_equal(sub, exp_sub)
 
 
