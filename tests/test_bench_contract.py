@@ -1,0 +1,41 @@
+"""bench.py contract checks that do not need a GPU: the reference arm runs on CPU and
+prints the agreed JSON line; the argument surface and synthetic generators are stable."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_contract_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1", "--cpu-sample-rows", "20000", "--rows", "100000"],
+                       capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert r.returncode == 0, r.stderr
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["unit"] == "queries/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("queries/sec over 10M-line corpus")
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
+    assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["value"] > 0 and d["config"]["rows"] == 100000
+
+
+def test_reference_arm_non_zero_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                       capture_output=True, text=True, cwd=ROOT, env=env, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_synthetic_generators_are_deterministic():
+    sys.path.insert(0, ROOT)
+    import bench
+    a, b = bench.gen_chunk_numpy(3, 5000), bench.gen_chunk_numpy(3, 5000)
+    assert np.array_equal(a, b) and a.shape == (5000, 256) and a.dtype == np.float32
+    norms = np.linalg.norm(a, axis=1)
+    assert (norms == 0).sum() >= 1 and np.allclose(norms[norms > 0], 1.0, atol=1e-5)     # zero rows injected
+    q = bench.gen_queries(8)
+    assert np.array_equal(q, bench.gen_queries(8)) and np.allclose(np.linalg.norm(q, axis=1), 1.0, atol=1e-5)
