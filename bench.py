@@ -449,6 +449,8 @@ def run_ours(args):
     def e2e_step(i):
         if world == 1:
             return corpus.search(queries_h[i % n_q], top_k=k)        # the C-ABI call a host makes
+        if xchg is not None and os.environ.get("STB_E2E_C"):
+            return xchg.search(corpus, queries_h[i % n_q], k)[0]     # stb_search_xchg (slower, under study)
         q_dev[i % n_q].copy_(q_pin[i % n_q], non_blocking=True)
         step(i % n_slots)
         out_pin.copy_(final_hits[i % n_slots], non_blocking=True)

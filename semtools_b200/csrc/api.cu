@@ -3,6 +3,9 @@
 // fallback ladder around the scan kernel.  No CPU implementation of any kernel
 // exists in this library: without an sm_100 device every entry point fails.
 #include <stdarg.h>
+#include <stdlib.h>
+
+#include <chrono>
 
 #include <algorithm>
 #include <mutex>
@@ -820,12 +823,22 @@ int stb_search_xchg(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint
   int rc = ctx_use(ctx);
   if (rc) return rc;
   if (!q || !out_hits || !out_n || !out_complete) { stb_set_error("search_xchg: null argument"); return STB_ERR_ARG; }
+  static const bool prof = getenv("STB_XCHG_PROFILE") != nullptr;
+  static double t_enq = 0, t_sync = 0; static long n_calls = 0;
+  auto t0 = std::chrono::steady_clock::now();
   memcpy(ctx->q_pin, q, STB_D * sizeof(float));
   STB_CUDA(cudaMemcpyAsync(ctx->q_dev, ctx->q_pin, STB_D * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   if ((rc = stb_search_topk_xchg(ctx, corpus, ctx->q_dev, top_k, x, ctx->hits_dev, ctx->status_dev)) != STB_OK) return rc;
   STB_CUDA(cudaMemcpyAsync(ctx->status_pin, ctx->status_dev, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   STB_CUDA(cudaMemcpyAsync(ctx->hits_pin, ctx->hits_dev, top_k * sizeof(stb_hit), cudaMemcpyDeviceToHost, ctx->stream));
+  auto t1 = std::chrono::steady_clock::now();
   STB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (prof) {
+    auto t2 = std::chrono::steady_clock::now();
+    t_enq += std::chrono::duration<double, std::micro>(t1 - t0).count();
+    t_sync += std::chrono::duration<double, std::micro>(t2 - t1).count();
+    if (++n_calls % 50 == 0) fprintf(stderr, "[stb_search_xchg rank %u] calls %ld  enqueue %.1f us  sync %.1f us (avg)\n", x->rank, n_calls, t_enq / n_calls, t_sync / n_calls);
+  }
   const uint32_t n = std::min<uint32_t>(ctx->status_pin[0], top_k);
   memcpy(out_hits, ctx->hits_pin, n * sizeof(stb_hit));
   *out_n = n;
