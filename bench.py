@@ -449,8 +449,8 @@ def run_ours(args):
     def e2e_step(i):
         if world == 1:
             return corpus.search(queries_h[i % n_q], top_k=k)        # the C-ABI call a host makes
-        if xchg is not None and os.environ.get("STB_E2E_C"):
-            return xchg.search(corpus, queries_h[i % n_q], k)[0]     # stb_search_xchg (slower, under study)
+        if xchg is not None:
+            return xchg.search(corpus, queries_h[i % n_q], k)[0]     # stb_search_xchg: the same call, sharded
         q_dev[i % n_q].copy_(q_pin[i % n_q], non_blocking=True)
         step(i % n_slots)
         out_pin.copy_(final_hits[i % n_slots], non_blocking=True)
@@ -533,8 +533,8 @@ def run_ours(args):
             "e2e": {"value": e2e_steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": 1024,
                     "d2h_bytes_per_step": 16 * k + 16, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
                     "timing": "wall clock around synchronous per-query host calls: pinned H2D of the query, kernel(s), "
-                              "D2H of the hits, stream sync (N=1: stb_search; N>1: pinned copy + stb_search_topk_xchg "
-                              "or NCCL path + pinned copy back, every rank)"},
+                              "D2H of the hits, stream sync (N=1: stb_search; N>1: stb_search_xchg on every rank, or the "
+                              "NCCL sequence with pinned copies when --exchange nccl)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "stb_scan_topk_kernel<E=1,U=2>", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
