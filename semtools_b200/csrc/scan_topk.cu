@@ -382,6 +382,7 @@ stb_scan_topk_kernel(const TopkArgs args) {
   constexpr int KP = 32 * E;
   __shared__ uint64_t skeys[STB_SORT_CAP];
   __shared__ unsigned int s_T, s_cnt, s_ticket;
+  __shared__ unsigned long long s_T64;
   __shared__ double sqd[STB_D];                  // query in f64 (exact conversion)
   __shared__ __align__(16) float srows[32 * STB_RR_STRIDE];
   __shared__ double s_d[KP], s_r2[KP], s_q2;
@@ -451,19 +452,37 @@ stb_scan_topk_kernel(const TopkArgs args) {
       __threadfence();
       if (threadIdx.x == 0) args.counters[lvl_cnt_off + group] = 0u;   // re-arm for the next launch
       {
+        // Pre-filter before sorting: every list is sorted best-first, so with
+        // r = ceil(KP / n_in) - 1 the worst of the lists' r-th keys is a lower bound of the
+        // group's KP-th best (n_in * (r+1) >= KP keys are at least that good).  Only keys at
+        // or above it can survive the merge -- typically ~100 of the 1024 -- and the sort
+        // shrinks from the 1024-key to the 256-key network.
         constexpr int PER = STB_SORT_CAP / STB_SCAN_THREADS;
         uint64_t v[PER];
+        const uint32_t r = (KP + n_in - 1) / n_in - 1;
+        if (threadIdx.x == 0) { s_T64 = 0ull; s_cnt = 0u; }
+        __syncthreads();
 #pragma unroll
         for (int u = 0; u < PER; ++u) {
           const int i = threadIdx.x + u * STB_SCAN_THREADS;
           const uint32_t li = i / KP;
           v[u] = (li < n_in) ? __ldcg(lvl + (size_t)(first + li) * KP + (i % KP)) : STB_KEY_INVALID;
+          if (li < n_in && (uint32_t)(i % KP) == r) atomicMax(&s_T64, v[u]);   // INVALID (all ones) disables the filter
         }
+        __syncthreads();
+        const uint64_t T = s_T64;
 #pragma unroll
-        for (int u = 0; u < PER; ++u) skeys[threadIdx.x + u * STB_SCAN_THREADS] = v[u];
+        for (int u = 0; u < PER; ++u) {
+          const bool take = v[u] != STB_KEY_INVALID && v[u] <= T;
+          const unsigned m = __ballot_sync(0xffffffffu, take);
+          unsigned base = 0u;
+          if (lane == 0 && m) base = atomicAdd(&s_cnt, (unsigned)__popc(m));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (take) skeys[base + __popc(m & ((1u << lane) - 1u))] = v[u];
+        }
       }
       __syncthreads();
-      stb_cta_sort_keys(skeys, (int)(n_in * KP) <= 256 ? 256 : STB_SORT_CAP);
+      stb_pad_and_sort(skeys, (int)s_cnt, KP);
       lvl_key_off += lists;
       const uint32_t groups = (lists + F - 1) / F;
       lvl_cnt_off += groups;
