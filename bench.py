@@ -236,6 +236,47 @@ def bench_batch(torch, dev, ctx, stream, corpus, rows, k, nq=1024, iters=5):
             "agrees_with_single_query_path": bool(agree)}
 
 
+def bench_batch_sharded(torch, dist, dev, ctx, stream, corpus, rows, k, world, nq=1024, iters=5):
+    """configs[2] sharded row-wise: every rank runs K2 on its shard, the nq x k hits are
+    all-gathered (NCCL, 160 KB per rank) and merged per query on every rank."""
+    qh = gen_queries(nq + 64)[64:]
+    q_dev = torch.from_numpy(qh).to(dev)
+    hits = torch.zeros((nq, k, 2), dtype=torch.float64, device=dev)
+    st = torch.zeros((nq, 2), dtype=torch.int32, device=dev)
+    gathered = torch.zeros((world, nq, k, 2), dtype=torch.float64, device=dev)
+    st_all = torch.zeros((world, nq, 2), dtype=torch.int32, device=dev)
+    merged = torch.zeros((nq, k, 2), dtype=torch.float64, device=dev)
+    corpus.prepare_batch()
+
+    def one():
+        corpus.search_batch_dev(q_dev.data_ptr(), nq, k, hits.data_ptr(), st.data_ptr())
+        dist.all_gather_into_tensor(gathered, hits)
+        dist.all_gather_into_tensor(st_all, st)
+        ctx.hits_merge_batch_dev(gathered.data_ptr(), world, nq, k, k, merged.data_ptr())
+
+    for _ in range(2):
+        one()
+    dist.barrier(); torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(iters):
+        one()
+    e1.record(stream)
+    dist.barrier(); torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ref = merged.clone()
+    dist.broadcast(ref, src=0)
+    agree = torch.tensor([int(torch.equal(ref.view(torch.int64), merged.view(torch.int64)))], device=dev)
+    dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+    return {"workload": f"{rows}-line corpus row-sharded x{world}, batch of {nq} queries, top-k={k} (configs[2], sharded)",
+            "value": nq / (ms * 1e-3), "unit": "queries/s", "ms_per_batch": ms,
+            "gemm_TFLOPs_pipeline": 2.0 * nq * rows * 256 / (ms * 1e-3) / 1e12,
+            "queries_proven_exact": int((st_all[:, :, 1].min(dim=0).values == 1).sum().item()), "queries": nq,
+            "ranks_agree": bool(agree.item()), "exchange": "nccl all_gather of nq x k hits + stb_hits_merge_batch_dev"}
+
+
 # ------------------------------------------------------------------ K5 side bench -----
 def bench_ivfpq(torch, dev, ctx, rows=4_000_000, nlist=4096, nprobe=64, n_centers=40_000, spread=0.6):
     """IVF-PQ (self-specified: the reference has no IVF_PQ, so no parity -- recall@10 against
@@ -492,6 +533,8 @@ def run_ours(args):
     k2 = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         k2 = bench_batch(torch, dev, ctx, stream, corpus, args.rows, k)
+    if world > 1 and not args.no_cpu_baseline:
+        k2 = bench_batch_sharded(torch, dist, dev, ctx, stream, corpus, args.rows, k, world)   # every rank takes part
 
     # ---- K5 (BASELINE configs[4] at single-GPU scale: IVF-PQ probe, recall-measured) ------
     k5 = None
@@ -547,7 +590,7 @@ def run_ours(args):
             "parity_spot_check": check,
         }
         if k2 is not None:
-            tpeak = float(peaks.get("bf16_tflops", 1590.0))
+            tpeak = float(peaks.get("bf16_tflops", 1590.0)) * world        # whole-job FLOP rate vs N GPUs' peak
             k2["roofline"] = {"bound": "tensor", "kernel": "stb_batch_gemm_kernel (tcgen05.mma kind::f16, bf16 in / f32 TMEM)",
                               "achieved": k2["gemm_TFLOPs_pipeline"], "peak": tpeak, "unit": "TFLOP/s",
                               "frac": k2["gemm_TFLOPs_pipeline"] / tpeak,

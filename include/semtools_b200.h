@@ -249,6 +249,10 @@ int stb_search_xchg(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint
  * (distance, row) to out_dev.  Asynchronous on the context's stream. */
 int stb_hits_merge_dev(stb_ctx *ctx, const stb_hit *lists_dev, uint32_t n_lists,
                        uint32_t per_list, uint32_t top_k, stb_hit *out_dev);
+/* Batched form for sharded K2: lists_dev[n_lists][nq][per_list] (e.g. the all-gathered
+ * per-rank results of stb_search_batch_dev) -> out_dev[nq][top_k]; n_lists*per_list <= 2048. */
+int stb_hits_merge_batch_dev(stb_ctx *ctx, const stb_hit *lists_dev, uint32_t n_lists,
+                             uint32_t nq, uint32_t per_list, uint32_t top_k, stb_hit *out_dev);
 /* Host-buffer convenience wrapper (copies in, merges on the GPU, copies out). */
 int stb_hits_merge(stb_ctx *ctx, const stb_hit *lists, uint32_t n_lists,
                    uint32_t per_list, uint32_t top_k, stb_hit *out,

@@ -26,7 +26,7 @@ SYMBOLS = [
     "stb_search_topk_dev", "stb_corpus_prepare_batch", "stb_search_batch", "stb_search_batch_dev",
     "stb_xchg_create", "stb_xchg_destroy", "stb_xchg_local_handle",
     "stb_xchg_connect", "stb_xchg_connect_local", "stb_search_topk_xchg", "stb_search_xchg", "stb_ivfpq_build",
-    "stb_ivfpq_destroy", "stb_ivfpq_stats", "stb_ivfpq_search", "stb_hits_merge_dev", "stb_hits_merge", "stb_fnv1a64", "stb_line_id",
+    "stb_ivfpq_destroy", "stb_ivfpq_stats", "stb_ivfpq_search", "stb_hits_merge_dev", "stb_hits_merge_batch_dev", "stb_hits_merge", "stb_fnv1a64", "stb_line_id",
     "stb_ctx_counters", "stb_debug_timestamps", "stb_debug_batch_gemm",
 ]
 
@@ -97,6 +97,7 @@ def lib() -> C.CDLL:
     L.stb_ivfpq_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)]
     L.stb_ivfpq_search.argtypes = [vp, vp, u32, u32, u32, vp, C.POINTER(u32), C.POINTER(u64)]
     L.stb_hits_merge_dev.argtypes = [vp, vp, u32, u32, u32, vp]
+    L.stb_hits_merge_batch_dev.argtypes = [vp, vp, u32, u32, u32, u32, vp]
     L.stb_hits_merge.argtypes = [vp, vp, u32, u32, u32, vp, C.POINTER(u32)]
     L.stb_fnv1a64.argtypes = [C.c_char_p, u64]
     L.stb_fnv1a64.restype = u64
@@ -175,6 +176,10 @@ class Context:
         _check(lib().stb_hits_merge(self._h, _np_ptr(lists), n_lists, per_list, top_k, _np_ptr(out),
                                     C.byref(n)))
         return out[: n.value]
+
+    def hits_merge_batch_dev(self, lists_dev: int, n_lists: int, nq: int, per_list: int, top_k: int, out_dev: int):
+        """lists_dev [n_lists][nq][per_list] -> out_dev [nq][top_k] (sharded K2)."""
+        _check(lib().stb_hits_merge_batch_dev(self._h, vp(lists_dev), n_lists, nq, per_list, top_k, vp(out_dev)))
 
     def hits_merge_dev(self, lists_dev: int, n_lists: int, per_list: int, top_k: int, out_dev: int):
         _check(lib().stb_hits_merge_dev(self._h, vp(lists_dev), n_lists, per_list, top_k, vp(out_dev)))

@@ -856,6 +856,15 @@ int stb_hits_merge_dev(stb_ctx *ctx, const stb_hit *lists_dev, uint32_t n_lists,
   return stb_launch_hits_merge(ctx, lists_dev, n_lists, per_list, top_k, out_dev);
 }
 
+int stb_hits_merge_batch_dev(stb_ctx *ctx, const stb_hit *lists_dev, uint32_t n_lists, uint32_t nq,
+                             uint32_t per_list, uint32_t top_k, stb_hit *out_dev) {
+  int rc = ctx_use(ctx);
+  if (rc) return rc;
+  if (!lists_dev || !out_dev || n_lists == 0 || per_list == 0 || top_k == 0) { stb_set_error("hits_merge_batch: bad argument"); return STB_ERR_ARG; }
+  if (nq == 0) return STB_OK;
+  return stb_launch_hits_merge_batch(ctx, lists_dev, n_lists, nq, per_list, top_k, out_dev);
+}
+
 int stb_hits_merge(stb_ctx *ctx, const stb_hit *lists, uint32_t n_lists, uint32_t per_list,
                    uint32_t top_k, stb_hit *out, uint32_t *out_n) {
   int rc = ctx_use(ctx);

@@ -163,6 +163,9 @@ int stb_launch_sort_hits(stb_ctx *ctx, stb_hit *hits, uint64_t m_padded);
 int stb_launch_hits_merge(stb_ctx *ctx, const stb_hit *lists_dev, uint32_t n_lists,
                           uint32_t per_list, uint32_t top_k, stb_hit *out_dev);
 
+int stb_launch_hits_merge_batch(stb_ctx *ctx, const stb_hit *lists_dev, uint32_t n_lists, uint32_t nq,
+                                uint32_t per_list, uint32_t top_k, stb_hit *out_dev);
+
 // ---- embed_pool.cu --------------------------------------------------------------
 int stb_launch_embed(stb_ctx *ctx, const stb_table *t, const uint64_t *offsets_dev,
                      const uint32_t *ids_dev, uint64_t n_lines, float *out_dev,

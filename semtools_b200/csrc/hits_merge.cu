@@ -50,6 +50,59 @@ stb_hits_merge_kernel(const stb_hit *lists, uint32_t total, uint32_t n_sort, uin
   }
 }
 
+// Batched form: lists[n_lists][nq][per_list] -> out[nq][top_k]; one CTA per query.
+__global__ void __launch_bounds__(128)
+stb_hits_merge_batch_kernel(const stb_hit *lists, uint32_t n_lists, uint32_t nq, uint32_t per_list,
+                            uint32_t n_sort, uint32_t top_k, stb_hit *out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  double *sd = reinterpret_cast<double *>(smem);
+  uint64_t *sr = reinterpret_cast<uint64_t *>(smem + (size_t)n_sort * sizeof(double));
+  const uint32_t q = blockIdx.x, total = n_lists * per_list;
+  for (uint32_t i = threadIdx.x; i < n_sort; i += blockDim.x) {
+    double d = CUDART_INF;
+    uint64_t r = 0xffffffffffffffffull;
+    if (i < total) {
+      const stb_hit h = lists[((size_t)(i / per_list) * nq + q) * per_list + (i % per_list)];
+      if (h.distance == h.distance && h.row != 0xffffffffffffffffull) { d = h.distance; r = h.row; }
+    }
+    sd[i] = d; sr[i] = r;
+  }
+  __syncthreads();
+  for (uint32_t k = 2; k <= n_sort; k <<= 1)
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = threadIdx.x; i < n_sort; i += blockDim.x) {
+        const uint32_t ixj = i ^ j;
+        if (ixj > i) {
+          const bool up = ((i & k) == 0);
+          const bool gt = stb_hit_less(sd[ixj], sr[ixj], sd[i], sr[i]);
+          if (gt == up) {
+            double td = sd[i]; uint64_t tr = sr[i];
+            sd[i] = sd[ixj]; sr[i] = sr[ixj]; sd[ixj] = td; sr[ixj] = tr;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  for (uint32_t i = threadIdx.x; i < top_k; i += blockDim.x) {
+    stb_hit h;
+    h.distance = (i < n_sort) ? sd[i] : CUDART_INF;
+    h.row = (i < n_sort) ? sr[i] : 0xffffffffffffffffull;
+    out[(size_t)q * top_k + i] = h;
+  }
+}
+
+int stb_launch_hits_merge_batch(stb_ctx *ctx, const stb_hit *lists_dev, uint32_t n_lists, uint32_t nq,
+                                uint32_t per_list, uint32_t top_k, stb_hit *out_dev) {
+  const uint64_t total = (uint64_t)n_lists * per_list;
+  if (total > 2048) { stb_set_error("hits_merge_batch: %llu hits per query exceed 2048", (unsigned long long)total); return STB_ERR_ARG; }
+  uint32_t n_sort = 2;
+  while (n_sort < total) n_sort <<= 1;
+  stb_hits_merge_batch_kernel<<<nq, 128, (size_t)n_sort * 16, ctx->stream>>>(lists_dev, n_lists, nq, per_list, n_sort, top_k, out_dev);
+  STB_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  return STB_OK;
+}
+
 int stb_launch_hits_merge(stb_ctx *ctx, const stb_hit *lists_dev, uint32_t n_lists,
                           uint32_t per_list, uint32_t top_k, stb_hit *out_dev) {
   uint64_t total = (uint64_t)n_lists * per_list;

@@ -116,3 +116,38 @@ def test_search_batch_sharded_row_base_and_rebuild_after_append(ctx):
         r, d = oracle.search_rows(rows, q, top_k=5)
         assert res[i]["row"].tolist() == [int(x) + 1_000_000 for x in r]
         assert np.array_equal(res[i]["distance"], d)
+
+
+def test_sharded_batch_search_merges_to_the_unsharded_answer(ctx):
+    """Sharded K2: per-shard stb_search_batch_dev + stb_hits_merge_batch_dev (what ranks do
+    after all-gathering their nq x k hits) == oracle over the whole corpus."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(77)
+    n, nq, k = 60_000, 70, 10
+    rows = unit_rows(rng, n)
+    rows[59_999] = rows[5]                      # cross-shard exact tie
+    queries = unit_rows(rng, nq)
+    queries[0] = rows[5]
+    bounds = [0, 20_000, 45_000, n]
+    dev = torch.device("cuda:0")
+    q_dev = torch.from_numpy(queries).to(dev)
+    world = len(bounds) - 1
+    lists = torch.zeros((world, nq, k, 2), dtype=torch.float64, device=dev)
+    status = torch.zeros((world, nq, 2), dtype=torch.int32, device=dev)
+    out = torch.zeros((nq, k, 2), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    shards = []
+    for r in range(world):
+        c = capi.Corpus(ctx, bounds[r + 1] - bounds[r], row_base=bounds[r])
+        c.append(rows[bounds[r]:bounds[r + 1]])
+        shards.append(c)
+        c.search_batch_dev(q_dev.data_ptr(), nq, k, lists[r].data_ptr(), status[r].data_ptr())
+    ctx.hits_merge_batch_dev(lists.data_ptr(), world, nq, k, k, out.data_ptr())
+    ctx.sync()
+    assert bool((status[:, :, 1] == 1).all())
+    got = np.ascontiguousarray(out.cpu().numpy()).view(capi.HIT_DTYPE).reshape(nq, k)
+    for i in range(nq):
+        r, d = oracle.search_rows(rows, queries[i], top_k=k)
+        assert got[i]["row"].tolist() == [int(x) for x in r], i
+        assert np.array_equal(got[i]["distance"], d), i
+    assert got[0]["row"][:2].tolist() == [5, 59_999]
