@@ -448,13 +448,16 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     # ---- value: inputs resident in HBM, device-timed ---------------------------------
+    # clock sampling starts before the warm-up (nvidia-smi needs ~0.2 s to come up) and runs
+    # through the timed region; both are under the same load
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.5)
     for i in range(args.warmup):
         step(i)
     barrier()
     launches0 = ctx.counters()["kernel_launches"]
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
