@@ -80,3 +80,104 @@ def test_cpp_cli_output_equals_python_mirror(binary, tmp_path, ctx, monkeypatch)
     cmds.search_cmd("fruit", [], 1, 2, None, False, True, None, model, stdin_lines=lines, stdin_is_tty=False, out=out)
     r = subprocess.run(base + ["fruit", "-n", "1", "--top-k", "2", "-j"], capture_output=True, text=True, input="\n".join(lines) + "\n")
     assert r.stdout == out.getvalue()
+
+
+# ---------------------------------------------------------------- C++ workspace / store mirror
+WSBIN = os.path.join(ROOT, "semtools_b200", "lib", "semtools_b200_workspace")
+
+
+def _fake_embedding(path: str, line: int, scale: float) -> np.ndarray:
+    """Same LCG as fake_embedding() in semtools_workspace_main.cpp."""
+    from semtools_b200 import capi
+    h = capi.line_id(path, line)
+    out = np.empty(256, np.float32)
+    for i in range(256):
+        h = (h * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+        out[i] = np.float32(scale) * np.float32((h >> 40) - (1 << 23)) / np.float32(1 << 23)
+    return out
+
+
+def _python_store_script(d):
+    """The mutations store_selftest() applies, through the Python Store."""
+    from semtools_b200.workspace import DocMeta, LineEmbedding, Store
+    s = Store.open(str(d))
+    b = 'dir/b "q".txt'
+    s.upsert_document_metadata([DocMeta("a.txt", 10, 1700000000), DocMeta(b, 20, 1700000001),
+                                DocMeta("cé.txt", 30, 1700000002), DocMeta("old.txt", 5, 1600000000, 1)])
+    ls = [LineEmbedding("a.txt", i, _fake_embedding("a.txt", i, 1.0)) for i in range(3)]
+    ls += [LineEmbedding(b, i, _fake_embedding(b, i, 1.0)) for i in range(2)]
+    ls += [LineEmbedding("cé.txt", i, _fake_embedding("cé.txt", i, 1.0)) for i in range(4)]
+    ls += [LineEmbedding("old.txt", 0, _fake_embedding("old.txt", 0, 1.0))]
+    s.upsert_line_embeddings(ls)
+    s.upsert_line_embeddings([LineEmbedding("a.txt", 1, _fake_embedding("a.txt", 1, 0.5))])
+    s.upsert_document_metadata([DocMeta("a.txt", 11, 1700000005)])
+    s.delete_documents([b, "old.txt"])
+    s.upsert_line_embeddings([LineEmbedding("a.txt", 3, _fake_embedding("a.txt", 3, 1.0))])
+    return s
+
+
+def test_cpp_store_and_python_store_write_the_same_files(binary, tmp_path):
+    """Store mutations (upsert / replace-by-id / delete / version-gated metadata delete,
+    store.rs:235-434) through the C++ mirror and the Python mirror leave identical stores, and
+    each side reads what the other wrote."""
+    from semtools_b200.workspace import Store
+    dc, dp = tmp_path / "cpp", tmp_path / "py"
+    r = subprocess.run([WSBIN, "store-selftest", str(dc)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    _python_store_script(dp)
+    r2 = subprocess.run([WSBIN, "store-dump", str(dp)], capture_output=True, text=True)     # C++ reads Python's files
+    assert r2.returncode == 0, r2.stderr
+    assert r.stdout == r2.stdout
+    assert "documents 3" in r.stdout and "line_embeddings 8" in r.stdout
+    for name in ("rows.i32", "line_embeddings.f32"):
+        assert (dc / "flat.b200" / name).read_bytes() == (dp / "flat.b200" / name).read_bytes()
+    assert json.loads((dc / "flat.b200" / "store.json").read_text()) == json.loads((dp / "flat.b200" / "store.json").read_text())
+    s = Store.open(str(dc))                                                               # Python reads C++'s files
+    assert s.get_all_document_paths() == ["a.txt", "cé.txt", "old.txt"]
+    assert s.count_line_embeddings() == 8
+    assert [(s._paths[pi], int(ln)) for pi, ln in s._rows] == \
+        [("a.txt", 0), ("a.txt", 1), ("a.txt", 2)] + [("cé.txt", i) for i in range(4)] + [("a.txt", 3)]
+    assert np.array_equal(s._emb[1], _fake_embedding("a.txt", 1, 0.5))
+    assert s._ranges_for(["a.txt"]).tolist() == [[0, 3], [7, 8]]
+
+
+def test_cpp_workspace_commands_match_python_mirror(binary, tmp_path):
+    """workspace use / status / prune (cmds/workspace.rs:11-176): C++ output == Python output."""
+    from semtools_b200 import cmds
+    from semtools_b200.workspace import DocMeta, Store
+    env = dict(os.environ, HOME=str(tmp_path))
+    env.pop("SEMTOOLS_WORKSPACE", None)
+    r = subprocess.run([WSBIN, "status"], capture_output=True, text=True, env=env)
+    assert r.returncode == 1 and r.stderr == "Error: No active workspace. Run: workspace use <name>\n"
+
+    old_home, old_ws = os.environ.get("HOME"), os.environ.pop("SEMTOOLS_WORKSPACE", None)
+    os.environ["HOME"] = str(tmp_path)
+    try:
+        for js in (False, True):
+            flags = ["--json"] if js else []
+            r = subprocess.run([WSBIN] + flags + ["use", "proj"], capture_output=True, text=True, env=env)
+            buf = io.StringIO(); cmds.workspace_use_cmd("proj", js, out=buf)
+            assert r.returncode == 0 and r.stdout == buf.getvalue()
+        cfg = json.loads((tmp_path / ".semtools" / "workspaces" / "proj" / "config.json").read_text())
+        assert cfg == {"name": "proj", "root_dir": str(tmp_path / ".semtools" / "workspaces" / "proj"),
+                       "in_batch_size": 5000, "oversample_factor": 3}
+        live = tmp_path / "live.txt"; live.write_text("x\n")
+        s = Store.open(cfg["root_dir"])
+        s.upsert_document_metadata([DocMeta(str(live), 2, 1), DocMeta(str(tmp_path / "gone.txt"), 3, 1)])
+        for js in (False, True):
+            flags = ["--json"] if js else []
+            r = subprocess.run([WSBIN] + flags + ["--workspace", "proj", "status"], capture_output=True, text=True, env=env)
+            buf = io.StringIO(); cmds.workspace_status_cmd(js, "proj", out=buf)
+            assert r.returncode == 0 and r.stdout == buf.getvalue()
+        env2 = dict(env, SEMTOOLS_WORKSPACE="proj")
+        r = subprocess.run([WSBIN, "prune"], capture_output=True, text=True, env=env2)
+        assert r.returncode == 0
+        assert r.stdout == f"Found 1 stale documents:\n  - {tmp_path / 'gone.txt'}\nRemoved 1 stale documents from workspace.\n"
+        assert Store.open(cfg["root_dir"]).get_all_document_paths() == [str(live)]
+        r = subprocess.run([WSBIN, "--json", "prune"], capture_output=True, text=True, env=env2)
+        buf = io.StringIO(); cmds.workspace_prune_cmd(True, "proj", out=buf)
+        assert r.stdout == buf.getvalue() and json.loads(r.stdout) == {"files_removed": 0, "files_remaining": 1}
+    finally:
+        os.environ["HOME"] = old_home
+        if old_ws is not None:
+            os.environ["SEMTOOLS_WORKSPACE"] = old_ws
