@@ -54,16 +54,34 @@ class ShardedCorpus:
     @classmethod
     def on_gpu(cls, ctx: capi.Context, corpus: capi.Corpus, dist, device):
         """Product wiring: CUDA kernels for search + merge, NCCL all-gather."""
-        import torch
-        rank, world = dist.get_rank(), dist.get_world_size()
-
         def local_search(q, top_k, max_distance, mode):
             return corpus.search(q, top_k, max_distance, mode)
 
-        def all_gather(local):
-            t = torch.from_numpy(local.view(np.float64).reshape(-1, 2).copy()).to(device)
-            out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=device)
-            dist.all_gather_into_tensor(out, t)
-            return np.ascontiguousarray(out.cpu().numpy()).view(capi.HIT_DTYPE).reshape(world, -1)
+        return cls(dist.get_rank(), dist.get_world_size(), local_search, ctx.hits_merge, _device_all_gather(dist, device))
 
-        return cls(rank, world, local_search, ctx.hits_merge, all_gather)
+    @classmethod
+    def on_gpu_ivfpq(cls, ctx: capi.Context, index: "capi.IvfPq", dist, device, nprobe: int = 64, rerank: int = 256):
+        """K5 sharded by ROW: every rank holds an IVF-PQ index over its own row
+        block (its corpus was created with row_base = the block's first global row, so the
+        exactly re-ranked hits already carry global rows); per-rank top-k, the same 16 B x k
+        all-gather, the same K4 merge.  Approximate per shard => approximate globally; the
+        merge itself is exact, so recall is the mean of the shard recalls' union."""
+        def local_search(q, top_k, max_distance, mode):
+            if max_distance is not None:
+                raise ValueError("the IVF-PQ probe has no distance threshold")
+            return index.search(q, nprobe=nprobe, top_k=top_k, rerank=rerank)[0]
+
+        return cls(dist.get_rank(), dist.get_world_size(), local_search, ctx.hits_merge, _device_all_gather(dist, device))
+
+
+def _device_all_gather(dist, device):
+    import torch
+    world = dist.get_world_size()
+
+    def all_gather(local):
+        t = torch.from_numpy(local.view(np.float64).reshape(-1, 2).copy()).to(device)
+        out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=device)
+        dist.all_gather_into_tensor(out, t)
+        return np.ascontiguousarray(out.cpu().numpy()).view(capi.HIT_DTYPE).reshape(world, -1)
+
+    return all_gather

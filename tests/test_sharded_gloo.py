@@ -54,6 +54,21 @@ def _worker(rank, world, port, q_out):
         r, d = oracle.search_rows(rows, q, top_k=k)
         res[k] = bool(got["row"].tolist() == [int(x) for x in r] and np.array_equal(got["distance"], d))
     res["tie"] = sc.search(q, 2)["row"].tolist() == [5, 1000]
+
+    # an APPROXIMATE shard-local search (IVF-PQ sharded by row: each shard may miss rows) --
+    # the global answer must be exactly the (distance,row)-ordered union of the shard lists
+    def approx_local(qv, top_k, max_distance, mode):
+        keep = np.arange(lo, hi)[(np.arange(lo, hi) % 3) != 1]        # every shard "probes" 2/3 of its rows
+        r, d = oracle.search_rows(rows[keep], qv, top_k=top_k)
+        out = np.zeros(len(r), dtype=capi.HIT_DTYPE)
+        out["row"], out["distance"] = keep[r], d
+        return out
+
+    sa = ShardedCorpus(rank, world, approx_local, merge, all_gather)
+    keep_all = np.arange(1003)[(np.arange(1003) % 3) != 1]
+    r, d = oracle.search_rows(rows[keep_all], q, top_k=7)
+    got = sa.search(q, 7)
+    res["approx_union"] = bool(got["row"].tolist() == keep_all[r].tolist() and np.array_equal(got["distance"], d))
     res["bounds"] = (lo, hi)
     q_out.put((rank, res))
     dist.barrier()
@@ -77,6 +92,7 @@ def test_sharded_search_gloo(world):
     assert bounds[0][0] == 0 and bounds[-1][1] == 1003
     assert all(a[1] == b[0] for a, b in zip(bounds[:-1], bounds[1:]))
     for rank, res in results:
+        assert res["approx_union"], f"rank {rank}: approximate shard lists merged wrongly"
         for k in (1, 3, 10, 600):
             assert res[k], (rank, k)
         assert res["tie"]
