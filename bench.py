@@ -633,6 +633,19 @@ def run_ours(args):
                           f"(linear in rows; favours the CPU, whose full-result sort is N log N)",
                 "host_cores": os.cpu_count(),
                 "all_cores_not_reference_behaviour": {"threads": nt, "value": vN}}
+        if world == 1 and not args.no_cpu_baseline:
+            # K2 pipeline v2 (sampled threshold -> emitting epilogue -> exact finish; opt-in in the
+            # library until validated).  Measured LAST so nothing above depends on it.
+            os.environ["STB_BATCH_V2"] = "1"
+            try:
+                v2 = side(bench_batch, torch, dev, ctx, stream, corpus, args.rows, k)
+            finally:
+                os.environ.pop("STB_BATCH_V2", None)
+            if "error" not in v2:
+                tpeak = float(peaks.get("bf16_tflops", 1590.0))
+                v2["roofline_frac_pipeline"] = v2["gemm_TFLOPs_pipeline"] / tpeak
+                v2["note"] = "opt-in pipeline (STB_BATCH_V2=1): same C-ABI call, same results; not the default path yet"
+            line["batch1024_v2"] = v2
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -139,6 +139,7 @@ int stb_ctx_destroy(stb_ctx *c) {
   cudaFree(c->status_dev); cudaFree(c->collect_rows); cudaFree(c->collect_count);
   cudaFree(c->collect_hits); cudaFree(c->ranges_dev); cudaFree(c->err_flag);
   cudaFree(c->dbg_dev); cudaFree(c->hist_dev); cudaFree(c->bq_tiles); cudaFree(c->b_submax); cudaFree(c->b_tilemax); cudaFree(c->b_cand);
+  cudaFree(c->b_thr); cudaFree(c->b_cnt); cudaFree(c->b_keys);
   cudaFree(c->bq_dev); cudaFree(c->bh_dev); cudaFree(c->bs_dev); cudaFree(c->embed_off_dev); cudaFree(c->embed_ids_dev); cudaFree(c->embed_out_dev);
   if (c->q_pin) cudaFreeHost(c->q_pin);
   if (c->hits_pin) cudaFreeHost(c->hits_pin);
@@ -720,6 +721,32 @@ int stb_search_batch_dev(stb_ctx *ctx, const stb_corpus *corpus_c, const float *
   if ((rc = corpus_ensure_shadow(ctx, corpus)) != STB_OK) return rc;
   const uint32_t m_tiles = (nq + 127) / 128, q_pad = m_tiles * 128;
   const uint32_t n_tiles = (uint32_t)((corpus->n + 255) / 256), n_sub = n_tiles * 8;
+  // pipeline v2 (threshold-emitting epilogue; see batch_scan.cu): opt-in until validated on hardware
+  const char *v2_env = getenv("STB_BATCH_V2");            // read per call so one process can compare both
+  const bool use_v2 = v2_env != nullptr && v2_env[0] == '1';
+  if (use_v2 && top_k <= 64) {
+    constexpr uint32_t kCandCap = 8192;
+    // sample only COMPLETE tiles (a padding row must never stand in for a real one)
+    const uint32_t n_full = (uint32_t)(corpus->n / 256);
+    const uint32_t n_sample = std::min<uint32_t>(n_full, std::min<uint32_t>(4u * (uint32_t)ctx->sm_count, 608u));
+    const uint32_t stride = n_sample ? n_full / n_sample : 1;
+    if ((rc = dev_reserve(&ctx->bq_tiles, &ctx->bq_tiles_cap, (size_t)q_pad * 512)) != STB_OK) return rc;
+    if ((rc = dev_reserve(&ctx->b_tilemax, &ctx->b_tilemax_cap, (size_t)std::max<uint32_t>(n_sample, 1) * q_pad)) != STB_OK) return rc;
+    if ((rc = dev_reserve(&ctx->b_thr, &ctx->b_thr_cap, (size_t)q_pad)) != STB_OK) return rc;
+    if ((rc = dev_reserve(&ctx->b_cnt, &ctx->b_cnt_cap, (size_t)q_pad)) != STB_OK) return rc;
+    if ((rc = dev_reserve(&ctx->b_keys, &ctx->b_keys_cap, (size_t)q_pad * kCandCap)) != STB_OK) return rc;
+    STB_CUDA(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), ctx->stream));
+    STB_CUDA(cudaMemsetAsync(ctx->b_cnt, 0, (size_t)q_pad * sizeof(uint32_t), ctx->stream));
+    if ((rc = stb_launch_shadow_build(ctx, q_dev, nq, 128, ctx->bq_tiles, ctx->err_flag)) != STB_OK) return rc;
+    if (n_sample &&
+        (rc = stb_launch_batch_gemm_strided(ctx, ctx->bq_tiles, m_tiles, corpus->shadow, n_sample, stride, nullptr,
+                                            ctx->b_tilemax, nullptr)) != STB_OK) return rc;
+    if ((rc = stb_launch_batch_thresh(ctx, ctx->b_tilemax, n_sample, nq, q_pad, top_k, ctx->b_thr)) != STB_OK) return rc;
+    if ((rc = stb_launch_batch_gemm_emit(ctx, ctx->bq_tiles, m_tiles, corpus->shadow, n_tiles, corpus->n, ctx->b_thr,
+                                         ctx->b_cnt, ctx->b_keys, kCandCap)) != STB_OK) return rc;
+    return stb_launch_batch_finish2(ctx, ctx->b_keys, ctx->b_cnt, kCandCap, nq, top_k, corpus->rows, corpus->n,
+                                    corpus->row_base, q_dev, out_hits_dev, out_status_dev);
+  }
   // selection slices: enough CTAs (m_tiles x n_slices) to hide the latency of the streaming
   // read; the finish kernel merges n_slices x 32 <= 4096 candidate tiles per query
   uint32_t n_slices = std::max<uint32_t>(1, std::min<uint32_t>(128, 1536 / m_tiles));

@@ -184,11 +184,21 @@ struct GemmArgs {
   float *submax;              // [m_tiles][n_tiles * 8][128]  per-32-row maxima
   float *tilemax;             // [m_tiles][n_tiles][128]      per-256-row maxima
   float *full_out;            // debug: full score matrix [m_tiles*128][n_tiles*256] or null
+  uint32_t tile_stride;       // corpus tile t of this launch is shadow tile t * tile_stride (sampling pass)
+  // EPI == 1 (candidate-emitting epilogue, pipeline v2):
+  const float *thr;           // [q_pad] per-query score threshold (+inf for padding queries)
+  uint32_t *cand_cnt;         // [q_pad] candidates emitted (may exceed cand_cap: overflow marker)
+  uint64_t *cand_keys;        // [q_pad][cand_cap] keys (score desc, local row)
+  uint32_t cand_cap;
+  uint64_t n_rows;            // real corpus rows (padding rows of the last tile are never emitted)
 };
 
 #define STB_GEMM_THREADS 256
 #define STB_GEMM_SMEM (STB_N_SLABS * STB_B_SLAB_BYTES + STB_A_RING * STB_A_SLAB_BYTES + 1024 + 256)
 
+// EPI 0: per-sub-tile / per-tile maxima (pipeline v1, and the sampling pass of v2).
+// EPI 1: emit every (query,row) whose approximate score reaches the query's threshold.
+template <int EPI>
 __global__ void __launch_bounds__(STB_GEMM_THREADS, 1)
 stb_batch_gemm_kernel(const GemmArgs args) {
   extern __shared__ uint8_t smem_raw[];
@@ -228,7 +238,7 @@ stb_batch_gemm_kernel(const GemmArgs args) {
         const uint64_t t = blockIdx.x + (uint64_t)it * gridDim.x;
         // corpus tile, slab by slab: slab s of the previous tile is released as soon as the
         // last query tile's MMAs on it retire, so the refill overlaps the remaining slabs
-        const uint8_t *src = args.b_tiles + t * (size_t)(STB_N_SLABS * STB_B_SLAB_BYTES);
+        const uint8_t *src = args.b_tiles + t * args.tile_stride * (size_t)(STB_N_SLABS * STB_B_SLAB_BYTES);
         for (int s = 0; s < STB_N_SLABS; ++s) {
           mbar_wait(b_empty + s, (it & 1) ^ 1);
           mbar_expect_tx(b_full + s, STB_B_SLAB_BYTES);
@@ -289,24 +299,52 @@ stb_batch_gemm_kernel(const GemmArgs args) {
         mbar_wait(d_full + acc, (d_cnt >> 1) & 1);
         tc_fence_after();
         const uint32_t q = m * STB_A_TILE + quarter * 32 + lane;
-        float tmx = -CUDART_INF_F;
+        if constexpr (EPI == 0) {
+          float tmx = -CUDART_INF_F;
 #pragma unroll 1
-        for (int c = 0; c < STB_B_TILE / STB_SUB; ++c) {
-          uint32_t r[32];
-          tc_ld_32x32b_x32(tmem_base + ((quarter * 32u) << 16) + acc * STB_B_TILE + c * STB_SUB, r);
-          tc_wait_ld();
-          float mx = __uint_as_float(r[0]);
+          for (int c = 0; c < STB_B_TILE / STB_SUB; ++c) {
+            uint32_t r[32];
+            tc_ld_32x32b_x32(tmem_base + ((quarter * 32u) << 16) + acc * STB_B_TILE + c * STB_SUB, r);
+            tc_wait_ld();
+            float mx = __uint_as_float(r[0]);
 #pragma unroll
-          for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-          args.submax[((size_t)m * n_sub + t * (STB_B_TILE / STB_SUB) + c) * STB_A_TILE + quarter * 32 + lane] = mx;
-          tmx = fmaxf(tmx, mx);
-          if (args.full_out) {
-            float *o = args.full_out + (size_t)q * ((size_t)args.n_tiles * STB_B_TILE) + t * STB_B_TILE + c * STB_SUB;
+            for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+            if (args.submax)
+              args.submax[((size_t)m * n_sub + t * (STB_B_TILE / STB_SUB) + c) * STB_A_TILE + quarter * 32 + lane] = mx;
+            tmx = fmaxf(tmx, mx);
+            if (args.full_out) {
+              float *o = args.full_out + (size_t)q * ((size_t)args.n_tiles * STB_B_TILE) + t * STB_B_TILE + c * STB_SUB;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(r[i]);
+              for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(r[i]);
+            }
+          }
+          args.tilemax[((size_t)m * args.n_tiles + t) * STB_A_TILE + quarter * 32 + lane] = tmx;
+        } else {
+          // thread = query: the threshold lives in a register; an emission is rare (the
+          // threshold is the k-th best score of a 1/66 sample, minus the rounding margin)
+          const float thr = __ldg(args.thr + q);
+          uint64_t *my_keys = args.cand_keys + (size_t)q * args.cand_cap;
+#pragma unroll 1
+          for (int c = 0; c < STB_B_TILE / STB_SUB; ++c) {
+            uint32_t r[32];
+            tc_ld_32x32b_x32(tmem_base + ((quarter * 32u) << 16) + acc * STB_B_TILE + c * STB_SUB, r);
+            tc_wait_ld();
+            float mx = __uint_as_float(r[0]);
+#pragma unroll
+            for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+            if (mx >= thr) {
+              const uint64_t row0 = t * STB_B_TILE + (uint64_t)c * STB_SUB;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float v = __uint_as_float(r[i]);
+                if (v >= thr && row0 + i < args.n_rows) {
+                  const uint32_t pos = atomicAdd(args.cand_cnt + q, 1u);
+                  if (pos < args.cand_cap) my_keys[pos] = stb_make_key(v, (uint32_t)(row0 + i));
+                }
+              }
+            }
           }
         }
-        args.tilemax[((size_t)m * args.n_tiles + t) * STB_A_TILE + quarter * 32 + lane] = tmx;
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(d_empty + acc);
@@ -336,22 +374,43 @@ int stb_launch_shadow_build(stb_ctx *ctx, const float *rows_dev, uint64_t n_rows
   return STB_OK;
 }
 
-int stb_launch_batch_gemm(stb_ctx *ctx, const uint8_t *a_tiles, uint32_t m_tiles, const uint8_t *b_tiles,
-                          uint32_t n_tiles, float *submax, float *tilemax, float *full_out) {
+template <int EPI>
+static int launch_gemm(stb_ctx *ctx, const GemmArgs &a) {
   static bool attr_set = false;
   if (!attr_set) {
-    STB_CUDA(cudaFuncSetAttribute(stb_batch_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STB_GEMM_SMEM));
+    STB_CUDA(cudaFuncSetAttribute(stb_batch_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, STB_GEMM_SMEM));
     attr_set = true;
   }
-  GemmArgs a;
-  a.a_tiles = a_tiles; a.b_tiles = b_tiles; a.m_tiles = m_tiles; a.n_tiles = n_tiles;
-  a.submax = submax; a.tilemax = tilemax; a.full_out = full_out;
-  unsigned grid = (unsigned)std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count);
+  unsigned grid = (unsigned)std::min<uint32_t>(a.n_tiles, (uint32_t)ctx->sm_count);
   if (grid == 0) return STB_OK;
-  stb_batch_gemm_kernel<<<grid, STB_GEMM_THREADS, STB_GEMM_SMEM, ctx->stream>>>(a);
+  stb_batch_gemm_kernel<EPI><<<grid, STB_GEMM_THREADS, STB_GEMM_SMEM, ctx->stream>>>(a);
   STB_CUDA(cudaGetLastError());
   ctx->kernel_launches++;
   return STB_OK;
+}
+
+int stb_launch_batch_gemm(stb_ctx *ctx, const uint8_t *a_tiles, uint32_t m_tiles, const uint8_t *b_tiles,
+                          uint32_t n_tiles, float *submax, float *tilemax, float *full_out) {
+  return stb_launch_batch_gemm_strided(ctx, a_tiles, m_tiles, b_tiles, n_tiles, 1, submax, tilemax, full_out);
+}
+
+// maxima epilogue over the tiles 0, stride, 2*stride, ... (n_tiles of them); submax may be null
+int stb_launch_batch_gemm_strided(stb_ctx *ctx, const uint8_t *a_tiles, uint32_t m_tiles, const uint8_t *b_tiles,
+                                  uint32_t n_tiles, uint32_t tile_stride, float *submax, float *tilemax, float *full_out) {
+  GemmArgs a{};
+  a.a_tiles = a_tiles; a.b_tiles = b_tiles; a.m_tiles = m_tiles; a.n_tiles = n_tiles;
+  a.submax = submax; a.tilemax = tilemax; a.full_out = full_out; a.tile_stride = tile_stride;
+  return launch_gemm<0>(ctx, a);
+}
+
+// candidate-emitting epilogue over all tiles
+int stb_launch_batch_gemm_emit(stb_ctx *ctx, const uint8_t *a_tiles, uint32_t m_tiles, const uint8_t *b_tiles,
+                               uint32_t n_tiles, uint64_t n_rows, const float *thr, uint32_t *cand_cnt,
+                               uint64_t *cand_keys, uint32_t cand_cap) {
+  GemmArgs a{};
+  a.a_tiles = a_tiles; a.b_tiles = b_tiles; a.m_tiles = m_tiles; a.n_tiles = n_tiles; a.tile_stride = 1;
+  a.thr = thr; a.cand_cnt = cand_cnt; a.cand_keys = cand_keys; a.cand_cap = cand_cap; a.n_rows = n_rows;
+  return launch_gemm<1>(ctx, a);
 }
 
 
@@ -589,6 +648,225 @@ int stb_launch_batch_finish(stb_ctx *ctx, const uint64_t *cand, uint32_t n_slice
   a.rows = reinterpret_cast<const float4 *>(rows); a.n_rows = n_rows; a.row_base = row_base;
   a.queries = queries_dev; a.out_hits = out_hits; a.out_status = out_status;
   stb_batch_finish_kernel<<<nq, 256, 0, ctx->stream>>>(a);
+  STB_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  return STB_OK;
+}
+
+// =========================================================================================
+// Pipeline v2 (dormant until validated on hardware; STB_BATCH_V2=1 selects it):
+//   sampling GEMM (maxima epilogue over ~4*SMs strided COMPLETE tiles) -> per-query threshold
+//   -> full GEMM whose epilogue emits the rows reaching the threshold -> exact finish.
+// Why the candidate set is sufficient, for ANY k (a = approximate score, c = exact cosine,
+// |a - c| <= EPS = STB_BATCH_EPS):
+//   S_k = k-th largest sampled tile maximum.  Each tile maximum is the score of a real row
+//   (only complete tiles are sampled), so k distinct rows have a >= S_k, hence c >= S_k - EPS,
+//   hence the k-th largest exact cosine C_k >= S_k - EPS.  A row of the exact top-k has
+//   c >= min(C_k, 1) (distance = max(0, 1 - c) is monotone in c and clamps at c >= 1), so
+//   a >= min(C_k, 1) - EPS >= S_k - 2 EPS (S_k <= 1 + EPS).  Emitting a >= S_k - 2 EPS loses none.
+//   The same argument with "sample" = all rows narrows the emitted set to a >= A_k - 2 EPS
+//   (A_k = k-th largest emitted score = k-th largest score overall) before the exact re-score.
+//   No further proof obligation: the result is complete unless a capacity overflowed.
+// =========================================================================================
+#define STB_V2_MAX_SAMPLE 608          // 19 values per lane in the threshold kernel
+#define STB_V2_MAX_K 64                // threshold kernel extracts k maxima serially
+#define STB_V2_RESCORE_CAP 1024        // exact re-scores per query
+
+struct ThreshArgs {
+  const float *tilemax;     // [m_tiles][n_sample][128]
+  uint32_t n_sample, nq, q_pad, top_k;
+  float *thr;               // [q_pad]
+};
+
+// one warp per query: lane l holds sampled tile maxima l, l+32, ...; k rounds of warp-max
+// extraction give the k-th largest.
+__global__ void __launch_bounds__(256)
+stb_batch_thresh_kernel(const ThreshArgs a) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t q = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (q >= a.q_pad) return;
+  if (q >= a.nq) { if (lane == 0) a.thr[q] = CUDART_INF_F; return; }       // padding query: never emits
+  float v[STB_V2_MAX_SAMPLE / 32];
+  const float *p = a.tilemax + (size_t)(q >> 7) * a.n_sample * 128 + (q & 127);
+#pragma unroll
+  for (int j = 0; j < STB_V2_MAX_SAMPLE / 32; ++j) {
+    const uint32_t idx = j * 32 + lane;
+    v[j] = (idx < a.n_sample) ? __ldg(p + (size_t)idx * 128) : -CUDART_INF_F;
+  }
+  float kth = -CUDART_INF_F;
+  if (a.top_k <= a.n_sample && a.top_k <= STB_V2_MAX_K) {
+    for (uint32_t round = 0; round < a.top_k; ++round) {
+      float lm = v[0];
+#pragma unroll
+      for (int j = 1; j < STB_V2_MAX_SAMPLE / 32; ++j) lm = fmaxf(lm, v[j]);
+      float wm = lm;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, off));
+      const unsigned owners = __ballot_sync(0xffffffffu, lm == wm);
+      if (lane == __ffs(owners) - 1) {                  // remove ONE instance of the maximum
+        bool removed = false;
+#pragma unroll
+        for (int j = 0; j < STB_V2_MAX_SAMPLE / 32; ++j)
+          if (!removed && v[j] == wm) { v[j] = -CUDART_INF_F; removed = true; }
+      }
+      kth = wm;
+    }
+  }
+  // fewer than k sampled tiles (or k too large): -inf = emit everything (tiny corpora fit the cap)
+  if (lane == 0) a.thr[q] = (kth == -CUDART_INF_F) ? -CUDART_INF_F : kth - 2.0f * (float)STB_BATCH_EPS;
+}
+
+struct Finish2Args {
+  const uint64_t *cand_keys;   // [q_pad][cand_cap]
+  const uint32_t *cand_cnt;    // [q_pad]
+  uint32_t cand_cap, nq, top_k;
+  const float4 *rows;
+  uint64_t n_rows, row_base;
+  const float *queries;        // [nq][256]
+  stb_hit *out_hits;           // [nq][top_k]
+  uint32_t *out_status;        // [nq][2]: hits, complete
+};
+
+// one CTA per query.  dynamic smem: keys[n_sort_max] | sd[1024] | sr[1024]
+__global__ void __launch_bounds__(256)
+stb_batch_finish2_kernel(const Finish2Args a) {
+  extern __shared__ uint64_t f2_smem[];
+  uint64_t *skeys = f2_smem;
+  double *sd = reinterpret_cast<double *>(f2_smem + a.cand_cap);
+  uint64_t *sr = f2_smem + a.cand_cap + STB_V2_RESCORE_CAP;
+  __shared__ double sqd[STB_D];
+  __shared__ double s_q2;
+  __shared__ int s_pass;
+  __shared__ unsigned s_m2;
+  const uint32_t q = blockIdx.x;
+  const int tid = threadIdx.x;
+  const uint32_t k = a.top_k;
+  const uint32_t m_all = a.cand_cnt[q];
+  auto give_up = [&]() {                               // capacity overflow: the host falls back to K1
+    for (uint32_t i = tid; i < k; i += 256) {
+      stb_hit h; h.distance = CUDART_INF; h.row = 0xffffffffffffffffull;
+      a.out_hits[(size_t)q * k + i] = h;
+    }
+    if (tid == 0) { a.out_status[2 * q] = 0; a.out_status[2 * q + 1] = 0; }
+  };
+  if (m_all > a.cand_cap) { give_up(); return; }       // uniform per CTA
+  // 1. sort the emitted keys (ascending key = descending score, then ascending row)
+  uint32_t n_sort = 64;
+  while (n_sort < m_all) n_sort <<= 1;
+  const uint64_t *src = a.cand_keys + (size_t)q * a.cand_cap;
+  for (uint32_t i = tid; i < n_sort; i += 256) skeys[i] = (i < m_all) ? src[i] : STB_KEY_INVALID;
+  for (int i = tid; i < STB_D; i += 256) sqd[i] = (double)__ldg(a.queries + (size_t)q * STB_D + i);
+  if (tid == 0) { s_pass = 0; s_m2 = 0; }
+  __syncthreads();
+  for (uint32_t kk = 2; kk <= n_sort; kk <<= 1)
+    for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = tid; i < n_sort; i += 256) {
+        const uint32_t ixj = i ^ j;
+        if (ixj > i) {
+          const uint64_t x = skeys[i], y = skeys[ixj];
+          const bool up = ((i & kk) == 0);
+          if ((x > y) == up) { skeys[i] = y; skeys[ixj] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  // 2. narrow to a >= A_k - 2 EPS (everything when fewer than k rows were emitted)
+  float cut = -CUDART_INF_F;
+  if (m_all >= k) cut = stb_key_score(skeys[k - 1]) - 2.0f * (float)STB_BATCH_EPS;
+  for (uint32_t i = tid; i < m_all; i += 256)
+    if (stb_key_score(skeys[i]) >= cut) atomicMax(&s_m2, i + 1);
+  if (tid == 0) {
+    double q2 = 0.0;
+    for (int i = 0; i < STB_D; ++i) q2 = fma(sqd[i], sqd[i], q2);
+    s_q2 = q2;
+  }
+  __syncthreads();
+  const uint32_t m2 = s_m2;
+  if (m2 > STB_V2_RESCORE_CAP) { give_up(); return; }
+  uint32_t n2 = 32;
+  while (n2 < m2) n2 <<= 1;
+  // 3. exact canonical distance (f64 accumulation in index order == oracle orc_cosine_f32)
+  const double q2 = s_q2;
+  for (uint32_t c = tid; c < n2; c += 256) {
+    double d = CUDART_INF;
+    uint64_t grow = 0xffffffffffffffffull;
+    if (c < m2) {
+      const uint64_t row = stb_key_row(skeys[c]);
+      const float4 *rp = a.rows + row * STB_ROW_F4;
+      double ab = 0.0, r2 = 0.0;
+#pragma unroll 8
+      for (int i = 0; i < STB_ROW_F4; ++i) {
+        const float4 v = __ldg(rp + i);
+        const double vx = (double)v.x, vy = (double)v.y, vz = (double)v.z, vw = (double)v.w;
+        ab = fma(sqd[4 * i + 0], vx, ab); r2 = fma(vx, vx, r2);
+        ab = fma(sqd[4 * i + 1], vy, ab); r2 = fma(vy, vy, r2);
+        ab = fma(sqd[4 * i + 2], vz, ab); r2 = fma(vz, vz, r2);
+        ab = fma(sqd[4 * i + 3], vw, ab); r2 = fma(vw, vw, r2);
+      }
+      double dist;
+      if (q2 == 0.0 && r2 == 0.0) dist = 0.0;
+      else if (ab == 0.0) dist = 1.0;
+      else {
+        const double t = 1.0 - ab / (sqrt(q2) * sqrt(r2));
+        dist = t > 0.0 ? t : 0.0;
+      }
+      if (dist < 100.0) { d = dist; grow = a.row_base + row; atomicAdd(&s_pass, 1); }
+    }
+    sd[c] = d; sr[c] = grow;
+  }
+  __syncthreads();
+  // 4. sort the (distance,row) pairs, write the top-k
+  for (uint32_t kk = 2; kk <= n2; kk <<= 1)
+    for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = tid; i < n2; i += 256) {
+        const uint32_t ixj = i ^ j;
+        if (ixj > i) {
+          const bool up = ((i & kk) == 0);
+          const bool gt = stb_hit_less(sd[ixj], sr[ixj], sd[i], sr[i]);
+          if (gt == up) {
+            const double td = sd[i]; const uint64_t tr = sr[i];
+            sd[i] = sd[ixj]; sr[i] = sr[ixj]; sd[ixj] = td; sr[ixj] = tr;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  const uint32_t n_out = min((uint32_t)s_pass, k);
+  for (uint32_t i = tid; i < k; i += 256) {
+    stb_hit h;
+    h.distance = (i < n_out) ? sd[i] : CUDART_INF;
+    h.row = (i < n_out) ? sr[i] : 0xffffffffffffffffull;
+    a.out_hits[(size_t)q * k + i] = h;
+  }
+  if (tid == 0) { a.out_status[2 * q] = n_out; a.out_status[2 * q + 1] = 1u; }
+}
+
+int stb_launch_batch_thresh(stb_ctx *ctx, const float *tilemax, uint32_t n_sample, uint32_t nq, uint32_t q_pad,
+                            uint32_t top_k, float *thr) {
+  if (n_sample > STB_V2_MAX_SAMPLE) { stb_set_error("batch_thresh: sample too large"); return STB_ERR_ARG; }
+  ThreshArgs a;
+  a.tilemax = tilemax; a.n_sample = n_sample; a.nq = nq; a.q_pad = q_pad; a.top_k = top_k; a.thr = thr;
+  stb_batch_thresh_kernel<<<(q_pad + 7) / 8, 256, 0, ctx->stream>>>(a);
+  STB_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  return STB_OK;
+}
+
+int stb_launch_batch_finish2(stb_ctx *ctx, const uint64_t *cand_keys, const uint32_t *cand_cnt, uint32_t cand_cap,
+                             uint32_t nq, uint32_t top_k, const float *rows, uint64_t n_rows, uint64_t row_base,
+                             const float *queries_dev, stb_hit *out_hits, uint32_t *out_status) {
+  if (top_k > STB_V2_RESCORE_CAP || (cand_cap & (cand_cap - 1)) || cand_cap < 64) { stb_set_error("batch_finish2: bad capacity"); return STB_ERR_ARG; }
+  const size_t smem = ((size_t)cand_cap + 2 * STB_V2_RESCORE_CAP) * 8;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    STB_CUDA(cudaFuncSetAttribute(stb_batch_finish2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  Finish2Args a;
+  a.cand_keys = cand_keys; a.cand_cnt = cand_cnt; a.cand_cap = cand_cap; a.nq = nq; a.top_k = top_k;
+  a.rows = reinterpret_cast<const float4 *>(rows); a.n_rows = n_rows; a.row_base = row_base;
+  a.queries = queries_dev; a.out_hits = out_hits; a.out_status = out_status;
+  stb_batch_finish2_kernel<<<nq, 256, smem, ctx->stream>>>(a);
   STB_CUDA(cudaGetLastError());
   ctx->kernel_launches++;
   return STB_OK;

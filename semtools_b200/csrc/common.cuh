@@ -67,6 +67,9 @@ struct stb_ctx {
   float *b_submax; size_t b_submax_cap;       // [n_sub][q_pad]
   float *b_tilemax; size_t b_tilemax_cap;     // [n_tiles][q_pad]
   uint64_t *b_cand; size_t b_cand_cap;        // [q_pad][slices][32]
+  float *b_thr; size_t b_thr_cap;             // v2: [q_pad] emission thresholds
+  uint32_t *b_cnt; size_t b_cnt_cap;          // v2: [q_pad] emitted-candidate counters
+  uint64_t *b_keys; size_t b_keys_cap;        // v2: [q_pad][cand_cap] emitted keys
   float *bq_dev; size_t bq_dev_cap;           // host-call staging: queries
   stb_hit *bh_dev; size_t bh_dev_cap;         // host-call staging: hits
   uint32_t *bs_dev; size_t bs_dev_cap;        // host-call staging: status
@@ -177,6 +180,19 @@ int stb_launch_shadow_build(stb_ctx *ctx, const float *rows_dev, uint64_t n_rows
 int stb_launch_batch_gemm(stb_ctx *ctx, const uint8_t *a_tiles, uint32_t m_tiles,
                           const uint8_t *b_tiles, uint32_t n_tiles, float *submax,
                           float *tilemax, float *full_out);
+int stb_launch_batch_gemm_strided(stb_ctx *ctx, const uint8_t *a_tiles, uint32_t m_tiles,
+                                  const uint8_t *b_tiles, uint32_t n_tiles, uint32_t tile_stride,
+                                  float *submax, float *tilemax, float *full_out);
+int stb_launch_batch_gemm_emit(stb_ctx *ctx, const uint8_t *a_tiles, uint32_t m_tiles,
+                               const uint8_t *b_tiles, uint32_t n_tiles, uint64_t n_rows,
+                               const float *thr, uint32_t *cand_cnt, uint64_t *cand_keys,
+                               uint32_t cand_cap);
+int stb_launch_batch_thresh(stb_ctx *ctx, const float *tilemax, uint32_t n_sample, uint32_t nq,
+                            uint32_t q_pad, uint32_t top_k, float *thr);
+int stb_launch_batch_finish2(stb_ctx *ctx, const uint64_t *cand_keys, const uint32_t *cand_cnt,
+                             uint32_t cand_cap, uint32_t nq, uint32_t top_k, const float *rows,
+                             uint64_t n_rows, uint64_t row_base, const float *queries_dev,
+                             stb_hit *out_hits, uint32_t *out_status);
 int stb_launch_batch_select(stb_ctx *ctx, const float *submax, uint32_t n_sub, uint32_t q_pad,
                             uint32_t n_slices, uint64_t *cand);
 int stb_launch_batch_finish(stb_ctx *ctx, const uint64_t *cand, uint32_t n_slices, uint32_t n_sub,

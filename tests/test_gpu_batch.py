@@ -151,3 +151,67 @@ def test_sharded_batch_search_merges_to_the_unsharded_answer(ctx):
         assert got[i]["row"].tolist() == [int(x) for x in r], i
         assert np.array_equal(got[i]["distance"], d), i
     assert got[0]["row"][:2].tolist() == [5, 59_999]
+
+
+# ------------------------------------------------------------------------------------------
+# Pipeline v2 (sampled threshold -> emitting epilogue -> exact finish).  Opt-in in the library
+# (STB_BATCH_V2=1) and in this suite (STB_TEST_V2=1) until it has been validated on hardware.
+import os
+
+v2 = pytest.mark.skipif(os.environ.get("STB_TEST_V2") != "1", reason="pipeline v2 is opt-in (STB_TEST_V2=1)")
+
+
+@pytest.fixture
+def batch_v2():
+    old = os.environ.get("STB_BATCH_V2")
+    os.environ["STB_BATCH_V2"] = "1"
+    yield
+    if old is None:
+        del os.environ["STB_BATCH_V2"]
+    else:
+        os.environ["STB_BATCH_V2"] = old
+
+
+@v2
+@pytest.mark.parametrize("nq,n,k", [(1, 40, 3), (5, 1000, 10), (130, 70_000, 10), (300, 20_001, 1), (64, 50_000, 40),
+                                    (3, 255, 5), (9, 256, 64), (20, 200_000, 10)])
+def test_v2_search_batch_matches_oracle_without_fallback(ctx, batch_v2, nq, n, k):
+    rng = np.random.default_rng(nq + n + k)
+    rows = unit_rows(rng, n)
+    queries = unit_rows(rng, nq)
+    c = capi.Corpus(ctx, n)
+    c.append(rows)
+    before = ctx.counters()["fallback_searches"]
+    res = c.search_batch(queries, top_k=k)
+    check_batch(res, rows, queries, k)
+    assert ctx.counters()["fallback_searches"] == before        # v2 proves every k <= 64 unless a capacity overflows
+
+
+@v2
+def test_v2_ties_zero_rows_dense_neighbourhoods(ctx, batch_v2):
+    rng = np.random.default_rng(42)
+    rows = unit_rows(rng, 30_000)
+    rows[rng.integers(0, 30_000, 20)] = rows[rng.integers(0, 30_000, 20)]
+    rows[[3, 999, 29_999]] = 0.0
+    queries = unit_rows(rng, 40)
+    queries[0] = rows[17]
+    queries[1] = 0.0                           # zero query: every row ties -> overflow -> K1 fallback
+    where = rng.choice(30_000, 600, replace=False)
+    rows[where] = (queries[2] + 0.005 * unit_rows(rng, 1)[0]).astype(np.float32)   # 600 identical best rows: 600 <= 1024 re-scores
+    where2 = rng.choice(30_000, 3000, replace=False)
+    rows[where2] = (queries[3] + 0.004 * unit_rows(rng, 1)[0]).astype(np.float32)  # 3000 > re-score cap -> fallback
+    c = capi.Corpus(ctx, 30_000, row_base=5_000_000_000)
+    c.append(rows)
+    before = ctx.counters()["fallback_searches"]
+    res = c.search_batch(queries, top_k=10)
+    for i, q in enumerate(queries):
+        r, d = oracle.search_rows(rows, q, top_k=10)
+        assert res[i]["row"].tolist() == [int(x) + 5_000_000_000 for x in r], i
+        assert np.array_equal(res[i]["distance"], d), i
+    # queries 1 and 3 overflow a capacity and go to K1 (whose own tie fallback counts again)
+    assert ctx.counters()["fallback_searches"] - before >= 2
+    # the 600 tied best rows of query 2 fit the in-kernel exact re-score: no fallback
+    before = ctx.counters()["fallback_searches"]
+    one = c.search_batch(queries[2:3], top_k=10)
+    assert np.array_equal(one[0], res[2])
+    assert ctx.counters()["fallback_searches"] == before
