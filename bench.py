@@ -646,6 +646,16 @@ def run_ours(args):
                 v2["roofline_frac_pipeline"] = v2["gemm_TFLOPs_pipeline"] / tpeak
                 v2["note"] = "opt-in pipeline (STB_BATCH_V2=1): same C-ABI call, same results; not the default path yet"
             line["batch1024_v2"] = v2
+            # K5 fused search (two launches, one sync; opt-in STB_IVFPQ_V2=1), same workload as `ivfpq`
+            os.environ["STB_IVFPQ_V2"] = "1"
+            try:
+                k5v2 = side(bench_ivfpq, torch, dev, ctx, rows=args.ivfpq_rows)
+            finally:
+                os.environ.pop("STB_IVFPQ_V2", None)
+            if "error" not in k5v2:
+                k5v2["note"] = ("opt-in fused search (STB_IVFPQ_V2=1); the exact-scan column inside this section "
+                                "is unaffected by the switch")
+            line["ivfpq_v2"] = k5v2
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

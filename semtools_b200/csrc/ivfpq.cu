@@ -44,6 +44,9 @@ struct stb_ivfpq {
   stb_hit *cand;              // candidate (-score,pos) hits, padded
   size_t cand_cap;
   uint32_t *cand_rows;        // local rows of the R best candidates
+  // fused search (v2)
+  uint64_t *keys2;            // [ADC2_MAX_CTAS][ADC2_KEEP] per-CTA best candidates (score desc, code position)
+  unsigned int *tickets;      // [2] last-CTA tickets of the two fused kernels (kernels re-zero them)
 };
 
 // ------------------------------------------------------------------ assignment GEMM ---
@@ -402,6 +405,250 @@ __global__ void ivf_pick_rows_kernel(const stb_hit *cand, uint32_t r, const uint
   else rows[i] = 0xffffffffu;
 }
 
+// ------------------------------------------------------------------ fused search (v2) ---
+// Two launches and ONE host synchronisation per query (v1: ~25 launches, 4-5 syncs):
+//   ivf_coarse_probe_kernel  coarse scores (warp per centroid); the LAST CTA to finish sorts
+//                            them, writes the probe list + prefix sums and the ADC table.
+//   ivf_adc_finish_kernel    ADC scan (32-row chunks dealt round-robin over CTAs first, then
+//                            warps, so a tight cluster's contiguous codes spread over every
+//                            CTA); each CTA keeps its ADC2_KEEP best; the LAST CTA sorts the
+//                            <= 8192 survivors, re-scores the best `rerank` rows exactly
+//                            (canonical f64, as K1) and writes the top-k hits.
+// Opt-in (STB_IVFPQ_V2=1) until validated on hardware.
+#define ADC2_THREADS 512
+#define ADC2_MAX_CTAS 32
+#define ADC2_KEEP 256
+#define ADC2_RERANK_CAP 1024
+#define ADC2_SMEM 65536
+
+struct Probe2Args {
+  const float *C; uint32_t nlist, nprobe; const float *q; float *coarse; const uint32_t *list_off; const float *cb;
+  uint32_t *probe; float *lut; unsigned int *ticket;
+};
+
+__global__ void __launch_bounds__(1024)
+ivf_coarse_probe_kernel(const Probe2Args a) {
+  extern __shared__ uint64_t p2_keys[];   // npow2 keys (last CTA only)
+  __shared__ float sq[STB_D];
+  __shared__ float s_inv;
+  __shared__ unsigned s_last;
+  const int lane = threadIdx.x & 31;
+  const uint32_t c = blockIdx.x * 32 + (threadIdx.x >> 5);
+  if (c < a.nlist) {
+    const float4 *cr = reinterpret_cast<const float4 *>(a.C + (size_t)c * STB_D), *q4 = reinterpret_cast<const float4 *>(a.q);
+    const float4 a0 = __ldg(cr + 2 * lane), a1 = __ldg(cr + 2 * lane + 1), b0 = __ldg(q4 + 2 * lane), b1 = __ldg(q4 + 2 * lane + 1);
+    float d = a0.x * b0.x + a0.y * b0.y + a0.z * b0.z + a0.w * b0.w + a1.x * b1.x + a1.y * b1.y + a1.z * b1.z + a1.w * b1.w;
+    float qq = b0.x * b0.x + b0.y * b0.y + b0.z * b0.z + b0.w * b0.w + b1.x * b1.x + b1.y * b1.y + b1.z * b1.z + b1.w * b1.w;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { d += __shfl_xor_sync(0xffffffffu, d, off); qq += __shfl_xor_sync(0xffffffffu, qq, off); }
+    if (lane == 0) { a.coarse[c] = qq > 0.f ? d * rsqrtf(qq) : 0.f; __threadfence(); }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // ---- last CTA: every coarse score is visible (read through L2)
+  uint32_t npow = 1; while (npow < a.nlist) npow <<= 1;
+  for (uint32_t i = threadIdx.x; i < npow; i += blockDim.x)
+    p2_keys[i] = (i < a.nlist) ? stb_make_key(__ldcg(a.coarse + i), i) : STB_KEY_INVALID;
+  if (threadIdx.x < STB_D) sq[threadIdx.x] = a.q[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) { float s = 0.f; for (int i = 0; i < STB_D; ++i) s += sq[i] * sq[i]; s_inv = s > 0.f ? rsqrtf(s) : 0.f; }
+  for (uint32_t kk = 2; kk <= npow; kk <<= 1)
+    for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = threadIdx.x; i < npow; i += blockDim.x) {
+        const uint32_t ixj = i ^ j;
+        if (ixj > i) {
+          const uint64_t x = p2_keys[i], y = p2_keys[ixj];
+          const bool up = ((i & kk) == 0);
+          if ((x > y) == up) { p2_keys[i] = y; p2_keys[ixj] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  if (threadIdx.x == 0) {
+    uint32_t acc = 0;
+    for (uint32_t p = 0; p < a.nprobe; ++p) {
+      const uint32_t l = stb_key_row(p2_keys[p]);
+      a.probe[p] = l;
+      a.probe[a.nprobe + p] = acc;
+      acc += a.list_off[l + 1] - a.list_off[l];
+    }
+    a.probe[2 * a.nprobe] = acc;
+    *a.ticket = 0;                                   // ready for the next query (stream-ordered)
+  }
+  const float inv = s_inv;
+  for (int i = threadIdx.x; i < PQ_M * PQ_KSUB; i += blockDim.x) {
+    const int sub = i / PQ_KSUB;
+    const float *e = a.cb + (size_t)i * PQ_DSUB;
+    float d = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) d = fmaf(sq[sub * 8 + t] * inv, e[t], d);
+    a.lut[i] = d;
+  }
+}
+
+struct Adc2Args {
+  const uint8_t *codes; const uint32_t *list_off; const uint32_t *probe; uint32_t nprobe;
+  const float *coarse; const float *lut; const uint32_t *order;
+  uint64_t *keys2; unsigned int *ticket;
+  const float4 *rows; uint64_t row_base; const float *q; uint32_t top_k, rerank;
+  stb_hit *out_hits; uint32_t *out_status;     // status: [0] hits, [1] codes scanned
+};
+
+__device__ __forceinline__ void adc2_sort_keys(uint64_t *k, uint32_t n, uint32_t tid, uint32_t nthreads) {
+  for (uint32_t kk = 2; kk <= n; kk <<= 1)
+    for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = tid; i < n; i += nthreads) {
+        const uint32_t ixj = i ^ j;
+        if (ixj > i) {
+          const uint64_t x = k[i], y = k[ixj];
+          const bool up = ((i & kk) == 0);
+          if ((x > y) == up) { k[i] = y; k[ixj] = x; }
+        }
+      }
+      __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(ADC2_THREADS, 1)
+ivf_adc_finish_kernel(const Adc2Args a) {
+  extern __shared__ __align__(16) uint8_t dyn[];          // 64 KiB
+  float *s_lut = reinterpret_cast<float *>(dyn);          // [0, 32 KiB) during the scan
+  uint64_t *s_keys = reinterpret_cast<uint64_t *>(dyn + 32768);   // 1024 keys during the CTA reduction
+  __shared__ double sqd[STB_D];
+  __shared__ double s_q2;
+  __shared__ unsigned s_last;
+  __shared__ int s_pass;
+  const uint32_t tid = threadIdx.x;
+  const int lane = tid & 31;
+  const uint32_t warp_in = tid >> 5, n_ctas = gridDim.x;
+  for (uint32_t i = tid; i < PQ_M * PQ_KSUB; i += ADC2_THREADS) s_lut[i] = a.lut[i];
+  __syncthreads();
+  const uint32_t total = a.probe[2 * a.nprobe];
+  AdcTop top;
+  top.init();
+  // chunk g (32 consecutive codes) -> CTA g % n_ctas, warp (g / n_ctas) % 16
+  for (uint64_t g = blockIdx.x + (uint64_t)n_ctas * warp_in; g * 32 < total; g += (uint64_t)n_ctas * (ADC2_THREADS / 32)) {
+    const uint64_t v = g * 32 + lane;
+    float s = -CUDART_INF_F;
+    uint32_t pos = 0;
+    if (v < total) {
+      uint32_t lo = 0, hi = a.nprobe;
+      while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.probe[a.nprobe + mid] <= v) lo = mid; else hi = mid; }
+      const uint32_t l = a.probe[lo];
+      pos = a.list_off[l] + (uint32_t)(v - a.probe[a.nprobe + lo]);
+      const uint4 *cp = reinterpret_cast<const uint4 *>(a.codes + (size_t)pos * PQ_M);
+      const uint4 c0 = __ldg(cp), c1 = __ldg(cp + 1);
+      const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+      s = a.coarse[l];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s += s_lut[(4 * i + 0) * PQ_KSUB + (w[i] & 0xff)];
+        s += s_lut[(4 * i + 1) * PQ_KSUB + ((w[i] >> 8) & 0xff)];
+        s += s_lut[(4 * i + 2) * PQ_KSUB + ((w[i] >> 16) & 0xff)];
+        s += s_lut[(4 * i + 3) * PQ_KSUB + (w[i] >> 24)];
+      }
+    }
+    top.push(s, pos);
+  }
+  // CTA reduction: 16 warps x 64 -> the ADC2_KEEP best of this CTA
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const bool ok = top.lr[e] != 0xffffffffu || top.ls[e] > -CUDART_INF_F;
+    s_keys[warp_in * 64 + e * 32 + lane] = ok ? stb_make_key(top.ls[e], top.lr[e]) : STB_KEY_INVALID;
+  }
+  __syncthreads();
+  adc2_sort_keys(s_keys, (ADC2_THREADS / 32) * 64, tid, ADC2_THREADS);
+  for (uint32_t i = tid; i < ADC2_KEEP; i += ADC2_THREADS) a.keys2[(size_t)blockIdx.x * ADC2_KEEP + i] = s_keys[i];
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last = (atomicAdd(a.ticket, 1u) == n_ctas - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // ---- last CTA: global selection + exact re-rank
+  uint64_t *fk = reinterpret_cast<uint64_t *>(dyn);       // up to 8192 keys = 64 KiB
+  const uint32_t n_all = n_ctas * ADC2_KEEP;
+  uint32_t n_sort = 64;
+  while (n_sort < n_all) n_sort <<= 1;
+  for (uint32_t i = tid; i < n_sort; i += ADC2_THREADS) fk[i] = (i < n_all) ? __ldcg(a.keys2 + i) : STB_KEY_INVALID;
+  for (uint32_t i = tid; i < STB_D; i += ADC2_THREADS) sqd[i] = (double)a.q[i];
+  if (tid == 0) s_pass = 0;
+  __syncthreads();
+  adc2_sort_keys(fk, n_sort, tid, ADC2_THREADS);
+  if (tid == 0) {
+    double q2 = 0.0;
+    for (int i = 0; i < STB_D; ++i) q2 = fma(sqd[i], sqd[i], q2);
+    s_q2 = q2;
+  }
+  __syncthreads();
+  const uint32_t r = min(min(a.rerank, (uint32_t)ADC2_RERANK_CAP), n_all);
+  uint32_t n2 = 32;
+  while (n2 < r) n2 <<= 1;
+  // keys 0..r) live in dyn[0, 8 KiB); the (distance,row) pairs go to dyn[16 KiB, 32 KiB)
+  double *sd = reinterpret_cast<double *>(dyn + 16384);
+  uint64_t *sr = reinterpret_cast<uint64_t *>(dyn + 16384 + 8 * ADC2_RERANK_CAP);
+  const double q2 = s_q2;
+  for (uint32_t c = tid; c < n2; c += ADC2_THREADS) {
+    double d = CUDART_INF;
+    uint64_t grow = 0xffffffffffffffffull;
+    const uint64_t key = (c < r) ? fk[c] : STB_KEY_INVALID;
+    if (key != STB_KEY_INVALID) {
+      const uint64_t row = a.order[stb_key_row(key)];
+      const float4 *rp = a.rows + row * STB_ROW_F4;
+      double ab = 0.0, r2 = 0.0;
+#pragma unroll 8
+      for (int i = 0; i < STB_ROW_F4; ++i) {
+        const float4 v = __ldg(rp + i);
+        const double vx = (double)v.x, vy = (double)v.y, vz = (double)v.z, vw = (double)v.w;
+        ab = fma(sqd[4 * i + 0], vx, ab); r2 = fma(vx, vx, r2);
+        ab = fma(sqd[4 * i + 1], vy, ab); r2 = fma(vy, vy, r2);
+        ab = fma(sqd[4 * i + 2], vz, ab); r2 = fma(vz, vz, r2);
+        ab = fma(sqd[4 * i + 3], vw, ab); r2 = fma(vw, vw, r2);
+      }
+      double dist;
+      if (q2 == 0.0 && r2 == 0.0) dist = 0.0;
+      else if (ab == 0.0) dist = 1.0;
+      else {
+        const double t = 1.0 - ab / (sqrt(q2) * sqrt(r2));
+        dist = t > 0.0 ? t : 0.0;
+      }
+      if (dist < 100.0) { d = dist; grow = a.row_base + row; atomicAdd(&s_pass, 1); }
+    }
+    sd[c] = d; sr[c] = grow;
+  }
+  __syncthreads();
+  for (uint32_t kk = 2; kk <= n2; kk <<= 1)
+    for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = tid; i < n2; i += ADC2_THREADS) {
+        const uint32_t ixj = i ^ j;
+        if (ixj > i) {
+          const bool up = ((i & kk) == 0);
+          const bool gt = stb_hit_less(sd[ixj], sr[ixj], sd[i], sr[i]);
+          if (gt == up) {
+            const double td = sd[i]; const uint64_t tr = sr[i];
+            sd[i] = sd[ixj]; sr[i] = sr[ixj]; sd[ixj] = td; sr[ixj] = tr;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  const uint32_t n_out = min((uint32_t)s_pass, a.top_k);
+  for (uint32_t i = tid; i < n_out; i += ADC2_THREADS) {
+    stb_hit h; h.distance = sd[i]; h.row = sr[i];
+    a.out_hits[i] = h;
+  }
+  if (tid == 0) { a.out_status[0] = n_out; a.out_status[1] = total; *a.ticket = 0; }
+}
+
 // ------------------------------------------------------------------ host side ---------
 extern "C" {
 
@@ -409,6 +656,7 @@ int stb_ivfpq_destroy(stb_ivfpq *x) {
   if (!x) return STB_OK;
   cudaFree(x->centroids); cudaFree(x->codebooks); cudaFree(x->codes); cudaFree(x->order); cudaFree(x->list_off);
   cudaFree(x->coarse); cudaFree(x->lut); cudaFree(x->probe); cudaFree(x->cand); cudaFree(x->cand_rows);
+  cudaFree(x->keys2); cudaFree(x->tickets);
   cudaGetLastError();
   delete x;
   return STB_OK;
@@ -438,6 +686,7 @@ int stb_ivfpq_build(stb_ctx *ctx, const stb_corpus *corpus, uint32_t nlist, uint
   x->ctx = ctx; x->corpus = corpus; x->nlist = nlist; x->n = n;
   x->centroids = nullptr; x->codebooks = nullptr; x->codes = nullptr; x->order = nullptr; x->list_off = nullptr;
   x->coarse = nullptr; x->lut = nullptr; x->probe = nullptr; x->cand = nullptr; x->cand_cap = 0; x->cand_rows = nullptr;
+  x->keys2 = nullptr; x->tickets = nullptr;
   cudaStream_t st = ctx->stream;
   // training sample: every `stride`-th row
   uint64_t ns = std::min<uint64_t>(n, std::max<uint32_t>(train_rows, nlist * 32u));
@@ -514,6 +763,9 @@ int stb_ivfpq_build(stb_ctx *ctx, const stb_corpus *corpus, uint32_t nlist, uint
   IVF_CUDA(cudaMalloc(&x->lut, (size_t)PQ_M * PQ_KSUB * 4));
   IVF_CUDA(cudaMalloc(&x->probe, (size_t)(2 * 1024 + 1) * 4));
   IVF_CUDA(cudaMalloc(&x->cand_rows, 4096 * 4 + 16));
+  IVF_CUDA(cudaMalloc(&x->keys2, (size_t)ADC2_MAX_CTAS * ADC2_KEEP * 8));
+  IVF_CUDA(cudaMalloc(&x->tickets, 2 * sizeof(unsigned int)));
+  IVF_CUDA(cudaMemsetAsync(x->tickets, 0, 2 * sizeof(unsigned int), ctx->stream));
   IVF_CUDA(cudaGetLastError());
   IVF_CUDA(cudaStreamSynchronize(st));
   cudaFree(sums); cudaFree(counts); cudaFree(pq_sums); cudaFree(pq_counts); cudaFree(assign); cudaFree(cursor);
@@ -547,6 +799,38 @@ int stb_ivfpq_search(stb_ivfpq *x, const float *q, uint32_t nprobe, uint32_t top
   cudaStream_t st = ctx->stream;
   memcpy(ctx->q_pin, q, STB_D * sizeof(float));
   STB_CUDA(cudaMemcpyAsync(ctx->q_dev, ctx->q_pin, STB_D * sizeof(float), cudaMemcpyHostToDevice, st));
+  const char *v2_env = getenv("STB_IVFPQ_V2");
+  if (v2_env && v2_env[0] == '1' && rerank <= ADC2_RERANK_CAP && top_k <= 1024) {
+    // fused search: two launches, one synchronisation
+    uint32_t npow2 = 1; while (npow2 < x->nlist) npow2 <<= 1;
+    static bool attr2 = false;
+    if (!attr2) {
+      STB_CUDA(cudaFuncSetAttribute(ivf_coarse_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+      STB_CUDA(cudaFuncSetAttribute(ivf_adc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ADC2_SMEM));
+      attr2 = true;
+    }
+    Probe2Args pa;
+    pa.C = x->centroids; pa.nlist = x->nlist; pa.nprobe = nprobe; pa.q = ctx->q_dev; pa.coarse = x->coarse;
+    pa.list_off = x->list_off; pa.cb = x->codebooks; pa.probe = x->probe; pa.lut = x->lut; pa.ticket = x->tickets;
+    ivf_coarse_probe_kernel<<<(x->nlist + 31) / 32, 1024, npow2 * 8, st>>>(pa);
+    STB_CUDA(cudaGetLastError());
+    Adc2Args aa;
+    aa.codes = x->codes; aa.list_off = x->list_off; aa.probe = x->probe; aa.nprobe = nprobe; aa.coarse = x->coarse;
+    aa.lut = x->lut; aa.order = x->order; aa.keys2 = x->keys2; aa.ticket = x->tickets + 1;
+    aa.rows = reinterpret_cast<const float4 *>(x->corpus->rows); aa.row_base = x->corpus->row_base; aa.q = ctx->q_dev;
+    aa.top_k = top_k; aa.rerank = rerank; aa.out_hits = ctx->hits_dev; aa.out_status = ctx->status_dev;
+    ivf_adc_finish_kernel<<<ADC2_MAX_CTAS, ADC2_THREADS, ADC2_SMEM, st>>>(aa);
+    STB_CUDA(cudaGetLastError());
+    STB_CUDA(cudaMemcpyAsync(ctx->status_pin, ctx->status_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    STB_CUDA(cudaMemcpyAsync(ctx->hits_pin, ctx->hits_dev, top_k * sizeof(stb_hit), cudaMemcpyDeviceToHost, st));
+    STB_CUDA(cudaStreamSynchronize(st));
+    const uint32_t n_out = std::min<uint32_t>(ctx->status_pin[0], top_k);
+    memcpy(out_hits, ctx->hits_pin, n_out * sizeof(stb_hit));
+    *out_n = n_out;
+    if (out_scanned) *out_scanned = ctx->status_pin[1];
+    ctx->kernel_launches += 2;
+    return STB_OK;
+  }
   ivf_coarse_kernel<<<(x->nlist + 7) / 8, 256, 0, st>>>(x->centroids, x->nlist, ctx->q_dev, x->coarse);
   uint32_t npow = 1; while (npow < x->nlist) npow <<= 1;
   static bool attr = false;
