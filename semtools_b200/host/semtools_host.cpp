@@ -38,6 +38,78 @@ std::string to_lowercase_ascii(const std::string &s) {
   return r;
 }
 
+// ---- str::to_lowercase (full Unicode mapping + Final_Sigma), mod.rs:63-67 ------------------
+namespace {
+#include "unicode_lower.inc"
+
+bool in_ranges(const CpRange *r, size_t n, uint32_t cp) {
+  size_t lo = 0, hi = n;
+  while (lo < hi) {
+    const size_t mid = (lo + hi) / 2;
+    if (cp > r[mid].hi) lo = mid + 1;
+    else if (cp < r[mid].lo) hi = mid;
+    else return true;
+  }
+  return false;
+}
+bool case_ignorable(uint32_t cp) { return in_ranges(kCaseIgnorable, sizeof(kCaseIgnorable) / sizeof(CpRange), cp); }
+bool cased_not_ignorable(uint32_t cp) { return in_ranges(kCasedNotIgn, sizeof(kCasedNotIgn) / sizeof(CpRange), cp); }
+
+// decodes one scalar value; a malformed byte is returned as 0x110000 + byte (passes through)
+uint32_t decode(const std::string &s, size_t &i) {
+  const unsigned char b0 = (unsigned char)s[i];
+  auto cont = [&](size_t k) { return i + k < s.size() && ((unsigned char)s[i + k] & 0xC0) == 0x80; };
+  if (b0 < 0x80) { i += 1; return b0; }
+  if (b0 >= 0xC2 && b0 <= 0xDF && cont(1)) { uint32_t c = ((b0 & 0x1Fu) << 6) | ((unsigned char)s[i + 1] & 0x3Fu); i += 2; return c; }
+  if (b0 >= 0xE0 && b0 <= 0xEF && cont(1) && cont(2)) {
+    uint32_t c = ((b0 & 0x0Fu) << 12) | (((unsigned char)s[i + 1] & 0x3Fu) << 6) | ((unsigned char)s[i + 2] & 0x3Fu);
+    if (c >= 0x800 && !(c >= 0xD800 && c <= 0xDFFF)) { i += 3; return c; }
+  }
+  if (b0 >= 0xF0 && b0 <= 0xF4 && cont(1) && cont(2) && cont(3)) {
+    uint32_t c = ((b0 & 0x07u) << 18) | (((unsigned char)s[i + 1] & 0x3Fu) << 12) | (((unsigned char)s[i + 2] & 0x3Fu) << 6) |
+                 ((unsigned char)s[i + 3] & 0x3Fu);
+    if (c >= 0x10000 && c <= 0x10FFFF) { i += 4; return c; }
+  }
+  i += 1;
+  return 0x110000u + b0;
+}
+void encode(uint32_t c, std::string &out) {
+  if (c >= 0x110000u) { out += (char)(c - 0x110000u); return; }      // malformed byte, unchanged
+  if (c < 0x80) out += (char)c;
+  else if (c < 0x800) { out += (char)(0xC0 | (c >> 6)); out += (char)(0x80 | (c & 0x3F)); }
+  else if (c < 0x10000) { out += (char)(0xE0 | (c >> 12)); out += (char)(0x80 | ((c >> 6) & 0x3F)); out += (char)(0x80 | (c & 0x3F)); }
+  else { out += (char)(0xF0 | (c >> 18)); out += (char)(0x80 | ((c >> 12) & 0x3F)); out += (char)(0x80 | ((c >> 6) & 0x3F)); out += (char)(0x80 | (c & 0x3F)); }
+}
+}  // namespace
+
+std::string to_lowercase(const std::string &s) {
+  std::vector<uint32_t> cps;
+  cps.reserve(s.size());
+  for (size_t i = 0; i < s.size();) cps.push_back(decode(s, i));
+  std::string out;
+  out.reserve(s.size());
+  const size_t n_map = sizeof(kLower) / sizeof(LowerMap);
+  for (size_t i = 0; i < cps.size(); ++i) {
+    const uint32_t c = cps[i];
+    if (c < 0x80) { out += (char)((c >= 'A' && c <= 'Z') ? c + 32 : c); continue; }
+    if (c == 0x3A3) {
+      // Final_Sigma: preceded by a cased letter (skipping case-ignorables) and not followed by one
+      size_t j = i;
+      bool before = false;
+      while (j > 0) { --j; if (!case_ignorable(cps[j])) { before = cased_not_ignorable(cps[j]); break; } }
+      bool after = false;
+      for (size_t k = i + 1; k < cps.size(); ++k) if (!case_ignorable(cps[k])) { after = cased_not_ignorable(cps[k]); break; }
+      encode(before && !after ? 0x3C2 : 0x3C3, out);
+      continue;
+    }
+    size_t lo = 0, hi = n_map;
+    while (lo < hi) { const size_t mid = (lo + hi) / 2; if (kLower[mid].cp < c) lo = mid + 1; else hi = mid; }
+    if (lo < n_map && kLower[lo].cp == c) for (int t = 0; t < kLower[lo].n; ++t) encode(kLower[lo].to[t], out);
+    else encode(c, out);
+  }
+  return out;
+}
+
 // shortest round-trip decimal digits and exponent: value = 0.d1d2... x 10^exp10
 static void shortest_digits(double x, std::string &digits, int &exp10) {
   char buf[64];
@@ -161,7 +233,7 @@ bool Searcher::add_document(const std::string &filename, const std::string &cont
   if (lines.empty()) return false;                             // mod.rs:57-59
   if (!table_) throw std::runtime_error("load_table first");
   std::vector<std::string> emb_lines = lines;
-  if (ignore_case) for (auto &l : emb_lines) l = to_lowercase_ascii(l);
+  if (ignore_case) for (auto &l : emb_lines) l = to_lowercase(l);
   std::vector<uint64_t> offsets;
   std::vector<uint32_t> ids;
   to_csr(emb_lines, tok, 2048, offsets, ids);                  // encode_with_args(.., Some(2048), 16384), mod.rs:69

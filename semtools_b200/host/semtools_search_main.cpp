@@ -53,6 +53,15 @@ int main(int argc, char **argv) {
     std::string a = argv[i];
     auto next = [&]() -> std::string { if (i + 1 >= argc) { fprintf(stderr, "error: %s needs a value\n", a.c_str()); exit(2); } return argv[++i]; };
     if (a == "--selftest") return selftest();
+    if (a == "--lower") {                          // test hook: stdin -> to_lowercase -> stdout
+      std::string in, line;
+      char buf[65536];
+      size_t n;
+      while ((n = fread(buf, 1, sizeof(buf), stdin)) > 0) in.append(buf, n);
+      const std::string out = to_lowercase(in);
+      fwrite(out.data(), 1, out.size(), stdout);
+      return 0;
+    }
     else if (a == "--vocab") vocab = next();
     else if (a == "--table") table = next();
     else if (a == "-n" || a == "--n-lines" || a == "--context") cfg.n_lines = std::stoul(next());
@@ -68,7 +77,7 @@ int main(int argc, char **argv) {
     return 2;
   }
   try {
-    if (cfg.ignore_case) query = to_lowercase_ascii(query);
+    if (cfg.ignore_case) query = to_lowercase(query);
     const bool stdin_tty = isatty(0);
     std::vector<std::pair<std::string, std::string>> inputs;      // (filename, content)
     if (files.empty() && !stdin_tty) {

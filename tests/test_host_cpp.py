@@ -181,3 +181,25 @@ def test_cpp_workspace_commands_match_python_mirror(binary, tmp_path):
         os.environ["HOME"] = old_home
         if old_ws is not None:
             os.environ["SEMTOOLS_WORKSPACE"] = old_ws
+
+
+def test_cpp_to_lowercase_is_full_unicode(binary):
+    """str::to_lowercase (mod.rs:63-67): full mapping, multi-char expansions, Final_Sigma,
+    case-ignorable skipping -- byte-identical to Python's str.lower() (same UCD algorithm)."""
+    samples = ["Hello WORLD", "ÀÉÎÕÜ Straße ẞ", "İstanbul I ı", "ΑΣ ΟΔΥΣΣΕΥΣ ΣΑΣ Σ", "ΑΣ.Β ΑΣ' Α­Σ ́Σ",
+               "ǅ ǈ Ǌ ᾈ ᾼ", "ԱԲԳ ᲐᲑᲒ 𐐀𐐁 𞤀𞤁", "Ⅷ Ⓐ Ｆｕｌｌ", "ǰ ŉ ΐ", "日本語 emoji 😀 ÇA", "AͅΣ", "ΣΣ", "aΣʰb", ""]
+    import random
+    rng = random.Random(7)
+    pool = [c for c in map(chr, list(range(0x20, 0x250)) + list(range(0x370, 0x530)) + list(range(0x1E00, 0x2000))
+                           + [0x3A3, 0x3C2, 0x3C3, 0x2019, 0x27, 0x2E, 0xAD, 0x301, 0x345, 0x2B0, 0x10400, 0x1E900])]
+    samples += ["".join(rng.choice(pool) for _ in range(40)) for _ in range(200)]
+    text = "\n".join(samples)
+    r = subprocess.run([binary, "--lower"], input=text.encode("utf-8"), capture_output=True)
+    assert r.returncode == 0
+    got = r.stdout.decode("utf-8").split("\n")
+    want = text.lower().split("\n")
+    # Final_Sigma looks across the '\n' separators identically on both sides (same whole string)
+    assert got == want
+    # malformed UTF-8 passes through byte for byte, ASCII around it is still lowered
+    r = subprocess.run([binary, "--lower"], input=b"AB\xff\xc3(\xe2\x82CD", capture_output=True)
+    assert r.stdout == b"ab\xff\xc3(\xe2\x82cd"
