@@ -376,11 +376,8 @@ int stb_launch_shadow_build(stb_ctx *ctx, const float *rows_dev, uint64_t n_rows
 
 template <int EPI>
 static int launch_gemm(stb_ctx *ctx, const GemmArgs &a) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    STB_CUDA(cudaFuncSetAttribute(stb_batch_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, STB_GEMM_SMEM));
-    attr_set = true;
-  }
+  STB_ATTR_ONCE(ctx, EPI == 0 ? STB_ATTR_GEMM0 : STB_ATTR_GEMM1,
+                cudaFuncSetAttribute(stb_batch_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, STB_GEMM_SMEM));
   unsigned grid = (unsigned)std::min<uint32_t>(a.n_tiles, (uint32_t)ctx->sm_count);
   if (grid == 0) return STB_OK;
   stb_batch_gemm_kernel<EPI><<<grid, STB_GEMM_THREADS, STB_GEMM_SMEM, ctx->stream>>>(a);
@@ -857,10 +854,9 @@ int stb_launch_batch_finish2(stb_ctx *ctx, const uint64_t *cand_keys, const uint
                              const float *queries_dev, stb_hit *out_hits, uint32_t *out_status) {
   if (top_k > STB_V2_RESCORE_CAP || (cand_cap & (cand_cap - 1)) || cand_cap < 64) { stb_set_error("batch_finish2: bad capacity"); return STB_ERR_ARG; }
   const size_t smem = ((size_t)cand_cap + 2 * STB_V2_RESCORE_CAP) * 8;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
+  if (smem > ctx->finish2_smem_set) {
     STB_CUDA(cudaFuncSetAttribute(stb_batch_finish2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
+    ctx->finish2_smem_set = smem;
   }
   Finish2Args a;
   a.cand_keys = cand_keys; a.cand_cnt = cand_cnt; a.cand_cap = cand_cap; a.nq = nq; a.top_k = top_k;

@@ -62,6 +62,10 @@ struct stb_ctx {
   int *err_flag;            // device int for K3 range errors
   unsigned int *hist_dev;       // 4096-bin score histogram (large-k path)
   unsigned long long *dbg_dev;  // 8 u64 phase timestamps (STB_TAIL_TIMING builds; else unused)
+  // cudaFuncSetAttribute is per DEVICE: remembered per context, never in function statics
+  // (one process may hold contexts on several GPUs)
+  uint32_t func_attr_mask;
+  size_t finish2_smem_set;
   // --- K2 scratch ---
   uint8_t *bq_tiles; size_t bq_tiles_cap;     // query shadow tiles
   float *b_submax; size_t b_submax_cap;       // [n_sub][q_pad]
@@ -168,6 +172,16 @@ int stb_launch_hits_merge(stb_ctx *ctx, const stb_hit *lists_dev, uint32_t n_lis
 
 int stb_launch_hits_merge_batch(stb_ctx *ctx, const stb_hit *lists_dev, uint32_t n_lists, uint32_t nq,
                                 uint32_t per_list, uint32_t top_k, stb_hit *out_dev);
+
+// opt-in to > 48 KiB dynamic shared memory (or another function attribute) once per context
+enum { STB_ATTR_GEMM0 = 0, STB_ATTR_GEMM1, STB_ATTR_MERGE, STB_ATTR_IVF_PROBE, STB_ATTR_IVF_V2 };
+#define STB_ATTR_ONCE(ctx, bit, call)                         \
+  do {                                                        \
+    if (!((ctx)->func_attr_mask & (1u << (bit)))) {           \
+      STB_CUDA(call);                                         \
+      (ctx)->func_attr_mask |= 1u << (bit);                   \
+    }                                                         \
+  } while (0)
 
 // ---- embed_pool.cu --------------------------------------------------------------
 int stb_launch_embed(stb_ctx *ctx, const stb_table *t, const uint64_t *offsets_dev,

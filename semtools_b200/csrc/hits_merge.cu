@@ -114,13 +114,9 @@ int stb_launch_hits_merge(stb_ctx *ctx, const stb_hit *lists_dev, uint32_t n_lis
   uint32_t n_sort = 2;
   while (n_sort < total) n_sort <<= 1;
   size_t smem = (size_t)n_sort * 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    STB_CUDA(cudaFuncSetAttribute(stb_hits_merge_kernel,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  STB_MERGE_CAP * 16));
-    attr_set = true;
-  }
+  STB_ATTR_ONCE(ctx, STB_ATTR_MERGE,
+                cudaFuncSetAttribute(stb_hits_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     STB_MERGE_CAP * 16));
   stb_hits_merge_kernel<<<1, 256, smem, ctx->stream>>>(lists_dev, (uint32_t)total, n_sort, top_k,
                                                       out_dev);
   STB_CUDA(cudaGetLastError());

@@ -803,11 +803,10 @@ int stb_ivfpq_search(stb_ivfpq *x, const float *q, uint32_t nprobe, uint32_t top
   if (v2_env && v2_env[0] == '1' && rerank <= ADC2_RERANK_CAP && top_k <= 1024) {
     // fused search: two launches, one synchronisation
     uint32_t npow2 = 1; while (npow2 < x->nlist) npow2 <<= 1;
-    static bool attr2 = false;
-    if (!attr2) {
+    if (!(ctx->func_attr_mask & (1u << STB_ATTR_IVF_V2))) {
       STB_CUDA(cudaFuncSetAttribute(ivf_coarse_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
       STB_CUDA(cudaFuncSetAttribute(ivf_adc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ADC2_SMEM));
-      attr2 = true;
+      ctx->func_attr_mask |= 1u << STB_ATTR_IVF_V2;
     }
     Probe2Args pa;
     pa.C = x->centroids; pa.nlist = x->nlist; pa.nprobe = nprobe; pa.q = ctx->q_dev; pa.coarse = x->coarse;
@@ -833,8 +832,8 @@ int stb_ivfpq_search(stb_ivfpq *x, const float *q, uint32_t nprobe, uint32_t top
   }
   ivf_coarse_kernel<<<(x->nlist + 7) / 8, 256, 0, st>>>(x->centroids, x->nlist, ctx->q_dev, x->coarse);
   uint32_t npow = 1; while (npow < x->nlist) npow <<= 1;
-  static bool attr = false;
-  if (!attr) { STB_CUDA(cudaFuncSetAttribute(ivf_probe_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8)); attr = true; }
+  STB_ATTR_ONCE(ctx, STB_ATTR_IVF_PROBE,
+                cudaFuncSetAttribute(ivf_probe_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
   ivf_probe_lut_kernel<<<1, 1024, npow * 8, st>>>(x->coarse, x->nlist, nprobe, x->list_off, x->codebooks, ctx->q_dev, x->probe, x->lut);
   uint32_t total = 0;
   STB_CUDA(cudaMemcpyAsync(&total, x->probe + 2 * nprobe, 4, cudaMemcpyDeviceToHost, st));
