@@ -1,0 +1,23 @@
+#!/usr/bin/env bash
+# First gpurun call of round 2: time and validate the two opt-in paths written at the end of
+# round 1 (K2 pipeline v2, fused IVF-PQ search v2) next to the default ones.
+#   bash scripts/gpu_round2_first.sh [tag]      (from the repo root on the GPU box)
+set -uo pipefail
+TAG=${1:-r02_v2}
+OUT=gpurun_out/$TAG
+mkdir -p "$OUT"
+echo "== gated tests (v2 paths)"
+STB_TEST_V2=1 timeout 600 python -m pytest tests/test_gpu_batch.py tests/test_gpu_ivfpq.py -x -q -m gpu 2>&1 | tail -15 | tee "$OUT/pytest_v2.log"
+echo "== K2 v1 vs v2, 10M x 1024"
+timeout 300 python scripts/batch_probe.py 10000000 1024 5 2>&1 | tail -2 | tee "$OUT/k2_v1.log"
+STB_BATCH_V2=1 timeout 300 python scripts/batch_probe.py 10000000 1024 5 2>&1 | tail -2 | tee "$OUT/k2_v2.log"
+echo "== K2 v2 launch list (per-kernel times)"
+STB_BATCH_V2=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file "$OUT/k2_v2_launches.csv" \
+  python scripts/batch_probe.py 10000000 1024 1 > "$OUT/k2_v2_ncu.log" 2>&1
+grep -E "stb_batch|stb_shadow" "$OUT/k2_v2_launches.csv" | cut -d, -f5,12- | cut -c1-140 | tail -16
+echo "== K5 v1 vs v2 (ivfpq_probe)"
+timeout 300 python scripts/ivfpq_probe.py 2>&1 | tail -6 | tee "$OUT/k5_v1.log"
+STB_IVFPQ_V2=1 timeout 300 python scripts/ivfpq_probe.py 2>&1 | tail -6 | tee "$OUT/k5_v2.log"
+echo "== full bench (side sections batch1024_v2 / ivfpq_v2 included)"
+timeout 900 python bench.py --gpus 1 --steps 200 --warmup 10 2>&1 | tail -2 | tee "$OUT/bench.log"
+ls -la "$OUT"
