@@ -111,7 +111,8 @@ std::string to_lowercase(const std::string &s) {
 }
 
 // shortest round-trip decimal digits and exponent: value = 0.d1d2... x 10^exp10
-static void shortest_digits(double x, std::string &digits, int &exp10) {
+template <class F>
+static void shortest_digits(F x, std::string &digits, int &exp10) {
   char buf[64];
   auto r = std::to_chars(buf, buf + sizeof(buf), x, std::chars_format::scientific);
   std::string s(buf, r.ptr);                       // d.ddddde[+-]XX
@@ -125,8 +126,9 @@ static void shortest_digits(double x, std::string &digits, int &exp10) {
   exp10 = ex + 1;                                  // digits as 0.DDDD x 10^exp10
 }
 
-static std::string positional(double x, bool keep_point_zero) {
-  if (x == 0.0) return keep_point_zero ? (std::signbit(x) ? "-0.0" : "0.0") : (std::signbit(x) ? "-0" : "0");
+template <class F>
+static std::string positional(F x, bool keep_point_zero) {
+  if (x == 0) return keep_point_zero ? (std::signbit(x) ? "-0.0" : "0.0") : (std::signbit(x) ? "-0" : "0");
   std::string d;
   int e;
   shortest_digits(std::fabs(x), d, e);
@@ -138,6 +140,12 @@ static std::string positional(double x, bool keep_point_zero) {
 }
 
 std::string rust_display_f64(double x) {
+  if (std::isnan(x)) return "NaN";
+  if (std::isinf(x)) return x > 0 ? "inf" : "-inf";
+  return positional(x, false);
+}
+
+std::string rust_display_f32(float x) {
   if (std::isnan(x)) return "NaN";
   if (std::isinf(x)) return x > 0 ? "inf" : "-inf";
   return positional(x, false);
@@ -242,6 +250,20 @@ bool Searcher::add_document(const std::string &filename, const std::string &cont
   check(stb_embed(ctx_, table_, offsets.data(), ids.empty() ? &dummy : ids.data(), d.lines.size(), nullptr, corpus_));
   docs_.push_back(std::move(d));
   return true;
+}
+
+std::vector<float> Searcher::embed_lines(const std::vector<std::string> &lines, const Tokenizer &tok, bool ignore_case) const {
+  if (!table_) throw std::runtime_error("load_table first");
+  std::vector<float> out(lines.size() * STB_DIM);
+  if (lines.empty()) return out;
+  std::vector<std::string> emb_lines = lines;
+  if (ignore_case) for (auto &l : emb_lines) l = to_lowercase(l);
+  std::vector<uint64_t> offsets;
+  std::vector<uint32_t> ids;
+  to_csr(emb_lines, tok, 2048, offsets, ids);
+  uint32_t dummy = 0;
+  check(stb_embed(ctx_, table_, offsets.data(), ids.empty() ? &dummy : ids.data(), lines.size(), out.data(), nullptr));
+  return out;
 }
 
 bool Searcher::add_document_embeddings(const std::string &filename, const std::vector<std::string> &lines, const float *emb) {

@@ -14,7 +14,7 @@
 #include <iostream>
 #include <iterator>
 
-#include "semtools_host.hpp"
+#include "semtools_store.hpp"
 
 using namespace semtools;
 
@@ -49,6 +49,7 @@ int main(int argc, char **argv) {
   std::vector<std::string> files;
   SearchConfig cfg;
   bool json = false, have_query = false;
+  std::optional<std::string> workspace_name;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
     auto next = [&]() -> std::string { if (i + 1 >= argc) { fprintf(stderr, "error: %s needs a value\n", a.c_str()); exit(2); } return argv[++i]; };
@@ -69,11 +70,12 @@ int main(int argc, char **argv) {
     else if (a == "-m" || a == "--max-distance" || a == "--threshold") cfg.max_distance = std::stod(next());
     else if (a == "-i" || a == "--ignore-case") cfg.ignore_case = true;
     else if (a == "-j" || a == "--json") json = true;
+    else if (a == "-w" || a == "--workspace") workspace_name = next();
     else if (!have_query) { query = a; have_query = true; }
     else files.push_back(a);
   }
   if (!have_query || vocab.empty() || table.empty()) {
-    fprintf(stderr, "usage: semtools_b200_search --vocab V --table T QUERY [FILES...] [-n N] [--top-k K] [-m D] [-i] [-j]\n");
+    fprintf(stderr, "usage: semtools_b200_search --vocab V --table T QUERY [FILES...] [-n N] [--top-k K] [-m D] [-i] [-j] [-w WORKSPACE]\n");
     return 2;
   }
   try {
@@ -90,15 +92,29 @@ int main(int argc, char **argv) {
       else fprintf(stderr, "Error: %s\n", msg);
       return 1;
     }
+    WordLevelTokenizer tok(vocab);
+    std::ifstream tf(table, std::ios::binary);
+    std::vector<char> raw((std::istreambuf_iterator<char>(tf)), std::istreambuf_iterator<char>());
+    if (raw.empty() || raw.size() % (STB_DIM * sizeof(float))) { fprintf(stderr, "Error: bad table file\n"); return 1; }
+    bool in_workspace = false;
+    if (!files.empty()) { try { Workspace::active(workspace_name); in_workspace = true; } catch (const std::exception &) {} }
+    if (in_workspace) {
+      // cmds/search.rs:194-241: persisted line embeddings, only new/changed files are embedded
+      Searcher s(0);
+      s.load_table(reinterpret_cast<const float *>(raw.data()), raw.size() / (STB_DIM * sizeof(float)), true);
+      auto ranked = search_with_workspace(
+          files, s.encode_single(query, tok),
+          [&](const std::vector<std::string> &lines) { return s.embed_lines(lines, tok, cfg.ignore_case); }, cfg, workspace_name,
+          [](const std::string &m) { fprintf(stderr, "%s\n", m.c_str()); });
+      if (json) printf("%s\n", workspace_output_json(ranked, cfg.n_lines).c_str());
+      else fputs(format_workspace_search_results(ranked, cfg.n_lines, isatty(1)).c_str(), stdout);
+      return 0;
+    }
     for (const auto &f : files) {
       std::ifstream in(f, std::ios::binary);
       if (!in) { fprintf(stderr, "Error: %s: No such file or directory (os error 2)\n", f.c_str()); return 1; }
       inputs.emplace_back(f, std::string((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>()));
     }
-    WordLevelTokenizer tok(vocab);
-    std::ifstream tf(table, std::ios::binary);
-    std::vector<char> raw((std::istreambuf_iterator<char>(tf)), std::istreambuf_iterator<char>());
-    if (raw.empty() || raw.size() % (STB_DIM * sizeof(float))) { fprintf(stderr, "Error: bad table file\n"); return 1; }
     Searcher s(0);
     s.load_table(reinterpret_cast<const float *>(raw.data()), raw.size() / (STB_DIM * sizeof(float)), true);
     for (const auto &in : inputs) s.add_document(in.first, in.second, tok, cfg.ignore_case);

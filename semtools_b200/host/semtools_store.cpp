@@ -333,4 +333,97 @@ std::vector<RankedLine> Store::search_line_embeddings(const std::vector<float> &
   return out;
 }
 
+// ------------------------------------------------------------------ search_with_workspace --
+std::vector<RankedLine> search_with_workspace(const std::vector<std::string> &files, const std::vector<float> &query_embedding,
+                                              const EmbedLinesFn &embed_lines, const SearchConfig &cfg,
+                                              const std::optional<std::string> &workspace_name,
+                                              const std::function<void(const std::string &)> &log, int device) {
+  Workspace ws = Workspace::open(workspace_name);
+  Store store = Store::open(ws.config.root_dir);
+  std::vector<LineEmbedding> to_upsert;
+  std::vector<DocMeta> docs;
+  for (auto &st : store.analyze_document_states(files)) {
+    if (st.kind == DocumentState::Unchanged) continue;
+    const std::vector<std::string> lines = rust_lines(st.content);
+    if (lines.empty()) continue;                                   // create_document_from_content -> None
+    const std::vector<float> emb = embed_lines(lines);
+    if (emb.size() != lines.size() * LINE_EMBEDDING_SIZE) throw std::runtime_error("embed_lines returned the wrong size");
+    for (size_t i = 0; i < lines.size(); ++i)
+      to_upsert.push_back({st.filename, (int32_t)i,                 // 0-based line numbers (mod.rs:178)
+                           std::vector<float>(emb.begin() + i * LINE_EMBEDDING_SIZE, emb.begin() + (i + 1) * LINE_EMBEDDING_SIZE)});
+    docs.push_back(st.meta);
+  }
+  if (!to_upsert.empty()) {
+    if (log) log("Updating workspace with " + std::to_string(to_upsert.size()) + " lines from new/changed docs...");
+    store.upsert_line_embeddings(to_upsert);
+  }
+  if (!docs.empty()) {
+    if (log) log("Updating workspace with " + std::to_string(docs.size()) + " new/changed documents...");
+    store.upsert_document_metadata(docs);
+  }
+  std::optional<float> max_d;
+  if (cfg.max_distance) max_d = (float)*cfg.max_distance;           // mod.rs:211 `as f32`
+  return store.search_line_embeddings(query_embedding, files, cfg.top_k, max_d, device);
+}
+
+static bool read_lines(const std::string &path, std::vector<std::string> &lines) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) return false;
+  std::stringstream ss; ss << f.rdbuf();
+  lines = rust_lines(ss.str());
+  return true;
+}
+
+std::string format_workspace_search_results(const std::vector<RankedLine> &ranked, size_t n_lines, bool is_tty) {
+  std::string out;
+  char num[32];
+  for (const auto &rl : ranked) {
+    const size_t m = (size_t)rl.line_number;
+    const size_t start = m > n_lines ? m - n_lines : 0;
+    const size_t end = m + n_lines + 1;                             // NOT clamped in the header (:77-79)
+    out += rl.path + ":" + std::to_string(start) + "::" + std::to_string(end) + " (" + rust_display_f32(rl.distance) + ")\n";
+    std::vector<std::string> lines;
+    if (read_lines(rl.path, lines)) {
+      const size_t actual_end = std::min(end, lines.size());
+      if (start > actual_end) throw std::runtime_error("slice index starts past the end (the reference panics here)");
+      for (size_t n = start; n < actual_end; ++n) {
+        snprintf(num, sizeof(num), "%4zu", n + 1);
+        if (n == m && is_tty) out += std::string("\x1b[43m\x1b[30m") + num + ": " + lines[n] + "\x1b[0m\n";
+        else out += std::string(num) + ": " + lines[n] + "\n";
+      }
+    } else {
+      out += "    [Error: Could not read file content]\n";
+    }
+    out += "\n";
+  }
+  return out;
+}
+
+std::string workspace_output_json(const std::vector<RankedLine> &ranked, size_t n_lines) {
+  if (ranked.empty()) return "{\n  \"results\": []\n}";
+  std::string o = "{\n  \"results\": [\n";
+  for (size_t i = 0; i < ranked.size(); ++i) {
+    const auto &rl = ranked[i];
+    const size_t m = (size_t)rl.line_number;
+    const size_t start = m > n_lines ? m - n_lines : 0, end = m + n_lines + 1;
+    std::string content;
+    std::vector<std::string> lines;
+    if (read_lines(rl.path, lines)) {
+      for (size_t n = start; n < std::min(end, lines.size()); ++n) { if (n > start) content += "\n"; content += lines[n]; }
+    } else {
+      content = "[Error: Could not read file content]";
+    }
+    o += "    {\n";
+    o += "      \"filename\": " + json_string(rl.path) + ",\n";
+    o += "      \"start_line_number\": " + std::to_string(start) + ",\n";
+    o += "      \"end_line_number\": " + std::to_string(end) + ",\n";
+    o += "      \"match_line_number\": " + std::to_string(m) + ",\n";
+    o += "      \"distance\": " + json_f64((double)rl.distance) + ",\n";   // f32 widened to f64 (:233)
+    o += "      \"content\": " + json_string(content) + "\n";
+    o += i + 1 < ranked.size() ? "    },\n" : "    }\n";
+  }
+  o += "  ]\n}";
+  return o;
+}
+
 }  // namespace semtools

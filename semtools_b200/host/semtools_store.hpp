@@ -5,6 +5,7 @@
 // GPU's (stb_search with row ranges, STB_MODE_STORE_QUERY); nothing here computes a distance.
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <map>
 #include <optional>
 #include <string>
@@ -94,6 +95,17 @@ class Store {
   std::vector<float> emb_;                          // N x 256
   std::unordered_map<uint64_t, size_t> id_row_;
 };
+
+// search_with_workspace (search/mod.rs:146-216): diff `files` against the store, embed only
+// New/Changed documents through `embed_lines` (lines -> N x 256 f32), upsert, filtered query.
+using EmbedLinesFn = std::function<std::vector<float>(const std::vector<std::string> &)>;
+std::vector<RankedLine> search_with_workspace(const std::vector<std::string> &files, const std::vector<float> &query_embedding,
+                                              const EmbedLinesFn &embed_lines, const SearchConfig &cfg,
+                                              const std::optional<std::string> &workspace_name,
+                                              const std::function<void(const std::string &)> &log = nullptr, int device = 0);
+// print_workspace_search_results (cmds/search.rs:66-110) and the workspace JSON (:208-237)
+std::string format_workspace_search_results(const std::vector<RankedLine> &ranked, size_t n_lines, bool is_tty);
+std::string workspace_output_json(const std::vector<RankedLine> &ranked, size_t n_lines);
 
 // minimal JSON value (enough for store.json / config.json)
 struct Json {

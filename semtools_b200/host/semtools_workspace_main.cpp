@@ -78,6 +78,25 @@ int main(int argc, char **argv) {
     }
     if (pos.size() == 2 && pos[0] == "store-dump") { dump(Store::open(pos[1])); return 0; }
     if (pos.size() == 2 && pos[0] == "store-selftest") return store_selftest(pos[1]);
+    if (pos.size() == 2 && pos[0] == "format-ranked") {
+      // test hook: stdin lines `path<TAB>line_number<TAB>f32 bits (decimal u32)` -> the workspace renderers
+      std::vector<RankedLine> ranked;
+      char buf[8192];
+      while (fgets(buf, sizeof(buf), stdin)) {
+        std::string l(buf);
+        if (!l.empty() && l.back() == '\n') l.pop_back();
+        const size_t t1 = l.find('\t'), t2 = l.find('\t', t1 + 1);
+        if (t1 == std::string::npos || t2 == std::string::npos) continue;
+        const uint32_t bits = (uint32_t)std::stoul(l.substr(t2 + 1));
+        float d;
+        memcpy(&d, &bits, 4);
+        ranked.push_back({l.substr(0, t1), (int32_t)std::stol(l.substr(t1 + 1, t2 - t1 - 1)), d});
+      }
+      const size_t n_lines = std::stoul(pos[1]);
+      if (json) printf("%s\n", workspace_output_json(ranked, n_lines).c_str());
+      else fputs(format_workspace_search_results(ranked, n_lines, false).c_str(), stdout);
+      return 0;
+    }
     if (pos.size() == 2 && pos[0] == "use") {                          // workspace.rs:11-67
       Workspace ws;
       ws.config.name = pos[1];

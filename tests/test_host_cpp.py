@@ -203,3 +203,76 @@ def test_cpp_to_lowercase_is_full_unicode(binary):
     # malformed UTF-8 passes through byte for byte, ASCII around it is still lowered
     r = subprocess.run([binary, "--lower"], input=b"AB\xff\xc3(\xe2\x82CD", capture_output=True)
     assert r.stdout == b"ab\xff\xc3(\xe2\x82cd"
+
+
+def test_cpp_workspace_renderers_match_python(binary, tmp_path):
+    """print_workspace_search_results / workspace JSON (cmds/search.rs:66-110, 208-237): C++ == Python,
+    including the f32 Display, the unclamped header end, unreadable files and CRLF lines."""
+    import struct
+    from semtools_b200 import cmds
+    from semtools_b200.search import RankedLine
+    f1 = tmp_path / "a b.txt"; f1.write_text("l0\nl1\r\nl2 \"q\"\nl3\n\nl5")
+    f2 = tmp_path / "é.txt"; f2.write_text("only\n")
+    gone = tmp_path / "gone.txt"
+    ranked = [RankedLine(str(f1), 2, float(np.float32(0.1))), RankedLine(str(f2), 0, 0.0), RankedLine(str(f1), 5, float(np.float32(1.5e-7))),
+              RankedLine(str(gone), 3, float(np.float32(0.33333334))), RankedLine(str(f1), 0, 1.0)]
+    feed = "".join(f"{r.path}\t{r.line_number}\t{struct.unpack('<I', struct.pack('<f', r.distance))[0]}\n" for r in ranked)
+    for n_lines in (0, 1, 3, 50):
+        r = subprocess.run([WSBIN, "format-ranked", str(n_lines)], input=feed, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert r.stdout == cmds.format_workspace_search_results(ranked, n_lines, False)
+        r = subprocess.run([WSBIN, "--json", "format-ranked", str(n_lines)], input=feed, capture_output=True, text=True)
+        assert r.stdout == cmds.to_string_pretty({"results": cmds.workspace_results_to_json(ranked, n_lines)}) + "\n"
+    r = subprocess.run([WSBIN, "--json", "format-ranked", "2"], input="", capture_output=True, text=True)
+    assert r.stdout == cmds.to_string_pretty({"results": []}) + "\n"
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("STB_TEST_V2") != "1", reason="written after the last GPU session of round 1; enable with STB_TEST_V2=1")
+def test_cpp_cli_workspace_mode_equals_python_mirror(binary, tmp_path, ctx, monkeypatch):
+    """search with an active workspace (search/mod.rs:146-216 + cmds/search.rs:194-241): the C++ CLI
+    and the Python mirror build their own workspaces over the same files and print the same
+    bytes; a second C++ run re-uses the store (nothing re-embedded), an edited file is re-embedded."""
+    from safetensors.numpy import save_file
+    from tokenizers import Tokenizer
+    from tokenizers.models import WordLevel
+    from tokenizers.pre_tokenizers import Whitespace
+    from semtools_b200 import cmds
+    from semtools_b200.model import StaticModel
+    vocab = {"[UNK]": 0, **{w: i + 1 for i, w in enumerate(WORDS)}}
+    d = tmp_path / "model"; d.mkdir()
+    tok = Tokenizer(WordLevel(vocab, unk_token="[UNK]")); tok.pre_tokenizer = Whitespace()
+    tok.save(str(d / "tokenizer.json"))
+    rng = np.random.default_rng(1)
+    E = (rng.standard_normal((len(vocab), 256)) * 0.1).astype(np.float32)
+    save_file({"embeddings": E}, str(d / "model.safetensors"))
+    (d / "config.json").write_text(json.dumps({"normalize": True}))
+    (tmp_path / "vocab.txt").write_text("\n".join(["\x00unused-unk"] + WORDS) + "\n")
+    (tmp_path / "table.f32").write_bytes(E.tobytes())
+    f1 = tmp_path / "a.txt"; f1.write_text("hello world\ngoodbye world\ntest line\n\napple banana zzz\n")
+    f2 = tmp_path / "b.txt"; f2.write_text("orange grape\r\nfruit fruit\r\nHELLO world")
+    files = [str(f1), str(f2)]
+    model = StaticModel.from_pretrained(str(d), ctx=ctx)
+    base = [binary, "--vocab", str(tmp_path / "vocab.txt"), "--table", str(tmp_path / "table.f32")]
+    home_py, home_cpp = tmp_path / "home_py", tmp_path / "home_cpp"
+    home_py.mkdir(); home_cpp.mkdir()
+    env = dict(os.environ, HOME=str(home_cpp), SEMTOOLS_WORKSPACE="ws")
+    monkeypatch.setenv("HOME", str(home_py))
+    monkeypatch.setenv("SEMTOOLS_WORKSPACE", "ws")
+    for extra, kw in [([], dict(n_lines=3, top_k=3, max_distance=None, json=False)),
+                      (["-n", "1", "--top-k", "5", "-j"], dict(n_lines=1, top_k=5, max_distance=None, json=True)),
+                      (["--threshold", "0.9", "--context", "0"], dict(n_lines=0, top_k=3, max_distance=0.9, json=False))]:
+        out, err = io.StringIO(), io.StringIO()
+        cmds.search_cmd("apple fruit", files, kw["n_lines"], kw["top_k"], kw["max_distance"], False, kw["json"], None, model,
+                        out=out, err=err)
+        r = subprocess.run(base + ["apple fruit"] + files + extra, capture_output=True, text=True, stdin=subprocess.DEVNULL, env=env)
+        assert r.returncode == 0, r.stderr
+        assert r.stdout == out.getvalue(), (extra, r.stdout, out.getvalue())
+        assert r.stderr == err.getvalue()                    # "Updating workspace with ..." only on the first pass
+    f1.write_text("hello world\napple fruit\n")              # changed: size differs -> re-embedded on both sides
+    out, err = io.StringIO(), io.StringIO()
+    cmds.search_cmd("apple fruit", files, 0, 1, None, False, False, None, model, out=out, err=err)
+    r = subprocess.run(base + ["apple fruit"] + files + ["-n", "0", "--top-k", "1"], capture_output=True, text=True,
+                       stdin=subprocess.DEVNULL, env=env)
+    assert r.stdout == out.getvalue() and r.stdout.startswith(f"{f1}:1::2 (")
+    assert "Updating workspace with 2 lines" in r.stderr and r.stderr == err.getvalue()
