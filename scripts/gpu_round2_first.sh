@@ -7,7 +7,7 @@ TAG=${1:-r02_v2}
 OUT=gpurun_out/$TAG
 mkdir -p "$OUT"
 echo "== gated tests (v2 paths)"
-STB_TEST_V2=1 timeout 600 python -m pytest tests/test_gpu_batch.py tests/test_gpu_ivfpq.py -x -q -m gpu 2>&1 | tail -15 | tee "$OUT/pytest_v2.log"
+STB_TEST_V2=1 timeout 600 python -m pytest tests/test_gpu_batch.py tests/test_gpu_ivfpq.py tests/test_host_cpp.py -x -q -m gpu 2>&1 | tail -15 | tee "$OUT/pytest_v2.log"
 echo "== K2 v1 vs v2, 10M x 1024"
 timeout 300 python scripts/batch_probe.py 10000000 1024 5 2>&1 | tail -2 | tee "$OUT/k2_v1.log"
 STB_BATCH_V2=1 timeout 300 python scripts/batch_probe.py 10000000 1024 5 2>&1 | tail -2 | tee "$OUT/k2_v2.log"
