@@ -7,7 +7,7 @@ TAG=${1:-r02_v2}
 OUT=gpurun_out/$TAG
 mkdir -p "$OUT"
 echo "== gated tests (v2 paths)"
-STB_TEST_V2=1 timeout 600 python -m pytest tests/test_gpu_batch.py tests/test_gpu_ivfpq.py tests/test_host_cpp.py -x -q -m gpu 2>&1 | tail -15 | tee "$OUT/pytest_v2.log"
+STB_TEST_V2=1 timeout 600 python -m pytest tests/test_gpu_batch.py tests/test_gpu_ivfpq.py tests/test_host_cpp.py tests/test_gpu_search.py -x -q -m gpu 2>&1 | tail -15 | tee "$OUT/pytest_v2.log"
 echo "== K2 v1 vs v2, 10M x 1024"
 timeout 300 python scripts/batch_probe.py 10000000 1024 5 2>&1 | tail -2 | tee "$OUT/k2_v1.log"
 STB_BATCH_V2=1 timeout 300 python scripts/batch_probe.py 10000000 1024 5 2>&1 | tail -2 | tee "$OUT/k2_v2.log"
@@ -18,6 +18,9 @@ grep -E "stb_batch|stb_shadow" "$OUT/k2_v2_launches.csv" | cut -d, -f5,12- | cut
 echo "== K5 v1 vs v2 (ivfpq_probe)"
 timeout 300 python scripts/ivfpq_probe.py 2>&1 | tail -6 | tee "$OUT/k5_v1.log"
 STB_IVFPQ_V2=1 timeout 300 python scripts/ivfpq_probe.py 2>&1 | tail -6 | tee "$OUT/k5_v2.log"
+echo "== K1 e2e with and without direct host output"
+timeout 300 python bench.py --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('default', d['value'], d['e2e']['value'])" | tee "$OUT/e2e_default.log"
+STB_DIRECT_OUT=1 timeout 300 python bench.py --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('direct ', d['value'], d['e2e']['value'])" | tee "$OUT/e2e_direct.log"
 echo "== full bench (side sections batch1024_v2 / ivfpq_v2 included)"
 timeout 900 python bench.py --gpus 1 --steps 200 --warmup 10 2>&1 | tail -2 | tee "$OUT/bench.log"
 ls -la "$OUT"

@@ -485,10 +485,19 @@ int stb_search(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint32_t 
   const stb_hit *src_dev = nullptr;   // sorted device hits to copy out (collect path)
   if (!threshold_all && top_k <= stb_scan_topk_max_k()) {
     // ---- fast path: one kernel, k*16+16 bytes back -----------------------------
-    if ((rc = stb_launch_scan_topk(ctx, corpus->rows, corpus->n, corpus->row_base, ctx->q_dev, top_k,
-                                   ranges_dev, n_loc, n_virtual, ctx->hits_dev, ctx->status_dev)) != STB_OK) return rc;
-    STB_CUDA(cudaMemcpyAsync(ctx->status_pin, ctx->status_dev, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    STB_CUDA(cudaMemcpyAsync(ctx->hits_pin, ctx->hits_dev, top_k * sizeof(stb_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    // STB_DIRECT_OUT=1 (opt-in until timed): the kernel's last CTA stores the k hits + status straight
+    // into the pinned host buffers (UVA: cudaMallocHost memory is device-accessible), which takes
+    // the two D2H copies off the stream; kernel completion makes the stores visible to the host.
+    const char *direct_env = getenv("STB_DIRECT_OUT");
+    if (direct_env && direct_env[0] == '1') {
+      if ((rc = stb_launch_scan_topk(ctx, corpus->rows, corpus->n, corpus->row_base, ctx->q_dev, top_k,
+                                     ranges_dev, n_loc, n_virtual, ctx->hits_pin, ctx->status_pin)) != STB_OK) return rc;
+    } else {
+      if ((rc = stb_launch_scan_topk(ctx, corpus->rows, corpus->n, corpus->row_base, ctx->q_dev, top_k,
+                                     ranges_dev, n_loc, n_virtual, ctx->hits_dev, ctx->status_dev)) != STB_OK) return rc;
+      STB_CUDA(cudaMemcpyAsync(ctx->status_pin, ctx->status_dev, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      STB_CUDA(cudaMemcpyAsync(ctx->hits_pin, ctx->hits_dev, top_k * sizeof(stb_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     STB_CUDA(cudaStreamSynchronize(ctx->stream));
     const uint32_t n_hits = ctx->status_pin[0];
     if (ctx->status_pin[1]) {

@@ -454,3 +454,22 @@ def test_large_k_histogram_path(ctx, n, k):
     r2, d2 = oracle.store_search(rows, ranges, q, k)
     got = c.search(q, top_k=k, mode=capi.STB_MODE_STORE_QUERY, row_ranges=ranges)
     assert got["row"].tolist() == [int(x) for x in r2]
+
+
+@pytest.mark.skipif(os.environ.get("STB_TEST_V2") != "1", reason="opt-in path written after the last GPU session of round 1 (STB_TEST_V2=1)")
+def test_direct_host_output_switch_gives_identical_hits(ctx, monkeypatch):
+    """STB_DIRECT_OUT=1: the scan kernel stores hits + status straight into pinned host memory."""
+    rng = np.random.default_rng(321)
+    rows = unit_rows(rng, 50_000)
+    rows[777] = rows[5]
+    c = capi.Corpus(ctx, 50_000)
+    c.append(rows)
+    for k in (1, 10, 96):
+        for qi in (5, 100, 49_999):
+            monkeypatch.delenv("STB_DIRECT_OUT", raising=False)
+            want = c.search(rows[qi], top_k=k)
+            monkeypatch.setenv("STB_DIRECT_OUT", "1")
+            got = c.search(rows[qi], top_k=k)
+            assert np.array_equal(got, want)
+            r, d = oracle.search_rows(rows, rows[qi], top_k=k)
+            assert got["row"].tolist() == [int(x) for x in r] and np.array_equal(got["distance"], d)
