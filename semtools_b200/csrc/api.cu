@@ -733,7 +733,11 @@ int stb_search_batch_dev(stb_ctx *ctx, const stb_corpus *corpus_c, const float *
   // pipeline v2 (threshold-emitting epilogue; see batch_scan.cu): opt-in until validated on hardware
   const char *v2_env = getenv("STB_BATCH_V2");            // read per call so one process can compare both
   const bool use_v2 = v2_env != nullptr && v2_env[0] == '1';
-  if (use_v2 && top_k <= 64) {
+  // v2's sample is capped at 608 tiles (threshold kernel: 19 values per lane), so the emitted set
+  // grows like top_k * n_tiles / 592 * ~2: keep its expectation under a quarter of the 8192-key
+  // capacity, otherwise the v1 pipeline (whose cost does not depend on that ratio) is used.
+  const bool v2_fits = (uint64_t)top_k * n_tiles * 2 <= 2048ull * 592;
+  if (use_v2 && top_k <= 64 && v2_fits) {
     constexpr uint32_t kCandCap = 8192;
     // sample only COMPLETE tiles (a padding row must never stand in for a real one)
     const uint32_t n_full = (uint32_t)(corpus->n / 256);
