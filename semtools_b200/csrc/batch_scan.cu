@@ -713,6 +713,55 @@ stb_batch_thresh_kernel(const ThreshArgs a) {
   if (lane == 0) a.thr[q] = (kth == -CUDART_INF_F) ? -CUDART_INF_F : kth - 2.0f * (float)STB_BATCH_EPS;
 }
 
+// Same result for samples beyond 608 tiles (large shards): CTA per query, the sampled maxima
+// staged in shared memory, k rounds of block-max extraction.
+#define STB_V2_BIG_SAMPLE 8192
+__global__ void __launch_bounds__(256)
+stb_batch_thresh_big_kernel(const ThreshArgs a) {
+  extern __shared__ float tb_vals[];          // n_sample floats
+  __shared__ float s_wm[8];
+  __shared__ int s_wi[8];
+  __shared__ float s_kth;
+  const uint32_t q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (q >= a.nq) { if (tid == 0) a.thr[q] = CUDART_INF_F; return; }
+  const float *p = a.tilemax + (size_t)(q >> 7) * a.n_sample * 128 + (q & 127);
+  for (uint32_t i = tid; i < a.n_sample; i += 256) tb_vals[i] = __ldg(p + (size_t)i * 128);
+  if (tid == 0) s_kth = -CUDART_INF_F;
+  __syncthreads();
+  if (a.top_k <= a.n_sample && a.top_k <= STB_V2_MAX_K) {
+    for (uint32_t round = 0; round < a.top_k; ++round) {
+      float lm = -CUDART_INF_F;
+      int li = -1;
+      for (uint32_t i = tid; i < a.n_sample; i += 256) {
+        const float v = tb_vals[i];
+        if (li < 0 || v > lm) { lm = v; li = (int)i; }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, lm, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, li, off);
+        if (oi >= 0 && (li < 0 || om > lm || (om == lm && oi < li))) { lm = om; li = oi; }
+      }
+      if (lane == 0) { s_wm[warp] = lm; s_wi[warp] = li; }
+      __syncthreads();
+      if (tid == 0) {
+        float bm = s_wm[0];
+        int bi = s_wi[0];
+        for (int w = 1; w < 8; ++w)
+          if (s_wi[w] >= 0 && (bi < 0 || s_wm[w] > bm || (s_wm[w] == bm && s_wi[w] < bi))) { bm = s_wm[w]; bi = s_wi[w]; }
+        s_kth = bm;
+        if (bi >= 0) tb_vals[bi] = -CUDART_INF_F;       // remove ONE instance
+      }
+      __syncthreads();
+    }
+  }
+  if (tid == 0) {
+    const float kth = (a.top_k <= a.n_sample && a.top_k <= STB_V2_MAX_K) ? s_kth : -CUDART_INF_F;
+    a.thr[q] = (kth == -CUDART_INF_F) ? -CUDART_INF_F : kth - 2.0f * (float)STB_BATCH_EPS;
+  }
+}
+
 struct Finish2Args {
   const uint64_t *cand_keys;   // [q_pad][cand_cap]
   const uint32_t *cand_cnt;    // [q_pad]
@@ -840,10 +889,11 @@ stb_batch_finish2_kernel(const Finish2Args a) {
 
 int stb_launch_batch_thresh(stb_ctx *ctx, const float *tilemax, uint32_t n_sample, uint32_t nq, uint32_t q_pad,
                             uint32_t top_k, float *thr) {
-  if (n_sample > STB_V2_MAX_SAMPLE) { stb_set_error("batch_thresh: sample too large"); return STB_ERR_ARG; }
+  if (n_sample > STB_V2_BIG_SAMPLE) { stb_set_error("batch_thresh: sample too large"); return STB_ERR_ARG; }
   ThreshArgs a;
   a.tilemax = tilemax; a.n_sample = n_sample; a.nq = nq; a.q_pad = q_pad; a.top_k = top_k; a.thr = thr;
-  stb_batch_thresh_kernel<<<(q_pad + 7) / 8, 256, 0, ctx->stream>>>(a);
+  if (n_sample <= STB_V2_MAX_SAMPLE) stb_batch_thresh_kernel<<<(q_pad + 7) / 8, 256, 0, ctx->stream>>>(a);
+  else stb_batch_thresh_big_kernel<<<q_pad, 256, (size_t)n_sample * sizeof(float), ctx->stream>>>(a);
   STB_CUDA(cudaGetLastError());
   ctx->kernel_launches++;
   return STB_OK;
