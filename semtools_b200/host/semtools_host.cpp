@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <fstream>
 #include <sstream>
+#include <thread>
 
 namespace semtools {
 
@@ -188,18 +189,66 @@ WordLevelTokenizer::WordLevelTokenizer(const std::string &vocab_path) {
   std::string tok;
   uint32_t id = 0;
   while (std::getline(f, tok)) vocab.emplace_back(tok, id++);
+  build_index();
+}
+
+WordLevelTokenizer::WordLevelTokenizer(std::vector<std::string> tokens) {
+  uint32_t id = 0;
+  for (auto &t : tokens) vocab.emplace_back(std::move(t), id++);
+  build_index();
+}
+
+void WordLevelTokenizer::build_index() {
   std::sort(vocab.begin(), vocab.end());
+  index_.reserve(vocab.size() * 2);
+  for (const auto &kv : vocab) index_.emplace(std::string_view(kv.first), kv.second);   // first id wins on duplicates
 }
 
 std::vector<uint32_t> WordLevelTokenizer::encode(const std::string &text) const {
   std::vector<uint32_t> ids;
-  std::istringstream ss(text);
-  std::string w;
-  while (ss >> w) {
-    auto it = std::lower_bound(vocab.begin(), vocab.end(), std::make_pair(w, (uint32_t)0));
-    if (it != vocab.end() && it->first == w) ids.push_back(it->second);   // unknown words: dropped (unk removal)
+  auto is_space = [](unsigned char c) { return c == ' ' || (c >= '\t' && c <= '\r'); };   // isspace, "C" locale
+  const size_t n = text.size();
+  size_t i = 0;
+  while (i < n) {
+    while (i < n && is_space((unsigned char)text[i])) ++i;
+    size_t j = i;
+    while (j < n && !is_space((unsigned char)text[j])) ++j;
+    if (j > i) {
+      auto it = index_.find(std::string_view(text.data() + i, j - i));
+      if (it != index_.end()) ids.push_back(it->second);       // unknown words: dropped (unk removal)
+    }
+    i = j;
   }
   return ids;
+}
+
+void tokenize_to_csr(const std::vector<std::string> &lines, const Tokenizer &tok, size_t max_len,
+                     std::vector<uint64_t> &offsets, std::vector<uint32_t> &ids, unsigned threads) {
+  const size_t n = lines.size();
+  if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
+  threads = (unsigned)std::min<size_t>(threads, std::max<size_t>(1, n / 256));     // no thread for < 256 lines
+  offsets.assign(n + 1, 0);
+  std::vector<std::vector<uint32_t>> part(threads);
+  auto work = [&](unsigned t) {
+    const size_t lo = n * t / threads, hi = n * (t + 1) / threads;
+    auto &out = part[t];
+    for (size_t i = lo; i < hi; ++i) {
+      auto v = tok.encode(lines[i]);
+      if (v.size() > max_len) v.resize(max_len);               // truncate(max_length)
+      offsets[i + 1] = v.size();                               // per-line count; prefix-summed below
+      out.insert(out.end(), v.begin(), v.end());
+    }
+  };
+  if (threads == 1) work(0);
+  else {
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < threads; ++t) pool.emplace_back(work, t);
+    for (auto &th : pool) th.join();
+  }
+  for (size_t i = 0; i < n; ++i) offsets[i + 1] += offsets[i];
+  ids.clear();
+  ids.reserve(offsets[n]);
+  for (auto &p : part) ids.insert(ids.end(), p.begin(), p.end());
 }
 
 Searcher::Searcher(int device) {
@@ -226,14 +275,7 @@ uint64_t Searcher::rows() const {
 
 static void to_csr(const std::vector<std::string> &lines, const Tokenizer &tok, size_t max_len,
                    std::vector<uint64_t> &offsets, std::vector<uint32_t> &ids) {
-  offsets.assign(1, 0);
-  ids.clear();
-  for (const auto &l : lines) {
-    auto t = tok.encode(l);
-    if (t.size() > max_len) t.resize(max_len);                 // truncate(max_length)
-    ids.insert(ids.end(), t.begin(), t.end());
-    offsets.push_back(ids.size());
-  }
+  tokenize_to_csr(lines, tok, max_len, offsets, ids);
 }
 
 bool Searcher::add_document(const std::string &filename, const std::string &content, const Tokenizer &tok, bool ignore_case) {

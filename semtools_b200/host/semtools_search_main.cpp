@@ -8,6 +8,11 @@
 // `--selftest` exercises the pure host functions without a GPU.
 #include <unistd.h>
 
+#include <chrono>
+#include <cmath>
+#include <random>
+#include <thread>
+
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -17,6 +22,43 @@
 #include "semtools_store.hpp"
 
 using namespace semtools;
+
+// Synthetic ingestion batch of SURVEY 8d: V = 500k words, line lengths ~ LogNormal(2.5, 0.8)
+// clipped to [0, 2048], word ranks ~ Zipf(1.1); reports lines/s and tokens/s of tokenize_to_csr.
+static int tokenize_bench(size_t n_lines, unsigned threads) {
+  std::vector<std::string> words;
+  words.reserve(500000);
+  for (uint64_t i = 0; i < 500000; ++i) words.push_back("t" + std::to_string(i * 7919 % 1000003));
+  WordLevelTokenizer tok(words);
+  std::mt19937_64 rng(12345);
+  std::lognormal_distribution<double> len(2.5, 0.8);
+  std::vector<double> cdf(500000);
+  double acc = 0;
+  for (int r = 0; r < 500000; ++r) { acc += 1.0 / std::pow(r + 1.0, 1.1); cdf[r] = acc; }
+  std::uniform_real_distribution<double> uni(0.0, acc);
+  std::vector<std::string> lines(n_lines);
+  for (auto &l : lines) {
+    const int nt = (int)std::min(2048.0, std::max(0.0, std::round(len(rng))));
+    for (int t = 0; t < nt; ++t) {
+      const size_t r = std::lower_bound(cdf.begin(), cdf.end(), uni(rng)) - cdf.begin();
+      if (t) l += ' ';
+      l += words[std::min<size_t>(r, 499999)];
+    }
+  }
+  std::vector<uint64_t> off; std::vector<uint32_t> ids;
+  for (unsigned th : {1u, threads}) {
+    double best = 1e30;
+    for (int rep = 0; rep < 3; ++rep) {
+      const auto t0 = std::chrono::steady_clock::now();
+      tokenize_to_csr(lines, tok, 2048, off, ids, th);
+      best = std::min(best, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
+    printf("{\"threads\": %u, \"lines\": %zu, \"tokens\": %zu, \"seconds\": %.4f, \"lines_per_s\": %.0f, \"tokens_per_s\": %.0f}\n",
+           th ? th : std::thread::hardware_concurrency(), n_lines, ids.size(), best, n_lines / best, ids.size() / best);
+    if (th == threads) break;
+  }
+  return 0;
+}
 
 static int selftest() {
   int bad = 0;
@@ -40,6 +82,28 @@ static int selftest() {
   SearchResult r{"f.txt", {"x", "y", "z"}, 4, 7, 5, 0.5};
   expect(format_search_results({r}, false), "f.txt:4::7 (0.5)\n   5: x\n   6: y\n   7: z\n\n");
   expect(search_output_json({}), "{\n  \"results\": []\n}");
+  {  // tokenize_to_csr: every thread count gives the serial result
+    std::vector<std::string> words;
+    for (int i = 0; i < 5000; ++i) words.push_back("w" + std::to_string(i));
+    WordLevelTokenizer tok(words);
+    std::vector<std::string> lines;
+    uint64_t h = 88172645463325252ull;
+    for (int i = 0; i < 3000; ++i) {
+      std::string l;
+      h ^= h << 13; h ^= h >> 7; h ^= h << 17;
+      const int nt = (int)(h % 40);
+      for (int t = 0; t < nt; ++t) { h ^= h << 13; h ^= h >> 7; h ^= h << 17; l += (t ? " " : "") + ((h % 7) ? "w" + std::to_string(h % 6000) : std::string("\tunk ")); }
+      lines.push_back(l);
+    }
+    std::vector<uint64_t> o1, oN; std::vector<uint32_t> i1, iN;
+    tokenize_to_csr(lines, tok, 16, o1, i1, 1);
+    for (unsigned th : {2u, 3u, 8u}) {
+      tokenize_to_csr(lines, tok, 16, oN, iN, th);
+      if (o1 != oN || i1 != iN) { fprintf(stderr, "selftest: tokenize_to_csr differs with %u threads\n", th); ++bad; }
+    }
+    if (o1.size() != 3001 || o1.back() != i1.size() || i1.empty()) { fprintf(stderr, "selftest: tokenize_to_csr shape\n"); ++bad; }
+    for (size_t i = 0; i < 3000; ++i) if (o1[i + 1] - o1[i] > 16) { fprintf(stderr, "selftest: truncation\n"); ++bad; break; }
+  }
   printf(bad ? "selftest FAILED\n" : "selftest ok\n");
   return bad ? 1 : 0;
 }
@@ -54,6 +118,11 @@ int main(int argc, char **argv) {
     std::string a = argv[i];
     auto next = [&]() -> std::string { if (i + 1 >= argc) { fprintf(stderr, "error: %s needs a value\n", a.c_str()); exit(2); } return argv[++i]; };
     if (a == "--selftest") return selftest();
+    if (a == "--tokenize-bench") {                 // host tokenisation throughput: LINES THREADS
+      const size_t n_lines = i + 1 < argc ? std::stoul(argv[i + 1]) : 1000000;
+      const unsigned threads = i + 2 < argc ? (unsigned)std::stoul(argv[i + 2]) : 0;
+      return tokenize_bench(n_lines, threads);
+    }
     if (a == "--lower") {                          // test hook: stdin -> to_lowercase -> stdout
       std::string in, line;
       char buf[65536];

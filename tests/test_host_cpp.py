@@ -276,3 +276,13 @@ def test_cpp_cli_workspace_mode_equals_python_mirror(binary, tmp_path, ctx, monk
                        stdin=subprocess.DEVNULL, env=env)
     assert r.stdout == out.getvalue() and r.stdout.startswith(f"{f1}:1::2 (")
     assert "Updating workspace with 2 lines" in r.stderr and r.stderr == err.getvalue()
+
+
+def test_cpp_tokenize_bench_hook_runs(binary):
+    """Host tokenisation throughput hook; `--selftest` already checks that every
+    thread count produces the serial CSR."""
+    r = subprocess.run([binary, "--tokenize-bench", "20000", "2"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    rows = [json.loads(l) for l in r.stdout.strip().splitlines()]
+    assert [x["threads"] for x in rows] == [1, 2]
+    assert rows[0]["tokens"] == rows[1]["tokens"] > 100_000 and rows[0]["lines"] == 20000
