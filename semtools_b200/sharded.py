@@ -51,6 +51,19 @@ class ShardedCorpus:
         lists = self.all_gather(local)
         return self.merge(lists, top_k)
 
+    def search_batch(self, queries, top_k: int, local_search_batch: Callable):
+        """Batched queries (K2) over the row shards: every rank answers all nq queries on its
+        shard (`local_search_batch(queries, top_k)` -> list of HIT_DTYPE arrays with global
+        rows, e.g. `Corpus.search_batch`), ONE all-gather of nq x top_k hits (16 B each), then the
+        per-query merge.  Returns a list of nq HIT_DTYPE arrays."""
+        queries = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = len(queries)
+        if nq == 0 or top_k == 0:
+            return [np.zeros(0, dtype=capi.HIT_DTYPE) for _ in range(nq)]
+        local = np.stack([pad_hits(h, top_k) for h in local_search_batch(queries, top_k)])   # (nq, k)
+        lists = self.all_gather(local.reshape(-1)).reshape(self.world, nq, top_k)
+        return [self.merge(np.ascontiguousarray(lists[:, i, :]), top_k) for i in range(nq)]
+
     @classmethod
     def on_gpu(cls, ctx: capi.Context, corpus: capi.Corpus, dist, device):
         """Product wiring: CUDA kernels for search + merge, NCCL all-gather."""

@@ -69,6 +69,16 @@ def _worker(rank, world, port, q_out):
     r, d = oracle.search_rows(rows[keep_all], q, top_k=7)
     got = sa.search(q, 7)
     res["approx_union"] = bool(got["row"].tolist() == keep_all[r].tolist() and np.array_equal(got["distance"], d))
+    # batched queries: one all-gather of nq x k hits, per-query merge
+    qs = np.stack([rows[5], rows[77], rows[1002], rows[400]])       # incl. a zero-row query
+    def local_batch(queries, top_k):
+        return [local_search(qv, top_k, None, None) for qv in queries]
+    got_b = sc.search_batch(qs, 6, local_batch)
+    ok = len(got_b) == 4
+    for i in range(4):
+        r, d = oracle.search_rows(rows, qs[i], top_k=6)
+        ok = ok and got_b[i]["row"].tolist() == [int(x) for x in r] and np.array_equal(got_b[i]["distance"], d)
+    res["batch"] = bool(ok)
     res["bounds"] = (lo, hi)
     q_out.put((rank, res))
     dist.barrier()
@@ -92,6 +102,7 @@ def test_sharded_search_gloo(world):
     assert bounds[0][0] == 0 and bounds[-1][1] == 1003
     assert all(a[1] == b[0] for a, b in zip(bounds[:-1], bounds[1:]))
     for rank, res in results:
+        assert res["batch"], f"rank {rank}: sharded batch search differs from the oracle"
         assert res["approx_union"], f"rank {rank}: approximate shard lists merged wrongly"
         for k in (1, 3, 10, 600):
             assert res[k], (rank, k)
