@@ -547,7 +547,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         k2 = side(bench_batch, torch, dev, ctx, stream, corpus, args.rows, k)
     if world > 1 and not args.no_cpu_baseline:
-        k2 = side(bench_batch_sharded, torch, dist, dev, ctx, stream, corpus, args.rows, k, world)   # every rank takes part
+        k2 = bench_batch_sharded(torch, dist, dev, ctx, stream, corpus, args.rows, k, world)   # every rank takes part: no side() here, a rank that swallowed an error would leave the others in the all-gather
 
     # ---- K5 (BASELINE configs[4] at single-GPU scale: IVF-PQ probe, recall-measured) ------
     k5 = None
