@@ -1,0 +1,62 @@
+"""CPU model of the K2 pipeline-v2 selection rule (semtools_b200/csrc/batch_scan.cu, "Pipeline
+v2"): with a = bf16 approximate score and c = exact cosine, |a - c| <= EPS, the rows with
+a >= S_k - 2 EPS (S_k = k-th largest sampled COMPLETE-tile maximum) contain the oracle's top-k,
+and so do the rows with a >= A_k - 2 EPS (A_k = k-th largest approximate score).  This checks
+the arithmetic claim on data with ties, duplicates, exact hits (c >= 1 clamps), zero rows and a
+ragged last tile; the kernels themselves are checked on the GPU (tests/test_gpu_batch.py)."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import unit_rows
+
+EPS = 0.0045          # STB_BATCH_EPS
+TILE = 256
+
+
+def bf16(x):
+    torch = pytest.importorskip("torch")
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+def approx_scores(rows, queries):
+    norm = np.linalg.norm(rows.astype(np.float64), axis=1, keepdims=True)
+    rn = bf16(np.divide(rows, norm, out=np.zeros_like(rows), where=norm > 0).astype(np.float32))
+    qn = bf16((queries / np.linalg.norm(queries.astype(np.float64), axis=1, keepdims=True)).astype(np.float32))
+    return qn @ rn.T                                            # f32 accumulation, like the TMEM accumulators
+
+
+@pytest.mark.parametrize("n,k,n_sample", [(20_000, 10, 37), (20_000, 1, 78), (20_001, 64, 78), (5_000, 3, 5), (300, 5, 1)])
+def test_threshold_rule_keeps_the_exact_topk(n, k, n_sample):
+    rng = np.random.default_rng(n + k)
+    rows = (unit_rows(rng, n) * rng.uniform(0.25, 4.0, (n, 1))).astype(np.float32)
+    queries = unit_rows(rng, 12)
+    rows[rng.integers(0, n, 30)] = rows[rng.integers(0, n, 30)]                 # duplicates
+    rows[[1, n // 2]] = 0.0                                                      # zero rows
+    queries[0] = rows[7] / np.linalg.norm(rows[7])                               # exact hit: c ~ 1
+    dense = rng.choice(n, 200, replace=False)
+    rows[dense] = (queries[1] + 0.01 * unit_rows(rng, 200)).astype(np.float32)   # 200 near-ties at the top
+    a = approx_scores(rows, queries)
+    n_full = n // TILE
+    stride = max(n_full // n_sample, 1)
+    for qi, q in enumerate(queries):
+        d = oracle.distances(rows, q)
+        c = 1.0 - d
+        live = d != 1.0                                                          # not the ab == 0 -> 1 special case (zero rows)
+        assert np.max(np.abs(a[qi][live] - c[live])) <= EPS                       # the bound the proof rests on
+        r_top, _ = oracle.search_rows(rows, q, top_k=k)
+        tile_max = a[qi][: n_full * TILE].reshape(n_full, TILE).max(axis=1)
+        sample = tile_max[::stride][:n_sample]
+        if len(sample) >= k:
+            s_k = np.sort(sample)[-k]
+            emitted = a[qi] >= np.float32(s_k) - np.float32(2 * EPS)
+        else:
+            emitted = np.ones(n, bool)                                           # thr = -inf
+        assert emitted[r_top].all(), (qi, "emission threshold lost a top-k row")
+        a_k = np.sort(a[qi][emitted])[-min(k, int(emitted.sum()))]
+        narrowed = emitted & (a[qi] >= np.float32(a_k) - np.float32(2 * EPS))
+        assert narrowed[r_top].all(), (qi, "narrowing lost a top-k row")
+        # and the exact order restricted to the narrowed set is the oracle's answer
+        idx = np.flatnonzero(narrowed)
+        order = idx[np.lexsort((idx, d[idx]))][:k]
+        assert order.tolist() == [int(x) for x in r_top]
