@@ -50,6 +50,8 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--ivfpq-rows", type=int, default=4_000_000,
                    help="rows of the IVF-PQ side section (BASELINE configs[4] names 100M; 4M keeps the default run short)")
+    p.add_argument("--ivfpq-sharded", action="store_true",
+                   help="N>1: also measure IVF-PQ sharded by row (off by default: collectives on every rank)")
     p.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                    help="N>1: p2p = fused in-kernel exchange over NVLink peer memory; nccl = all-gather + merge kernel")
     return p.parse_args()
@@ -322,6 +324,49 @@ def bench_ivfpq(torch, dev, ctx, rows=4_000_000, nlist=4096, nprobe=64, n_center
             "code_bytes_per_query": float(np.mean(scanned)) * 32, "index_bytes": st["index_bytes"], "max_list": st["max_list"]}
 
 
+def bench_ivfpq_sharded(torch, dist, dev, ctx, world, rank, rows=4_000_000, nlist=4096, nprobe=64, spread=0.6):
+    """IVF-PQ sharded by ROW: the clustered corpus of `bench_ivfpq` split into `world`
+    contiguous row blocks, one index per rank over its block (nlist lists each), per-rank
+    top-k, all-gather of k hits, K4 merge (semtools_b200.sharded.ShardedCorpus.on_gpu_ivfpq).
+    Off by default (--ivfpq-sharded): every rank takes part in collectives."""
+    from semtools_b200 import capi
+    from semtools_b200.sharded import ShardedCorpus, shard_bounds
+    n_centers = max(rows // 100, 1000)
+    lo, hi = shard_bounds(rows, world, rank)
+    g = torch.Generator(device=dev); g.manual_seed(SEED + 5)                  # same centers on every rank
+    centers = torch.randn((n_centers, 256), generator=g, device=dev); centers /= centers.norm(dim=1, keepdim=True)
+    c = capi.Corpus(ctx, max(hi - lo, 1), row_base=lo)
+    for chunk_id in range(lo // CHUNK, (hi + CHUNK - 1) // CHUNK):            # chunk-seeded: identical rows for any world size
+        gc = torch.Generator(device=dev); gc.manual_seed(SEED + 1000 + chunk_id)
+        idx = torch.randint(0, n_centers, (CHUNK,), generator=gc, device=dev)
+        x = centers[idx] + spread / 16.0 * torch.randn((CHUNK, 256), generator=gc, device=dev)
+        x /= x.norm(dim=1, keepdim=True)
+        a, b = max(lo, chunk_id * CHUNK), min(hi, (chunk_id + 1) * CHUNK)
+        part = x[a - chunk_id * CHUNK: b - chunk_id * CHUNK].contiguous()
+        torch.cuda.synchronize(dev); c.append_dev(part.data_ptr(), b - a)
+    gq = torch.Generator(device=dev); gq.manual_seed(SEED + 6)
+    idx = torch.randint(0, n_centers, (64,), generator=gq, device=dev)
+    q = centers[idx] + spread / 16.0 * torch.randn((64, 256), generator=gq, device=dev); q /= q.norm(dim=1, keepdim=True)
+    qh = q.cpu().numpy()
+    del x, centers
+    t0 = time.perf_counter()
+    index = capi.IvfPq(c, nlist=nlist, train_rows=262144, iters=8)
+    build_s = time.perf_counter() - t0
+    exact = ShardedCorpus.on_gpu(ctx, c, dist, dev)
+    approx = ShardedCorpus.on_gpu_ivfpq(ctx, index, dist, dev, nprobe=nprobe, rerank=512)
+    want = [exact.search(qh[i], 10) for i in range(64)]
+    dist.barrier()
+    t0 = time.perf_counter()
+    got = [approx.search(qh[i], 10) for i in range(64)]
+    dist.barrier()
+    ms = (time.perf_counter() - t0) / 64 * 1e3
+    rec = [len(set(got[i]["row"].tolist()) & set(want[i]["row"].tolist())) / 10.0 for i in range(64)]
+    index.close(); c.close()
+    return {"workload": f"{rows} clustered rows row-sharded x{world}, nlist={nlist} per shard, nprobe={nprobe}, rerank=512, top-k=10",
+            "recall_at_10": float(np.mean(rec)), "min_recall": float(np.min(rec)), "ms_per_query_e2e": ms,
+            "build_s": build_s, "exchange": "nccl all_gather of k hits + stb_hits_merge (host-staged, as ShardedCorpus.on_gpu)"}
+
+
 # ------------------------------------------------------------------ K3 side bench -----
 def bench_embed(torch, dev, ctx, stream, V=500_000, n_lines=1_000_000):
     """K3 on SURVEY 8d's synthetic ingestion batch: V=500k x 256 table (0.5 GB), line
@@ -549,6 +594,10 @@ def run_ours(args):
     if world > 1 and not args.no_cpu_baseline:
         k2 = bench_batch_sharded(torch, dist, dev, ctx, stream, corpus, args.rows, k, world)   # every rank takes part: no side() here, a rank that swallowed an error would leave the others in the all-gather
 
+    k5s = None
+    if world > 1 and args.ivfpq_sharded:
+        k5s = bench_ivfpq_sharded(torch, dist, dev, ctx, world, rank, rows=args.ivfpq_rows)
+
     # ---- K5 (BASELINE configs[4] at single-GPU scale: IVF-PQ probe, recall-measured) ------
     k5 = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -615,6 +664,8 @@ def run_ours(args):
             line["batch1024"] = k2
         if k5 is not None:
             line["ivfpq"] = k5
+        if k5s is not None:
+            line["ivfpq_sharded"] = k5s
         if k3 is not None and "error" in k3:
             line["k3_embed"] = k3
         elif k3 is not None:
