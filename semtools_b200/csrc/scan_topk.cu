@@ -63,7 +63,10 @@ __device__ __forceinline__ uint32_t stb_map_row(const ScanArgs &a, uint64_t v) {
 
 // Approximate-cosine scan.  Calls sink(score, local_row) once per 4*U-row tile with
 // a warp-uniform control flow; lanes that do not represent a row pass -inf.
-template <int U, bool RANGES, class Sink>
+// RANGES: 0 = whole corpus; 1 = row ranges, binary search per row; 2 = row ranges, every warp
+// walks ONE contiguous block of virtual rows and advances its range index as it goes
+// (one search per warp instead of one per row; opt-in, STB_RANGES_WALK=1).
+template <int U, int RANGES, class Sink>
 __device__ __forceinline__ void stb_scan_rows(const ScanArgs &args, Sink &sink) {
   const int lane = threadIdx.x & 31;
   const int g = lane >> 3;   // row group inside the warp
@@ -99,7 +102,15 @@ __device__ __forceinline__ void stb_scan_rows(const ScanArgs &args, Sink &sink) 
   const uint64_t warps_total = (uint64_t)gridDim.x * (blockDim.x >> 5);
   const uint64_t warp_id = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
 
-  for (uint64_t tile = warp_id; tile < n_tiles; tile += warps_total) {
+  uint64_t t_begin = warp_id, t_end = n_tiles, t_step = warps_total;
+  if constexpr (RANGES == 2) {
+    const uint64_t per = (n_tiles + warps_total - 1) / warps_total;
+    t_begin = warp_id * per;
+    t_end = t_begin + per < n_tiles ? t_begin + per : n_tiles;
+    t_step = 1;
+  }
+  [[maybe_unused]] uint32_t rlo = 0xffffffffu;       // RANGES == 2: current range of this lane's rows
+  for (uint64_t tile = t_begin; tile < t_end; tile += t_step) {
     float4 a[U][8];
     uint32_t row[U];
     bool valid[U];
@@ -108,7 +119,22 @@ __device__ __forceinline__ void stb_scan_rows(const ScanArgs &args, Sink &sink) 
       uint64_t v = tile * tile_rows + (uint64_t)(u * 4 + g);
       valid[u] = v < args.n_virtual;
       uint64_t vc = valid[u] ? v : (args.n_virtual - 1);
-      row[u] = RANGES ? stb_map_row(args, vc) : (uint32_t)vc;
+      if constexpr (RANGES == 2) {
+        // this lane's virtual rows only grow: search once, then step to the next range(s)
+        if (rlo == 0xffffffffu) {
+          uint32_t lo = 0, hi = args.n_ranges;
+          while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(args.vstart + mid) <= vc) lo = mid; else hi = mid;
+          }
+          rlo = lo;
+        } else {
+          while (rlo + 1 < args.n_ranges && __ldg(args.vstart + rlo + 1) <= vc) ++rlo;
+        }
+        row[u] = (uint32_t)(__ldg(args.rbegin + rlo) + (vc - __ldg(args.vstart + rlo)));
+      } else {
+        row[u] = RANGES ? stb_map_row(args, vc) : (uint32_t)vc;
+      }
       const float4 *p = args.rows + (size_t)row[u] * STB_ROW_F4 + j;
 #pragma unroll
       for (int i = 0; i < 8; ++i) a[u][i] = stb_ld_stream(p + 8 * i);
@@ -376,7 +402,7 @@ __device__ __forceinline__ int stb_pad_and_sort(uint64_t *skeys, int c, int min_
 
 #define STB_RR_STRIDE 260   // floats per staged row (1 KiB + 16 B pad: conflict-free LDS.128)
 
-template <int E, int U, bool RANGES>
+template <int E, int U, int RANGES>
 __global__ void __launch_bounds__(STB_SCAN_THREADS, STB_SCAN_MINB)
 stb_scan_topk_kernel(const TopkArgs args) {
   constexpr int KP = 32 * E;
@@ -706,7 +732,7 @@ static int stb_pick_e(uint32_t top_k) {
   return 4;                    // K' = 128
 }
 
-template <int E, bool RANGES>
+template <int E, int RANGES>
 static int stb_launch_topk_t(stb_ctx *ctx, const TopkArgs &a) {
   auto kern = stb_scan_topk_kernel<E, STB_SCAN_U, RANGES>;
   int occ = 0;
@@ -761,10 +787,18 @@ int stb_launch_scan_topk(stb_ctx *ctx, const float *rows, uint64_t n_rows,
   if (xchg) a.xchg = *xchg; else memset(&a.xchg, 0, sizeof(a.xchg));
   a.dbg = ctx->dbg_dev;
   const bool rg = n_ranges > 0;
+  const char *walk_env = getenv("STB_RANGES_WALK");        // opt-in until timed: RANGES mode 2
+  if (rg && walk_env && walk_env[0] == '1') {
+    switch (stb_pick_e(top_k)) {
+      case 1: return stb_launch_topk_t<1, 2>(ctx, a);
+      case 2: return stb_launch_topk_t<2, 2>(ctx, a);
+      default: return stb_launch_topk_t<4, 2>(ctx, a);
+    }
+  }
   switch (stb_pick_e(top_k)) {
-    case 1: return rg ? stb_launch_topk_t<1, true>(ctx, a) : stb_launch_topk_t<1, false>(ctx, a);
-    case 2: return rg ? stb_launch_topk_t<2, true>(ctx, a) : stb_launch_topk_t<2, false>(ctx, a);
-    default: return rg ? stb_launch_topk_t<4, true>(ctx, a) : stb_launch_topk_t<4, false>(ctx, a);
+    case 1: return rg ? stb_launch_topk_t<1, 1>(ctx, a) : stb_launch_topk_t<1, 0>(ctx, a);
+    case 2: return rg ? stb_launch_topk_t<2, 1>(ctx, a) : stb_launch_topk_t<2, 0>(ctx, a);
+    default: return rg ? stb_launch_topk_t<4, 1>(ctx, a) : stb_launch_topk_t<4, 0>(ctx, a);
   }
 }
 

@@ -473,3 +473,24 @@ def test_direct_host_output_switch_gives_identical_hits(ctx, monkeypatch):
             assert np.array_equal(got, want)
             r, d = oracle.search_rows(rows, rows[qi], top_k=k)
             assert got["row"].tolist() == [int(x) for x in r] and np.array_equal(got["distance"], d)
+
+
+@pytest.mark.skipif(os.environ.get("STB_TEST_V2") != "1", reason="opt-in path written after the last GPU session of round 1 (STB_TEST_V2=1)")
+@pytest.mark.parametrize("n,n_ranges", [(9_000, 5), (20_000, 700), (300_000, 20_000), (70_000, 1)])
+def test_range_walk_mode_matches_the_oracle(ctx, monkeypatch, n, n_ranges):
+    """STB_RANGES_WALK=1: every warp walks one contiguous block of the selected rows and steps
+    its range index instead of searching per row; the answer must be the store query's."""
+    rng = np.random.default_rng(n + n_ranges)
+    rows = unit_rows(rng, n)
+    rows[n // 3] = rows[n // 3 + 1]                                     # a tie inside / across ranges
+    q = unit_rows(rng, 1)[0]
+    c = make_corpus(ctx, rows)
+    step = max(n // n_ranges, 2)
+    starts = np.sort(rng.choice(np.arange(0, n - step, step), min(n_ranges, (n - step) // step), replace=False))
+    ranges = [[int(s), int(s + rng.integers(1, step + 1))] for s in starts]
+    monkeypatch.setenv("STB_RANGES_WALK", "1")
+    for k, thr in [(1, None), (10, None), (64, None), (10, 0.95)]:
+        r, d32 = oracle.store_search(rows, ranges, q, k, thr)
+        hits = c.search(q, top_k=k, max_distance=thr, mode=capi.STB_MODE_STORE_QUERY, row_ranges=ranges)
+        assert hits["row"].tolist() == [int(x) for x in r]
+        assert np.array_equal(hits["distance"].astype(np.float32), d32)
