@@ -488,6 +488,8 @@ def test_range_walk_mode_matches_the_oracle(ctx, monkeypatch, n, n_ranges):
     step = max(n // n_ranges, 2)
     starts = np.sort(rng.choice(np.arange(0, n - step, step), min(n_ranges, (n - step) // step), replace=False))
     ranges = [[int(s), int(s + rng.integers(1, step + 1))] for s in starts]
+    if n_ranges == 1:
+        ranges = [[1000, n - 1000]]
     monkeypatch.setenv("STB_RANGES_WALK", "1")
     for k, thr in [(1, None), (10, None), (64, None), (10, 0.95)]:
         r, d32 = oracle.store_search(rows, ranges, q, k, thr)
