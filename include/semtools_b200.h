@@ -279,6 +279,9 @@ int stb_debug_timestamps(stb_ctx *ctx, int reset, uint64_t out[8]);
  * NULL) the per-32-row maxima [ceil(nq/128)][ceil(n/256)*8][128]. */
 int stb_debug_batch_gemm(stb_ctx *ctx, const float *q, uint32_t nq, const float *rows,
                          uint64_t n, float *out_full, float *out_submax);
+/* Build parameters of K2 (host-only): element type of the shadow the tensor-core pass runs on
+ * (0 = bf16, 1 = fp16) and the bound |approximate - exact cosine| <= eps its selection uses. */
+int stb_debug_batch_params(int *shadow_is_f16, double *eps);
 
 #ifdef __cplusplus
 }

@@ -27,7 +27,7 @@ SYMBOLS = [
     "stb_xchg_create", "stb_xchg_destroy", "stb_xchg_local_handle",
     "stb_xchg_connect", "stb_xchg_connect_local", "stb_search_topk_xchg", "stb_search_xchg", "stb_ivfpq_build",
     "stb_ivfpq_destroy", "stb_ivfpq_stats", "stb_ivfpq_search", "stb_hits_merge_dev", "stb_hits_merge_batch_dev", "stb_hits_merge", "stb_fnv1a64", "stb_line_id",
-    "stb_ctx_counters", "stb_debug_timestamps", "stb_debug_batch_gemm",
+    "stb_ctx_counters", "stb_debug_timestamps", "stb_debug_batch_gemm", "stb_debug_batch_params",
 ]
 
 
@@ -106,6 +106,7 @@ def lib() -> C.CDLL:
     L.stb_ctx_counters.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.stb_debug_timestamps.argtypes = [vp, i32, vp]
     L.stb_debug_batch_gemm.argtypes = [vp, vp, u32, vp, u64, vp, vp]
+    L.stb_debug_batch_params.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_double)]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("stb_version", "stb_device_count"):
@@ -126,6 +127,13 @@ def _np_ptr(a):
 
 def device_count() -> int:
     return int(lib().stb_device_count())
+
+
+def batch_params():
+    """(shadow_is_f16, eps) of this build's K2 path (stb_debug_batch_params; host-only)."""
+    f16, eps = C.c_int(0), C.c_double(0.0)
+    _check(lib().stb_debug_batch_params(C.byref(f16), C.byref(eps)))
+    return bool(f16.value), float(eps.value)
 
 
 def fnv1a64(data: bytes) -> int:

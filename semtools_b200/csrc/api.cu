@@ -826,6 +826,11 @@ int stb_search_batch(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uin
   return STB_OK;
 }
 
+int stb_debug_batch_params(int *shadow_is_f16, double *eps) {
+  stb_batch_build_params(shadow_is_f16, eps);
+  return STB_OK;
+}
+
 // ------------------------------------------------------------------- K2 debug hook ---
 // Runs shadow build + tcgen05 GEMM on host inputs and returns the FULL approximate score
 // matrix (tests only: validates descriptors / TMEM / epilogue against a reference matmul).

@@ -207,6 +207,7 @@ int stb_launch_batch_finish2(stb_ctx *ctx, const uint64_t *cand_keys, const uint
                              uint32_t cand_cap, uint32_t nq, uint32_t top_k, const float *rows,
                              uint64_t n_rows, uint64_t row_base, const float *queries_dev,
                              stb_hit *out_hits, uint32_t *out_status);
+void stb_batch_build_params(int *shadow_is_f16, double *eps);
 int stb_launch_batch_select(stb_ctx *ctx, const float *submax, uint32_t n_sub, uint32_t q_pad,
                             uint32_t n_slices, uint64_t *cand);
 int stb_launch_batch_finish(stb_ctx *ctx, const uint64_t *cand, uint32_t n_slices, uint32_t n_sub,

@@ -10,7 +10,7 @@ import pytest
 import oracle
 from conftest import unit_rows
 
-EPS = 0.0045          # STB_BATCH_EPS
+EPS = 0.0045          # STB_BATCH_EPS of the default (bf16) build; the fp16 option is modelled below
 TILE = 256
 
 
@@ -60,3 +60,21 @@ def test_threshold_rule_keeps_the_exact_topk(n, k, n_sample):
         idx = np.flatnonzero(narrowed)
         order = idx[np.lexsort((idx, d[idx]))][:k]
         assert order.tolist() == [int(x) for x in r_top]
+
+
+def test_fp16_shadow_bound():
+    """-DSTB_SHADOW_F16=1: |fp16 approximate - exact cosine| <= 0.0012 on unit rows, including rows with
+    many tiny (fp16-subnormal) components."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(11)
+    rows = unit_rows(rng, 4000)
+    spiky = rng.standard_normal((200, 256)).astype(np.float32) * np.float32(1e-6)      # components far below 2^-14 ...
+    spiky[np.arange(200), rng.integers(0, 256, 200)] = 1.0                              # ... next to one dominant one
+    rows[:200] = spiky / np.linalg.norm(spiky, axis=1, keepdims=True)
+    queries = unit_rows(rng, 6)
+    queries[0] = rows[3]
+    h = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(torch.float16).to(torch.float32).numpy()
+    a = h(queries) @ h(rows).T
+    for qi, q in enumerate(queries):
+        c = 1.0 - oracle.distances(rows, q)
+        assert np.max(np.abs(a[qi] - c)) <= 0.0012

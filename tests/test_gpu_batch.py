@@ -13,8 +13,10 @@ pytestmark = pytest.mark.gpu
 
 
 def bf16_round(x):
+    """Rounds to the element type of this build's shadow (bf16 by default, fp16 with -DSTB_SHADOW_F16=1)."""
     torch = pytest.importorskip("torch")
-    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(torch.bfloat16).to(torch.float32).numpy()
+    dt = torch.float16 if capi.batch_params()[0] else torch.bfloat16
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(dt).to(torch.float32).numpy()
 
 
 @pytest.mark.parametrize("nq,n", [(128, 256), (200, 1000), (1, 5), (384, 40_000)])
@@ -38,7 +40,7 @@ def test_tcgen05_gemm_matches_bf16_reference(ctx, nq, n):
     # exact cosine is within the rigorous bf16 bound used by the completeness proof
     exact = 1.0 - np.stack([oracle.distances(rows, q[i]) for i in range(min(nq, 4))])
     exact[:, n // 2] = 0.0
-    assert np.max(np.abs(got[: exact.shape[0]] - exact)) < 0.0045
+    assert np.max(np.abs(got[: exact.shape[0]] - exact)) < capi.batch_params()[1]
     # padding rows / queries are zeros; sub-tile maxima agree with the full matrix
     assert np.all(full[:, n:] == 0.0)
     exp_sub = full.reshape(mt, 128, nt * 8, 32).max(axis=3).transpose(0, 2, 1)
