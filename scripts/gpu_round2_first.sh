@@ -24,6 +24,11 @@ STB_DIRECT_OUT=1 timeout 300 python bench.py --no-cpu-baseline 2>&1 | tail -1 | 
 echo "== store query over 20k ranges: binary search per row vs range walk"
 timeout 300 python scripts/modes_probe.py 10000000 2>&1 | tail -12 | tee "$OUT/modes_default.log"
 STB_RANGES_WALK=1 timeout 300 python scripts/modes_probe.py 10000000 2>&1 | tail -12 | tee "$OUT/modes_walk.log"
+echo "== fp16 shadow variant: batch tests + timing"
+mkdir -p semtools_b200/lib/variants
+STB_NVCC_EXTRA=-DSTB_SHADOW_F16=1 STB_LIB_OUT=semtools_b200/lib/variants/libstb_f16.so bash scripts/build_lib.sh
+STB_LIB_PATH=$PWD/semtools_b200/lib/variants/libstb_f16.so STB_TEST_V2=1 timeout 600 python -m pytest tests/test_gpu_batch.py -x -q -m gpu 2>&1 | tail -5 | tee "$OUT/pytest_f16.log"
+STB_LIB_PATH=$PWD/semtools_b200/lib/variants/libstb_f16.so STB_BATCH_V2=1 timeout 300 python scripts/batch_probe.py 10000000 1024 5 2>&1 | tail -2 | tee "$OUT/k2_v2_f16.log"
 echo "== full bench (side sections batch1024_v2 / ivfpq_v2 included)"
 timeout 900 python bench.py --gpus 1 --steps 200 --warmup 10 2>&1 | tail -2 | tee "$OUT/bench.log"
 ls -la "$OUT"
