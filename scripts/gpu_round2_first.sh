@@ -21,6 +21,9 @@ STB_IVFPQ_V2=1 timeout 300 python scripts/ivfpq_probe.py 2>&1 | tail -6 | tee "$
 echo "== K1 e2e with and without direct host output"
 timeout 300 python bench.py --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('default', d['value'], d['e2e']['value'])" | tee "$OUT/e2e_default.log"
 STB_DIRECT_OUT=1 timeout 300 python bench.py --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('direct ', d['value'], d['e2e']['value'])" | tee "$OUT/e2e_direct.log"
+echo "== K1 half-width shadow scan (value through search_topk_dev needs the shadow: bench builds it for K2)"
+timeout 300 python scripts/tail_probe.py 10000000 32 2>&1 | tail -3 | tee "$OUT/k1_f32.log"
+STB_SCAN_SHADOW=1 STB_PROBE_PREPARE=1 timeout 300 python scripts/tail_probe.py 10000000 32 2>&1 | tail -3 | tee "$OUT/k1_shadow.log"
 echo "== store query over 20k ranges: binary search per row vs range walk"
 timeout 300 python scripts/modes_probe.py 10000000 2>&1 | tail -12 | tee "$OUT/modes_default.log"
 STB_RANGES_WALK=1 timeout 300 python scripts/modes_probe.py 10000000 2>&1 | tail -12 | tee "$OUT/modes_walk.log"

@@ -11,6 +11,8 @@ ctx = capi.Context(0, s.cuda_stream)
 g = torch.Generator(device=dev); g.manual_seed(1)
 x = torch.randn((rows, 256), generator=g, device=dev); x /= x.norm(dim=1, keepdim=True)
 c = capi.Corpus(ctx, rows); torch.cuda.synchronize(); c.append_dev(x.data_ptr(), rows)
+if os.environ.get("STB_PROBE_PREPARE") == "1":      # build the 16-bit shadow (STB_SCAN_SHADOW=1 then scans it)
+    c.prepare_batch()
 q = torch.randn((16, 256), generator=g, device=dev); q /= q.norm(dim=1, keepdim=True)
 hits = torch.zeros((16, 10, 2), dtype=torch.float64, device=dev); st = torch.zeros((16, 4), dtype=torch.int32, device=dev)
 for i in range(iters):
@@ -21,4 +23,11 @@ e0.record(s)
 for i in range(iters):
     c.search_topk_dev(q[i % 16].data_ptr(), 10, hits[i % 16].data_ptr(), st[i % 16].data_ptr())
 e1.record(s); torch.cuda.synchronize()
-print("rows", rows, "us/query", e0.elapsed_time(e1) / iters * 1e3, "complete", bool((st[:, 1] == 1).all()))
+h32 = None
+if os.environ.get("STB_SCAN_SHADOW") == "1":        # cross-check the shadow scan against the f32 scan
+    got = hits.clone(); os.environ.pop("STB_SCAN_SHADOW")
+    for i in range(16):
+        c.search_topk_dev(q[i].data_ptr(), 10, hits[i].data_ptr(), st[i].data_ptr())
+    torch.cuda.synchronize()
+    h32 = bool(torch.equal(got.view(torch.int64), hits.view(torch.int64)))
+print("rows", rows, "us/query", e0.elapsed_time(e1) / iters * 1e3, "complete", bool((st[:, 1] == 1).all()), "same_as_f32_scan", h32)

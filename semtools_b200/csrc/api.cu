@@ -387,6 +387,8 @@ int stb_embed_status(stb_ctx *ctx) {
 }
 
 // --------------------------------------------------------------------- search ---
+static int corpus_ensure_shadow(stb_ctx *ctx, stb_corpus *c);   // defined with the K2 entry points
+
 static int ensure_hits_pin(stb_ctx *ctx, size_t need) {
   if (need <= ctx->hits_pin_cap) return STB_OK;
   stb_hit *np = nullptr;
@@ -489,16 +491,37 @@ int stb_search(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint32_t 
     // into the pinned host buffers (UVA: cudaMallocHost memory is device-accessible), which takes
     // the two D2H copies off the stream; kernel completion makes the stores visible to the host.
     const char *direct_env = getenv("STB_DIRECT_OUT");
-    if (direct_env && direct_env[0] == '1') {
-      if ((rc = stb_launch_scan_topk(ctx, corpus->rows, corpus->n, corpus->row_base, ctx->q_dev, top_k,
-                                     ranges_dev, n_loc, n_virtual, ctx->hits_pin, ctx->status_pin)) != STB_OK) return rc;
-    } else {
-      if ((rc = stb_launch_scan_topk(ctx, corpus->rows, corpus->n, corpus->row_base, ctx->q_dev, top_k,
-                                     ranges_dev, n_loc, n_virtual, ctx->hits_dev, ctx->status_dev)) != STB_OK) return rc;
-      STB_CUDA(cudaMemcpyAsync(ctx->status_pin, ctx->status_dev, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-      STB_CUDA(cudaMemcpyAsync(ctx->hits_pin, ctx->hits_dev, top_k * sizeof(stb_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    const bool direct = direct_env && direct_env[0] == '1';
+    auto run_fast = [&](const uint8_t *shadow) -> int {
+      int r;
+      if (direct) {
+        if ((r = stb_launch_scan_topk(ctx, corpus->rows, corpus->n, corpus->row_base, ctx->q_dev, top_k, ranges_dev, n_loc,
+                                      n_virtual, ctx->hits_pin, ctx->status_pin, nullptr, shadow)) != STB_OK) return r;
+      } else {
+        if ((r = stb_launch_scan_topk(ctx, corpus->rows, corpus->n, corpus->row_base, ctx->q_dev, top_k, ranges_dev, n_loc,
+                                      n_virtual, ctx->hits_dev, ctx->status_dev, nullptr, shadow)) != STB_OK) return r;
+        STB_CUDA(cudaMemcpyAsync(ctx->status_pin, ctx->status_dev, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        STB_CUDA(cudaMemcpyAsync(ctx->hits_pin, ctx->hits_dev, top_k * sizeof(stb_hit), cudaMemcpyDeviceToHost, ctx->stream));
+      }
+      STB_CUDA(cudaStreamSynchronize(ctx->stream));
+      return STB_OK;
+    };
+    // STB_SCAN_SHADOW=1 (opt-in until validated on hardware): whole-shard queries first run over the
+    // 16-bit normalised shadow (half the bytes; K2's operand, built lazily).  Same exact re-rank,
+    // wider proof margin; a result it cannot prove is retried on the f32 rows below.
+    const char *shadow_env = getenv("STB_SCAN_SHADOW");
+    bool proven_on_shadow = false;
+    if (shadow_env && shadow_env[0] == '1' && !ranges_dev) {
+      stb_corpus *cm = const_cast<stb_corpus *>(corpus);
+      const int src = corpus_ensure_shadow(ctx, cm);                 // STB_ERR_STATE: rows that cannot be normalised
+      if (src == STB_OK) {
+        if ((rc = run_fast(corpus->shadow)) != STB_OK) return rc;
+        proven_on_shadow = ctx->status_pin[1] != 0;
+      } else if (src != STB_ERR_STATE) {
+        return src;
+      }
     }
-    STB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!proven_on_shadow && (rc = run_fast(nullptr)) != STB_OK) return rc;
     const uint32_t n_hits = ctx->status_pin[0];
     if (ctx->status_pin[1]) {
       uint64_t n = 0;
@@ -566,8 +589,15 @@ int stb_search_topk_dev(stb_ctx *ctx, const stb_corpus *corpus, const float *q_d
   if (corpus->ctx != ctx) { stb_set_error("search_topk_dev: corpus belongs to another context"); return STB_ERR_ARG; }
   if (top_k == 0 || top_k > stb_scan_topk_max_k()) { stb_set_error("search_topk_dev: top_k must be 1..%u", stb_scan_topk_max_k()); return STB_ERR_ARG; }
   if (corpus->n == 0) { stb_set_error("search_topk_dev: empty corpus"); return STB_ERR_STATE; }
+  // STB_SCAN_SHADOW=1: use the 16-bit shadow when stb_corpus_prepare_batch has built it (this
+  // asynchronous entry point never builds it; status[1] says whether the result is proven, the
+  // caller's fallback is unchanged)
+  const char *shadow_env = getenv("STB_SCAN_SHADOW");
+  const uint8_t *shadow = nullptr;
+  if (shadow_env && shadow_env[0] == '1' && corpus->shadow && corpus->shadow_rows == corpus->n && !corpus->shadow_bad)
+    shadow = corpus->shadow;
   return stb_launch_scan_topk(ctx, corpus->rows, corpus->n, corpus->row_base, q_dev, top_k, nullptr, 0,
-                              corpus->n, out_hits_dev, out_status_dev);
+                              corpus->n, out_hits_dev, out_status_dev, nullptr, shadow);
 }
 
 // ------------------------------------------------------------ peer-memory exchange ---

@@ -25,6 +25,19 @@
 // in DESIGN.md "Candidate completeness".  Rows outside that range are forced
 // into the candidate set instead of being scored.
 #define STB_SCORE_EPS 1.0e-5
+// Element type of the 16-bit L2-normalised corpus shadow (K2 operand; K1's opt-in half-width
+// scan): bf16 by default, fp16 with -DSTB_SHADOW_F16=1.
+#ifndef STB_SHADOW_F16
+#define STB_SHADOW_F16 0
+#endif
+// |q^ . shadow(x) - exact cosine| when only the ROW is rounded (K1 shadow scan: the query stays
+// f32): <= u * ||q^|| * ||x^|| = u (2^-9 bf16, 2^-11 fp16; fp16 components below 2^-14 add
+// <= 16 * 2^-25 * ||q^||_1 <= 8e-6), plus f32 accumulation and rsqrt (< 2e-5).
+#if STB_SHADOW_F16
+#define STB_SHADOW_SCAN_EPS 0.00052
+#else
+#define STB_SHADOW_SCAN_EPS 0.0020
+#endif
 
 void stb_set_error(const char *fmt, ...);
 
@@ -144,7 +157,8 @@ int stb_launch_scan_topk(stb_ctx *ctx, const float *rows, uint64_t n_rows,
                          uint64_t row_base, const float *q_dev, uint32_t top_k,
                          const uint64_t *ranges_dev, uint32_t n_ranges,
                          uint64_t n_virtual, stb_hit *out_hits_dev,
-                         uint32_t *out_status_dev, const StbXchgArgs *xchg = nullptr);
+                         uint32_t *out_status_dev, const StbXchgArgs *xchg = nullptr,
+                         const uint8_t *shadow = nullptr);
 // Largest top_k the fast path serves.
 uint32_t stb_scan_topk_max_k(void);
 // Collect path: every row whose approximate cosine >= cos_floor (or that cannot be

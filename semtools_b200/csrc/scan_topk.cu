@@ -19,6 +19,8 @@
 // path below, which is exact for any input.
 #include <math_constants.h>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 #ifndef STB_SCAN_U
@@ -172,6 +174,105 @@ __device__ __forceinline__ void stb_scan_rows(const ScanArgs &args, Sink &sink) 
         s = nz ? CUDART_INF_F : (q_zero ? 1.f : 0.f);
       } else if (q_bad || !(a2 >= 1e-30f && a2 <= 1e30f)) s = CUDART_INF_F;  // forced candidate
       else s = ab * rsqrtf(a2) * rq;
+      sc[u] = valid[u] ? s : -CUDART_INF_F;
+    }
+    float s = -CUDART_INF_F;
+    uint32_t r = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (j == u) { s = sc[u]; r = row[u]; }
+    sink.template consume<4 * U>(s, r);
+  }
+}
+
+// Half-width scan (opt-in, STB_SCAN_SHADOW=1): the same running top-K' selection, but the scores
+// come from the 16-bit L2-normalised shadow that K2 uses (512 B per row instead of 1 KiB), so
+// the HBM-bound pass moves half the bytes.  The exact f64 re-rank and the completeness proof
+// are unchanged except for the margin (STB_SHADOW_SCAN_EPS: only the row is rounded, the query
+// stays f32).  Shadow layout (batch_scan.cu): tile t = row / 256 -> 4 K-slabs x [256 rows x 128 B],
+// 16-byte chunk index XOR (row % 8).  Lane j of a row's 8-lane group reads PHYSICAL chunk
+// j ^ (row % 8) of every slab, i.e. LOGICAL chunk j = elements s*64 + 8j .. +8 (s = 0..3), so
+// each lane pairs a fixed 32-element slice of the query with every row; the group still
+// covers each 128-byte line completely.
+__device__ __forceinline__ float2 stb_shadow_pair(uint32_t w) {
+#if STB_SHADOW_F16
+  return __half22float2(*reinterpret_cast<const __half2 *>(&w));
+#else
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+#endif
+}
+
+template <int U, class Sink>
+__device__ __forceinline__ void stb_scan_shadow(const ScanArgs &args, const uint8_t *shadow, Sink &sink) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 3;   // row group inside the warp
+  const int j = lane & 7;    // logical 16-byte chunk of every K-slab
+  // query slice: elements s*64 + 8j + e  (s < 4, e < 8) = float4 index s*16 + 2j + {0,1}
+  float4 q[8];
+  const float4 *q4 = reinterpret_cast<const float4 *>(args.q);
+#pragma unroll
+  for (int sl = 0; sl < 4; ++sl) { q[2 * sl] = __ldg(q4 + sl * 16 + 2 * j); q[2 * sl + 1] = __ldg(q4 + sl * 16 + 2 * j + 1); }
+  float qx = 0.f, qy = 0.f, qz = 0.f, qw = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    qx = fmaf(q[i].x, q[i].x, qx); qy = fmaf(q[i].y, q[i].y, qy);
+    qz = fmaf(q[i].z, q[i].z, qz); qw = fmaf(q[i].w, q[i].w, qw);
+  }
+  float b2 = (qx + qy) + (qz + qw);
+  b2 += __shfl_xor_sync(0xffffffffu, b2, 4);
+  b2 += __shfl_xor_sync(0xffffffffu, b2, 2);
+  b2 += __shfl_xor_sync(0xffffffffu, b2, 1);
+  bool q_any = false;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    q_any |= (q[i].x != 0.f) | (q[i].y != 0.f) | (q[i].z != 0.f) | (q[i].w != 0.f);
+  q_any = __any_sync(0xffffffffu, q_any);
+  const bool q_zero = (b2 == 0.f) && !q_any;
+  const bool q_bad = !q_zero && !(b2 >= 1e-30f && b2 <= 1e30f);
+  const float rq = q_zero ? 0.f : rsqrtf(b2);
+
+  const uint64_t tile_rows = 4 * U;
+  const uint64_t n_tiles = (args.n_virtual + tile_rows - 1) / tile_rows;
+  const uint64_t warps_total = (uint64_t)gridDim.x * (blockDim.x >> 5);
+  const uint64_t warp_id = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  for (uint64_t tile = warp_id; tile < n_tiles; tile += warps_total) {
+    uint4 a[U][4];
+    uint32_t row[U];
+    bool valid[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t v = tile * tile_rows + (uint64_t)(u * 4 + g);
+      valid[u] = v < args.n_virtual;
+      const uint64_t vc = valid[u] ? v : (args.n_virtual - 1);
+      row[u] = (uint32_t)vc;
+      const uint32_t rr = (uint32_t)(vc & 255u);
+      const uint8_t *p = shadow + (vc >> 8) * (size_t)(256 * 512) + (size_t)(rr >> 3) * 1024 + (size_t)(rr & 7u) * 128 +
+                         (size_t)((j ^ (int)(rr & 7u)) * 16);
+#pragma unroll
+      for (int sl = 0; sl < 4; ++sl) {
+        const float4 t = stb_ld_stream(reinterpret_cast<const float4 *>(p + (size_t)sl * (256 * 128)));
+        a[u][sl] = make_uint4(__float_as_uint(t.x), __float_as_uint(t.y), __float_as_uint(t.z), __float_as_uint(t.w));
+      }
+    }
+    float sc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float dx = 0.f, dy = 0.f, dz = 0.f, dw = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < 4; ++sl) {
+        const float2 e0 = stb_shadow_pair(a[u][sl].x), e1 = stb_shadow_pair(a[u][sl].y);
+        const float2 e2 = stb_shadow_pair(a[u][sl].z), e3 = stb_shadow_pair(a[u][sl].w);
+        dx = fmaf(e0.x, q[2 * sl].x, dx); dy = fmaf(e0.y, q[2 * sl].y, dy);
+        dz = fmaf(e1.x, q[2 * sl].z, dz); dw = fmaf(e1.y, q[2 * sl].w, dw);
+        dx = fmaf(e2.x, q[2 * sl + 1].x, dx); dy = fmaf(e2.y, q[2 * sl + 1].y, dy);
+        dz = fmaf(e3.x, q[2 * sl + 1].z, dz); dw = fmaf(e3.y, q[2 * sl + 1].w, dw);
+      }
+      float ab = (dx + dy) + (dz + dw);
+      ab += __shfl_xor_sync(0xffffffffu, ab, 4);
+      ab += __shfl_xor_sync(0xffffffffu, ab, 2);
+      ab += __shfl_xor_sync(0xffffffffu, ab, 1);
+      // the shadow row is already unit-norm (zero rows stay zero: score 0 = distance 1)
+      const float s = q_bad ? CUDART_INF_F : ab * rq;
       sc[u] = valid[u] ? s : -CUDART_INF_F;
     }
     float s = -CUDART_INF_F;
@@ -350,6 +451,7 @@ struct TopkArgs {
   uint32_t top_k;
   StbXchgArgs xchg;          // world == 0: no cross-GPU exchange
   unsigned long long *dbg;   // STB_TAIL_TIMING builds only: phase timestamps (ns)
+  const uint8_t *shadow;     // SRC == 1 only: 16-bit normalised corpus shadow (UMMA tile layout)
 };
 
 __device__ __forceinline__ unsigned long long stb_globaltimer() {
@@ -402,9 +504,11 @@ __device__ __forceinline__ int stb_pad_and_sort(uint64_t *skeys, int c, int min_
 
 #define STB_RR_STRIDE 260   // floats per staged row (1 KiB + 16 B pad: conflict-free LDS.128)
 
-template <int E, int U, int RANGES>
+template <int E, int U, int RANGES, int SRC = 0>
 __global__ void __launch_bounds__(STB_SCAN_THREADS, STB_SCAN_MINB)
 stb_scan_topk_kernel(const TopkArgs args) {
+  // SRC 0: scores from the f32 rows; SRC 1: from the 16-bit shadow (wider proof margin)
+  constexpr double kScoreEps = SRC ? STB_SHADOW_SCAN_EPS : STB_SCORE_EPS;
   constexpr int KP = 32 * E;
   __shared__ uint64_t skeys[STB_SORT_CAP];
   __shared__ unsigned int s_T, s_cnt, s_ticket;
@@ -418,7 +522,8 @@ stb_scan_topk_kernel(const TopkArgs args) {
   STB_T_MIN(0);                      // first CTA starts
   TopSink<E> sink;
   sink.init();
-  stb_scan_rows<U, RANGES>(args.scan, sink);
+  if constexpr (SRC == 1) stb_scan_shadow<U>(args.scan, args.shadow, sink);
+  else stb_scan_rows<U, RANGES>(args.scan, sink);
   STB_T_MAX(1);                      // last CTA leaves the scan loop
   // Programmatic dependent launch: the scan above reads only the corpus and the query,
   // so the NEXT query's kernel may start streaming as soon as every CTA of this one has
@@ -625,7 +730,7 @@ stb_scan_topk_kernel(const TopkArgs args) {
   if (n_valid < KP) complete = true;   // every scorable row is in the candidate set
   else {
     float s_min = stb_key_score(skeys[KP - 1]);
-    complete = (n_out == k) && ((1.0 - (double)s_min - STB_SCORE_EPS) > s_d[k - 1]);
+    complete = (n_out == k) && ((1.0 - (double)s_min - kScoreEps) > s_d[k - 1]);
   }
   if (args.xchg.world <= 1) {
     for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
@@ -732,13 +837,16 @@ static int stb_pick_e(uint32_t top_k) {
   return 4;                    // K' = 128
 }
 
-template <int E, int RANGES>
+#define STB_SHADOW_SCAN_U 4     // 4 rows x 4 LDG.128 per lane in flight = the f32 path's 2 x 8
+
+template <int E, int RANGES, int SRC = 0>
 static int stb_launch_topk_t(stb_ctx *ctx, const TopkArgs &a) {
-  auto kern = stb_scan_topk_kernel<E, STB_SCAN_U, RANGES>;
+  constexpr int kU = SRC ? STB_SHADOW_SCAN_U : STB_SCAN_U;
+  auto kern = stb_scan_topk_kernel<E, kU, RANGES, SRC>;
   int occ = 0;
   STB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, STB_SCAN_THREADS, 0));
   if (occ < 1) occ = 1;
-  uint64_t tiles = (a.scan.n_virtual + 4 * STB_SCAN_U - 1) / (4 * STB_SCAN_U);
+  uint64_t tiles = (a.scan.n_virtual + 4 * kU - 1) / (4 * kU);
   uint64_t want = (tiles + STB_SCAN_WARPS - 1) / STB_SCAN_WARPS;
   uint64_t grid = (uint64_t)ctx->sm_count * occ;
   if (want < grid) grid = want < 1 ? 1 : want;
@@ -769,7 +877,7 @@ int stb_launch_scan_topk(stb_ctx *ctx, const float *rows, uint64_t n_rows,
                          uint64_t row_base, const float *q_dev, uint32_t top_k,
                          const uint64_t *ranges_dev, uint32_t n_ranges,
                          uint64_t n_virtual, stb_hit *out_hits_dev,
-                         uint32_t *out_status_dev, const StbXchgArgs *xchg) {
+                         uint32_t *out_status_dev, const StbXchgArgs *xchg, const uint8_t *shadow) {
   (void)n_rows;
   TopkArgs a;
   a.scan.rows = reinterpret_cast<const float4 *>(rows);
@@ -786,7 +894,15 @@ int stb_launch_scan_topk(stb_ctx *ctx, const float *rows, uint64_t n_rows,
   a.top_k = top_k;
   if (xchg) a.xchg = *xchg; else memset(&a.xchg, 0, sizeof(a.xchg));
   a.dbg = ctx->dbg_dev;
+  a.shadow = shadow;
   const bool rg = n_ranges > 0;
+  if (shadow && !rg) {                                     // half-width scan (whole shard only)
+    switch (stb_pick_e(top_k)) {
+      case 1: return stb_launch_topk_t<1, 0, 1>(ctx, a);
+      case 2: return stb_launch_topk_t<2, 0, 1>(ctx, a);
+      default: return stb_launch_topk_t<4, 0, 1>(ctx, a);
+    }
+  }
   const char *walk_env = getenv("STB_RANGES_WALK");        // opt-in until timed: RANGES mode 2
   if (rg && walk_env && walk_env[0] == '1') {
     switch (stb_pick_e(top_k)) {

@@ -78,3 +78,26 @@ def test_fp16_shadow_bound():
     for qi, q in enumerate(queries):
         c = 1.0 - oracle.distances(rows, q)
         assert np.max(np.abs(a[qi] - c)) <= 0.0012
+
+
+@pytest.mark.parametrize("dtype,eps", [("bfloat16", 0.0020), ("float16", 0.00052)])
+def test_shadow_scan_margin_with_f32_query(dtype, eps):
+    """K1's half-width scan (STB_SCAN_SHADOW=1) rounds only the ROW; the query stays f32:
+    |q^ . round(x^) - exact cosine| <= STB_SHADOW_SCAN_EPS."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(21)
+    rows = (unit_rows(rng, 6000) * rng.uniform(0.1, 10.0, (6000, 1))).astype(np.float32)
+    spiky = rng.standard_normal((300, 256)).astype(np.float32) * np.float32(1e-6)
+    spiky[np.arange(300), rng.integers(0, 256, 300)] = 1.0
+    rows[:300] = spiky
+    rows[300] = 0.0
+    queries = unit_rows(rng, 8) * np.float32(3.0)
+    queries[0] = rows[5]
+    norm = np.linalg.norm(rows.astype(np.float64), axis=1, keepdims=True)
+    xn = np.divide(rows, norm, out=np.zeros_like(rows), where=norm > 0).astype(np.float32)
+    xs = torch.from_numpy(xn).to(getattr(torch, dtype)).to(torch.float32).numpy()
+    for q in queries:
+        qn = (q / np.float32(np.linalg.norm(q.astype(np.float64)))).astype(np.float32)
+        a = xs @ qn
+        c = 1.0 - oracle.distances(rows, q)
+        assert np.max(np.abs(a - c)) <= eps, np.max(np.abs(a - c))

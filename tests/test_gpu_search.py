@@ -496,3 +496,34 @@ def test_range_walk_mode_matches_the_oracle(ctx, monkeypatch, n, n_ranges):
         hits = c.search(q, top_k=k, max_distance=thr, mode=capi.STB_MODE_STORE_QUERY, row_ranges=ranges)
         assert hits["row"].tolist() == [int(x) for x in r]
         assert np.array_equal(hits["distance"].astype(np.float32), d32)
+
+
+@pytest.mark.skipif(os.environ.get("STB_TEST_V2") != "1", reason="opt-in path written after the last GPU session of round 1 (STB_TEST_V2=1)")
+@pytest.mark.parametrize("n", [1, 7, 255, 256, 257, 5_000, 70_001, 300_000])
+def test_half_width_shadow_scan_matches_the_oracle(ctx, monkeypatch, n):
+    """STB_SCAN_SHADOW=1: K1 selects its candidates from the 16-bit normalised shadow (half the
+    bytes); the re-rank is the same exact f64 pass, so hits, order and distances are the oracle's.
+    Unprovable queries (zero query, mass ties) are retried on the f32 rows / the collect path."""
+    rng = np.random.default_rng(1000 + n)
+    rows = (unit_rows(rng, n) * rng.uniform(0.2, 5.0, (n, 1))).astype(np.float32)
+    if n > 300:
+        rows[n // 2] = rows[3]                         # exact duplicate: tie broken by row
+        rows[17] = 0.0                                 # zero row
+    c = make_corpus(ctx, rows)
+    queries = [rows[3 % n], unit_rows(rng, 1)[0], unit_rows(rng, 1)[0] * np.float32(1e-3)]
+    if n > 300:
+        queries.append(np.zeros(256, np.float32))      # zero query: everything ties -> fallback
+    monkeypatch.setenv("STB_SCAN_SHADOW", "1")
+    for q in queries:
+        for k in (1, 10, 96):
+            r, d = oracle.search_rows(rows, q, top_k=k)
+            hits = c.search(q, top_k=k)
+            assert hits["row"].tolist() == [int(x) for x in r]
+            assert np.array_equal(hits["distance"], d)
+    # a corpus with a row that cannot be normalised in fp32: the shadow is refused, f32 path answers
+    if n >= 5_000:
+        rows2 = rows.copy(); rows2[11] *= np.float32(1e-25)
+        c2 = make_corpus(ctx, rows2)
+        r, d = oracle.search_rows(rows2, queries[1], top_k=5)
+        hits = c2.search(queries[1], top_k=5)
+        assert hits["row"].tolist() == [int(x) for x in r] and np.array_equal(hits["distance"], d)
