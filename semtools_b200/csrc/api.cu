@@ -707,8 +707,12 @@ int stb_search_topk_xchg(stb_ctx *ctx, const stb_corpus *corpus, const float *q_
   a.world = x->world; a.rank = x->rank; a.max_k = x->max_k;
   a.seq = ++x->seq;
   a.slot = (uint32_t)(a.seq % STB_XCHG_SLOTS);
+  const char *shadow_env = getenv("STB_SCAN_SHADOW");      // as in stb_search_topk_dev: only a shadow that already exists
+  const uint8_t *shadow = nullptr;
+  if (shadow_env && shadow_env[0] == '1' && corpus->shadow && corpus->shadow_rows == corpus->n && !corpus->shadow_bad)
+    shadow = corpus->shadow;
   return stb_launch_scan_topk(ctx, corpus->rows, corpus->n, corpus->row_base, q_dev, top_k, nullptr, 0,
-                              corpus->n, out_hits_dev, out_status_dev, &a);
+                              corpus->n, out_hits_dev, out_status_dev, &a, shadow);
 }
 
 // ----------------------------------------------------------------- K2 batched search ---
