@@ -281,6 +281,43 @@ def bench_batch_sharded(torch, dist, dev, ctx, stream, corpus, rows, k, world, n
             "ranks_agree": bool(agree.item()), "exchange": "nccl all_gather of nq x k hits + stb_hits_merge_batch_dev"}
 
 
+def bench_shadow_scan(torch, dev, ctx, stream, corpus, q_dev, k, rows, peak_gbs, steps=50):
+    """K1 with STB_SCAN_SHADOW=1: candidate scores from the 16-bit normalised shadow (half the HBM
+    bytes), exact f64 re-rank and proof as in the default path.  Same device-timed loop as
+    `value`, plus a bit-for-bit comparison with the default (f32-row) scan on every query."""
+    n_q = q_dev.shape[0]
+    corpus.prepare_batch()                                   # builds the shadow if K2 has not already
+    ref = torch.zeros((n_q, k, 2), dtype=torch.float64, device=dev)
+    got = torch.zeros((n_q, k, 2), dtype=torch.float64, device=dev)
+    st = torch.zeros((n_q, 4), dtype=torch.int32, device=dev)
+    for i in range(n_q):
+        corpus.search_topk_dev(q_dev[i].data_ptr(), k, ref[i].data_ptr(), st[i].data_ptr())
+    torch.cuda.synchronize(dev)
+    os.environ["STB_SCAN_SHADOW"] = "1"
+    try:
+        for i in range(n_q):
+            corpus.search_topk_dev(q_dev[i].data_ptr(), k, got[i].data_ptr(), st[i].data_ptr())
+        torch.cuda.synchronize(dev)
+        proven = int((st[:, 1] == 1).sum().item())
+        same = bool(torch.equal(ref.view(torch.int64), got.view(torch.int64)))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            corpus.search_topk_dev(q_dev[i % n_q].data_ptr(), k, got[i % n_q].data_ptr(), st[i % n_q].data_ptr())
+        e1.record(stream); torch.cuda.synchronize(dev)
+    finally:
+        os.environ.pop("STB_SCAN_SHADOW", None)
+    ms = e0.elapsed_time(e1) / steps
+    return {"workload": f"{rows}-line corpus, single query, top-k={k}, candidates from the 16-bit shadow (512 B/row)",
+            "value": 1e3 / ms, "unit": "queries/s", "ms_per_step": ms, "steps": steps,
+            "queries_proven_exact": proven, "queries": n_q, "bit_identical_to_f32_scan": same,
+            "roofline": {"bound": "hbm", "algorithmic_GBps": rows * 1024 / (ms * 1e-3) / 1e9,
+                         "frac_of_measured_peak_algorithmic": rows * 1024 / (ms * 1e-3) / 1e9 / peak_gbs,
+                         "bytes_read_per_query": rows * 512,
+                         "frac_of_measured_peak_bytes_read": rows * 512 / (ms * 1e-3) / 1e9 / peak_gbs},
+            "note": "opt-in (STB_SCAN_SHADOW=1); unproven queries fall back to the f32 scan in stb_search"}
+
+
 # ------------------------------------------------------------------ K5 side bench -----
 def bench_ivfpq(torch, dev, ctx, rows=4_000_000, nlist=4096, nprobe=64, n_centers=None, spread=0.6):
     """IVF-PQ (self-specified: the reference has no IVF_PQ, so no parity -- recall@10 against
@@ -697,6 +734,7 @@ def run_ours(args):
                 v2["roofline_frac_pipeline"] = v2["gemm_TFLOPs_pipeline"] / tpeak
                 v2["note"] = "opt-in pipeline (STB_BATCH_V2=1): same C-ABI call, same results; not the default path yet"
             line["batch1024_v2"] = v2
+            line["k1_shadow_scan"] = side(bench_shadow_scan, torch, dev, ctx, stream, corpus, q_dev, k, args.rows, peak)
             # K5 fused search (two launches, one sync; opt-in STB_IVFPQ_V2=1), same workload as `ivfpq`
             os.environ["STB_IVFPQ_V2"] = "1"
             try:
