@@ -290,6 +290,7 @@ static int corpus_append_impl(stb_corpus *c, const float *rows, uint64_t n, cuda
   STB_CUDA(cudaStreamSynchronize(c->ctx->stream));
   c->n += n;
   c->shadow_rows = 0;     // K2 shadow is rebuilt lazily
+  c->shadow_tries = c->shadow_proven = 0;
   return STB_OK;
 }
 
@@ -511,12 +512,15 @@ int stb_search(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint32_t 
     // wider proof margin; a result it cannot prove is retried on the f32 rows below.
     const char *shadow_env = getenv("STB_SCAN_SHADOW");
     bool proven_on_shadow = false;
-    if (shadow_env && shadow_env[0] == '1' && !ranges_dev) {
+    const bool shadow_pays = corpus->shadow_tries < 8 || 2 * corpus->shadow_proven >= corpus->shadow_tries;
+    if (shadow_env && shadow_env[0] == '1' && !ranges_dev && shadow_pays) {
       stb_corpus *cm = const_cast<stb_corpus *>(corpus);
       const int src = corpus_ensure_shadow(ctx, cm);                 // STB_ERR_STATE: rows that cannot be normalised
       if (src == STB_OK) {
         if ((rc = run_fast(corpus->shadow)) != STB_OK) return rc;
         proven_on_shadow = ctx->status_pin[1] != 0;
+        cm->shadow_tries++;
+        if (proven_on_shadow) cm->shadow_proven++;
       } else if (src != STB_ERR_STATE) {
         return src;
       }

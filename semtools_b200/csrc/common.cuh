@@ -147,6 +147,8 @@ struct stb_corpus {
   uint64_t shadow_rows;      // rows covered by `shadow` (== n when valid)
   uint64_t shadow_cap_tiles;
   int shadow_bad;            // 1: some row cannot be normalised in fp32 -> tensor path refused
+  uint32_t shadow_tries, shadow_proven;   // STB_SCAN_SHADOW bookkeeping: the half-width scan is skipped
+                                          // once it proves fewer than half of its results on this corpus
 };
 
 // ---- scan_topk.cu -------------------------------------------------------------
