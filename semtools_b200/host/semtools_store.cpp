@@ -180,6 +180,8 @@ Store Store::open(const std::string &workspace_dir) {
     LineEmbedding le{s.paths_[s.rows_[2 * r]], s.rows_[2 * r + 1], {}};
     s.id_row_[le.id()] = r;
   }
+  s.n_disk_ = s.rows_.size() / 2;
+  s.rewrite_ = false;
   return s;
 }
 
@@ -195,8 +197,29 @@ void Store::flush() const {
         << ", \"mtime\": " << docs_[i].mtime << ", \"_version\": " << docs_[i].version << "}";
     f << "]}";
   }
-  { std::ofstream f(dir_ + "/rows.i32", std::ios::binary); f.write(reinterpret_cast<const char *>(rows_.data()), (std::streamsize)(rows_.size() * 4)); }
-  { std::ofstream f(dir_ + "/line_embeddings.f32", std::ios::binary); f.write(reinterpret_cast<const char *>(emb_.data()), (std::streamsize)(emb_.size() * 4)); }
+  // the two row files are appended to / patched in place; only deletions rewrite them
+  const std::string rows_p = dir_ + "/rows.i32", emb_p = dir_ + "/line_embeddings.f32";
+  const size_t n = rows_.size() / 2;
+  auto file_size = [](const std::string &p) -> long long { struct stat st; return ::stat(p.c_str(), &st) == 0 ? (long long)st.st_size : -1; };
+  if (rewrite_ || file_size(rows_p) != (long long)(n_disk_ * 8) || file_size(emb_p) != (long long)(n_disk_ * LINE_EMBEDDING_SIZE * 4)) {
+    { std::ofstream f(rows_p, std::ios::binary); f.write(reinterpret_cast<const char *>(rows_.data()), (std::streamsize)(rows_.size() * 4)); }
+    { std::ofstream f(emb_p, std::ios::binary); f.write(reinterpret_cast<const char *>(emb_.data()), (std::streamsize)(emb_.size() * 4)); }
+    ++full_rewrites;
+  } else {
+    std::fstream fr(rows_p, std::ios::in | std::ios::out | std::ios::binary), fe(emb_p, std::ios::in | std::ios::out | std::ios::binary);
+    for (size_t r : dirty_) {
+      if (r >= n_disk_) continue;
+      fr.seekp((std::streamoff)(r * 8)); fr.write(reinterpret_cast<const char *>(rows_.data() + 2 * r), 8);
+      fe.seekp((std::streamoff)(r * LINE_EMBEDDING_SIZE * 4));
+      fe.write(reinterpret_cast<const char *>(emb_.data() + r * LINE_EMBEDDING_SIZE), LINE_EMBEDDING_SIZE * 4);
+    }
+    if (n > n_disk_) {
+      fr.seekp(0, std::ios::end); fr.write(reinterpret_cast<const char *>(rows_.data() + 2 * n_disk_), (std::streamsize)((n - n_disk_) * 8));
+      fe.seekp(0, std::ios::end);
+      fe.write(reinterpret_cast<const char *>(emb_.data() + n_disk_ * LINE_EMBEDDING_SIZE), (std::streamsize)((n - n_disk_) * LINE_EMBEDDING_SIZE * 4));
+    }
+  }
+  n_disk_ = n; rewrite_ = false; dirty_.clear();
   std::rename(tmp.c_str(), (dir_ + "/store.json").c_str());
 }
 
@@ -249,7 +272,7 @@ void Store::upsert_line_embeddings(const std::vector<LineEmbedding> &lines) {
     const uint64_t rid = le.id();
     auto rit = id_row_.find(rid);
     size_t row;
-    if (rit != id_row_.end()) row = rit->second;                    // upsert replaces by id
+    if (rit != id_row_.end()) { row = rit->second; dirty_.insert(row); }   // upsert replaces by id
     else { row = rows_.size() / 2; id_row_[rid] = row; rows_.resize(rows_.size() + 2); emb_.resize(emb_.size() + LINE_EMBEDDING_SIZE); }
     rows_[2 * row] = pi; rows_[2 * row + 1] = le.line_number;
     std::memcpy(emb_.data() + row * LINE_EMBEDDING_SIZE, le.embedding.data(), LINE_EMBEDDING_SIZE * 4);
@@ -278,6 +301,7 @@ void Store::delete_line_embeddings(const std::vector<std::string> &paths) {
     ++w;
   }
   rows_.resize(2 * w); emb_.resize(w * LINE_EMBEDDING_SIZE);
+  if (w != n) rewrite_ = true;                                      // rows moved: the files are rewritten
   id_row_.clear();
   for (size_t r = 0; r < w; ++r) { LineEmbedding le{paths_[rows_[2 * r]], rows_[2 * r + 1], {}}; id_row_[le.id()] = r; }
   flush();

@@ -8,6 +8,7 @@
 #include <functional>
 #include <map>
 #include <optional>
+#include <set>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -94,6 +95,13 @@ class Store {
   std::vector<int32_t> rows_;                       // (path idx, line_number) pairs
   std::vector<float> emb_;                          // N x 256
   std::unordered_map<uint64_t, size_t> id_row_;
+  // persistence bookkeeping (same policy as the Python store): rows [0, n_disk_) are on disk and
+  // equal to memory except dirty_; rewrite_ forces a full rewrite (first flush, deletions)
+  mutable size_t n_disk_ = 0;
+  mutable std::set<size_t> dirty_;
+  mutable bool rewrite_ = true;
+ public:
+  mutable unsigned full_rewrites = 0;
 };
 
 // search_with_workspace (search/mod.rs:146-216): diff `files` against the store, embed only

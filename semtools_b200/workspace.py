@@ -166,6 +166,13 @@ class Store:
         self._emb = np.zeros((0, LINE_EMBEDDING_SIZE), dtype=np.float32)
         self._id_row: dict = {}                # LineEmbedding id -> row
         self._corpus = None                    # capi.Corpus mirror of self._emb (lazy)
+        self._corpus_n = 0                     # rows of self._emb already uploaded to it
+        # persistence bookkeeping: rows [0, _n_disk) are on disk and equal to memory except
+        # _dirty_rows; _rewrite forces a full rewrite (first flush, deletions)
+        self._n_disk = 0
+        self._dirty_rows: set = set()
+        self._rewrite = True
+        self.full_rewrites = 0                 # how many flushes rewrote the row files (tests, diagnostics)
 
     # -- Store::open, store.rs:113-183 (creates the directories on first use)
     @classmethod
@@ -188,17 +195,37 @@ class Store:
                 raise RuntimeError("store files disagree on the row count")
             for r, (pi, ln) in enumerate(s._rows):
                 s._id_row[capi.line_id(s._paths[pi], int(ln))] = r
+            s._n_disk, s._rewrite = len(s._rows), False
         return s
 
     # -- flush_documents / flush_line_embeddings, store.rs:639-648
     def _flush(self) -> None:
+        """store.json is rewritten every time (path table + DocMeta: small); the two row files
+        are appended to / patched in place, and only rewritten after deletions -- an upsert of
+        a few files into a multi-GB store writes a few MB."""
         tmp = os.path.join(self.dir, "store.json.tmp")
         with open(tmp, "w") as f:
             json.dump({"format": FORMAT, "dim": LINE_EMBEDDING_SIZE, "rows": int(len(self._rows)),
                        "paths": self._paths, "docs": [asdict(m) for m in self._docs.values()]}, f)
-        self._rows.astype(np.int32).tofile(os.path.join(self.dir, "rows.i32"))
-        self._emb.astype(np.float32).tofile(os.path.join(self.dir, "line_embeddings.f32"))
+        rows_p, emb_p = os.path.join(self.dir, "rows.i32"), os.path.join(self.dir, "line_embeddings.f32")
+        n = len(self._rows)
+        if self._rewrite or not (os.path.exists(rows_p) and os.path.exists(emb_p)) \
+                or os.path.getsize(rows_p) != self._n_disk * 8 or os.path.getsize(emb_p) != self._n_disk * LINE_EMBEDDING_SIZE * 4:
+            self._rows.astype(np.int32).tofile(rows_p)
+            self._emb.astype(np.float32).tofile(emb_p)
+            self.full_rewrites += 1
+        else:
+            with open(rows_p, "r+b") as fr, open(emb_p, "r+b") as fe:
+                for r in sorted(self._dirty_rows):
+                    if r < self._n_disk:
+                        fr.seek(r * 8); fr.write(self._rows[r].astype(np.int32).tobytes())
+                        fe.seek(r * LINE_EMBEDDING_SIZE * 4); fe.write(self._emb[r].astype(np.float32).tobytes())
+                if n > self._n_disk:
+                    fr.seek(0, os.SEEK_END); fr.write(self._rows[self._n_disk:].astype(np.int32).tobytes())
+                    fe.seek(0, os.SEEK_END); fe.write(self._emb[self._n_disk:].astype(np.float32).tobytes())
         os.replace(tmp, os.path.join(self.dir, "store.json"))
+        self._n_disk, self._rewrite = n, False
+        self._dirty_rows.clear()
 
     def flush_documents(self) -> None:
         self._flush()
@@ -257,6 +284,8 @@ class Store:
             if row is not None and row < len(self._emb):
                 self._emb[row] = emb                                  # upsert replaces by id
                 self._rows[row] = (pi, le.line_number)
+                self._dirty_rows.add(row)
+                self._corpus = None                                   # GPU mirror: re-upload (in-place change)
             elif row is not None:                                     # replaced inside this same batch
                 new_emb[row - len(self._emb)] = emb
             else:
@@ -266,8 +295,7 @@ class Store:
         if new_emb:
             self._emb = np.concatenate([self._emb, np.stack(new_emb)]) if len(self._emb) else np.stack(new_emb)
             self._rows = np.concatenate([self._rows, np.asarray(new_rows, dtype=np.int32).reshape(-1, 2)])
-        self._corpus = None
-        self._flush()
+        self._flush()                                                 # appended rows reach the GPU mirror lazily
 
     # -- store.rs:235-296: only metadata of the CURRENT embedding version is deleted
     def delete_document_metadata(self, paths) -> None:
@@ -289,6 +317,7 @@ class Store:
             self._emb = np.ascontiguousarray(self._emb[keep])
             self._id_row = {capi.line_id(self._paths[pi], int(ln)): r for r, (pi, ln) in enumerate(self._rows)}
             self._corpus = None
+            self._rewrite = True                                      # rows moved: the files are rewritten
         self._flush()
 
     # -- store.rs:360-370
@@ -318,9 +347,11 @@ class Store:
         if self.ctx is None:
             self.ctx = capi.Context(0)                               # no GPU -> StbError, never a CPU scan
         if self._corpus is None:
-            c = capi.Corpus(self.ctx, max(len(self._emb), 1))
-            c.append(self._emb)
-            self._corpus = c
+            self._corpus = capi.Corpus(self.ctx, max(len(self._emb), 1))
+            self._corpus_n = 0
+        if self._corpus_n < len(self._emb):                           # only the rows appended since the last query
+            self._corpus.append(self._emb[self._corpus_n:])
+            self._corpus_n = len(self._emb)
         return self._corpus
 
     def _ranges_for(self, subset_paths) -> np.ndarray:

@@ -219,3 +219,36 @@ def test_search_with_workspace_flow_matches_oracle(tmp_path, ctx, monkeypatch):
     got = st.search_line_embeddings(q, files[1:3], 3)
     assert [(g.path, g.line_number) for g in got] == [(st._paths[st._rows[int(x)][0]], int(st._rows[int(x)][1])) for x in r]
     assert [np.float32(g.distance) for g in got] == list(d)
+
+
+def test_incremental_flush_appends_and_patches_in_place(tmp_path):
+    """Upserts append to / patch the row files; only deletions rewrite them.  The files always
+    equal what a from-scratch write of the same state produces."""
+    def emb(v):
+        return np.full(256, v, dtype=np.float32)
+
+    s = Store.open(str(tmp_path))
+    s.upsert_line_embeddings([LineEmbedding("a.txt", i, emb(i)) for i in range(4)])
+    assert s.full_rewrites == 1                                    # first flush creates the files
+    s = Store.open(str(tmp_path))
+    s.upsert_line_embeddings([LineEmbedding("b.txt", i, emb(10 + i)) for i in range(3)])      # append
+    s.upsert_line_embeddings([LineEmbedding("a.txt", 2, emb(99.0)), LineEmbedding("c.txt", 0, emb(20))])   # patch + append
+    s.upsert_document_metadata([DocMeta("a.txt", 1, 2)])           # metadata only
+    assert s.full_rewrites == 0
+    d = tmp_path / "flat.b200"
+    rows = np.fromfile(d / "rows.i32", dtype=np.int32).reshape(-1, 2)
+    e = np.fromfile(d / "line_embeddings.f32", dtype=np.float32).reshape(-1, 256)
+    assert rows.tolist() == [[0, 0], [0, 1], [0, 2], [0, 3], [1, 0], [1, 1], [1, 2], [2, 0]]
+    assert e[:, 0].tolist() == [0, 1, 99, 3, 10, 11, 12, 20]
+    s2 = Store.open(str(tmp_path))                                 # a fresh load sees the same state
+    assert np.array_equal(s2._emb, s._emb) and np.array_equal(s2._rows, s._rows) and s2._paths == s._paths
+    s2.delete_documents(["b.txt"])                                 # rows move -> rewrite
+    assert s2.full_rewrites == 1
+    s3 = Store.open(str(tmp_path))
+    assert s3.count_line_embeddings() == 5 and s3._emb[:, 0].tolist() == [0, 1, 99, 3, 20]
+    # a truncated / foreign row file is detected by its size and rewritten instead of appended to
+    with open(d / "rows.i32", "ab") as f:
+        f.write(b"\0" * 8)
+    s3.upsert_line_embeddings([LineEmbedding("d.txt", 0, emb(30))])
+    assert s3.full_rewrites == 1
+    assert Store.open(str(tmp_path)).count_line_embeddings() == 6
