@@ -189,8 +189,12 @@ class Store:
             s._path_idx = {p: i for i, p in enumerate(s._paths)}
             s._docs = {m["path"]: DocMeta(**m) for m in d["docs"]}
             s._rows = np.fromfile(os.path.join(s.dir, "rows.i32"), dtype=np.int32).reshape(-1, 2)
-            s._emb = np.fromfile(os.path.join(s.dir, "line_embeddings.f32"), dtype=np.float32).reshape(
-                -1, LINE_EMBEDDING_SIZE)
+            emb_p = os.path.join(s.dir, "line_embeddings.f32")
+            n_emb = os.path.getsize(emb_p) // (LINE_EMBEDDING_SIZE * 4)
+            # copy-on-write map: a query-only process pages the matrix in once, straight into the
+            # chunked GPU upload, instead of holding a second copy in RAM
+            s._emb = np.memmap(emb_p, dtype=np.float32, mode="c", shape=(n_emb, LINE_EMBEDDING_SIZE)) if n_emb \
+                else np.zeros((0, LINE_EMBEDDING_SIZE), dtype=np.float32)
             if len(s._rows) != len(s._emb):
                 raise RuntimeError("store files disagree on the row count")
             for r, (pi, ln) in enumerate(s._rows):
@@ -349,9 +353,10 @@ class Store:
         if self._corpus is None:
             self._corpus = capi.Corpus(self.ctx, max(len(self._emb), 1))
             self._corpus_n = 0
-        if self._corpus_n < len(self._emb):                           # only the rows appended since the last query
-            self._corpus.append(self._emb[self._corpus_n:])
-            self._corpus_n = len(self._emb)
+        while self._corpus_n < len(self._emb):                        # only rows not uploaded yet, 256 MiB at a time
+            hi = min(len(self._emb), self._corpus_n + 262144)
+            self._corpus.append(self._emb[self._corpus_n:hi])
+            self._corpus_n = hi
         return self._corpus
 
     def _ranges_for(self, subset_paths) -> np.ndarray:
