@@ -47,7 +47,9 @@
 // Shadow element type.  bf16 (default, the configuration validated on hardware) or fp16
 // (-DSTB_SHADOW_F16=1; same tcgen05 kind::f16 rate).  For L2-normalised rows every element is
 // <= 1, so fp16's range suffices and its 10-bit mantissa shrinks the selection margin ~4x:
-//   bf16: |approx - exact cosine| <= (2u+u^2), u = 2^-9, + f32 accumulation + rsqrt  < 0.0040
+//   bf16: 8 significand bits -> unit roundoff u = 2^-8; both operands rounded:
+//         |approx - exact cosine| <= (2u+u^2) = 0.00783, + f32 accumulation + rsqrt  < 0.0079
+//         (attained within 2%: tests/test_batch_v2_model.py builds the adversarial row)
 //   fp16: u = 2^-11 for |x| >= 2^-14; smaller elements err by <= 2^-25 absolutely, at most
 //         2*256*2^-25 = 1.5e-5 over a row pair; total < 0.00101
 #ifndef STB_SHADOW_F16
@@ -56,7 +58,7 @@
 #if STB_SHADOW_F16
 #define STB_BATCH_EPS 0.0012
 #else
-#define STB_BATCH_EPS 0.0045
+#define STB_BATCH_EPS 0.0080
 #endif
 
 // ------------------------------------------------------------------ PTX wrappers ---

@@ -31,12 +31,12 @@
 #define STB_SHADOW_F16 0
 #endif
 // |q^ . shadow(x) - exact cosine| when only the ROW is rounded (K1 shadow scan: the query stays
-// f32): <= u * ||q^|| * ||x^|| = u (2^-9 bf16, 2^-11 fp16; fp16 components below 2^-14 add
+// f32): <= u * ||q^|| * ||x^|| = u (unit roundoff: 2^-8 bf16, 2^-11 fp16; fp16 components below 2^-14 add
 // <= 16 * 2^-25 * ||q^||_1 <= 8e-6), plus f32 accumulation and rsqrt (< 2e-5).
 #if STB_SHADOW_F16
 #define STB_SHADOW_SCAN_EPS 0.00052
 #else
-#define STB_SHADOW_SCAN_EPS 0.0020
+#define STB_SHADOW_SCAN_EPS 0.0040
 #endif
 
 void stb_set_error(const char *fmt, ...);
