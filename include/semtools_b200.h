@@ -23,6 +23,11 @@
  *
  * Vector width is fixed at 256 f32 (LINE_EMBEDDING_SIZE,
  * src/workspace/store.rs:37); other widths fail with STB_ERR_ARG.
+ *
+ * Environment switches (read per call; all default off; results are identical
+ * with and without them -- they select how candidates are found, never how the
+ * returned distances are computed): STB_SCAN_SHADOW, STB_BATCH_V2,
+ * STB_IVFPQ_V2, STB_RANGES_WALK, STB_DIRECT_OUT.
  */
 #ifndef SEMTOOLS_B200_H
 #define SEMTOOLS_B200_H
