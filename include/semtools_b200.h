@@ -24,10 +24,11 @@
  * Vector width is fixed at 256 f32 (LINE_EMBEDDING_SIZE,
  * src/workspace/store.rs:37); other widths fail with STB_ERR_ARG.
  *
- * Environment switches (read per call; all default off; results are identical
- * with and without them -- they select how candidates are found, never how the
- * returned distances are computed): STB_SCAN_SHADOW, STB_BATCH_V2,
- * STB_IVFPQ_V2, STB_RANGES_WALK, STB_DIRECT_OUT.
+ * Environment switches (read per call; results are identical whatever their
+ * value -- they select how candidates are found, never how the returned
+ * distances are computed): STB_SCAN_TIER=f32|h16|q8 (narrowest candidate copy K1
+ * may read, default q8), STB_DIRECT_OUT=0, STB_BATCH_V1=1, STB_IVFPQ_V1=1
+ * (INTEGRATION.md, 5b).
  */
 #ifndef SEMTOOLS_B200_H
 #define SEMTOOLS_B200_H
@@ -164,12 +165,33 @@ int stb_search(stb_ctx *ctx, const stb_corpus *corpus, const float *q,
                const uint64_t *row_ranges, uint32_t n_ranges, stb_hit *out_hits,
                uint64_t cap, uint64_t *out_n);
 
+/* Candidate tiers.  The scan is HBM-bound, so the way to go faster than the f32 roofline is
+ * to read fewer bytes: stb_search can draw its candidates from a reduced-width copy of the
+ * corpus -- "q8": int8 codes + one f32 scale per row, 260 B/row, top_k <= 16; "h16": the
+ * 16-bit L2-normalised shadow K2 multiplies, 512 B/row -- and re-ranks them in the canonical
+ * f64 arithmetic on the f32 rows exactly as before.  Each tier proves its own result (rounding
+ * bound of the copy vs. the gap to the best row it dropped); an unproven query is retried on
+ * the next wider tier, so the hits are identical to the f32 path's.  stb_search builds the
+ * copies lazily (second query on an unchanged corpus of >= 32768 rows);
+ * stb_corpus_prepare builds them now.  Costs +25 % / +50 % HBM.  No reference analogue
+ * (the reference keeps Vec<Vec<f32>>, src/search/mod.rs:18-22). */
+#define STB_PREPARE_Q8 1
+#define STB_PREPARE_H16 2
+int stb_corpus_prepare(stb_corpus *corpus, int what);
+/* Per-tier bookkeeping of stb_search on this corpus since its last change, index = tier
+ * (0 f32, 1 h16, 2 q8): fast-path scans tried / proven, and the rows each copy covers
+ * (0 = not built or refused).  Any pointer may be NULL. */
+int stb_corpus_tier_stats(const stb_corpus *corpus, uint32_t tries[3], uint32_t proven[3],
+                          uint64_t built_rows[3]);
+
 /* Asynchronous device-resident form of the top-k search (no threshold, no
  * ranges): query and results stay in HBM, nothing synchronises.  out_hits_dev
  * receives top_k entries (unused tail: distance = +inf, row = UINT64_MAX) and
  * out_status_dev[0] the hit count, out_status_dev[1] a completeness flag
  * (1 = provably the exact top-k; 0 = the candidate margin check failed and the
- * caller must fall back to stb_search, which handles it internally). */
+ * caller must fall back to stb_search, which handles it internally),
+ * out_status_dev[3] = K' | tier << 16 (tier: 0 f32, 1 h16, 2 q8).  Reads the
+ * narrowest copy that is already built (never builds one). */
 int stb_search_topk_dev(stb_ctx *ctx, const stb_corpus *corpus,
                         const float *q_dev, uint32_t top_k, stb_hit *out_hits_dev,
                         uint32_t *out_status_dev);
@@ -274,6 +296,9 @@ uint64_t stb_line_id(const uint8_t *path, uint64_t path_len, int32_t line_number
  * context, and how many searches needed the fallback pass. */
 int stb_ctx_counters(const stb_ctx *ctx, uint64_t *kernel_launches,
                      uint64_t *fallback_searches);
+/* Consistency check of K1's dynamic tile schedule (synchronises): the device-side ticket counter
+ * must equal the value the host booked over all launches so far; STB_ERR_STATE otherwise. */
+int stb_debug_ticket_check(stb_ctx *ctx, uint64_t *device_value, uint64_t *host_value);
 /* Tuning aid: phase timestamps (ns, %globaltimer) of the last K1 launch; only filled by
  * libraries built with -DSTB_TAIL_TIMING.  reset=1 arms, reset=0 reads 8 values:
  * [0] first CTA start, [1] last scan end, [2] last CTA merge end, [3] final ticket,

@@ -6,7 +6,10 @@
  * Restates search_documents (src/search/mod.rs:77-120) the way it executes on
  * the host: one cosine per row (simsimd-style f32 SIMD lanes, FMA allowed),
  * the FULL result vector, a stable sort, take(top_k).  Built with
- * -O3 -march=x86-64-v3 (AVX2+FMA; portable to the GPU box host) -fopenmp.  threads == 1 is the faithful configuration (the
+ * -O3 -march=x86-64-v3 (AVX2+FMA; portable to the GPU box host) -fopenmp, plus an AVX-512
+ * kernel (function-level target attribute) picked at run time when the host has it -- simsimd
+ * 6.5 dispatches the same way (its skylake / sapphire back ends), so an AVX-512 Xeon runs the
+ * wider kernel here too (orc_baseline_isa() says which).  threads == 1 is the faithful configuration (the
  * reference loop is single-threaded); threads > 1 is reported separately and
  * labelled "not reference behaviour".
  */
@@ -77,6 +80,36 @@ static inline double orc_cosine_simd_like(const float *a, const float *b) {
   return r > 0.0 ? r : 0.0;
 }
 
+/* simsimd-style Skylake-X kernel: 16-lane f32 FMA accumulators, reduce, normalise in f64. */
+__attribute__((target("avx512f"))) static double orc_cosine_avx512(const float *a, const float *b) {
+  __m512 ab = _mm512_setzero_ps(), a2 = _mm512_setzero_ps(), b2 = _mm512_setzero_ps();
+  for (int i = 0; i < 256; i += 16) {
+    __m512 x = _mm512_loadu_ps(a + i), y = _mm512_loadu_ps(b + i);
+    ab = _mm512_fmadd_ps(x, y, ab);
+    a2 = _mm512_fmadd_ps(x, x, a2);
+    b2 = _mm512_fmadd_ps(y, y, b2);
+  }
+  double sab = (double)_mm512_reduce_add_ps(ab), sa2 = (double)_mm512_reduce_add_ps(a2), sb2 = (double)_mm512_reduce_add_ps(b2);
+  if (sa2 == 0.0 && sb2 == 0.0) return 0.0;
+  if (sab == 0.0) return 1.0;
+  double r = 1.0 - sab / (sqrt(sa2) * sqrt(sb2));
+  return r > 0.0 ? r : 0.0;
+}
+
+static int orc_have_avx512(void) {
+  static int have = -1;
+  if (have < 0) { __builtin_cpu_init(); have = __builtin_cpu_supports("avx512f") ? 1 : 0; }
+  return have;
+}
+const char *orc_baseline_isa(void) { return orc_have_avx512() ? "avx512f" : "avx2+fma"; }
+
+__attribute__((target("avx512f"))) static void orc_distances_avx512(const float *rows, int64_t r0, int64_t r1, const float *q, double *dist) {
+  for (int64_t r = r0; r < r1; ++r) dist[r] = orc_cosine_avx512(q, rows + (uint64_t)r * 256);
+}
+static void orc_distances_avx2(const float *rows, int64_t r0, int64_t r1, const float *q, double *dist) {
+  for (int64_t r = r0; r < r1; ++r) dist[r] = orc_cosine_simd_like(q, rows + (uint64_t)r * 256);
+}
+
 int orc_baseline_search(const float *rows, uint64_t n_rows, const float *q,
                         uint64_t top_k, int has_max, double max_distance,
                         int threads, uint64_t cap, uint64_t *out_row,
@@ -85,10 +118,17 @@ int orc_baseline_search(const float *rows, uint64_t n_rows, const float *q,
   orc_hit *hits = (orc_hit *)malloc(sizeof(orc_hit) * (n_rows ? n_rows : 1));
   if (!hits) return ORC_ERR_NOMEM;
   uint64_t m = 0;
+  const int wide = orc_have_avx512();
   if (threads <= 1) {
-    for (uint64_t r = 0; r < n_rows; ++r) {
-      double d = orc_cosine_simd_like(q, rows + r * 256);
-      if (d < thr) { hits[m].d = d; hits[m].row = r; m++; }
+    /* one cosine per row, pushed straight into the result vector (mod.rs:84-104); processed in
+     * blocks of 4096 rows only so that the ISA dispatch sits outside the inner loop */
+    double blk[4096];
+    for (uint64_t r0 = 0; r0 < n_rows; r0 += 4096) {
+      const uint64_t r1 = r0 + 4096 < n_rows ? r0 + 4096 : n_rows;
+      if (wide) orc_distances_avx512(rows, (int64_t)r0, (int64_t)r1, q, blk - r0);
+      else orc_distances_avx2(rows, (int64_t)r0, (int64_t)r1, q, blk - r0);
+      for (uint64_t r = r0; r < r1; ++r)
+        if (blk[r - r0] < thr) { hits[m].d = blk[r - r0]; hits[m].row = r; m++; }
     }
   } else {
     /* "not reference behaviour": all-cores variant.  Distances in parallel,
@@ -98,8 +138,11 @@ int orc_baseline_search(const float *rows, uint64_t n_rows, const float *q,
 #ifdef _OPENMP
 #pragma omp parallel for schedule(static) num_threads(threads)
 #endif
-    for (int64_t r = 0; r < (int64_t)n_rows; ++r)
-      dist[r] = orc_cosine_simd_like(q, rows + (uint64_t)r * 256);
+    for (int64_t b = 0; b < (int64_t)((n_rows + 4095) / 4096); ++b) {
+      const int64_t r0 = b * 4096, r1 = r0 + 4096 < (int64_t)n_rows ? r0 + 4096 : (int64_t)n_rows;
+      if (wide) orc_distances_avx512(rows, r0, r1, q, dist);
+      else orc_distances_avx2(rows, r0, r1, q, dist);
+    }
     for (uint64_t r = 0; r < n_rows; ++r)
       if (dist[r] < thr) { hits[m].d = dist[r]; hits[m].row = r; m++; }
     free(dist);

@@ -86,6 +86,7 @@ def baseline_lib():
         L.orc_baseline_search.argtypes = [f32p, C.c_uint64, f32p, C.c_uint64, C.c_int, C.c_double,
                                           C.c_int, C.c_uint64, u64p, f64p, u64p]
         L.orc_baseline_threads.restype = C.c_int
+        L.orc_baseline_isa.restype = C.c_char_p
         _base = L
     return _base
 
@@ -252,6 +253,11 @@ def baseline_search(rows, q, top_k=10, max_distance=None, threads=1):
         raise RuntimeError(f"orc_baseline_search rc={rc}")
     m = min(int(o_n.value), cap)
     return o_row[:m], o_d[:m]
+
+
+def baseline_isa() -> str:
+    """SIMD kernel the timed baseline dispatches to on this host ("avx512f" or "avx2+fma")."""
+    return baseline_lib().orc_baseline_isa().decode()
 
 
 def baseline_threads() -> int:

@@ -23,11 +23,11 @@ SYMBOLS = [
     "stb_corpus_destroy", "stb_corpus_append", "stb_corpus_append_dev", "stb_corpus_clear",
     "stb_corpus_rows", "stb_corpus_data_dev", "stb_corpus_read", "stb_embed", "stb_embed_dev",
     "stb_embed_status", "stb_search",
-    "stb_search_topk_dev", "stb_corpus_prepare_batch", "stb_search_batch", "stb_search_batch_dev",
+    "stb_search_topk_dev", "stb_corpus_prepare", "stb_corpus_tier_stats", "stb_corpus_prepare_batch", "stb_search_batch", "stb_search_batch_dev",
     "stb_xchg_create", "stb_xchg_destroy", "stb_xchg_local_handle",
     "stb_xchg_connect", "stb_xchg_connect_local", "stb_search_topk_xchg", "stb_search_xchg", "stb_ivfpq_build",
     "stb_ivfpq_destroy", "stb_ivfpq_stats", "stb_ivfpq_search", "stb_hits_merge_dev", "stb_hits_merge_batch_dev", "stb_hits_merge", "stb_fnv1a64", "stb_line_id",
-    "stb_ctx_counters", "stb_debug_timestamps", "stb_debug_batch_gemm", "stb_debug_batch_params",
+    "stb_ctx_counters", "stb_debug_ticket_check", "stb_debug_timestamps", "stb_debug_batch_gemm", "stb_debug_batch_params",
 ]
 
 
@@ -83,6 +83,8 @@ def lib() -> C.CDLL:
     L.stb_search.argtypes = [vp, vp, vp, u32, i32, f64, i32, vp, u32, vp, u64, C.POINTER(u64)]
     L.stb_search_topk_dev.argtypes = [vp, vp, vp, u32, vp, vp]
     L.stb_corpus_prepare_batch.argtypes = [vp]
+    L.stb_corpus_prepare.argtypes = [vp, i32]
+    L.stb_corpus_tier_stats.argtypes = [vp, vp, vp, vp]
     L.stb_search_batch.argtypes = [vp, vp, vp, u32, u32, vp, vp]
     L.stb_search_batch_dev.argtypes = [vp, vp, vp, u32, u32, vp, vp]
     L.stb_xchg_create.argtypes = [vp, u32, u32, u32, C.POINTER(vp)]
@@ -105,6 +107,7 @@ def lib() -> C.CDLL:
     L.stb_line_id.restype = u64
     L.stb_ctx_counters.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.stb_debug_timestamps.argtypes = [vp, i32, vp]
+    L.stb_debug_ticket_check.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.stb_debug_batch_gemm.argtypes = [vp, vp, u32, vp, u64, vp, vp]
     L.stb_debug_batch_params.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_double)]
     for name in SYMBOLS:
@@ -115,8 +118,8 @@ def lib() -> C.CDLL:
     return L
 
 
-def _check(rc: int) -> int:
-    if rc < 0 and rc != STB_ERR_CAPACITY:
+def _check(rc: int, allow_capacity: bool = False) -> int:
+    if rc < 0 and not (allow_capacity and rc == STB_ERR_CAPACITY):
         raise StbError(rc, lib().stb_last_error().decode("utf-8", "replace"))
     return rc
 
@@ -173,6 +176,12 @@ class Context:
         a, b = u64(0), u64(0)
         _check(lib().stb_ctx_counters(self._h, C.byref(a), C.byref(b)))
         return {"kernel_launches": int(a.value), "fallback_searches": int(b.value)}
+
+    def ticket_check(self):
+        """stb_debug_ticket_check: (device counter, host-booked value); raises StbError on a mismatch."""
+        a, b = u64(0), u64(0)
+        _check(lib().stb_debug_ticket_check(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     # -- K4 ------------------------------------------------------------------
     def hits_merge(self, lists: np.ndarray, top_k: int) -> np.ndarray:
@@ -281,13 +290,26 @@ class Corpus:
             n = u64(0)
             rc = _check(lib().stb_search(self.ctx._h, self._h, _np_ptr(q), top_k,
                                          int(max_distance is not None), float(max_distance or 0.0), mode,
-                                         _np_ptr(rr), n_rr, _np_ptr(out), cap, C.byref(n)))
+                                         _np_ptr(rr), n_rr, _np_ptr(out), cap, C.byref(n)), allow_capacity=True)
             if rc == STB_ERR_CAPACITY:
                 cap = int(n.value)
                 continue
             return out[: int(n.value)]
 
     # -- K2 -----------------------------------------------------------------
+    def prepare(self, what: int = 3):
+        """stb_corpus_prepare: build the reduced-width candidate copies now
+        (STB_PREPARE_Q8 = 1, STB_PREPARE_H16 = 2)."""
+        _check(lib().stb_corpus_prepare(self._h, what))
+
+    def tier_stats(self):
+        """stb_corpus_tier_stats -> {"f32"|"h16"|"q8": {"tries", "proven", "built_rows"}}."""
+        tries, proven = np.zeros(3, np.uint32), np.zeros(3, np.uint32)
+        built = np.zeros(3, np.uint64)
+        _check(lib().stb_corpus_tier_stats(self._h, _np_ptr(tries), _np_ptr(proven), _np_ptr(built)))
+        return {name: {"tries": int(tries[i]), "proven": int(proven[i]), "built_rows": int(built[i])}
+                for i, name in enumerate(("f32", "h16", "q8"))}
+
     def prepare_batch(self):
         """stb_corpus_prepare_batch: build the bf16 tensor-core shadow now."""
         _check(lib().stb_corpus_prepare_batch(self._h))

@@ -95,7 +95,7 @@ int stb_ctx_create(int device, void *cuda_stream, stb_ctx **out) {
   }
   int rc = STB_OK;
   const size_t max_grid = (size_t)c->sm_count * 8;
-  if ((rc = dev_reserve(&c->block_keys, &c->block_keys_cap, 2 * max_grid * 128 + STB_SORT_CAP)) != STB_OK) goto fail;
+  if ((rc = dev_reserve(&c->block_keys, &c->block_keys_cap, 2 * max_grid * 129 + STB_SORT_CAP)) != STB_OK) goto fail;
   if ((rc = dev_reserve(&c->counters, &c->counters_cap, max_grid + 64)) != STB_OK) goto fail;
   {
     size_t one = 0;
@@ -110,9 +110,12 @@ int stb_ctx_create(int device, void *cuda_stream, stb_ctx **out) {
     if ((rc = dev_reserve(&c->dbg_dev, &one, 8)) != STB_OK) goto fail;
     one = 0;
     if ((rc = dev_reserve(&c->hist_dev, &one, 4096)) != STB_OK) goto fail;
+    one = 0;
+    if ((rc = dev_reserve(&c->tickets, &one, 1)) != STB_OK) goto fail;
   }
   if ((rc = dev_reserve(&c->hits_dev, &c->hits_cap, 1024)) != STB_OK) goto fail;
   if (cudaMemset(c->counters, 0, c->counters_cap * sizeof(unsigned int)) != cudaSuccess ||
+      cudaMemset(c->tickets, 0, sizeof(unsigned long long)) != cudaSuccess ||
       cudaMemset(c->err_flag, 0, sizeof(int)) != cudaSuccess ||
       cudaMallocHost((void **)&c->q_pin, STB_D * sizeof(float)) != cudaSuccess ||
       cudaMallocHost((void **)&c->status_pin, 8 * sizeof(uint32_t)) != cudaSuccess ||
@@ -138,6 +141,7 @@ int stb_ctx_destroy(stb_ctx *c) {
   cudaFree(c->block_keys); cudaFree(c->counters); cudaFree(c->q_dev); cudaFree(c->hits_dev);
   cudaFree(c->status_dev); cudaFree(c->collect_rows); cudaFree(c->collect_count);
   cudaFree(c->collect_hits); cudaFree(c->ranges_dev); cudaFree(c->err_flag);
+  cudaFree(c->tickets);
   cudaFree(c->dbg_dev); cudaFree(c->hist_dev); cudaFree(c->bq_tiles); cudaFree(c->b_submax); cudaFree(c->b_tilemax); cudaFree(c->b_cand);
   cudaFree(c->b_thr); cudaFree(c->b_cnt); cudaFree(c->b_keys);
   cudaFree(c->bq_dev); cudaFree(c->bh_dev); cudaFree(c->bs_dev); cudaFree(c->embed_off_dev); cudaFree(c->embed_ids_dev); cudaFree(c->embed_out_dev);
@@ -171,6 +175,21 @@ int stb_debug_timestamps(stb_ctx *ctx, int reset, uint64_t out[8]) {
     STB_CUDA(cudaMemcpyAsync(out, ctx->dbg_dev, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     STB_CUDA(cudaStreamSynchronize(ctx->stream));
   }
+  return STB_OK;
+}
+
+// K1's tile tickets: every top-k launch must advance the device counter by exactly what the host
+// booked for it (n_tickets + total_warps); a mismatch would make later launches skip or repeat
+// tiles.  Synchronises; returns STB_ERR_STATE on a mismatch.
+int stb_debug_ticket_check(stb_ctx *ctx, uint64_t *device_value, uint64_t *host_value) {
+  int rc = ctx_use(ctx);
+  if (rc) return rc;
+  unsigned long long v = 0;
+  STB_CUDA(cudaStreamSynchronize(ctx->stream));
+  STB_CUDA(cudaMemcpy(&v, ctx->tickets, sizeof(v), cudaMemcpyDeviceToHost));
+  if (device_value) *device_value = v;
+  if (host_value) *host_value = ctx->ticket_next;
+  if (v != ctx->ticket_next) { stb_set_error("ticket counter %llu, host expects %llu", v, ctx->ticket_next); return STB_ERR_STATE; }
   return STB_OK;
 }
 
@@ -273,10 +292,21 @@ int stb_corpus_destroy(stb_corpus *c) {
   if (c->ctx && ctx_alive(c->ctx)) { cudaSetDevice(c->ctx->device); cudaStreamSynchronize(c->ctx->stream); }
   else cudaDeviceSynchronize();
   cudaFree(c->shadow);
+  cudaFree(c->q8);
+  cudaFree(c->q8_scale);
   cudaFree(c->rows);
   cudaGetLastError();
   delete c;
   return STB_OK;
+}
+
+// the reduced-width copies (K2 shadow, K1 tiers) are rebuilt lazily after any change
+static void corpus_changed(stb_corpus *c) {
+  c->shadow_rows = 0;
+  c->q8_rows = 0;
+  c->searches_since_change = 0;
+  memset(c->tier_tries, 0, sizeof(c->tier_tries));
+  memset(c->tier_proven, 0, sizeof(c->tier_proven));
 }
 
 static int corpus_append_impl(stb_corpus *c, const float *rows, uint64_t n, cudaMemcpyKind kind) {
@@ -289,8 +319,7 @@ static int corpus_append_impl(stb_corpus *c, const float *rows, uint64_t n, cuda
   STB_CUDA(cudaMemcpyAsync(c->rows + c->n * STB_D, rows, n * STB_D * sizeof(float), kind, c->ctx->stream));
   STB_CUDA(cudaStreamSynchronize(c->ctx->stream));
   c->n += n;
-  c->shadow_rows = 0;     // K2 shadow is rebuilt lazily
-  c->shadow_tries = c->shadow_proven = 0;
+  corpus_changed(c);
   return STB_OK;
 }
 
@@ -304,7 +333,7 @@ int stb_corpus_clear(stb_corpus *c) {
   if (!c) { stb_set_error("null corpus"); return STB_ERR_ARG; }
   if (!ctx_alive(c->ctx)) { stb_set_error("context was destroyed"); return STB_ERR_STATE; }
   c->n = 0;
-  c->shadow_rows = 0;
+  corpus_changed(c);
   return STB_OK;
 }
 int stb_corpus_rows(const stb_corpus *c, uint64_t *n) {
@@ -362,7 +391,7 @@ int stb_embed(stb_ctx *ctx, const stb_table *table, const uint64_t *offsets, con
   if (out) STB_CUDA(cudaMemcpyAsync(out, dst, n_lines * STB_D * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   STB_CUDA(cudaStreamSynchronize(ctx->stream));
   if (flag) { stb_set_error("embed: a token id maps outside the %llu-row table", (unsigned long long)table->V); return STB_ERR_RANGE; }
-  if (append_to) { append_to->n += n_lines; append_to->shadow_rows = 0; }
+  if (append_to) { append_to->n += n_lines; corpus_changed(append_to); }
   return STB_OK;
 }
 
@@ -389,6 +418,27 @@ int stb_embed_status(stb_ctx *ctx) {
 
 // --------------------------------------------------------------------- search ---
 static int corpus_ensure_shadow(stb_ctx *ctx, stb_corpus *c);   // defined with the K2 entry points
+static int corpus_ensure_q8(stb_ctx *ctx, stb_corpus *c);
+
+// STB_SCAN_TIER = f32 | h16 | q8: the narrowest candidate tier K1 may use (default q8).  Read per
+// call so one process can compare tiers; results are identical whatever the value.
+static int stb_env_max_tier() {
+  const char *e = getenv("STB_SCAN_TIER");
+  if (!e || !e[0]) return STB_TIER_Q8;
+  if (e[0] == 'f') return STB_TIER_F32;
+  if (e[0] == 'h') return STB_TIER_H16;
+  return STB_TIER_Q8;
+}
+static bool stb_env_direct_out() {
+  const char *e = getenv("STB_DIRECT_OUT");
+  return !(e && e[0] == '0');
+}
+static int best_built_tier(const stb_corpus *c, uint32_t top_k) {
+  const int max_tier = stb_env_max_tier();
+  if (max_tier >= STB_TIER_Q8 && top_k <= STB_Q8_MAX_K && c->q8 && c->q8_rows == c->n && !c->q8_bad) return STB_TIER_Q8;
+  if (max_tier >= STB_TIER_H16 && c->shadow && c->shadow_rows == c->n && !c->shadow_bad) return STB_TIER_H16;
+  return STB_TIER_F32;
+}
 
 static int ensure_hits_pin(stb_ctx *ctx, size_t need) {
   if (need <= ctx->hits_pin_cap) return STB_OK;
@@ -488,44 +538,55 @@ int stb_search(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint32_t 
   const stb_hit *src_dev = nullptr;   // sorted device hits to copy out (collect path)
   if (!threshold_all && top_k <= stb_scan_topk_max_k()) {
     // ---- fast path: one kernel, k*16+16 bytes back -----------------------------
-    // STB_DIRECT_OUT=1 (opt-in until timed): the kernel's last CTA stores the k hits + status straight
-    // into the pinned host buffers (UVA: cudaMallocHost memory is device-accessible), which takes
-    // the two D2H copies off the stream; kernel completion makes the stores visible to the host.
-    const char *direct_env = getenv("STB_DIRECT_OUT");
-    const bool direct = direct_env && direct_env[0] == '1';
-    auto run_fast = [&](const uint8_t *shadow) -> int {
+    // The kernel's last CTA stores the k hits + status straight into the pinned host buffers
+    // (UVA: cudaMallocHost memory is device-accessible), which takes the two D2H copies off the
+    // stream; kernel completion makes the stores visible to the host.  STB_DIRECT_OUT=0 restores
+    // the device buffers + two cudaMemcpyAsync.
+    const bool direct = stb_env_direct_out();
+    auto run_fast = [&](int tier) -> int {
       int r;
       if (direct) {
-        if ((r = stb_launch_scan_topk(ctx, corpus->rows, corpus->n, corpus->row_base, ctx->q_dev, top_k, ranges_dev, n_loc,
-                                      n_virtual, ctx->hits_pin, ctx->status_pin, nullptr, shadow)) != STB_OK) return r;
+        if ((r = stb_launch_scan_topk(ctx, corpus, tier, ctx->q_dev, top_k, ranges_dev, n_loc, n_virtual, ctx->hits_pin,
+                                      ctx->status_pin)) != STB_OK) return r;
       } else {
-        if ((r = stb_launch_scan_topk(ctx, corpus->rows, corpus->n, corpus->row_base, ctx->q_dev, top_k, ranges_dev, n_loc,
-                                      n_virtual, ctx->hits_dev, ctx->status_dev, nullptr, shadow)) != STB_OK) return r;
+        if ((r = stb_launch_scan_topk(ctx, corpus, tier, ctx->q_dev, top_k, ranges_dev, n_loc, n_virtual, ctx->hits_dev,
+                                      ctx->status_dev)) != STB_OK) return r;
         STB_CUDA(cudaMemcpyAsync(ctx->status_pin, ctx->status_dev, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         STB_CUDA(cudaMemcpyAsync(ctx->hits_pin, ctx->hits_dev, top_k * sizeof(stb_hit), cudaMemcpyDeviceToHost, ctx->stream));
       }
       STB_CUDA(cudaStreamSynchronize(ctx->stream));
       return STB_OK;
     };
-    // STB_SCAN_SHADOW=1 (opt-in until validated on hardware): whole-shard queries first run over the
-    // 16-bit normalised shadow (half the bytes; K2's operand, built lazily).  Same exact re-rank,
-    // wider proof margin; a result it cannot prove is retried on the f32 rows below.
-    const char *shadow_env = getenv("STB_SCAN_SHADOW");
-    bool proven_on_shadow = false;
-    const bool shadow_pays = corpus->shadow_tries < 8 || 2 * corpus->shadow_proven >= corpus->shadow_tries;
-    if (shadow_env && shadow_env[0] == '1' && !ranges_dev && shadow_pays) {
-      stb_corpus *cm = const_cast<stb_corpus *>(corpus);
-      const int src = corpus_ensure_shadow(ctx, cm);                 // STB_ERR_STATE: rows that cannot be normalised
-      if (src == STB_OK) {
-        if ((rc = run_fast(corpus->shadow)) != STB_OK) return rc;
-        proven_on_shadow = ctx->status_pin[1] != 0;
-        cm->shadow_tries++;
-        if (proven_on_shadow) cm->shadow_proven++;
-      } else if (src != STB_ERR_STATE) {
-        return src;
-      }
+    // Tier ladder: q8 (260 B/row) -> h16 (512 B/row) -> f32 (1 KiB/row).  Every tier ends in the
+    // same exact f64 re-rank and proves its own result; one that cannot is retried one tier up, so
+    // the answer is the oracle's whichever tier produced it.  Reduced-width copies are used when
+    // they exist (stb_corpus_prepare) and built lazily from the second query on an unchanged
+    // corpus of >= 32768 rows (a one-shot CLI query must not pay a full extra pass to save half
+    // of one); a tier that keeps failing its proofs on this corpus is dropped.
+    stb_corpus *cm = const_cast<stb_corpus *>(corpus);
+    const int max_tier = stb_env_max_tier();
+    const bool lazy_ok = cm->searches_since_change >= 1 && cm->n >= 32768;
+    cm->searches_since_change++;
+    bool proven = false;
+    for (int tier = STB_TIER_Q8; tier >= STB_TIER_H16 && !proven; --tier) {
+      if (tier > max_tier) continue;
+      if (tier == STB_TIER_Q8 && top_k > STB_Q8_MAX_K) continue;
+      if (cm->tier_tries[tier] >= 8 && 2 * cm->tier_proven[tier] < cm->tier_tries[tier]) continue;
+      const bool built = (tier == STB_TIER_Q8) ? (cm->q8 && cm->q8_rows == cm->n) : (cm->shadow && cm->shadow_rows == cm->n);
+      if (!built && !lazy_ok) continue;
+      const int src = (tier == STB_TIER_Q8) ? corpus_ensure_q8(ctx, cm) : corpus_ensure_shadow(ctx, cm);
+      if (src == STB_ERR_STATE) continue;                  // rows that cannot be normalised in fp32
+      if (src != STB_OK) return src;
+      if ((rc = run_fast(tier)) != STB_OK) return rc;
+      proven = ctx->status_pin[1] != 0;
+      cm->tier_tries[tier]++;
+      if (proven) cm->tier_proven[tier]++;
     }
-    if (!proven_on_shadow && (rc = run_fast(nullptr)) != STB_OK) return rc;
+    if (!proven) {
+      if ((rc = run_fast(STB_TIER_F32)) != STB_OK) return rc;
+      cm->tier_tries[STB_TIER_F32]++;
+      if (ctx->status_pin[1]) cm->tier_proven[STB_TIER_F32]++;
+    }
     const uint32_t n_hits = ctx->status_pin[0];
     if (ctx->status_pin[1]) {
       uint64_t n = 0;
@@ -593,15 +654,11 @@ int stb_search_topk_dev(stb_ctx *ctx, const stb_corpus *corpus, const float *q_d
   if (corpus->ctx != ctx) { stb_set_error("search_topk_dev: corpus belongs to another context"); return STB_ERR_ARG; }
   if (top_k == 0 || top_k > stb_scan_topk_max_k()) { stb_set_error("search_topk_dev: top_k must be 1..%u", stb_scan_topk_max_k()); return STB_ERR_ARG; }
   if (corpus->n == 0) { stb_set_error("search_topk_dev: empty corpus"); return STB_ERR_STATE; }
-  // STB_SCAN_SHADOW=1: use the 16-bit shadow when stb_corpus_prepare_batch has built it (this
-  // asynchronous entry point never builds it; status[1] says whether the result is proven, the
-  // caller's fallback is unchanged)
-  const char *shadow_env = getenv("STB_SCAN_SHADOW");
-  const uint8_t *shadow = nullptr;
-  if (shadow_env && shadow_env[0] == '1' && corpus->shadow && corpus->shadow_rows == corpus->n && !corpus->shadow_bad)
-    shadow = corpus->shadow;
-  return stb_launch_scan_topk(ctx, corpus->rows, corpus->n, corpus->row_base, q_dev, top_k, nullptr, 0,
-                              corpus->n, out_hits_dev, out_status_dev, nullptr, shadow);
+  // candidates from the narrowest copy that already exists (this asynchronous entry point never
+  // builds one: stb_corpus_prepare does); status[1] says whether the result is proven, the
+  // caller's fallback is unchanged
+  return stb_launch_scan_topk(ctx, corpus, best_built_tier(corpus, top_k), q_dev, top_k, nullptr, 0, corpus->n,
+                              out_hits_dev, out_status_dev, nullptr);
 }
 
 // ------------------------------------------------------------ peer-memory exchange ---
@@ -711,12 +768,8 @@ int stb_search_topk_xchg(stb_ctx *ctx, const stb_corpus *corpus, const float *q_
   a.world = x->world; a.rank = x->rank; a.max_k = x->max_k;
   a.seq = ++x->seq;
   a.slot = (uint32_t)(a.seq % STB_XCHG_SLOTS);
-  const char *shadow_env = getenv("STB_SCAN_SHADOW");      // as in stb_search_topk_dev: only a shadow that already exists
-  const uint8_t *shadow = nullptr;
-  if (shadow_env && shadow_env[0] == '1' && corpus->shadow && corpus->shadow_rows == corpus->n && !corpus->shadow_bad)
-    shadow = corpus->shadow;
-  return stb_launch_scan_topk(ctx, corpus->rows, corpus->n, corpus->row_base, q_dev, top_k, nullptr, 0,
-                              corpus->n, out_hits_dev, out_status_dev, &a, shadow);
+  return stb_launch_scan_topk(ctx, corpus, best_built_tier(corpus, top_k), q_dev, top_k, nullptr, 0, corpus->n,
+                              out_hits_dev, out_status_dev, &a);
 }
 
 // ----------------------------------------------------------------- K2 batched search ---
@@ -747,6 +800,61 @@ static int corpus_ensure_shadow(stb_ctx *ctx, stb_corpus *c) {
   return STB_OK;
 }
 
+static int corpus_ensure_q8(stb_ctx *ctx, stb_corpus *c) {
+  if (c->q8 && c->q8_rows == c->n) {
+    if (c->q8_bad) { stb_set_error("q8 tier: corpus holds rows whose norm is not a normal fp32 number"); return STB_ERR_STATE; }
+    return STB_OK;
+  }
+  if (c->n > c->q8_cap_rows || !c->q8) {
+    uint8_t *np = nullptr;
+    float *ns = nullptr;
+    const uint64_t cap = std::max<uint64_t>(c->n, c->capacity);
+    cudaError_t e = cudaMalloc((void **)&np, cap * 256ull);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&ns, cap * sizeof(float));
+    if (e != cudaSuccess) { cudaGetLastError(); cudaFree(np); stb_set_error("q8 tier: cannot allocate %llu MiB", (unsigned long long)(cap * 260 >> 20)); return STB_ERR_NOMEM; }
+    cudaFree(c->q8); cudaFree(c->q8_scale);
+    c->q8 = np; c->q8_scale = ns; c->q8_cap_rows = cap;
+  }
+  int rc;
+  STB_CUDA(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), ctx->stream));
+  if ((rc = stb_launch_q8_build(ctx, c->rows, 0, c->n, c->q8, c->q8_scale, ctx->err_flag)) != STB_OK) return rc;
+  int flag = 0;
+  STB_CUDA(cudaMemcpyAsync(&flag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  STB_CUDA(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), ctx->stream));
+  STB_CUDA(cudaStreamSynchronize(ctx->stream));
+  c->q8_rows = c->n;
+  c->q8_bad = flag;
+  if (flag) { stb_set_error("q8 tier: corpus holds rows whose norm is not a normal fp32 number"); return STB_ERR_STATE; }
+  return STB_OK;
+}
+
+int stb_corpus_prepare(stb_corpus *corpus, int what) {
+  if (!corpus) { stb_set_error("null corpus"); return STB_ERR_ARG; }
+  if (what & ~(STB_PREPARE_Q8 | STB_PREPARE_H16)) { stb_set_error("corpus_prepare: unknown flag"); return STB_ERR_ARG; }
+  int rc = ctx_use(corpus->ctx);
+  if (rc) return rc;
+  if (corpus->n == 0) return STB_OK;
+  // rows that cannot be normalised in fp32 make a copy unusable (STB_ERR_STATE): not an error of
+  // this call -- searches simply stay on the f32 rows
+  if (what & STB_PREPARE_Q8) { rc = corpus_ensure_q8(corpus->ctx, corpus); if (rc != STB_OK && rc != STB_ERR_STATE) return rc; }
+  if (what & STB_PREPARE_H16) { rc = corpus_ensure_shadow(corpus->ctx, corpus); if (rc != STB_OK && rc != STB_ERR_STATE) return rc; }
+  return STB_OK;
+}
+
+int stb_corpus_tier_stats(const stb_corpus *corpus, uint32_t tries[3], uint32_t proven[3], uint64_t built_rows[3]) {
+  if (!corpus) { stb_set_error("null corpus"); return STB_ERR_ARG; }
+  for (int t = 0; t < 3; ++t) {
+    if (tries) tries[t] = corpus->tier_tries[t];
+    if (proven) proven[t] = corpus->tier_proven[t];
+  }
+  if (built_rows) {
+    built_rows[STB_TIER_F32] = corpus->n;
+    built_rows[STB_TIER_H16] = (corpus->shadow && !corpus->shadow_bad) ? corpus->shadow_rows : 0;
+    built_rows[STB_TIER_Q8] = (corpus->q8 && !corpus->q8_bad) ? corpus->q8_rows : 0;
+  }
+  return STB_OK;
+}
+
 int stb_corpus_prepare_batch(stb_corpus *corpus) {
   if (!corpus) { stb_set_error("null corpus"); return STB_ERR_ARG; }
   int rc = ctx_use(corpus->ctx);
@@ -768,40 +876,44 @@ int stb_search_batch_dev(stb_ctx *ctx, const stb_corpus *corpus_c, const float *
   if ((rc = corpus_ensure_shadow(ctx, corpus)) != STB_OK) return rc;
   const uint32_t m_tiles = (nq + 127) / 128, q_pad = m_tiles * 128;
   const uint32_t n_tiles = (uint32_t)((corpus->n + 255) / 256), n_sub = n_tiles * 8;
-  // pipeline v2 (threshold-emitting epilogue; see batch_scan.cu): opt-in until validated on hardware
-  const char *v2_env = getenv("STB_BATCH_V2");            // read per call so one process can compare both
-  const bool use_v2 = v2_env != nullptr && v2_env[0] == '1';
-  // v2 sampling: ~4 tiles per SM (the size validated on hardware); shards so large that this would
-  // let more than ~4096 rows per query through (emitted ~ top_k * n_full / n_sample * 4 with the
-  // 2 * 0.0080 margin: e^(x/sigma^2 * 0.016) ~ 3.8 at the benchmark's score distribution) take a
-  // sample of 1/64 of the tiles instead (threshold kernel: CTA-per-query variant, <= 8192 tiles).
-  // sample only COMPLETE tiles (a padding row must never stand in for a real one)
+  // Pipeline v2 (default): sampled threshold -> candidate-emitting tcgen05 epilogue -> exact finish
+  // (batch_scan.cu).  Proves every query for any top_k <= 64 unless a capacity overflows.
+  // STB_BATCH_V1=1 forces the round-1 maxima/select/finish pipeline (also used when v2 does not fit).
+  const char *v1_env = getenv("STB_BATCH_V1");            // read per call so one process can compare both
+  const bool force_v1 = v1_env != nullptr && v1_env[0] == '1';
+  // v2 sampling: ~4 COMPLETE tiles per SM, strided over the shard (a padding row must never stand
+  // in for a real one).  Expected candidates per query ~ top_k * n_full / n_sample * e^(2 EPS x / sigma^2)
+  // (x = top score, sigma = 1/16 for the benchmark's rows: factor ~1.2 with the fp16 shadow's
+  // EPS = 0.0012, ~3.8 with bf16's 0.0080).  Shards so large that this exceeds half of the finish
+  // kernel's 4096-key capacity sample 1/64 of the tiles instead (threshold kernel: CTA-per-query
+  // variant, <= 8192 tiles); beyond that, v1.
   const uint32_t n_full = (uint32_t)(corpus->n / 256);
   uint32_t n_sample = std::min<uint32_t>(n_full, std::min<uint32_t>(4u * (uint32_t)ctx->sm_count, 608u));
-  auto expected_emitted = [&](uint32_t ns) { return ns ? (uint64_t)top_k * 4 * ((n_full + ns - 1) / ns) : 0; };
-  if (expected_emitted(n_sample) > 4096) {
+  const uint32_t margin_factor = STB_SHADOW_F16 ? 2u : 4u;
+  auto expected_emitted = [&](uint32_t ns) { return ns ? (uint64_t)top_k * margin_factor * ((n_full + ns - 1) / ns) : 0; };
+  if (expected_emitted(n_sample) > 2048) {
     const uint32_t sm = (uint32_t)ctx->sm_count;
     n_sample = std::min<uint32_t>(std::min<uint32_t>(n_full, 8192u), (n_full / 64 + sm - 1) / sm * sm);
   }
-  const bool v2_fits = expected_emitted(n_sample) <= 4096;
-  if (use_v2 && top_k <= 64 && v2_fits) {
-    constexpr uint32_t kCandCap = 8192;
-    const uint32_t stride = n_sample ? n_full / n_sample : 1;
+  const bool v2_fits = n_sample >= top_k && expected_emitted(n_sample) <= 2048;
+  if (!force_v1 && top_k <= 64 && v2_fits) {
+    constexpr uint32_t kSegCap = 64;                      // per (query, CTA): ~5 expected at 10M rows / 148 CTAs
+    const uint32_t n_seg = stb_batch_emit_grid(ctx, n_tiles);
+    const uint32_t stride = n_full / n_sample;
     if ((rc = dev_reserve(&ctx->bq_tiles, &ctx->bq_tiles_cap, (size_t)q_pad * 512)) != STB_OK) return rc;
-    if ((rc = dev_reserve(&ctx->b_tilemax, &ctx->b_tilemax_cap, (size_t)std::max<uint32_t>(n_sample, 1) * q_pad)) != STB_OK) return rc;
+    if ((rc = dev_reserve(&ctx->b_tilemax, &ctx->b_tilemax_cap, (size_t)n_sample * q_pad)) != STB_OK) return rc;
     if ((rc = dev_reserve(&ctx->b_thr, &ctx->b_thr_cap, (size_t)q_pad)) != STB_OK) return rc;
-    if ((rc = dev_reserve(&ctx->b_cnt, &ctx->b_cnt_cap, (size_t)q_pad)) != STB_OK) return rc;
-    if ((rc = dev_reserve(&ctx->b_keys, &ctx->b_keys_cap, (size_t)q_pad * kCandCap)) != STB_OK) return rc;
+    if ((rc = dev_reserve(&ctx->b_cnt, &ctx->b_cnt_cap, (size_t)q_pad * n_seg)) != STB_OK) return rc;
+    if ((rc = dev_reserve(&ctx->b_keys, &ctx->b_keys_cap, (size_t)q_pad * n_seg * kSegCap)) != STB_OK) return rc;
     STB_CUDA(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), ctx->stream));
-    STB_CUDA(cudaMemsetAsync(ctx->b_cnt, 0, (size_t)q_pad * sizeof(uint32_t), ctx->stream));
+    STB_CUDA(cudaMemsetAsync(ctx->b_cnt, 0, (size_t)q_pad * n_seg * sizeof(uint32_t), ctx->stream));
     if ((rc = stb_launch_shadow_build(ctx, q_dev, nq, 128, ctx->bq_tiles, ctx->err_flag)) != STB_OK) return rc;
-    if (n_sample &&
-        (rc = stb_launch_batch_gemm_strided(ctx, ctx->bq_tiles, m_tiles, corpus->shadow, n_sample, stride, nullptr,
+    if ((rc = stb_launch_batch_gemm_strided(ctx, ctx->bq_tiles, m_tiles, corpus->shadow, n_sample, stride, nullptr,
                                             ctx->b_tilemax, nullptr)) != STB_OK) return rc;
     if ((rc = stb_launch_batch_thresh(ctx, ctx->b_tilemax, n_sample, nq, q_pad, top_k, ctx->b_thr)) != STB_OK) return rc;
     if ((rc = stb_launch_batch_gemm_emit(ctx, ctx->bq_tiles, m_tiles, corpus->shadow, n_tiles, corpus->n, ctx->b_thr,
-                                         ctx->b_cnt, ctx->b_keys, kCandCap)) != STB_OK) return rc;
-    return stb_launch_batch_finish2(ctx, ctx->b_keys, ctx->b_cnt, kCandCap, nq, top_k, corpus->rows, corpus->n,
+                                         ctx->b_cnt, ctx->b_keys, kSegCap)) != STB_OK) return rc;
+    return stb_launch_batch_finish2(ctx, ctx->b_keys, ctx->b_cnt, n_seg, kSegCap, nq, top_k, corpus->rows, corpus->n,
                                     corpus->row_base, q_dev, out_hits_dev, out_status_dev);
   }
   // selection slices: enough CTAs (m_tiles x n_slices) to hide the latency of the streaming

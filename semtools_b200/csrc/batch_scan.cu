@@ -52,9 +52,6 @@
 //         (attained within 2%: tests/test_batch_v2_model.py builds the adversarial row)
 //   fp16: u = 2^-11 for |x| >= 2^-14; smaller elements err by <= 2^-25 absolutely, at most
 //         2*256*2^-25 = 1.5e-5 over a row pair; total < 0.00101
-#ifndef STB_SHADOW_F16
-#define STB_SHADOW_F16 0
-#endif
 #if STB_SHADOW_F16
 #define STB_BATCH_EPS 0.0012
 #else
@@ -212,9 +209,9 @@ struct GemmArgs {
   uint32_t tile_stride;       // corpus tile t of this launch is shadow tile t * tile_stride (sampling pass)
   // EPI == 1 (candidate-emitting epilogue, pipeline v2):
   const float *thr;           // [q_pad] per-query score threshold (+inf for padding queries)
-  uint32_t *cand_cnt;         // [q_pad] candidates emitted (may exceed cand_cap: overflow marker)
-  uint64_t *cand_keys;        // [q_pad][cand_cap] keys (score desc, local row)
-  uint32_t cand_cap;
+  uint32_t *cand_cnt;         // [q_pad][grid] candidates emitted per (query, CTA) (> cand_cap: overflow marker)
+  uint64_t *cand_keys;        // [q_pad][grid][cand_cap] keys (score desc, local row)
+  uint32_t cand_cap;          // per-segment capacity
   uint64_t n_rows;            // real corpus rows (padding rows of the last tile are never emitted)
 };
 
@@ -346,9 +343,18 @@ stb_batch_gemm_kernel(const GemmArgs args) {
           args.tilemax[((size_t)m * args.n_tiles + t) * STB_A_TILE + quarter * 32 + lane] = tmx;
         } else {
           // thread = query: the threshold lives in a register; an emission is rare (the
-          // threshold is the k-th best score of a 1/66 sample, minus the rounding margin)
+          // threshold is the k-th best score of a ~1.5 % sample, minus the rounding margin).
+          // Each (query, CTA) pair owns a private segment of the candidate buffer and its own
+          // cursor, written by this thread only: no atomics, and the slow path is ONE divergent
+          // region per 32-row chunk (hit mask -> ffs loop), not 32 predicated blocks.
+          // (Round 1's per-hit global atomicAdd made this epilogue the bottleneck: 6.95 ms
+          // against 3.3 ms for the maxima epilogue, profiles/r02_k2_v2_launches.txt.)
           const float thr = __ldg(args.thr + q);
-          uint64_t *my_keys = args.cand_keys + (size_t)q * args.cand_cap;
+          const size_t seg_id = (size_t)q * gridDim.x + blockIdx.x;
+          uint32_t *cnt_p = args.cand_cnt + seg_id;
+          const uint32_t cnt0 = *cnt_p;
+          uint32_t cnt = cnt0;
+          uint64_t *seg = args.cand_keys + seg_id * args.cand_cap;
 #pragma unroll 1
           for (int c = 0; c < STB_B_TILE / STB_SUB; ++c) {
             uint32_t r[32];
@@ -358,17 +364,23 @@ stb_batch_gemm_kernel(const GemmArgs args) {
 #pragma unroll
             for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
             if (mx >= thr) {
-              const uint64_t row0 = t * STB_B_TILE + (uint64_t)c * STB_SUB;
+              uint32_t hit = 0u;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float v = __uint_as_float(r[i]);
-                if (v >= thr && row0 + i < args.n_rows) {
-                  const uint32_t pos = atomicAdd(args.cand_cnt + q, 1u);
-                  if (pos < args.cand_cap) my_keys[pos] = stb_make_key(v, (uint32_t)(row0 + i));
-                }
+              for (int i = 0; i < 32; ++i) hit |= (__uint_as_float(r[i]) >= thr ? 1u : 0u) << i;
+              const uint64_t row0 = t * STB_B_TILE + (uint64_t)c * STB_SUB;
+              if (row0 + 32 > args.n_rows) hit &= (row0 < args.n_rows) ? ((1u << (uint32_t)(args.n_rows - row0)) - 1u) : 0u;   // padding rows
+              while (hit) {
+                const int i = __ffs(hit) - 1;
+                hit &= hit - 1u;
+                uint32_t bits = r[0];
+#pragma unroll
+                for (int jj = 1; jj < 32; ++jj) bits = (i == jj) ? r[jj] : bits;      // register select, no local memory
+                if (cnt < args.cand_cap) seg[cnt] = stb_make_key(__uint_as_float(bits), (uint32_t)(row0 + i));
+                ++cnt;                                                                 // > cand_cap = overflow marker
               }
             }
           }
+          if (cnt != cnt0) *cnt_p = cnt;
         }
         tc_fence_before();
         __syncwarp();
@@ -697,7 +709,6 @@ int stb_launch_batch_finish(stb_ctx *ctx, const uint64_t *cand, uint32_t n_slice
 // =========================================================================================
 #define STB_V2_MAX_SAMPLE 608          // 19 values per lane in the threshold kernel
 #define STB_V2_MAX_K 64                // threshold kernel extracts k maxima serially
-#define STB_V2_RESCORE_CAP 1024        // exact re-scores per query
 
 struct ThreshArgs {
   const float *tilemax;     // [m_tiles][n_sample][128]
@@ -793,9 +804,9 @@ stb_batch_thresh_big_kernel(const ThreshArgs a) {
 }
 
 struct Finish2Args {
-  const uint64_t *cand_keys;   // [q_pad][cand_cap]
-  const uint32_t *cand_cnt;    // [q_pad]
-  uint32_t cand_cap, nq, top_k;
+  const uint64_t *cand_keys;   // [q_pad][n_seg][seg_cap]
+  const uint32_t *cand_cnt;    // [q_pad][n_seg]
+  uint32_t n_seg, seg_cap, nq, top_k;
   const float4 *rows;
   uint64_t n_rows, row_base;
   const float *queries;        // [nq][256]
@@ -803,95 +814,143 @@ struct Finish2Args {
   uint32_t *out_status;        // [nq][2]: hits, complete
 };
 
-// one CTA per query.  dynamic smem: keys[n_sort_max] | sd[1024] | sr[1024]
+#define STB_F2_KEYS 4096         // emitted candidates one query may bring (sum over its segments)
+#define STB_F2_RESCORE 1024      // exact re-scores per query after narrowing (dense neighbourhoods)
+#define STB_F2_STRIDE 260        // floats per staged row (1 KiB + 16 B: conflict-free LDS.128)
+
+// One CTA (256 threads) per query: gather the query's segments, sort by approximate score
+// (register/shuffle bitonic network), narrow to a >= A_k - 2 EPS, re-score those rows exactly
+// (rows staged through shared memory with coalesced loads, f64 chains on 4 warps -- K1's re-rank)
+// and sort the (distance,row) pairs.  A capacity overflow anywhere marks the query unproven.
 __global__ void __launch_bounds__(256)
 stb_batch_finish2_kernel(const Finish2Args a) {
-  extern __shared__ uint64_t f2_smem[];
-  uint64_t *skeys = f2_smem;
-  double *sd = reinterpret_cast<double *>(f2_smem + a.cand_cap);
-  uint64_t *sr = f2_smem + a.cand_cap + STB_V2_RESCORE_CAP;
+  extern __shared__ __align__(16) uint8_t f2_smem[];      // keys[4096] | 32 staged rows
+  uint64_t *skeys = reinterpret_cast<uint64_t *>(f2_smem);
+  float *srows = reinterpret_cast<float *>(f2_smem + STB_F2_KEYS * sizeof(uint64_t));
   __shared__ double sqd[STB_D];
+  __shared__ double sd[STB_F2_RESCORE];
+  __shared__ uint64_t sr[STB_F2_RESCORE];
   __shared__ double s_q2;
-  __shared__ int s_pass;
+  __shared__ uint32_t s_off[256 + 1];
+  __shared__ int s_pass, s_over;
   __shared__ unsigned s_m2;
   const uint32_t q = blockIdx.x;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t k = a.top_k;
-  const uint32_t m_all = a.cand_cnt[q];
-  auto give_up = [&]() {                               // capacity overflow: the host falls back to K1
+  auto give_up = [&]() {                               // the host answers this query through K1
     for (uint32_t i = tid; i < k; i += 256) {
       stb_hit h; h.distance = CUDART_INF; h.row = 0xffffffffffffffffull;
       a.out_hits[(size_t)q * k + i] = h;
     }
     if (tid == 0) { a.out_status[2 * q] = 0; a.out_status[2 * q + 1] = 0; }
   };
-  if (m_all > a.cand_cap) { give_up(); return; }       // uniform per CTA
-  // 1. sort the emitted keys (ascending key = descending score, then ascending row)
-  uint32_t n_sort = 64;
-  while (n_sort < m_all) n_sort <<= 1;
-  const uint64_t *src = a.cand_keys + (size_t)q * a.cand_cap;
-  for (uint32_t i = tid; i < n_sort; i += 256) skeys[i] = (i < m_all) ? src[i] : STB_KEY_INVALID;
-  for (int i = tid; i < STB_D; i += 256) sqd[i] = (double)__ldg(a.queries + (size_t)q * STB_D + i);
-  if (tid == 0) { s_pass = 0; s_m2 = 0; }
+  // 1. segment counts -> offsets (n_seg <= 256: one thread per segment, warp scans + 8-entry fix-up)
+  if (tid == 0) { s_pass = 0; s_over = 0; s_m2 = 0; }
   __syncthreads();
-  for (uint32_t kk = 2; kk <= n_sort; kk <<= 1)
-    for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
-      for (uint32_t i = tid; i < n_sort; i += 256) {
-        const uint32_t ixj = i ^ j;
-        if (ixj > i) {
-          const uint64_t x = skeys[i], y = skeys[ixj];
-          const bool up = ((i & kk) == 0);
-          if ((x > y) == up) { skeys[i] = y; skeys[ixj] = x; }
-        }
-      }
-      __syncthreads();
-    }
-  // 2. narrow to a >= A_k - 2 EPS (everything when fewer than k rows were emitted)
+  uint32_t c = 0;
+  if ((uint32_t)tid < a.n_seg) {
+    c = a.cand_cnt[(size_t)q * a.n_seg + tid];
+    if (c > a.seg_cap) { s_over = 1; c = a.seg_cap; }
+  }
+  uint32_t incl = c;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += v;
+  }
+  __shared__ uint32_t s_wsum[8];
+  if (lane == 31) s_wsum[warp] = incl;
+  __syncthreads();
+  uint32_t base = 0;
+  for (int w = 0; w < warp; ++w) base += s_wsum[w];
+  s_off[tid] = base + incl - c;
+  if (tid == 255) s_off[256] = base + incl;
+  for (int i = tid; i < STB_D; i += 256) sqd[i] = (double)__ldg(a.queries + (size_t)q * STB_D + i);
+  __syncthreads();
+  const uint32_t m_all = s_off[256];
+  if (s_over || m_all > STB_F2_KEYS) { give_up(); return; }          // uniform per CTA
+  // 2. gather (each thread copies its own segment: ~5 keys) and sort best-first
+  {
+    const uint64_t *src = a.cand_keys + ((size_t)q * a.n_seg + tid) * a.seg_cap;
+    const uint32_t o = s_off[tid];
+    for (uint32_t i = 0; i < c; ++i) skeys[o + i] = src[i];
+  }
+  int n_sort = 256;
+  while ((uint32_t)n_sort < m_all) n_sort <<= 1;
+  const int span = n_sort <= 256 ? 256 : (n_sort <= 1024 ? 1024 : STB_F2_KEYS);   // the register sort writes back its whole span
+  __syncthreads();
+  for (int i = (int)m_all + tid; i < span; i += 256) skeys[i] = STB_KEY_INVALID;
+  __syncthreads();
+  if (n_sort <= 256) stb_cta_sort_keys_t<1>(skeys, n_sort);
+  else if (n_sort <= 1024) stb_cta_sort_keys_t<4>(skeys, n_sort);
+  else stb_cta_sort_keys_t<16>(skeys, n_sort);
+  // 3. narrow to a >= A_k - 2 EPS (everything when fewer than k rows were emitted)
   float cut = -CUDART_INF_F;
   if (m_all >= k) cut = stb_key_score(skeys[k - 1]) - 2.0f * (float)STB_BATCH_EPS;
   for (uint32_t i = tid; i < m_all; i += 256)
     if (stb_key_score(skeys[i]) >= cut) atomicMax(&s_m2, i + 1);
-  if (tid == 0) {
+  if (tid == 5 * 32) {
     double q2 = 0.0;
+#pragma unroll 8
     for (int i = 0; i < STB_D; ++i) q2 = fma(sqd[i], sqd[i], q2);
     s_q2 = q2;
   }
   __syncthreads();
   const uint32_t m2 = s_m2;
-  if (m2 > STB_V2_RESCORE_CAP) { give_up(); return; }
+  if (m2 > STB_F2_RESCORE) { give_up(); return; }
+  // 4. exact canonical distances, 32 rows per pass (f64 accumulation in index order == orc_cosine_f32)
+  const double q2 = s_q2;
+  for (uint32_t c0 = 0; c0 < m2; c0 += 32) {
+    {
+      constexpr int PER = 32 * STB_ROW_F4 / 256;
+      float4 v[PER];
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const int t = tid + u * 256;
+        const uint32_t ci = c0 + (t >> 6);
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ci < m2) v[u] = __ldg(a.rows + (size_t)stb_key_row(skeys[ci]) * STB_ROW_F4 + (t & 63));
+      }
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const int t = tid + u * 256;
+        *reinterpret_cast<float4 *>(srows + (t >> 6) * STB_F2_STRIDE + (t & 63) * 4) = v[u];
+      }
+    }
+    __syncthreads();
+    if (tid < 128 && lane < 8) {
+      const int cl = warp * 8 + lane;
+      const uint32_t ci = c0 + cl;
+      if (ci < m2) {
+        const float4 *rp = reinterpret_cast<const float4 *>(srows + cl * STB_F2_STRIDE);
+        double ab = 0.0, r2 = 0.0;
+#pragma unroll 8
+        for (int i = 0; i < STB_ROW_F4; ++i) {
+          const float4 v = rp[i];
+          const double vx = (double)v.x, vy = (double)v.y, vz = (double)v.z, vw = (double)v.w;
+          ab = fma(sqd[4 * i + 0], vx, ab); r2 = fma(vx, vx, r2);
+          ab = fma(sqd[4 * i + 1], vy, ab); r2 = fma(vy, vy, r2);
+          ab = fma(sqd[4 * i + 2], vz, ab); r2 = fma(vz, vz, r2);
+          ab = fma(sqd[4 * i + 3], vw, ab); r2 = fma(vw, vw, r2);
+        }
+        double dist;
+        if (q2 == 0.0 && r2 == 0.0) dist = 0.0;
+        else if (ab == 0.0) dist = 1.0;
+        else {
+          const double t = 1.0 - ab / (sqrt(q2) * sqrt(r2));
+          dist = t > 0.0 ? t : 0.0;
+        }
+        if (dist < 100.0) { sd[ci] = dist; sr[ci] = a.row_base + (uint64_t)stb_key_row(skeys[ci]); atomicAdd(&s_pass, 1); }
+        else { sd[ci] = CUDART_INF; sr[ci] = 0xffffffffffffffffull; }
+      }
+    }
+    __syncthreads();
+  }
+  // 5. sort the (distance,row) pairs, write the top-k
   uint32_t n2 = 32;
   while (n2 < m2) n2 <<= 1;
-  // 3. exact canonical distance (f64 accumulation in index order == oracle orc_cosine_f32)
-  const double q2 = s_q2;
-  for (uint32_t c = tid; c < n2; c += 256) {
-    double d = CUDART_INF;
-    uint64_t grow = 0xffffffffffffffffull;
-    if (c < m2) {
-      const uint64_t row = stb_key_row(skeys[c]);
-      const float4 *rp = a.rows + row * STB_ROW_F4;
-      double ab = 0.0, r2 = 0.0;
-#pragma unroll 8
-      for (int i = 0; i < STB_ROW_F4; ++i) {
-        const float4 v = __ldg(rp + i);
-        const double vx = (double)v.x, vy = (double)v.y, vz = (double)v.z, vw = (double)v.w;
-        ab = fma(sqd[4 * i + 0], vx, ab); r2 = fma(vx, vx, r2);
-        ab = fma(sqd[4 * i + 1], vy, ab); r2 = fma(vy, vy, r2);
-        ab = fma(sqd[4 * i + 2], vz, ab); r2 = fma(vz, vz, r2);
-        ab = fma(sqd[4 * i + 3], vw, ab); r2 = fma(vw, vw, r2);
-      }
-      double dist;
-      if (q2 == 0.0 && r2 == 0.0) dist = 0.0;
-      else if (ab == 0.0) dist = 1.0;
-      else {
-        const double t = 1.0 - ab / (sqrt(q2) * sqrt(r2));
-        dist = t > 0.0 ? t : 0.0;
-      }
-      if (dist < 100.0) { d = dist; grow = a.row_base + row; atomicAdd(&s_pass, 1); }
-    }
-    sd[c] = d; sr[c] = grow;
-  }
+  for (uint32_t i = m2 + tid; i < n2; i += 256) { sd[i] = CUDART_INF; sr[i] = 0xffffffffffffffffull; }
   __syncthreads();
-  // 4. sort the (distance,row) pairs, write the top-k
   for (uint32_t kk = 2; kk <= n2; kk <<= 1)
     for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
       for (uint32_t i = tid; i < n2; i += 256) {
@@ -929,19 +988,20 @@ int stb_launch_batch_thresh(stb_ctx *ctx, const float *tilemax, uint32_t n_sampl
   return STB_OK;
 }
 
-int stb_launch_batch_finish2(stb_ctx *ctx, const uint64_t *cand_keys, const uint32_t *cand_cnt, uint32_t cand_cap,
-                             uint32_t nq, uint32_t top_k, const float *rows, uint64_t n_rows, uint64_t row_base,
-                             const float *queries_dev, stb_hit *out_hits, uint32_t *out_status) {
-  if (top_k > STB_V2_RESCORE_CAP || (cand_cap & (cand_cap - 1)) || cand_cap < 64) { stb_set_error("batch_finish2: bad capacity"); return STB_ERR_ARG; }
-  const size_t smem = ((size_t)cand_cap + 2 * STB_V2_RESCORE_CAP) * 8;
-  if (smem > ctx->finish2_smem_set) {
-    STB_CUDA(cudaFuncSetAttribute(stb_batch_finish2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ctx->finish2_smem_set = smem;
-  }
+uint32_t stb_batch_emit_grid(const stb_ctx *ctx, uint32_t n_tiles) {
+  return std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count);
+}
+
+int stb_launch_batch_finish2(stb_ctx *ctx, const uint64_t *cand_keys, const uint32_t *cand_cnt, uint32_t n_seg,
+                             uint32_t seg_cap, uint32_t nq, uint32_t top_k, const float *rows, uint64_t n_rows,
+                             uint64_t row_base, const float *queries_dev, stb_hit *out_hits, uint32_t *out_status) {
+  if (top_k > STB_F2_RESCORE || n_seg > 256 || n_seg == 0) { stb_set_error("batch_finish2: bad shape"); return STB_ERR_ARG; }
   Finish2Args a;
-  a.cand_keys = cand_keys; a.cand_cnt = cand_cnt; a.cand_cap = cand_cap; a.nq = nq; a.top_k = top_k;
+  a.cand_keys = cand_keys; a.cand_cnt = cand_cnt; a.n_seg = n_seg; a.seg_cap = seg_cap; a.nq = nq; a.top_k = top_k;
   a.rows = reinterpret_cast<const float4 *>(rows); a.n_rows = n_rows; a.row_base = row_base;
   a.queries = queries_dev; a.out_hits = out_hits; a.out_status = out_status;
+  constexpr size_t smem = STB_F2_KEYS * sizeof(uint64_t) + 32 * STB_F2_STRIDE * sizeof(float);
+  STB_ATTR_ONCE(ctx, STB_ATTR_FINISH2, cudaFuncSetAttribute(stb_batch_finish2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   stb_batch_finish2_kernel<<<nq, 256, smem, ctx->stream>>>(a);
   STB_CUDA(cudaGetLastError());
   ctx->kernel_launches++;

@@ -26,9 +26,10 @@
 // into the candidate set instead of being scored.
 #define STB_SCORE_EPS 1.0e-5
 // Element type of the 16-bit L2-normalised corpus shadow (K2 operand; K1's opt-in half-width
-// scan): bf16 by default, fp16 with -DSTB_SHADOW_F16=1.
+// scan): fp16 by default (same tcgen05 kind::f16 rate as bf16, 8x smaller rounding bound for unit
+// rows; validated on hardware in round 2), bf16 with -DSTB_SHADOW_F16=0.
 #ifndef STB_SHADOW_F16
-#define STB_SHADOW_F16 0
+#define STB_SHADOW_F16 1
 #endif
 // |q^ . shadow(x) - exact cosine| when only the ROW is rounded (K1 shadow scan: the query stays
 // f32): <= u * ||q^|| * ||x^|| = u (unit roundoff: 2^-8 bf16, 2^-11 fp16; fp16 components below 2^-14 add
@@ -38,6 +39,18 @@
 #else
 #define STB_SHADOW_SCAN_EPS 0.0040
 #endif
+// K1 candidate tiers (which copy of the corpus the streaming pass reads; the exact f64 re-rank
+// and the completeness proof are common to all): f32 rows (1 KiB/row), 16-bit normalised shadow
+// (512 B/row, also K2's operand), int8 codes + per-row scale (260 B/row).
+#define STB_TIER_F32 0
+#define STB_TIER_H16 1
+#define STB_TIER_Q8 2
+// q8 scores are upper bounds of the exact cosine up to the fp32 evaluation of the bound itself
+// and of the two normalisations (< 4e-6, scan_topk.cu: stb_scan_q8); proof slack:
+#define STB_Q8_SCAN_EPS 2.0e-5
+// the q8 tier always keeps K' = 128 candidates; beyond this top_k the gap between the k-th and
+// the 128th best is too small for its ~0.01 per-row error term to prove anything
+#define STB_Q8_MAX_K 16
 
 void stb_set_error(const char *fmt, ...);
 
@@ -61,6 +74,8 @@ struct stb_ctx {
   size_t block_keys_cap;    // in keys
   unsigned int *counters;   // tree arrival counters (zeroed; kernels re-zero)
   size_t counters_cap;
+  unsigned long long *tickets;      // K1 tile-ticket counter (monotonic; scan_topk.cu: stb_for_each_tile)
+  unsigned long long ticket_next;   // its value when the next top-k launch starts
   float *q_dev;             // 256 f32 staging for host queries
   stb_hit *hits_dev;        // result hits (top-k path)
   size_t hits_cap;
@@ -147,20 +162,30 @@ struct stb_corpus {
   uint64_t shadow_rows;      // rows covered by `shadow` (== n when valid)
   uint64_t shadow_cap_tiles;
   int shadow_bad;            // 1: some row cannot be normalised in fp32 -> tensor path refused
-  uint32_t shadow_tries, shadow_proven;   // STB_SCAN_SHADOW bookkeeping: the half-width scan is skipped
-                                          // once it proves fewer than half of its results on this corpus
+  // K1 tier q8: int8 codes [capacity][256] + per-row scale, built lazily / by stb_corpus_prepare
+  uint8_t *q8;
+  float *q8_scale;
+  uint64_t q8_rows;          // rows covered (== n when valid)
+  uint64_t q8_cap_rows;
+  int q8_bad;
+  // per-tier bookkeeping: a reduced-width tier is skipped once it proves fewer than half of its
+  // results on this corpus (index = STB_TIER_*)
+  uint32_t tier_tries[3], tier_proven[3];
+  uint32_t searches_since_change;   // lazy builds wait for the second query on an unchanged corpus
 };
 
 // ---- scan_topk.cu -------------------------------------------------------------
 // Fast path: one kernel = scan + per-warp running top-K' + CTA/tree merge +
 // exact f64 re-rank + completeness check.  q_dev: 256 f32 on device.
 // n_ranges > 0: ranges_dev holds local [begin,end,vstart] triples.
-int stb_launch_scan_topk(stb_ctx *ctx, const float *rows, uint64_t n_rows,
-                         uint64_t row_base, const float *q_dev, uint32_t top_k,
+// tier: STB_TIER_* -- which copy of `c` the streaming pass reads (must exist and be current).
+int stb_launch_scan_topk(stb_ctx *ctx, const stb_corpus *c, int tier, const float *q_dev, uint32_t top_k,
                          const uint64_t *ranges_dev, uint32_t n_ranges,
                          uint64_t n_virtual, stb_hit *out_hits_dev,
-                         uint32_t *out_status_dev, const StbXchgArgs *xchg = nullptr,
-                         const uint8_t *shadow = nullptr);
+                         uint32_t *out_status_dev, const StbXchgArgs *xchg = nullptr);
+// int8 codes + scales of rows [first_row, n_rows) (q8 tier)
+int stb_launch_q8_build(stb_ctx *ctx, const float *rows_dev, uint64_t first_row, uint64_t n_rows, uint8_t *out,
+                        float *scale, int *bad_flag_dev);
 // Largest top_k the fast path serves.
 uint32_t stb_scan_topk_max_k(void);
 // Collect path: every row whose approximate cosine >= cos_floor (or that cannot be
@@ -190,7 +215,7 @@ int stb_launch_hits_merge_batch(stb_ctx *ctx, const stb_hit *lists_dev, uint32_t
                                 uint32_t per_list, uint32_t top_k, stb_hit *out_dev);
 
 // opt-in to > 48 KiB dynamic shared memory (or another function attribute) once per context
-enum { STB_ATTR_GEMM0 = 0, STB_ATTR_GEMM1, STB_ATTR_MERGE, STB_ATTR_IVF_PROBE, STB_ATTR_IVF_V2 };
+enum { STB_ATTR_GEMM0 = 0, STB_ATTR_GEMM1, STB_ATTR_MERGE, STB_ATTR_IVF_PROBE, STB_ATTR_IVF_V2, STB_ATTR_FINISH2 };
 #define STB_ATTR_ONCE(ctx, bit, call)                         \
   do {                                                        \
     if (!((ctx)->func_attr_mask & (1u << (bit)))) {           \
@@ -219,8 +244,11 @@ int stb_launch_batch_gemm_emit(stb_ctx *ctx, const uint8_t *a_tiles, uint32_t m_
                                uint32_t cand_cap);
 int stb_launch_batch_thresh(stb_ctx *ctx, const float *tilemax, uint32_t n_sample, uint32_t nq,
                             uint32_t q_pad, uint32_t top_k, float *thr);
-int stb_launch_batch_finish2(stb_ctx *ctx, const uint64_t *cand_keys, const uint32_t *cand_cnt,
-                             uint32_t cand_cap, uint32_t nq, uint32_t top_k, const float *rows,
+// candidates live in per-(query, CTA) segments: keys [q_pad][n_seg][seg_cap], counts [q_pad][n_seg];
+// n_seg = stb_batch_emit_grid() = the grid the emitting GEMM runs with
+uint32_t stb_batch_emit_grid(const stb_ctx *ctx, uint32_t n_tiles);
+int stb_launch_batch_finish2(stb_ctx *ctx, const uint64_t *cand_keys, const uint32_t *cand_cnt, uint32_t n_seg,
+                             uint32_t seg_cap, uint32_t nq, uint32_t top_k, const float *rows,
                              uint64_t n_rows, uint64_t row_base, const float *queries_dev,
                              stb_hit *out_hits, uint32_t *out_status);
 void stb_batch_build_params(int *shadow_is_f16, double *eps);
@@ -257,4 +285,62 @@ __device__ __forceinline__ bool stb_hit_less(double da, uint64_t ra, double db,
                                              uint64_t rb) {
   return (da < db) || (da == db && ra < rb);
 }
+
+// Ascending bitonic sort of n keys (power of two, <= R*256) held in shared memory,
+// done in registers: element i = r*256 + tid lives in register k[r] of thread tid, so a
+// compare-exchange at distance j is a register swap (j >= 256), a shuffle (j < 32) or a
+// shared-memory exchange (32 <= j < 256; the only steps that need __syncthreads).
+// Requires blockDim.x == 256.
+template <int R>
+__device__ __forceinline__ void stb_cta_sort_keys_t(uint64_t *keys, int n) {
+  const int tid = threadIdx.x;
+  uint64_t k[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) k[r] = (r * 256 + tid < n) ? keys[r * 256 + tid] : STB_KEY_INVALID;
+  __syncthreads();
+  for (int kk = 2; kk <= n; kk <<= 1) {
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      if (j >= 256) {
+        // in-thread exchange; dr spelled out so k[] stays in registers
+#pragma unroll
+        for (int dr = 1; dr < R; dr <<= 1) {
+          if (j == dr * 256) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              if ((r & dr) == 0) {
+                const bool up = (((r * 256 + tid) & kk) == 0);
+                uint64_t x = k[r], y = k[r | dr];
+                if ((x > y) == up) { k[r] = y; k[r | dr] = x; }
+              }
+            }
+          }
+        }
+      } else if (j >= 32) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) keys[r * 256 + tid] = k[r];
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int i = r * 256 + tid;
+          const uint64_t other = keys[i ^ j];
+          const bool keep_min = (((i & j) == 0) == ((i & kk) == 0));
+          k[r] = keep_min ? (k[r] < other ? k[r] : other) : (k[r] > other ? k[r] : other);
+        }
+        __syncthreads();
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int i = r * 256 + tid;
+          const uint64_t other = __shfl_xor_sync(0xffffffffu, k[r], j);
+          const bool keep_min = (((i & j) == 0) == ((i & kk) == 0));
+          k[r] = keep_min ? (k[r] < other ? k[r] : other) : (k[r] > other ? k[r] : other);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) keys[r * 256 + tid] = k[r];
+  __syncthreads();
+}
+
 #endif

@@ -21,6 +21,8 @@
 
 #include <cuda_fp16.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 #ifndef STB_SCAN_U
@@ -51,34 +53,87 @@ struct ScanArgs {
   const uint64_t *vstart;    // [n_ranges+1] virtual prefix (ranges mode)
   const uint64_t *rbegin;    // [n_ranges]   local first row of each range
   uint32_t n_ranges;
+  // dynamic tile schedule (top-k kernel; null = static warp-strided schedule):
+  unsigned long long *tickets;   // monotonic counter shared by every launch of the context
+  unsigned long long t_base;     // its value when this launch starts (host-tracked)
+  uint64_t t_bulk;               // tickets [0, t_bulk) cover STB_TICKET_TILES tiles each, later ones one tile
 };
+#define STB_TICKET_TILES 4
 
-// virtual row -> local row (ranges mode): largest idx with vstart[idx] <= v.
-__device__ __forceinline__ uint32_t stb_map_row(const ScanArgs &a, uint64_t v) {
-  uint32_t lo = 0, hi = a.n_ranges;
-  while (hi - lo > 1) {
-    uint32_t mid = (lo + hi) >> 1;
-    if (__ldg(a.vstart + mid) <= v) lo = mid; else hi = mid;
+// ---- tile schedule + row map shared by the three scans -----------------------------------
+// RANGES == 0: whole shard, tiles are warp-strided (the grid streams one contiguous window).
+// RANGES == 1: row ranges (workspace path filter).  Blocks of WB consecutive tiles are
+// warp-strided and a warp walks each block in order, so the virtual->local row map costs one
+// binary search per block per lane and a forward step per row afterwards (the per-row
+// 15-step search of round 1 held this mode at 0.52 of the HBM peak).
+// Dynamic schedule (args.tickets != null): warps draw tickets from one atomic counter; a ticket is
+// STB_TICKET_TILES consecutive tiles, except that the last ~2 tiles per warp are handed out one
+// by one so the grid drains evenly.  Tickets are issued in row order, so the grid still streams
+// one contiguous window.  Why: the grid fills every CTA slot, and with a static partition a CTA
+// that starts late finishes late -- under PDL the next query's last CTA cannot start before this
+// query's final (merge) CTA exits, which exposed the whole tail (10 us at K'=32, 77 us at
+// K'=128) on every pipelined query.  With tickets a late CTA simply finds less work.
+// Every warp makes exactly one failing draw, so a launch advances the counter by
+// n_tickets + total_warps -- the host tracks the base of the next launch with that.
+template <int RANGES, int WB, class Body>
+__device__ __forceinline__ void stb_for_each_tile(const ScanArgs &args, uint64_t n_tiles, Body &&body) {
+  if (args.tickets) {
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+      unsigned long long t = 0;
+      if (lane == 0) t = atomicAdd(args.tickets, 1ull);
+      t = __shfl_sync(0xffffffffu, t, 0) - args.t_base;
+      uint64_t t0, t1;
+      if (t < args.t_bulk) { t0 = t * STB_TICKET_TILES; t1 = t0 + STB_TICKET_TILES; }
+      else { t0 = args.t_bulk * STB_TICKET_TILES + (t - args.t_bulk); t1 = t0 + 1; }
+      if (t0 >= n_tiles) break;
+      for (uint64_t tile = t0; tile < t1; ++tile) body(tile, tile == t0);
+    }
+    return;
   }
-  return (uint32_t)(__ldg(a.rbegin + lo) + (v - __ldg(a.vstart + lo)));
+  const uint64_t warps_total = (uint64_t)gridDim.x * (blockDim.x >> 5);
+  const uint64_t warp_id = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if constexpr (RANGES == 0) {
+    for (uint64_t tile = warp_id; tile < n_tiles; tile += warps_total) body(tile, false);
+  } else {
+    const uint64_t n_blocks = (n_tiles + WB - 1) / WB;
+    for (uint64_t blk = warp_id; blk < n_blocks; blk += warps_total) {
+      const uint64_t t0 = blk * WB;
+      const uint64_t t1 = t0 + WB < n_tiles ? t0 + WB : n_tiles;
+      for (uint64_t tile = t0; tile < t1; ++tile) body(tile, tile == t0);
+    }
+  }
 }
 
-// Approximate-cosine scan.  Calls sink(score, local_row) once per 4*U-row tile with
-// a warp-uniform control flow; lanes that do not represent a row pass -inf.
-// RANGES: 0 = whole corpus; 1 = row ranges, binary search per row; 2 = row ranges, every warp
-// walks ONE contiguous block of virtual rows and advances its range index as it goes
-// (one search per warp instead of one per row; opt-in, STB_RANGES_WALK=1).
-template <int U, int RANGES, class Sink>
-__device__ __forceinline__ void stb_scan_rows(const ScanArgs &args, Sink &sink) {
-  const int lane = threadIdx.x & 31;
-  const int g = lane >> 3;   // row group inside the warp
-  const int j = lane & 7;    // 16-byte column slot inside the group
-  // query slice of this lane: float4 index j + 8*i
-  float4 q[8];
-  const float4 *q4 = reinterpret_cast<const float4 *>(args.q);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) q[i] = __ldg(q4 + j + 8 * i);
-  // ||q||^2 in the same fixed order as every row norm
+template <int RANGES>
+struct StbRowMap {
+  uint32_t rlo;
+  bool fresh;
+  __device__ __forceinline__ void restart() { fresh = true; }
+  // virtual row -> local row: largest idx with vstart[idx] <= v.  A lane's virtual rows only
+  // grow inside a block: search once, then step to the next range(s).
+  __device__ __forceinline__ uint32_t map(const ScanArgs &a, uint64_t v) {
+    if constexpr (RANGES == 0) return (uint32_t)v;
+    else {
+      if (fresh) {
+        uint32_t lo = 0, hi = a.n_ranges;
+        while (hi - lo > 1) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (__ldg(a.vstart + mid) <= v) lo = mid; else hi = mid;
+        }
+        rlo = lo;
+        fresh = false;
+      } else {
+        while (rlo + 1 < a.n_ranges && __ldg(a.vstart + rlo + 1) <= v) ++rlo;
+      }
+      return (uint32_t)(__ldg(a.rbegin + rlo) + (v - __ldg(a.vstart + rlo)));
+    }
+  }
+};
+
+// fixed-order ||q||^2 of a lane's 8 float4 + 8-lane group reduction; classifies the query
+struct StbQueryNorm { float rq; bool q_zero, q_bad; };
+__device__ __forceinline__ StbQueryNorm stb_query_norm(const float4 (&q)[8]) {
   float qx = 0.f, qy = 0.f, qz = 0.f, qw = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -95,24 +150,35 @@ __device__ __forceinline__ void stb_scan_rows(const ScanArgs &args, Sink &sink) 
   for (int i = 0; i < 8; ++i)
     q_any |= (q[i].x != 0.f) | (q[i].y != 0.f) | (q[i].z != 0.f) | (q[i].w != 0.f);
   q_any = __any_sync(0xffffffffu, q_any);   // all four groups hold the same query
-  const bool q_zero = (b2 == 0.f) && !q_any;
-  const bool q_bad = !q_zero && !(b2 >= 1e-30f && b2 <= 1e30f);  // NaN/inf/denormal/underflow
-  const float rq = q_zero ? 0.f : rsqrtf(b2);
+  StbQueryNorm r;
+  r.q_zero = (b2 == 0.f) && !q_any;
+  r.q_bad = !r.q_zero && !(b2 >= 1e-30f && b2 <= 1e30f);  // NaN/inf/denormal/underflow
+  r.rq = r.q_zero ? 0.f : rsqrtf(b2);
+  return r;
+}
 
-  const uint64_t tile_rows = 4 * U;
+// Approximate-cosine scan over the f32 rows.  Calls sink(score, local_row) once per 4*U-row
+// tile with a warp-uniform control flow; lanes that do not represent a row pass -inf.
+template <int U, int RANGES, class Sink>
+__device__ __forceinline__ void stb_scan_rows(const ScanArgs &args, Sink &sink) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 3;   // row group inside the warp
+  const int j = lane & 7;    // 16-byte column slot inside the group
+  // query slice of this lane: float4 index j + 8*i
+  float4 q[8];
+  const float4 *q4 = reinterpret_cast<const float4 *>(args.q);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) q[i] = __ldg(q4 + j + 8 * i);
+  const StbQueryNorm qn = stb_query_norm(q);
+  const bool q_zero = qn.q_zero, q_bad = qn.q_bad;
+  const float rq = qn.rq;
+
+  constexpr uint64_t tile_rows = 4 * U;
   const uint64_t n_tiles = (args.n_virtual + tile_rows - 1) / tile_rows;
-  const uint64_t warps_total = (uint64_t)gridDim.x * (blockDim.x >> 5);
-  const uint64_t warp_id = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-
-  uint64_t t_begin = warp_id, t_end = n_tiles, t_step = warps_total;
-  if constexpr (RANGES == 2) {
-    const uint64_t per = (n_tiles + warps_total - 1) / warps_total;
-    t_begin = warp_id * per;
-    t_end = t_begin + per < n_tiles ? t_begin + per : n_tiles;
-    t_step = 1;
-  }
-  [[maybe_unused]] uint32_t rlo = 0xffffffffu;       // RANGES == 2: current range of this lane's rows
-  for (uint64_t tile = t_begin; tile < t_end; tile += t_step) {
+  StbRowMap<RANGES> rmap;
+  rmap.restart();
+  stb_for_each_tile<RANGES, 64 / (4 * U)>(args, n_tiles, [&](uint64_t tile, bool first) {
+    if (first) rmap.restart();
     float4 a[U][8];
     uint32_t row[U];
     bool valid[U];
@@ -121,22 +187,7 @@ __device__ __forceinline__ void stb_scan_rows(const ScanArgs &args, Sink &sink) 
       uint64_t v = tile * tile_rows + (uint64_t)(u * 4 + g);
       valid[u] = v < args.n_virtual;
       uint64_t vc = valid[u] ? v : (args.n_virtual - 1);
-      if constexpr (RANGES == 2) {
-        // this lane's virtual rows only grow: search once, then step to the next range(s)
-        if (rlo == 0xffffffffu) {
-          uint32_t lo = 0, hi = args.n_ranges;
-          while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (__ldg(args.vstart + mid) <= vc) lo = mid; else hi = mid;
-          }
-          rlo = lo;
-        } else {
-          while (rlo + 1 < args.n_ranges && __ldg(args.vstart + rlo + 1) <= vc) ++rlo;
-        }
-        row[u] = (uint32_t)(__ldg(args.rbegin + rlo) + (vc - __ldg(args.vstart + rlo)));
-      } else {
-        row[u] = RANGES ? stb_map_row(args, vc) : (uint32_t)vc;
-      }
+      row[u] = rmap.map(args, vc);
       const float4 *p = args.rows + (size_t)row[u] * STB_ROW_F4 + j;
 #pragma unroll
       for (int i = 0; i < 8; ++i) a[u][i] = stb_ld_stream(p + 8 * i);
@@ -182,14 +233,14 @@ __device__ __forceinline__ void stb_scan_rows(const ScanArgs &args, Sink &sink) 
     for (int u = 0; u < U; ++u)
       if (j == u) { s = sc[u]; r = row[u]; }
     sink.template consume<4 * U>(s, r);
-  }
+  });
 }
 
-// Half-width scan (opt-in, STB_SCAN_SHADOW=1): the same running top-K' selection, but the scores
-// come from the 16-bit L2-normalised shadow that K2 uses (512 B per row instead of 1 KiB), so
-// the HBM-bound pass moves half the bytes.  The exact f64 re-rank and the completeness proof
-// are unchanged except for the margin (STB_SHADOW_SCAN_EPS: only the row is rounded, the query
-// stays f32).  Shadow layout (batch_scan.cu): tile t = row / 256 -> 4 K-slabs x [256 rows x 128 B],
+// Half-width scan (tier "h16"): the same running top-K' selection, but the scores come from the
+// 16-bit L2-normalised shadow that K2 uses (512 B per row instead of 1 KiB), so the HBM-bound
+// pass moves half the bytes.  The exact f64 re-rank and the completeness proof are unchanged
+// except for the margin (STB_SHADOW_SCAN_EPS: only the row is rounded, the query stays f32).
+// Shadow layout (batch_scan.cu): tile t = row / 256 -> 4 K-slabs x [256 rows x 128 B],
 // 16-byte chunk index XOR (row % 8).  Lane j of a row's 8-lane group reads PHYSICAL chunk
 // j ^ (row % 8) of every slab, i.e. LOGICAL chunk j = elements s*64 + 8j .. +8 (s = 0..3), so
 // each lane pairs a fixed 32-element slice of the query with every row; the group still
@@ -202,7 +253,7 @@ __device__ __forceinline__ float2 stb_shadow_pair(uint32_t w) {
 #endif
 }
 
-template <int U, class Sink>
+template <int U, int RANGES, class Sink>
 __device__ __forceinline__ void stb_scan_shadow(const ScanArgs &args, const uint8_t *shadow, Sink &sink) {
   const int lane = threadIdx.x & 31;
   const int g = lane >> 3;   // row group inside the warp
@@ -212,30 +263,16 @@ __device__ __forceinline__ void stb_scan_shadow(const ScanArgs &args, const uint
   const float4 *q4 = reinterpret_cast<const float4 *>(args.q);
 #pragma unroll
   for (int sl = 0; sl < 4; ++sl) { q[2 * sl] = __ldg(q4 + sl * 16 + 2 * j); q[2 * sl + 1] = __ldg(q4 + sl * 16 + 2 * j + 1); }
-  float qx = 0.f, qy = 0.f, qz = 0.f, qw = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    qx = fmaf(q[i].x, q[i].x, qx); qy = fmaf(q[i].y, q[i].y, qy);
-    qz = fmaf(q[i].z, q[i].z, qz); qw = fmaf(q[i].w, q[i].w, qw);
-  }
-  float b2 = (qx + qy) + (qz + qw);
-  b2 += __shfl_xor_sync(0xffffffffu, b2, 4);
-  b2 += __shfl_xor_sync(0xffffffffu, b2, 2);
-  b2 += __shfl_xor_sync(0xffffffffu, b2, 1);
-  bool q_any = false;
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    q_any |= (q[i].x != 0.f) | (q[i].y != 0.f) | (q[i].z != 0.f) | (q[i].w != 0.f);
-  q_any = __any_sync(0xffffffffu, q_any);
-  const bool q_zero = (b2 == 0.f) && !q_any;
-  const bool q_bad = !q_zero && !(b2 >= 1e-30f && b2 <= 1e30f);
-  const float rq = q_zero ? 0.f : rsqrtf(b2);
+  const StbQueryNorm qn = stb_query_norm(q);
+  const bool q_bad = qn.q_bad;
+  const float rq = qn.rq;
 
-  const uint64_t tile_rows = 4 * U;
+  constexpr uint64_t tile_rows = 4 * U;
   const uint64_t n_tiles = (args.n_virtual + tile_rows - 1) / tile_rows;
-  const uint64_t warps_total = (uint64_t)gridDim.x * (blockDim.x >> 5);
-  const uint64_t warp_id = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  for (uint64_t tile = warp_id; tile < n_tiles; tile += warps_total) {
+  StbRowMap<RANGES> rmap;
+  rmap.restart();
+  stb_for_each_tile<RANGES, 64 / (4 * U)>(args, n_tiles, [&](uint64_t tile, bool first) {
+    if (first) rmap.restart();
     uint4 a[U][4];
     uint32_t row[U];
     bool valid[U];
@@ -244,9 +281,9 @@ __device__ __forceinline__ void stb_scan_shadow(const ScanArgs &args, const uint
       const uint64_t v = tile * tile_rows + (uint64_t)(u * 4 + g);
       valid[u] = v < args.n_virtual;
       const uint64_t vc = valid[u] ? v : (args.n_virtual - 1);
-      row[u] = (uint32_t)vc;
-      const uint32_t rr = (uint32_t)(vc & 255u);
-      const uint8_t *p = shadow + (vc >> 8) * (size_t)(256 * 512) + (size_t)(rr >> 3) * 1024 + (size_t)(rr & 7u) * 128 +
+      row[u] = rmap.map(args, vc);
+      const uint32_t rr = row[u] & 255u;
+      const uint8_t *p = shadow + (size_t)(row[u] >> 8) * (size_t)(256 * 512) + (size_t)(rr >> 3) * 1024 + (size_t)(rr & 7u) * 128 +
                          (size_t)((j ^ (int)(rr & 7u)) * 16);
 #pragma unroll
       for (int sl = 0; sl < 4; ++sl) {
@@ -281,7 +318,172 @@ __device__ __forceinline__ void stb_scan_shadow(const ScanArgs &args, const uint
     for (int u = 0; u < U; ++u)
       if (j == u) { s = sc[u]; r = row[u]; }
     sink.template consume<4 * U>(s, r);
+  });
+}
+
+// Quarter-width scan (tier "q8"): candidates come from an 8-bit copy of the corpus -- row x is
+// L2-normalised in fp32 (x^), scaled by its own s = max|x^_i| / 127 and rounded to int8
+// (stb_q8_build_kernel): 256 B + one f32 scale per row = 260 B instead of 1 KiB.  The query is
+// normalised and quantised to 16 bits per component (q16 = rint(q^ * S), S = 32639 / max|q^_i|),
+// split into two signed bytes (q16 = 256 * hi + lo) so the dot product is two dp4a chains,
+// exact in int32 (|dot| <= 127 * 32639 * 256 < 2^31).  What the list ranks by is not the
+// approximate cosine a = s * dot / S but an UPPER BOUND of the exact one:
+//     |c - a| <= sum_i |q~_i| |x^_i - s x8_i|  +  sum_i |q^_i - q~_i| |x^_i|
+//             <= s * (0.5 + 3e-5) * ||q16||_1 / S   +   (0.6 / S) * ||x^||_1 ,  ||x^||_1 <= 16.001
+//     u = s * (dot / S + 0.50025 * ||q16||_1 / S) + 9.7 / S          >=  c - 1e-5
+// (||q16||_1 is an exact integer sum).  Every row dropped from the lists has u <= u_min, hence
+// exact cosine <= u_min + 1e-5: the completeness proof is the f32 one with the per-row error
+// term folded into the score, so rows with a large scale are promoted instead of widening a
+// global margin.  A zero or unscorable query makes every score +inf: the proof fails and the
+// caller falls through to the f32 tiers.
+template <int U, int RANGES, class Sink>
+__device__ __forceinline__ void stb_scan_q8(const ScanArgs &args, const uint8_t *q8, const float *q8_scale, Sink &sink) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 3;   // row group inside the warp
+  const int j = lane & 7;    // this lane reads row bytes [16j, 16j+16) and [128+16j, 128+16j+16)
+  float4 q[8];
+  const float4 *q4 = reinterpret_cast<const float4 *>(args.q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { q[i] = __ldg(q4 + 4 * j + i); q[4 + i] = __ldg(q4 + 32 + 4 * j + i); }
+  const StbQueryNorm qn = stb_query_norm(q);
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(q[i].x), fabsf(q[i].y)), fmaxf(fabsf(q[i].z), fabsf(q[i].w))));
   }
+  amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+  amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+  amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+  amax *= qn.rq;                                            // max |q^_i|
+  const bool q_unusable = qn.q_zero || qn.q_bad || !(amax > 0.f && amax <= 1.0001f);
+  const float S = q_unusable ? 1.f : 32639.0f / amax;
+  const float qs = qn.rq * S;
+  uint32_t qhi[8], qlo[8];
+  int l1 = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float f[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
+    uint32_t hw = 0, lw = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      int v = q_unusable ? 0 : __float2int_rn(f[e] * qs);
+      v = max(-32639, min(32639, v));
+      l1 += abs(v);
+      const int lo = ((v + 128) & 255) - 128;               // signed low byte
+      const int hi = (v - lo) >> 8;                         // exact: v - lo is a multiple of 256
+      hw |= (uint32_t)(hi & 255) << (8 * e);
+      lw |= (uint32_t)(lo & 255) << (8 * e);
+    }
+    qhi[i] = hw; qlo[i] = lw;
+  }
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 4);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  const float inv_S = 1.0f / S;
+  const float h_l1 = 0.50025f * (float)l1 * inv_S;          // (0.5 + 3e-5 + fp slack) * ||q~||_1
+  const float e_q = 9.7f * inv_S;
+
+  constexpr uint64_t tile_rows = 4 * U;
+  const uint64_t n_tiles = (args.n_virtual + tile_rows - 1) / tile_rows;
+  StbRowMap<RANGES> rmap;
+  rmap.restart();
+  stb_for_each_tile<RANGES, 2>(args, n_tiles, [&](uint64_t tile, bool first) {
+    if (first) rmap.restart();
+    uint4 a[U][2];
+    float sc_row[U];
+    uint32_t row[U];
+    bool valid[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t v = tile * tile_rows + (uint64_t)(u * 4 + g);
+      valid[u] = v < args.n_virtual;
+      const uint64_t vc = valid[u] ? v : (args.n_virtual - 1);
+      row[u] = rmap.map(args, vc);
+      const uint8_t *p = q8 + (size_t)row[u] * 256 + (size_t)j * 16;
+      const float4 t0 = stb_ld_stream(reinterpret_cast<const float4 *>(p));
+      const float4 t1 = stb_ld_stream(reinterpret_cast<const float4 *>(p + 128));
+      a[u][0] = make_uint4(__float_as_uint(t0.x), __float_as_uint(t0.y), __float_as_uint(t0.z), __float_as_uint(t0.w));
+      a[u][1] = make_uint4(__float_as_uint(t1.x), __float_as_uint(t1.y), __float_as_uint(t1.z), __float_as_uint(t1.w));
+      sc_row[u] = __ldg(q8_scale + row[u]);                 // 8 lanes, one address
+    }
+    float sc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int dh = 0, dl = 0;
+      const uint32_t w[8] = {a[u][0].x, a[u][0].y, a[u][0].z, a[u][0].w, a[u][1].x, a[u][1].y, a[u][1].z, a[u][1].w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        dh = __dp4a((int)w[i], (int)qhi[i], dh);
+        dl = __dp4a((int)w[i], (int)qlo[i], dl);
+      }
+      int dot = dh * 256 + dl;
+      dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+      const float s = q_unusable ? CUDART_INF_F : fmaf(sc_row[u], fmaf((float)dot, inv_S, h_l1), e_q);
+      sc[u] = valid[u] ? s : -CUDART_INF_F;
+    }
+    float s = -CUDART_INF_F;
+    uint32_t r = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (j == u) { s = sc[u]; r = row[u]; }
+    sink.template consume<4 * U>(s, r);
+  });
+}
+
+// q8 builder: one warp per row; lane l owns elements 8l .. 8l+7.  Rows whose fp32 squared norm
+// is not a normal number set *bad_flag (the tier is then refused for this corpus, like the
+// 16-bit shadow); true zero rows get scale 0 and all-zero codes (score = the query's slack).
+__global__ void __launch_bounds__(256)
+stb_q8_build_kernel(const float4 *__restrict__ rows, uint64_t first_row, uint64_t n_rows, uint8_t *__restrict__ out,
+                    float *__restrict__ scale, int *bad_flag) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t row = first_row + (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const float4 v0 = __ldg(rows + row * STB_ROW_F4 + 2 * lane);
+  const float4 v1 = __ldg(rows + row * STB_ROW_F4 + 2 * lane + 1);
+  float ss = v0.x * v0.x + v0.y * v0.y + v0.z * v0.z + v0.w * v0.w + v1.x * v1.x + v1.y * v1.y + v1.z * v1.z + v1.w * v1.w;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  float inv = 0.f;
+  if (ss != 0.f) {
+    if (!(ss >= 1e-30f && ss <= 1e30f)) { if (lane == 0) atomicExch(bad_flag, 1); }   // NaN/inf/extreme
+    else inv = rsqrtf(ss);
+  } else {
+    const bool nz = (v0.x != 0.f) | (v0.y != 0.f) | (v0.z != 0.f) | (v0.w != 0.f) | (v1.x != 0.f) | (v1.y != 0.f) |
+                    (v1.z != 0.f) | (v1.w != 0.f);
+    if (__any_sync(0xffffffffu, nz) && lane == 0) atomicExch(bad_flag, 1);             // underflowed tiny row
+  }
+  const float x[8] = {v0.x * inv, v0.y * inv, v0.z * inv, v0.w * inv, v1.x * inv, v1.y * inv, v1.z * inv, v1.w * inv};
+  float am = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) am = fmaxf(am, fabsf(x[e]));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, off));
+  const float s = am * (1.0f / 127.0f);
+  const float inv_s = am > 0.f ? 127.0f / am : 0.f;
+  uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int c0 = max(-127, min(127, __float2int_rn(x[e] * inv_s)));
+    const int c1 = max(-127, min(127, __float2int_rn(x[4 + e] * inv_s)));
+    w0 |= (uint32_t)(c0 & 255) << (8 * e);
+    w1 |= (uint32_t)(c1 & 255) << (8 * e);
+  }
+  *reinterpret_cast<uint2 *>(out + row * 256 + (size_t)lane * 8) = make_uint2(w0, w1);
+  if (lane == 0) scale[row] = s;
+}
+
+int stb_launch_q8_build(stb_ctx *ctx, const float *rows_dev, uint64_t first_row, uint64_t n_rows, uint8_t *out,
+                        float *scale, int *bad_flag_dev) {
+  if (first_row >= n_rows) return STB_OK;
+  const unsigned blocks = (unsigned)((n_rows - first_row + 7) / 8);
+  stb_q8_build_kernel<<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const float4 *>(rows_dev), first_row, n_rows, out, scale,
+                                                       bad_flag_dev);
+  STB_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  return STB_OK;
 }
 
 // ---------------------------------------------------------------- top-K' sink ---
@@ -378,63 +580,6 @@ struct TopSink {
   }
 };
 
-// Ascending bitonic sort of n keys (power of two, <= R*256) held in shared memory,
-// done in registers: element i = r*256 + tid lives in register k[r] of thread tid, so a
-// compare-exchange at distance j is a register swap (j >= 256), a shuffle (j < 32) or a
-// shared-memory exchange (32 <= j < 256; the only steps that need __syncthreads).
-// Requires blockDim.x == 256.
-template <int R>
-__device__ __forceinline__ void stb_cta_sort_keys_t(uint64_t *keys, int n) {
-  const int tid = threadIdx.x;
-  uint64_t k[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) k[r] = (r * 256 + tid < n) ? keys[r * 256 + tid] : STB_KEY_INVALID;
-  __syncthreads();
-  for (int kk = 2; kk <= n; kk <<= 1) {
-    for (int j = kk >> 1; j > 0; j >>= 1) {
-      if (j >= 256) {
-        // in-thread exchange; dr spelled out so k[] stays in registers
-#pragma unroll
-        for (int dr = 1; dr < R; dr <<= 1) {
-          if (j == dr * 256) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-              if ((r & dr) == 0) {
-                const bool up = (((r * 256 + tid) & kk) == 0);
-                uint64_t x = k[r], y = k[r | dr];
-                if ((x > y) == up) { k[r] = y; k[r | dr] = x; }
-              }
-            }
-          }
-        }
-      } else if (j >= 32) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) keys[r * 256 + tid] = k[r];
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const int i = r * 256 + tid;
-          const uint64_t other = keys[i ^ j];
-          const bool keep_min = (((i & j) == 0) == ((i & kk) == 0));
-          k[r] = keep_min ? (k[r] < other ? k[r] : other) : (k[r] > other ? k[r] : other);
-        }
-        __syncthreads();
-      } else {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const int i = r * 256 + tid;
-          const uint64_t other = __shfl_xor_sync(0xffffffffu, k[r], j);
-          const bool keep_min = (((i & j) == 0) == ((i & kk) == 0));
-          k[r] = keep_min ? (k[r] < other ? k[r] : other) : (k[r] > other ? k[r] : other);
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < R; ++r) keys[r * 256 + tid] = k[r];
-  __syncthreads();
-}
-
 __device__ __forceinline__ void stb_cta_sort_keys(uint64_t *keys, int n) {
   static_assert(STB_SCAN_THREADS == 256, "register sort assumes 256 threads");
   if (n <= 256) stb_cta_sort_keys_t<1>(keys, n);
@@ -451,7 +596,9 @@ struct TopkArgs {
   uint32_t top_k;
   StbXchgArgs xchg;          // world == 0: no cross-GPU exchange
   unsigned long long *dbg;   // STB_TAIL_TIMING builds only: phase timestamps (ns)
-  const uint8_t *shadow;     // SRC == 1 only: 16-bit normalised corpus shadow (UMMA tile layout)
+  const uint8_t *shadow;     // SRC == 1: 16-bit normalised corpus shadow (UMMA tile layout)
+  const uint8_t *q8;         // SRC == 2: int8 codes [n][256] ...
+  const float *q8_scale;     //           ... and per-row scales [n]
 };
 
 __device__ __forceinline__ unsigned long long stb_globaltimer() {
@@ -504,25 +651,37 @@ __device__ __forceinline__ int stb_pad_and_sort(uint64_t *skeys, int c, int min_
 
 #define STB_RR_STRIDE 260   // floats per staged row (1 KiB + 16 B pad: conflict-free LDS.128)
 
-template <int E, int U, int RANGES, int SRC = 0>
+// E: 32*E candidates per warp / CTA / inner tree list.  EF: the ROOT of the merge tree (the CTA
+// itself when the grid is one CTA) keeps 32*EF >= 32*E candidates for the exact re-rank.
+// EF > E lets a tier with a wide error term (q8) re-rank 128 rows while every level below the
+// root moves 32-key lists -- the tail costs what the f32 tier's does.  Completeness is tracked
+// explicitly: every node that drops keys publishes the best score it dropped (<= its last kept
+// key), the bounds are max-reduced up the tree, and the proof compares the k-th exact distance
+// with that bound instead of "the K'-th key of one uniform list".
+template <int E, int U, int RANGES, int SRC = 0, int EF = E>
 __global__ void __launch_bounds__(STB_SCAN_THREADS, STB_SCAN_MINB)
 stb_scan_topk_kernel(const TopkArgs args) {
-  // SRC 0: scores from the f32 rows; SRC 1: from the 16-bit shadow (wider proof margin)
-  constexpr double kScoreEps = SRC ? STB_SHADOW_SCAN_EPS : STB_SCORE_EPS;
-  constexpr int KP = 32 * E;
+  // SRC 0: scores from the f32 rows; SRC 1: from the 16-bit shadow (wider proof margin);
+  // SRC 2: upper bounds of the exact cosine from the int8 copy (margin folded into the score)
+  constexpr double kScoreEps = SRC == 1 ? STB_SHADOW_SCAN_EPS : (SRC == 2 ? STB_Q8_SCAN_EPS : STB_SCORE_EPS);
+  constexpr int KP = 32 * E;          // list length below the root
+  constexpr int KF = 32 * EF;         // candidates the root keeps
+  constexpr int KPS = KP + 1;         // published list stride: KP keys + the node's drop bound
+  static_assert(EF >= E && 8 * KP <= STB_SORT_CAP && KF <= STB_SORT_CAP / 2, "list sizes");
   __shared__ uint64_t skeys[STB_SORT_CAP];
-  __shared__ unsigned int s_T, s_cnt, s_ticket;
+  __shared__ unsigned int s_T, s_cnt, s_ticket, s_bound, s_nin;
   __shared__ unsigned long long s_T64;
   __shared__ double sqd[STB_D];                  // query in f64 (exact conversion)
   __shared__ __align__(16) float srows[32 * STB_RR_STRIDE];
-  __shared__ double s_d[KP], s_r2[KP], s_q2;
-  __shared__ uint64_t s_r[KP];
+  __shared__ double s_d[KF], s_r2[KF], s_q2;
+  __shared__ uint64_t s_r[KF];
   __shared__ int s_nv[2];
 
   STB_T_MIN(0);                      // first CTA starts
   TopSink<E> sink;
   sink.init();
-  if constexpr (SRC == 1) stb_scan_shadow<U>(args.scan, args.shadow, sink);
+  if constexpr (SRC == 2) stb_scan_q8<U, RANGES>(args.scan, args.q8, args.q8_scale, sink);
+  else if constexpr (SRC == 1) stb_scan_shadow<U, RANGES>(args.scan, args.shadow, sink);
   else stb_scan_rows<U, RANGES>(args.scan, sink);
   STB_T_MAX(1);                      // last CTA leaves the scan loop
   // Programmatic dependent launch: the scan above reads only the corpus and the query,
@@ -534,7 +693,9 @@ stb_scan_topk_kernel(const TopkArgs args) {
   // T = max over warps of the warp list minimum is a lower bound of the CTA's KP-th
   // best score (that warp alone holds KP keys >= its minimum), so only keys >= T can
   // matter: compact those (typically ~KP..2KP of the 8*KP) and sort the small set.
+  // Drop bounds are ordered scores (stb_f2ord); 0 = "nothing dropped so far".
   const int lane = threadIdx.x & 31;
+  const unsigned kOrdNegInf = 0x007fffffu;       // stb_f2ord(-inf): a list that never filled
   if (threadIdx.x == 0) { s_T = 0u; s_cnt = 0u; }
   __syncthreads();
   if (lane == 0) atomicMax(&s_T, stb_f2ord(sink.thr));
@@ -552,8 +713,15 @@ stb_scan_topk_kernel(const TopkArgs args) {
     }
   }
   __syncthreads();
-  int c = (int)s_cnt;
-  stb_pad_and_sort(skeys, c, KP);
+  unsigned bound;                                // uniform per CTA from here on
+  {
+    const int c = (int)s_cnt;
+    stb_pad_and_sort(skeys, c, KP);
+    const int keep = (gridDim.x == 1) ? KF : KP;
+    // warps dropped keys below their own minimum (<= T); the compaction dropped keys < T
+    bound = (s_T > kOrdNegInf) ? s_T : 0u;
+    if (c > keep) bound = max(bound, stb_f2ord(stb_key_score(skeys[keep - 1])));
+  }
   STB_T_MAX(2);                      // last CTA-level merge done
 
   // Everything below writes scratch shared with the PREVIOUS launch on this stream
@@ -561,18 +729,18 @@ stb_scan_topk_kernel(const TopkArgs args) {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // ---- tree merge across CTAs ------------------------------------------------------------
-  // Lists of KP sorted keys are merged F = 1024/KP at a time by the last CTA to arrive in
-  // each group (atomic ticket + fences), level by level: 296 -> 10 -> 1 lists at E = 1.
-  // Each merge is one register/shuffle bitonic sort of <= 1024 keys; the groups of a level
-  // run in parallel on different SMs (measured: ~20 us for the two levels at E = 1, hidden
-  // behind the next query's scan by PDL when queries are pipelined).  Level l's lists live at key offset
-  // lvl_key_off*KP, its tickets at counters[lvl_cnt_off + group].
+  // Lists of KP sorted keys (+ their drop bound) are merged F = 1024/KP at a time by the last
+  // CTA to arrive in each group (atomic ticket + fences), level by level: 296 -> 10 -> 1 lists
+  // at E = 1.  Each merge is one register/shuffle bitonic sort of <= 1024 keys; the groups of a
+  // level run in parallel on different SMs.  Level l's lists live at key offset
+  // lvl_key_off*KPS, its tickets at counters[lvl_cnt_off + group].
   {
     constexpr int F = STB_SORT_CAP / KP;
     uint32_t lists = gridDim.x, my_id = blockIdx.x, lvl_key_off = 0, lvl_cnt_off = 0;
     while (lists > 1) {
-      uint64_t *lvl = args.keys + (size_t)lvl_key_off * KP;
-      for (int i = threadIdx.x; i < KP; i += blockDim.x) lvl[(size_t)my_id * KP + i] = skeys[i];
+      uint64_t *lvl = args.keys + (size_t)lvl_key_off * KPS;
+      for (int i = threadIdx.x; i < KP; i += blockDim.x) lvl[(size_t)my_id * KPS + i] = skeys[i];
+      if (threadIdx.x == 0) lvl[(size_t)my_id * KPS + KP] = (uint64_t)bound;
       __threadfence();
       __syncthreads();
       const uint32_t group = my_id / F, first = group * F;
@@ -582,24 +750,32 @@ stb_scan_topk_kernel(const TopkArgs args) {
       if (s_ticket != n_in - 1) return;            // not the last of my group: done
       __threadfence();
       if (threadIdx.x == 0) args.counters[lvl_cnt_off + group] = 0u;   // re-arm for the next launch
+      const uint32_t groups = (lists + F - 1) / F;
+      const int keep = (groups == 1) ? KF : KP;     // the root keeps the re-rank set
       {
         // Pre-filter before sorting: every list is sorted best-first, so with
-        // r = ceil(KP / n_in) - 1 the worst of the lists' r-th keys is a lower bound of the
-        // group's KP-th best (n_in * (r+1) >= KP keys are at least that good).  Only keys at
+        // r = ceil(keep / n_in) - 1 the worst of the lists' r-th keys is a lower bound of the
+        // group's keep-th best (n_in * (r+1) >= keep keys are at least that good).  Only keys at
         // or above it can survive the merge -- typically ~100 of the 1024 -- and the sort
-        // shrinks from the 1024-key to the 256-key network.
+        // shrinks from the 1024-key to the 256-key network.  r >= KP (fewer than `keep` keys
+        // in total): nothing can be filtered.
         constexpr int PER = STB_SORT_CAP / STB_SCAN_THREADS;
         uint64_t v[PER];
-        const uint32_t r = (KP + n_in - 1) / n_in - 1;
-        if (threadIdx.x == 0) { s_T64 = 0ull; s_cnt = 0u; }
+        const uint32_t r = (keep + n_in - 1) / n_in - 1;
+        if (threadIdx.x == 0) { s_T64 = (r >= (uint32_t)KP) ? STB_KEY_INVALID : 0ull; s_cnt = 0u; s_bound = 0u; s_nin = 0u; }
         __syncthreads();
+        unsigned my_valid = 0;
 #pragma unroll
         for (int u = 0; u < PER; ++u) {
           const int i = threadIdx.x + u * STB_SCAN_THREADS;
           const uint32_t li = i / KP;
-          v[u] = (li < n_in) ? __ldcg(lvl + (size_t)(first + li) * KP + (i % KP)) : STB_KEY_INVALID;
+          v[u] = (li < n_in) ? __ldcg(lvl + (size_t)(first + li) * KPS + (i % KP)) : STB_KEY_INVALID;
+          my_valid += (v[u] != STB_KEY_INVALID) ? 1u : 0u;
           if (li < n_in && (uint32_t)(i % KP) == r) atomicMax(&s_T64, v[u]);   // INVALID (all ones) disables the filter
         }
+        if (threadIdx.x < n_in) atomicMax(&s_bound, (unsigned)__ldcg(lvl + (size_t)(first + threadIdx.x) * KPS + KP));
+        my_valid = __reduce_add_sync(0xffffffffu, my_valid);
+        if (lane == 0 && my_valid) atomicAdd(&s_nin, my_valid);
         __syncthreads();
         const uint64_t T = s_T64;
 #pragma unroll
@@ -614,23 +790,24 @@ stb_scan_topk_kernel(const TopkArgs args) {
       }
       __syncthreads();
       stb_pad_and_sort(skeys, (int)s_cnt, KP);
+      bound = s_bound;
+      if ((int)s_nin > keep) bound = max(bound, stb_f2ord(stb_key_score(skeys[keep - 1])));
       lvl_key_off += lists;
-      const uint32_t groups = (lists + F - 1) / F;
       lvl_cnt_off += groups;
       lists = groups;
       my_id = group;
     }
   }
-  STB_T_MAX(3);                      // survivor holds the global best KP
+  STB_T_MAX(3);                      // survivor holds the global best KF
   STB_T_MAX(4);
 
-  // ---- exact re-rank of the best KP in canonical arithmetic --------------------------
+  // ---- exact re-rank of the best KF in canonical arithmetic --------------------------
   // Rows are staged through shared memory (coalesced, one DRAM latency), then one
   // thread per candidate accumulates (ab, q2, r2) with f64 FMAs in index order:
   // f32 x f32 products are exact in f64, so this equals orc_cosine_f32 bit for bit.
   for (int i = threadIdx.x; i < STB_D; i += blockDim.x) sqd[i] = (double)__ldg(args.scan.q + i);
   if (threadIdx.x < 2) s_nv[threadIdx.x] = 0;
-  if (threadIdx.x < KP) { s_d[threadIdx.x] = CUDART_INF; s_r[threadIdx.x] = 0xffffffffffffffffull; }
+  if (threadIdx.x < KF) { s_d[threadIdx.x] = CUDART_INF; s_r[threadIdx.x] = 0xffffffffffffffffull; }
   __syncthreads();
   if (threadIdx.x == 5 * 32) {                       // an otherwise idle warp: ||q||^2 once
     double q2 = 0.0;
@@ -638,7 +815,8 @@ stb_scan_topk_kernel(const TopkArgs args) {
     for (int i = 0; i < STB_D; ++i) q2 = fma(sqd[i], sqd[i], q2);
     s_q2 = q2;
   }
-  for (int chunk = 0; chunk < E; ++chunk) {
+  for (int chunk = 0; chunk < EF; ++chunk) {
+    if (chunk > 0 && skeys[chunk * 32] == STB_KEY_INVALID) break;     // sorted: nothing valid beyond (uniform)
     {
       constexpr int PER = 32 * STB_ROW_F4 / STB_SCAN_THREADS;   // float4 per thread
       float4 v[PER];
@@ -681,7 +859,7 @@ stb_scan_topk_kernel(const TopkArgs args) {
     }
     __syncthreads();
   }
-  if (threadIdx.x < KP) {
+  if (threadIdx.x < KF) {
     const uint64_t key = skeys[threadIdx.x];
     double d = CUDART_INF;
     uint64_t grow = 0xffffffffffffffffull;
@@ -705,11 +883,11 @@ stb_scan_topk_kernel(const TopkArgs args) {
     s_r[threadIdx.x] = grow;
   }
   __syncthreads();
-  // bitonic sort of the KP (distance,row) pairs
-  for (int k = 2; k <= KP; k <<= 1) {
+  // bitonic sort of the KF (distance,row) pairs
+  for (int k = 2; k <= KF; k <<= 1) {
     for (int jj = k >> 1; jj > 0; jj >>= 1) {
       int i = threadIdx.x;
-      if (i < KP) {
+      if (i < KF) {
         int ixj = i ^ jj;
         if (ixj > i) {
           double da = s_d[i], db = s_d[ixj];
@@ -727,10 +905,11 @@ stb_scan_topk_kernel(const TopkArgs args) {
   const uint32_t k = args.top_k;
   const uint32_t n_out = min((uint32_t)n_pass, k);
   bool complete;
-  if (n_valid < KP) complete = true;   // every scorable row is in the candidate set
+  if (bound == 0u) complete = true;    // no node dropped a key: every scorable row is a candidate
   else {
-    float s_min = stb_key_score(skeys[KP - 1]);
-    complete = (n_out == k) && ((1.0 - (double)s_min - kScoreEps) > s_d[k - 1]);
+    // every row that is not a candidate scored <= the best dropped score
+    const float s_drop = stb_ord2f(bound);
+    complete = (n_out == k) && ((1.0 - (double)s_drop - kScoreEps) > s_d[k - 1]);
   }
   if (args.xchg.world <= 1) {
     for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
@@ -743,7 +922,7 @@ stb_scan_topk_kernel(const TopkArgs args) {
       args.out_status[0] = n_out;
       args.out_status[1] = complete ? 1u : 0u;
       args.out_status[2] = (uint32_t)n_valid;
-      args.out_status[3] = (uint32_t)KP;
+      args.out_status[3] = (uint32_t)KF | ((uint32_t)SRC << 16);
     }
     return;
   }
@@ -825,7 +1004,7 @@ stb_scan_topk_kernel(const TopkArgs args) {
     args.out_status[0] = min(total, k);
     args.out_status[1] = all_complete;
     args.out_status[2] = s_timeout ? 0xfffffffeu : (uint32_t)n_valid;
-    args.out_status[3] = (uint32_t)KP;
+    args.out_status[3] = (uint32_t)KF | ((uint32_t)SRC << 16);
   }
 }
 
@@ -838,23 +1017,51 @@ static int stb_pick_e(uint32_t top_k) {
 }
 
 #define STB_SHADOW_SCAN_U 4     // 4 rows x 4 LDG.128 per lane in flight = the f32 path's 2 x 8
+#define STB_Q8_SCAN_U 8         // 8 rows x 2 LDG.128
 
-template <int E, int RANGES, int SRC = 0>
-static int stb_launch_topk_t(stb_ctx *ctx, const TopkArgs &a) {
-  constexpr int kU = SRC ? STB_SHADOW_SCAN_U : STB_SCAN_U;
-  auto kern = stb_scan_topk_kernel<E, kU, RANGES, SRC>;
+// STB_SCAN_CTAS_PER_SM (tuning aid): resident CTAs per SM the top-k grid is sized for
+// (default: what the occupancy calculator allows, 2 with the 128-register budget).
+// STB_SCAN_TICKETS=0 (tuning aid): static warp-strided tile partition instead of tickets.
+static bool stb_scan_tickets_enabled() {
+  static const bool v = [] { const char *e = getenv("STB_SCAN_TICKETS"); return !(e && e[0] == '0'); }();
+  return v;
+}
+static int stb_scan_ctas_per_sm_override() {
+  static const int v = [] { const char *e = getenv("STB_SCAN_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+  return v;
+}
+
+template <int E, int RANGES, int SRC = 0, int EF = E>
+static int stb_launch_topk_t(stb_ctx *ctx, const TopkArgs &a_in) {
+  constexpr int kU = SRC == 2 ? STB_Q8_SCAN_U : (SRC == 1 ? STB_SHADOW_SCAN_U : STB_SCAN_U);
+  auto kern = stb_scan_topk_kernel<E, kU, RANGES, SRC, EF>;
   int occ = 0;
   STB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, STB_SCAN_THREADS, 0));
   if (occ < 1) occ = 1;
-  uint64_t tiles = (a.scan.n_virtual + 4 * kU - 1) / (4 * kU);
+  const int ovr = stb_scan_ctas_per_sm_override();
+  if (ovr >= 1 && ovr < occ) occ = ovr;
+  TopkArgs a = a_in;
+  const uint64_t tiles = (a.scan.n_virtual + 4 * kU - 1) / (4 * kU);
   uint64_t want = (tiles + STB_SCAN_WARPS - 1) / STB_SCAN_WARPS;
   uint64_t grid = (uint64_t)ctx->sm_count * occ;
   if (want < grid) grid = want < 1 ? 1 : want;
-  // scratch: keys for all tree levels (< 2 * grid lists), counters (< grid groups)
-  size_t need_keys = (size_t)2 * grid * 32 * E + STB_SORT_CAP;
+  // scratch: lists (KP keys + bound) for all tree levels (< 2 * grid lists), counters (< grid groups)
+  size_t need_keys = (size_t)2 * grid * (32 * E + 1) + STB_SORT_CAP;
   if (need_keys > ctx->block_keys_cap || grid + 8 > ctx->counters_cap) {
     stb_set_error("scan scratch too small (grid=%llu)", (unsigned long long)grid);
     return STB_ERR_STATE;
+  }
+  // tile tickets (stb_for_each_tile): bulk tickets of STB_TICKET_TILES tiles, then the last ~2 tiles
+  // per warp one by one.  The launch advances the counter by n_tickets + total_warps exactly.
+  const uint64_t warps_total = grid * STB_SCAN_WARPS;
+  const bool use_tickets = stb_scan_tickets_enabled();
+  if (use_tickets) {
+    const uint64_t single = std::min<uint64_t>(tiles, 2 * warps_total);
+    a.scan.t_bulk = (tiles - single) / STB_TICKET_TILES;
+    const uint64_t n_tickets = a.scan.t_bulk + (tiles - a.scan.t_bulk * STB_TICKET_TILES);
+    a.scan.tickets = ctx->tickets;
+    a.scan.t_base = ctx->ticket_next;
+    ctx->ticket_next += n_tickets + warps_total;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -873,20 +1080,38 @@ static int stb_launch_topk_t(stb_ctx *ctx, const TopkArgs &a) {
   return STB_OK;
 }
 
-int stb_launch_scan_topk(stb_ctx *ctx, const float *rows, uint64_t n_rows,
-                         uint64_t row_base, const float *q_dev, uint32_t top_k,
+template <int RANGES>
+static int stb_launch_topk_r(stb_ctx *ctx, const TopkArgs &a, int tier, uint32_t top_k) {
+  const int e = stb_pick_e(top_k);
+  // q8: 32-key lists below the root, 128 candidates re-ranked at the root (see stb_scan_q8)
+  if (tier == STB_TIER_Q8) return stb_launch_topk_t<1, RANGES, 2, 4>(ctx, a);
+  if (tier == STB_TIER_H16) {
+    switch (e) {
+      case 1: return stb_launch_topk_t<1, RANGES, 1>(ctx, a);
+      case 2: return stb_launch_topk_t<2, RANGES, 1>(ctx, a);
+      default: return stb_launch_topk_t<4, RANGES, 1>(ctx, a);
+    }
+  }
+  switch (e) {
+    case 1: return stb_launch_topk_t<1, RANGES, 0>(ctx, a);
+    case 2: return stb_launch_topk_t<2, RANGES, 0>(ctx, a);
+    default: return stb_launch_topk_t<4, RANGES, 0>(ctx, a);
+  }
+}
+
+int stb_launch_scan_topk(stb_ctx *ctx, const stb_corpus *c, int tier, const float *q_dev, uint32_t top_k,
                          const uint64_t *ranges_dev, uint32_t n_ranges,
                          uint64_t n_virtual, stb_hit *out_hits_dev,
-                         uint32_t *out_status_dev, const StbXchgArgs *xchg, const uint8_t *shadow) {
-  (void)n_rows;
+                         uint32_t *out_status_dev, const StbXchgArgs *xchg) {
   TopkArgs a;
-  a.scan.rows = reinterpret_cast<const float4 *>(rows);
+  a.scan.rows = reinterpret_cast<const float4 *>(c->rows);
   a.scan.n_virtual = n_virtual;
   a.scan.q = q_dev;
   a.scan.vstart = ranges_dev;
   a.scan.rbegin = ranges_dev ? ranges_dev + (n_ranges + 1) : nullptr;
   a.scan.n_ranges = n_ranges;
-  a.row_base = row_base;
+  a.scan.tickets = nullptr; a.scan.t_base = 0; a.scan.t_bulk = 0;
+  a.row_base = c->row_base;
   a.keys = ctx->block_keys;
   a.counters = ctx->counters;
   a.out_hits = out_hits_dev;
@@ -894,28 +1119,12 @@ int stb_launch_scan_topk(stb_ctx *ctx, const float *rows, uint64_t n_rows,
   a.top_k = top_k;
   if (xchg) a.xchg = *xchg; else memset(&a.xchg, 0, sizeof(a.xchg));
   a.dbg = ctx->dbg_dev;
-  a.shadow = shadow;
-  const bool rg = n_ranges > 0;
-  if (shadow && !rg) {                                     // half-width scan (whole shard only)
-    switch (stb_pick_e(top_k)) {
-      case 1: return stb_launch_topk_t<1, 0, 1>(ctx, a);
-      case 2: return stb_launch_topk_t<2, 0, 1>(ctx, a);
-      default: return stb_launch_topk_t<4, 0, 1>(ctx, a);
-    }
-  }
-  const char *walk_env = getenv("STB_RANGES_WALK");        // opt-in until timed: RANGES mode 2
-  if (rg && walk_env && walk_env[0] == '1') {
-    switch (stb_pick_e(top_k)) {
-      case 1: return stb_launch_topk_t<1, 2>(ctx, a);
-      case 2: return stb_launch_topk_t<2, 2>(ctx, a);
-      default: return stb_launch_topk_t<4, 2>(ctx, a);
-    }
-  }
-  switch (stb_pick_e(top_k)) {
-    case 1: return rg ? stb_launch_topk_t<1, 1>(ctx, a) : stb_launch_topk_t<1, 0>(ctx, a);
-    case 2: return rg ? stb_launch_topk_t<2, 1>(ctx, a) : stb_launch_topk_t<2, 0>(ctx, a);
-    default: return rg ? stb_launch_topk_t<4, 1>(ctx, a) : stb_launch_topk_t<4, 0>(ctx, a);
-  }
+  a.shadow = c->shadow;
+  a.q8 = c->q8;
+  a.q8_scale = c->q8_scale;
+  if (tier == STB_TIER_Q8 && (top_k > STB_Q8_MAX_K || !c->q8)) { stb_set_error("scan_topk: q8 tier unavailable"); return STB_ERR_STATE; }
+  if (tier == STB_TIER_H16 && !c->shadow) { stb_set_error("scan_topk: h16 tier unavailable"); return STB_ERR_STATE; }
+  return n_ranges > 0 ? stb_launch_topk_r<1>(ctx, a, tier, top_k) : stb_launch_topk_r<0>(ctx, a, tier, top_k);
 }
 
 // ------------------------------------------------------------------ collect path ---
@@ -969,6 +1178,7 @@ int stb_launch_scan_collect(stb_ctx *ctx, const float *rows, uint64_t n_rows,
   a.scan.vstart = ranges_dev;
   a.scan.rbegin = ranges_dev ? ranges_dev + (n_ranges + 1) : nullptr;
   a.scan.n_ranges = n_ranges;
+  a.scan.tickets = nullptr; a.scan.t_base = 0; a.scan.t_bulk = 0;
   a.cos_floor = cos_floor;
   a.out = ctx->collect_rows;
   a.count = ctx->collect_count;
@@ -1027,6 +1237,7 @@ int stb_launch_scan_hist(stb_ctx *ctx, const float *rows, const float *q_dev, co
   a.vstart = ranges_dev;
   a.rbegin = ranges_dev ? ranges_dev + (n_ranges + 1) : nullptr;
   a.n_ranges = n_ranges;
+  a.tickets = nullptr; a.t_base = 0; a.t_bulk = 0;
   STB_CUDA(cudaMemsetAsync(hist_dev, 0, STB_HIST_BINS * sizeof(unsigned int), ctx->stream));
   uint64_t tiles = (n_virtual + 4 * STB_SCAN_U - 1) / (4 * STB_SCAN_U);
   uint64_t want = (tiles + STB_SCAN_WARPS - 1) / STB_SCAN_WARPS;

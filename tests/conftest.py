@@ -19,6 +19,8 @@ def ctx():
     from semtools_b200 import capi
     c = capi.Context(0)
     yield c
+    dev, host = c.ticket_check()      # K1's dynamic tile schedule stayed consistent over the whole session
+    assert dev == host
     c.close()
 
 

@@ -11,6 +11,27 @@ from semtools_b200 import capi
 
 pytestmark = pytest.mark.gpu
 
+# ------------------------------------------------------------------------------------------
+# Pipeline v2 (sampled threshold -> emitting epilogue -> exact finish) is the default since
+# round 2; STB_BATCH_V1=1 forces the round-1 maxima/select/finish pipeline.  Both run here.
+import os
+
+
+@pytest.fixture(params=["v2", "v1"])
+def batch_pipeline(request, monkeypatch):
+    if request.param == "v1":
+        monkeypatch.setenv("STB_BATCH_V1", "1")
+    else:
+        monkeypatch.delenv("STB_BATCH_V1", raising=False)
+    return request.param
+
+
+@pytest.fixture
+def batch_v2(monkeypatch):
+    monkeypatch.delenv("STB_BATCH_V1", raising=False)
+
+
+
 
 def bf16_round(x):
     """Rounds to the element type of this build's shadow (bf16 by default, fp16 with -DSTB_SHADOW_F16=1)."""
@@ -55,7 +76,7 @@ def check_batch(res, rows, queries, k):
 
 
 @pytest.mark.parametrize("nq,n,k", [(1, 40, 3), (5, 1000, 10), (130, 70_000, 10), (300, 20_000, 1), (64, 50_000, 40)])
-def test_search_batch_matches_oracle(ctx, nq, n, k):
+def test_search_batch_matches_oracle(ctx, batch_pipeline, nq, n, k):
     rng = np.random.default_rng(nq + n + k)
     rows = unit_rows(rng, n)
     queries = unit_rows(rng, nq)
@@ -72,7 +93,7 @@ def test_search_batch_matches_oracle(ctx, nq, n, k):
         assert ctx.counters()["fallback_searches"] - before <= max(2, nq // 8)
 
 
-def test_search_batch_ties_zero_rows_and_unprovable_queries(ctx):
+def test_search_batch_ties_zero_rows_and_unprovable_queries(ctx, batch_pipeline):
     rng = np.random.default_rng(42)
     rows = unit_rows(rng, 30_000)
     rows[rng.integers(0, 30_000, 20)] = rows[rng.integers(0, 30_000, 20)]      # duplicates
@@ -122,7 +143,7 @@ def test_search_batch_sharded_row_base_and_rebuild_after_append(ctx):
         assert np.array_equal(res[i]["distance"], d)
 
 
-def test_sharded_batch_search_merges_to_the_unsharded_answer(ctx):
+def test_sharded_batch_search_merges_to_the_unsharded_answer(ctx, batch_pipeline):
     """Sharded K2: per-shard stb_search_batch_dev + stb_hits_merge_batch_dev (what ranks do
     after all-gathering their nq x k hits) == oracle over the whole corpus."""
     torch = pytest.importorskip("torch")
@@ -161,26 +182,6 @@ def test_sharded_batch_search_merges_to_the_unsharded_answer(ctx):
         assert got[0]["row"][:2].tolist() == [5, 59_999]
 
 
-# ------------------------------------------------------------------------------------------
-# Pipeline v2 (sampled threshold -> emitting epilogue -> exact finish).  Opt-in in the library
-# (STB_BATCH_V2=1) and in this suite (STB_TEST_V2=1) until it has been validated on hardware.
-import os
-
-v2 = pytest.mark.skipif(os.environ.get("STB_TEST_V2") != "1", reason="pipeline v2 is opt-in (STB_TEST_V2=1)")
-
-
-@pytest.fixture
-def batch_v2():
-    old = os.environ.get("STB_BATCH_V2")
-    os.environ["STB_BATCH_V2"] = "1"
-    yield
-    if old is None:
-        del os.environ["STB_BATCH_V2"]
-    else:
-        os.environ["STB_BATCH_V2"] = old
-
-
-@v2
 @pytest.mark.parametrize("nq,n,k", [(1, 40, 3), (5, 1000, 10), (130, 70_000, 10), (300, 20_001, 1), (64, 50_000, 40),
                                     (3, 255, 5), (9, 256, 64), (20, 200_000, 10)])
 def test_v2_search_batch_matches_oracle_without_fallback(ctx, batch_v2, nq, n, k):
@@ -195,7 +196,6 @@ def test_v2_search_batch_matches_oracle_without_fallback(ctx, batch_v2, nq, n, k
     assert ctx.counters()["fallback_searches"] == before        # v2 proves every k <= 64 unless a capacity overflows
 
 
-@v2
 def test_v2_ties_zero_rows_dense_neighbourhoods(ctx, batch_v2):
     rng = np.random.default_rng(42)
     rows = unit_rows(rng, 30_000)
@@ -205,7 +205,7 @@ def test_v2_ties_zero_rows_dense_neighbourhoods(ctx, batch_v2):
     queries[0] = rows[17]
     queries[1] = 0.0                           # zero query: every row ties -> overflow -> K1 fallback
     where = rng.choice(30_000, 600, replace=False)
-    rows[where] = (queries[2] + 0.005 * unit_rows(rng, 1)[0]).astype(np.float32)   # 600 identical best rows: 600 <= 1024 re-scores
+    rows[where] = (queries[2] + 0.005 * unit_rows(rng, 1)[0]).astype(np.float32)   # 600 identical best rows: 600 <= 1024 re-scores, ~5 per (query, CTA) segment
     where2 = rng.choice(30_000, 3000, replace=False)
     rows[where2] = (queries[3] + 0.004 * unit_rows(rng, 1)[0]).astype(np.float32)  # 3000 > re-score cap -> fallback
     c = capi.Corpus(ctx, 30_000, row_base=5_000_000_000)

@@ -456,9 +456,9 @@ def test_large_k_histogram_path(ctx, n, k):
     assert got["row"].tolist() == [int(x) for x in r2]
 
 
-@pytest.mark.skipif(os.environ.get("STB_TEST_V2") != "1", reason="opt-in path written after the last GPU session of round 1 (STB_TEST_V2=1)")
 def test_direct_host_output_switch_gives_identical_hits(ctx, monkeypatch):
-    """STB_DIRECT_OUT=1: the scan kernel stores hits + status straight into pinned host memory."""
+    """Default: the scan kernel stores hits + status straight into pinned host memory;
+    STB_DIRECT_OUT=0 goes through device buffers + two D2H copies.  Same hits either way."""
     rng = np.random.default_rng(321)
     rows = unit_rows(rng, 50_000)
     rows[777] = rows[5]
@@ -466,64 +466,159 @@ def test_direct_host_output_switch_gives_identical_hits(ctx, monkeypatch):
     c.append(rows)
     for k in (1, 10, 96):
         for qi in (5, 100, 49_999):
-            monkeypatch.delenv("STB_DIRECT_OUT", raising=False)
+            monkeypatch.setenv("STB_DIRECT_OUT", "0")
             want = c.search(rows[qi], top_k=k)
-            monkeypatch.setenv("STB_DIRECT_OUT", "1")
+            monkeypatch.delenv("STB_DIRECT_OUT", raising=False)
             got = c.search(rows[qi], top_k=k)
             assert np.array_equal(got, want)
             r, d = oracle.search_rows(rows, rows[qi], top_k=k)
             assert got["row"].tolist() == [int(x) for x in r] and np.array_equal(got["distance"], d)
 
 
-@pytest.mark.skipif(os.environ.get("STB_TEST_V2") != "1", reason="opt-in path written after the last GPU session of round 1 (STB_TEST_V2=1)")
-@pytest.mark.parametrize("n,n_ranges", [(9_000, 5), (20_000, 700), (300_000, 20_000), (70_000, 1)])
-def test_range_walk_mode_matches_the_oracle(ctx, monkeypatch, n, n_ranges):
-    """STB_RANGES_WALK=1: every warp walks one contiguous block of the selected rows and steps
-    its range index instead of searching per row; the answer must be the store query's."""
-    rng = np.random.default_rng(n + n_ranges)
-    rows = unit_rows(rng, n)
-    rows[n // 3] = rows[n // 3 + 1]                                     # a tie inside / across ranges
-    q = unit_rows(rng, 1)[0]
-    c = make_corpus(ctx, rows)
+def _ranges_for(rng, n, n_ranges):
     step = max(n // n_ranges, 2)
     starts = np.sort(rng.choice(np.arange(0, n - step, step), min(n_ranges, (n - step) // step), replace=False))
     ranges = [[int(s), int(s + rng.integers(1, step + 1))] for s in starts]
     if n_ranges == 1:
         ranges = [[1000, n - 1000]]
-    monkeypatch.setenv("STB_RANGES_WALK", "1")
+    return ranges
+
+
+@pytest.mark.parametrize("tier", ["f32", "h16", "q8"])
+@pytest.mark.parametrize("n,n_ranges", [(9_000, 5), (20_000, 700), (300_000, 20_000), (70_000, 1)])
+def test_row_range_walk_matches_the_oracle_on_every_tier(ctx, monkeypatch, n, n_ranges, tier):
+    """Workspace path filter (store.rs:495-523) = row ranges: warps walk blocks of the selected
+    rows and step their range index; candidates from the f32 rows, the 16-bit shadow or the int8
+    copy -- the answer must be the store query's."""
+    rng = np.random.default_rng(n + n_ranges)
+    rows = unit_rows(rng, n)
+    rows[n // 3] = rows[n // 3 + 1]                                     # a tie inside / across ranges
+    q = unit_rows(rng, 1)[0]
+    c = make_corpus(ctx, rows)
+    c.prepare()
+    ranges = _ranges_for(rng, n, n_ranges)
+    monkeypatch.setenv("STB_SCAN_TIER", tier)
     for k, thr in [(1, None), (10, None), (64, None), (10, 0.95)]:
         r, d32 = oracle.store_search(rows, ranges, q, k, thr)
         hits = c.search(q, top_k=k, max_distance=thr, mode=capi.STB_MODE_STORE_QUERY, row_ranges=ranges)
         assert hits["row"].tolist() == [int(x) for x in r]
         assert np.array_equal(hits["distance"].astype(np.float32), d32)
+    st = c.tier_stats()
+    if tier != "f32":
+        assert st[tier]["tries"] >= 2, st                              # the reduced-width copy really was scanned
 
 
-@pytest.mark.skipif(os.environ.get("STB_TEST_V2") != "1", reason="opt-in path written after the last GPU session of round 1 (STB_TEST_V2=1)")
+@pytest.mark.parametrize("tier", ["h16", "q8"])
 @pytest.mark.parametrize("n", [1, 7, 255, 256, 257, 5_000, 70_001, 300_000])
-def test_half_width_shadow_scan_matches_the_oracle(ctx, monkeypatch, n):
-    """STB_SCAN_SHADOW=1: K1 selects its candidates from the 16-bit normalised shadow (half the
-    bytes); the re-rank is the same exact f64 pass, so hits, order and distances are the oracle's.
-    Unprovable queries (zero query, mass ties) are retried on the f32 rows / the collect path."""
+def test_reduced_width_tiers_match_the_oracle(ctx, monkeypatch, n, tier):
+    """K1 candidates from the 16-bit normalised shadow (half the bytes) or the int8 copy (a
+    quarter); the re-rank is the same exact f64 pass on the f32 rows, so hits, order and distances
+    are the oracle's.  Unprovable queries (zero query, mass ties, k too close to K') are retried on
+    the next wider tier / the collect path."""
     rng = np.random.default_rng(1000 + n)
     rows = (unit_rows(rng, n) * rng.uniform(0.2, 5.0, (n, 1))).astype(np.float32)
     if n > 300:
         rows[n // 2] = rows[3]                         # exact duplicate: tie broken by row
         rows[17] = 0.0                                 # zero row
     c = make_corpus(ctx, rows)
+    c.prepare()
     queries = [rows[3 % n], unit_rows(rng, 1)[0], unit_rows(rng, 1)[0] * np.float32(1e-3)]
     if n > 300:
         queries.append(np.zeros(256, np.float32))      # zero query: everything ties -> fallback
-    monkeypatch.setenv("STB_SCAN_SHADOW", "1")
+    monkeypatch.setenv("STB_SCAN_TIER", tier)
     for q in queries:
-        for k in (1, 10, 96):
+        for k in (1, 10, 16, 96):
             r, d = oracle.search_rows(rows, q, top_k=k)
             hits = c.search(q, top_k=k)
             assert hits["row"].tolist() == [int(x) for x in r]
             assert np.array_equal(hits["distance"], d)
-    # a corpus with a row that cannot be normalised in fp32: the shadow is refused, f32 path answers
+    st = c.tier_stats()
+    assert st[tier]["built_rows"] == n and st[tier]["tries"] > 0, st
+    if n >= 5_000:
+        assert 3 * st[tier]["proven"] >= st[tier]["tries"], st         # random data: the tier proves most queries itself
+    # a corpus with a row that cannot be normalised in fp32: the copies are refused, f32 path answers
     if n >= 5_000:
         rows2 = rows.copy(); rows2[11] *= np.float32(1e-25)
         c2 = make_corpus(ctx, rows2)
+        c2.prepare()
         r, d = oracle.search_rows(rows2, queries[1], top_k=5)
         hits = c2.search(queries[1], top_k=5)
         assert hits["row"].tolist() == [int(x) for x in r] and np.array_equal(hits["distance"], d)
+        assert c2.tier_stats()[tier]["built_rows"] == 0
+
+
+def test_q8_upper_bound_really_bounds_the_exact_cosine(ctx, monkeypatch):
+    """Adversarial rows for the int8 tier: components just below a rounding boundary, one
+    dominant component (large per-row scale), tiny components; queries with one dominant
+    component.  Whatever the tier can or cannot prove, the hits must be the oracle's."""
+    rng = np.random.default_rng(4242)
+    n = 40_000
+    rows = unit_rows(rng, n)
+    rows[:2000, 0] += np.float32(3.0)                                   # dominant component -> scale ~ 1/127
+    rows[2000:4000] = np.round(rows[2000:4000] * 254.0 + 0.49) / np.float32(254.0)   # near half-step boundaries
+    rows[4000:4100] *= np.float32(1e-4)
+    qs = [unit_rows(rng, 1)[0] for _ in range(3)]
+    spike = unit_rows(rng, 1)[0]; spike[5] = 4.0
+    qs.append(spike.astype(np.float32))
+    qs.append(rows[100].copy())
+    c = make_corpus(ctx, rows)
+    c.prepare()
+    monkeypatch.setenv("STB_SCAN_TIER", "q8")
+    for q in qs:
+        for k in (1, 5, 16):
+            r, d = oracle.search_rows(rows, q, top_k=k)
+            hits = c.search(q, top_k=k)
+            assert hits["row"].tolist() == [int(x) for x in r]
+            assert np.array_equal(hits["distance"], d)
+
+
+def test_lazy_tier_build_waits_for_the_second_query(ctx, monkeypatch):
+    monkeypatch.delenv("STB_SCAN_TIER", raising=False)
+    rng = np.random.default_rng(99)
+    rows = unit_rows(rng, 40_000)
+    q = unit_rows(rng, 1)[0]
+    c = make_corpus(ctx, rows)
+    r, d = oracle.search_rows(rows, q, top_k=10)
+    check(c.search(q, top_k=10), r, d)
+    assert c.tier_stats()["q8"]["built_rows"] == 0                      # one-shot query: f32 rows only
+    check(c.search(q, top_k=10), r, d)
+    st = c.tier_stats()
+    assert st["q8"]["built_rows"] == 40_000 and st["q8"]["proven"] == 1, st
+    c.append(rows[:10])                                                 # any change drops the copies
+    assert c.tier_stats()["q8"]["built_rows"] == 0
+    small = make_corpus(ctx, rows[:5000])
+    small.search(q, top_k=3); small.search(q, top_k=3)
+    assert small.tier_stats()["q8"]["built_rows"] == 0                  # below 32768 rows: never lazily
+
+
+@pytest.mark.parametrize("tier", ["f32", "h16", "q8"])
+def test_ticket_schedule_stays_consistent_and_order_independent(ctx, monkeypatch, tier):
+    """The dynamic tile tickets must (a) leave the device counter exactly where the host booked it
+    after launches of many shapes, including back-to-back PDL launches, and (b) give the same hits
+    as the static partition (STB_SCAN_TICKETS is read once per process, so (b) is covered by the
+    oracle comparison here and by every other test in this file)."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(2024)
+    monkeypatch.setenv("STB_SCAN_TIER", tier)
+    dev = torch.device("cuda:0")
+    for n in (1, 33, 2_000, 9_473, 150_000, 700_001):
+        rows = unit_rows(rng, n)
+        c = make_corpus(ctx, rows)
+        c.prepare()
+        qs = unit_rows(rng, 6)
+        q_dev = torch.from_numpy(qs).to(dev)
+        hits = torch.zeros((6, 10, 2), dtype=torch.float64, device=dev)
+        status = torch.zeros((6, 4), dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        for rep in range(3):
+            for i in range(6):                                   # back to back: PDL overlaps tails and scans
+                c.search_topk_dev(q_dev[i].data_ptr(), 10, hits[i].data_ptr(), status[i].data_ptr())
+        ctx.sync()
+        d, h = ctx.ticket_check()
+        assert d == h
+        raw, st = hits.cpu().numpy(), status.cpu().numpy()
+        for i in range(6):
+            r, dd = oracle.search_rows(rows, qs[i], top_k=10)
+            got = np.ascontiguousarray(raw[i]).view(capi.HIT_DTYPE).reshape(-1)[: st[i, 0]]
+            assert st[i, 1] == 1, (n, i, st[i])
+            check(got, r, dd)
