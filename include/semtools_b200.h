@@ -290,6 +290,10 @@ int stb_hits_merge(stb_ctx *ctx, const stb_hit *lists, uint32_t n_lists,
  * stb_fnv1a64(path); LineEmbedding::id (:82-89) is stb_line_id. Pure host code. */
 uint64_t stb_fnv1a64(const uint8_t *bytes, uint64_t len);
 uint64_t stb_line_id(const uint8_t *path, uint64_t path_len, int32_t line_number);
+/* stb_line_id for n_rows (path index, line_number) int32 pairs at once (rebuilding a store's
+ * id map): paths = one byte blob + n_paths+1 offsets.  STB_ERR_RANGE on a bad path index. */
+int stb_line_ids(const uint8_t *path_bytes, const uint64_t *path_offsets, uint32_t n_paths,
+                 const int32_t *rows, uint64_t n_rows, uint64_t *out_ids);
 
 /* ---- introspection (bench / tests) -------------------------------------------------
  * Counters since context creation: kernels launched by this library on the

@@ -7,6 +7,7 @@ import os
 import sys
 
 from . import cmds
+from .workspace import _rust_lines
 from .model import MODEL_NAME, StaticModel
 
 
@@ -49,7 +50,11 @@ def main(argv=None) -> int:
         return 1
     model = StaticModel.from_pretrained(model_dir)
     stdin_tty = sys.stdin.isatty()
-    lines = None if stdin_tty or a.files else [l.rstrip("\n").rstrip("\r") for l in sys.stdin]
+    # io::stdin().lock().lines() (cmds/search.rs:160-163): BufRead::lines splits on '\n' and drops one
+    # '\r' before it; a bare '\r' is text.  Read bytes: text mode would translate newlines.
+    lines = None
+    if not (stdin_tty or a.files):
+        lines = _rust_lines(sys.stdin.buffer.read().decode("utf-8"))       # same rules as str::lines()
     return cmds.search_cmd(a.query, a.files, a.n_lines, a.top_k, a.max_distance, a.ignore_case, a.json, a.workspace,
                            model, stdin_lines=lines, stdin_is_tty=stdin_tty, stdout_is_tty=sys.stdout.isatty())
 

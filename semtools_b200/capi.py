@@ -26,7 +26,7 @@ SYMBOLS = [
     "stb_search_topk_dev", "stb_corpus_prepare", "stb_corpus_tier_stats", "stb_corpus_prepare_batch", "stb_search_batch", "stb_search_batch_dev",
     "stb_xchg_create", "stb_xchg_destroy", "stb_xchg_local_handle",
     "stb_xchg_connect", "stb_xchg_connect_local", "stb_search_topk_xchg", "stb_search_xchg", "stb_ivfpq_build",
-    "stb_ivfpq_destroy", "stb_ivfpq_stats", "stb_ivfpq_search", "stb_hits_merge_dev", "stb_hits_merge_batch_dev", "stb_hits_merge", "stb_fnv1a64", "stb_line_id",
+    "stb_ivfpq_destroy", "stb_ivfpq_stats", "stb_ivfpq_search", "stb_hits_merge_dev", "stb_hits_merge_batch_dev", "stb_hits_merge", "stb_fnv1a64", "stb_line_id", "stb_line_ids",
     "stb_ctx_counters", "stb_debug_ticket_check", "stb_debug_timestamps", "stb_debug_batch_gemm", "stb_debug_batch_params",
 ]
 
@@ -104,6 +104,7 @@ def lib() -> C.CDLL:
     L.stb_fnv1a64.argtypes = [C.c_char_p, u64]
     L.stb_fnv1a64.restype = u64
     L.stb_line_id.argtypes = [C.c_char_p, u64, C.c_int32]
+    L.stb_line_ids.argtypes = [vp, vp, u32, vp, u64, vp]
     L.stb_line_id.restype = u64
     L.stb_ctx_counters.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.stb_debug_timestamps.argtypes = [vp, i32, vp]
@@ -148,6 +149,20 @@ def line_id(path: str, line_number: int) -> int:
     """LineEmbedding::id (reference src/workspace/store.rs:82-89)."""
     b = path.encode("utf-8")
     return int(lib().stb_line_id(b, len(b), line_number))
+
+
+def line_ids(paths, rows) -> np.ndarray:
+    """stb_line_ids: LineEmbedding ids of all rows ((path index, line_number) int32 pairs) in one
+    native call (a store with millions of rows used to make one ctypes call per row)."""
+    rows = np.ascontiguousarray(rows, dtype=np.int32).reshape(-1, 2)
+    enc = [p.encode("utf-8") for p in paths]
+    offs = np.zeros(len(enc) + 1, dtype=np.uint64)
+    if enc:
+        offs[1:] = np.cumsum([len(b) for b in enc])
+    blob = np.frombuffer(b"".join(enc) or b"\0", dtype=np.uint8)
+    out = np.zeros(len(rows), dtype=np.uint64)
+    _check(lib().stb_line_ids(_np_ptr(blob), _np_ptr(offs), len(enc), _np_ptr(rows), len(rows), _np_ptr(out)))
+    return out
 
 
 class Context:

@@ -12,7 +12,7 @@ import numpy as np
 
 from . import capi
 from .search import SearchConfig, SearchResult, Searcher
-from .workspace import Store, Workspace, WorkspaceConfig, _rust_lines, search_with_workspace
+from .workspace import Store, Workspace, WorkspaceConfig, _rust_lines, read_to_string, search_with_workspace
 
 
 # ------------------------------------------------------------------ Rust formatting ------
@@ -112,8 +112,7 @@ def format_search_results(results, is_tty: bool) -> str:      # cmds/search.rs:3
 
 def _read_lines(path):
     try:
-        with open(path, encoding="utf-8") as f:
-            return _rust_lines(f.read())
+        return _rust_lines(read_to_string(path))
     except (OSError, UnicodeDecodeError):
         return None
 
@@ -170,8 +169,7 @@ def search_files(files, query: str, model, config: SearchConfig, ctx: capi.Conte
         model.ctx = ctx or capi.Context(0)
     searcher = Searcher(model.ctx, capi.Corpus(model.ctx, 1024))
     for f in files:
-        with open(f, encoding="utf-8") as fh:                   # read_to_string(f)? -> error propagates
-            content = fh.read()
+        content = read_to_string(f)                             # read_to_string(f)? -> error propagates
         create_document_from_content(searcher, f, content, model, config.ignore_case)
     q = model.encode_single(query)
     return searcher.search_documents(q, config)
@@ -210,7 +208,8 @@ def search_cmd(query, files, n_lines, top_k, max_distance, ignore_case, json, wo
             model.ctx = capi.Context(0)
         q = model.encode_single(query)
         ranked = search_with_workspace(files, q, lambda ls: model.encode_with_args(ls, 2048, 16384), cfg,
-                                       workspace_name, ctx=model.ctx, log=lambda m: err.write(m + "\n"))
+                                       workspace_name, ctx=model.ctx, log=lambda m: err.write(m + "\n"),
+                                       model_fingerprint=model.fingerprint() if hasattr(model, "fingerprint") else None)
         out.write(to_string_pretty({"results": workspace_results_to_json(ranked, n_lines)}) + "\n" if json
                   else format_workspace_search_results(ranked, n_lines, stdout_is_tty))
     else:

@@ -1029,9 +1029,13 @@ int stb_search_xchg(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint
   auto t0 = std::chrono::steady_clock::now();
   memcpy(ctx->q_pin, q, STB_D * sizeof(float));
   STB_CUDA(cudaMemcpyAsync(ctx->q_dev, ctx->q_pin, STB_D * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = stb_search_topk_xchg(ctx, corpus, ctx->q_dev, top_k, x, ctx->hits_dev, ctx->status_dev)) != STB_OK) return rc;
-  STB_CUDA(cudaMemcpyAsync(ctx->status_pin, ctx->status_dev, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  STB_CUDA(cudaMemcpyAsync(ctx->hits_pin, ctx->hits_dev, top_k * sizeof(stb_hit), cudaMemcpyDeviceToHost, ctx->stream));
+  if (stb_env_direct_out()) {        // the merge CTA stores the hits + status straight into pinned host memory
+    if ((rc = stb_search_topk_xchg(ctx, corpus, ctx->q_dev, top_k, x, ctx->hits_pin, ctx->status_pin)) != STB_OK) return rc;
+  } else {
+    if ((rc = stb_search_topk_xchg(ctx, corpus, ctx->q_dev, top_k, x, ctx->hits_dev, ctx->status_dev)) != STB_OK) return rc;
+    STB_CUDA(cudaMemcpyAsync(ctx->status_pin, ctx->status_dev, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    STB_CUDA(cudaMemcpyAsync(ctx->hits_pin, ctx->hits_dev, top_k * sizeof(stb_hit), cudaMemcpyDeviceToHost, ctx->stream));
+  }
   auto t1 = std::chrono::steady_clock::now();
   STB_CUDA(cudaStreamSynchronize(ctx->stream));
   if (prof) {
@@ -1103,6 +1107,28 @@ uint64_t stb_line_id(const uint8_t *path, uint64_t path_len, int32_t line_number
   const uint32_t u = (uint32_t)line_number;
   for (int b = 0; b < 4; ++b) { h ^= (u >> (8 * b)) & 0xffu; h *= 0x100000001b3ull; }
   return h;
+}
+
+// LineEmbedding::id for many rows at once: rows = n_rows x (path index, line_number) int32, paths
+// given as one byte blob + n_paths+1 offsets.  The FNV state after each path is computed once.
+int stb_line_ids(const uint8_t *path_bytes, const uint64_t *path_offsets, uint32_t n_paths, const int32_t *rows,
+                 uint64_t n_rows, uint64_t *out_ids) {
+  if ((n_paths && (!path_bytes || !path_offsets)) || (n_rows && (!rows || !out_ids))) { stb_set_error("line_ids: null argument"); return STB_ERR_ARG; }
+  std::vector<uint64_t> prefix(n_paths);
+  for (uint32_t p = 0; p < n_paths; ++p) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (uint64_t i = path_offsets[p]; i < path_offsets[p + 1]; ++i) { h ^= path_bytes[i]; h *= 0x100000001b3ull; }
+    prefix[p] = h;
+  }
+  for (uint64_t r = 0; r < n_rows; ++r) {
+    const int32_t pi = rows[2 * r];
+    if (pi < 0 || (uint32_t)pi >= n_paths) { stb_set_error("line_ids: row %llu refers to path %d of %u", (unsigned long long)r, pi, n_paths); return STB_ERR_RANGE; }
+    uint64_t h = prefix[pi];
+    const uint32_t u = (uint32_t)rows[2 * r + 1];
+    for (int b = 0; b < 4; ++b) { h ^= (u >> (8 * b)) & 0xffu; h *= 0x100000001b3ull; }
+    out_ids[r] = h;
+  }
+  return STB_OK;
 }
 
 }  // extern "C"

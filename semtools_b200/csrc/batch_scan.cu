@@ -314,6 +314,16 @@ stb_batch_gemm_kernel(const GemmArgs args) {
     const uint32_t quarter = warp & 3;
     const uint64_t n_sub = (uint64_t)args.n_tiles * (STB_B_TILE / STB_SUB);
     uint32_t d_cnt = 0;
+    [[maybe_unused]] float thr_r[8];
+    [[maybe_unused]] uint32_t cnt_r[8];
+    [[maybe_unused]] const bool reg_state = (EPI == 1) && args.m_tiles <= 8;
+    if constexpr (EPI == 1) {
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        cnt_r[jj] = 0u;
+        thr_r[jj] = (reg_state && (uint32_t)jj < args.m_tiles) ? __ldg(args.thr + jj * STB_A_TILE + quarter * 32 + lane) : CUDART_INF_F;
+      }
+    }
     for (uint32_t it = 0; it < my_tiles; ++it) {
       const uint64_t t = blockIdx.x + (uint64_t)it * gridDim.x;
       for (uint32_t m = 0; m < args.m_tiles; ++m, ++d_cnt) {
@@ -349,17 +359,28 @@ stb_batch_gemm_kernel(const GemmArgs args) {
           // region per 32-row chunk (hit mask -> ffs loop), not 32 predicated blocks.
           // (Round 1's per-hit global atomicAdd made this epilogue the bottleneck: 6.95 ms
           // against 3.3 ms for the maxima epilogue, profiles/r02_k2_v2_launches.txt.)
-          const float thr = __ldg(args.thr + q);
+          // Threshold and cursor of this thread's (query, CTA) segment.  Up to 8 query tiles (1024
+          // queries) they live in registers for the whole kernel (select chains, no dynamic
+          // indexing): two dependent L2 round trips per accumulator would otherwise sit on the
+          // epilogue's critical path, which is already ~90 % of the tile's MMA time.
           const size_t seg_id = (size_t)q * gridDim.x + blockIdx.x;
           uint32_t *cnt_p = args.cand_cnt + seg_id;
-          const uint32_t cnt0 = *cnt_p;
-          uint32_t cnt = cnt0;
+          float thr;
+          uint32_t cnt, cnt0 = 0;
+          if (reg_state) {
+            thr = thr_r[0]; cnt = cnt_r[0];
+#pragma unroll
+            for (int jj = 1; jj < 8; ++jj) { thr = (m == (uint32_t)jj) ? thr_r[jj] : thr; cnt = (m == (uint32_t)jj) ? cnt_r[jj] : cnt; }
+          } else {
+            thr = __ldg(args.thr + q);
+            cnt0 = *cnt_p;
+            cnt = cnt0;
+          }
           uint64_t *seg = args.cand_keys + seg_id * args.cand_cap;
-#pragma unroll 1
-          for (int c = 0; c < STB_B_TILE / STB_SUB; ++c) {
-            uint32_t r[32];
-            tc_ld_32x32b_x32(tmem_base + ((quarter * 32u) << 16) + acc * STB_B_TILE + c * STB_SUB, r);
-            tc_wait_ld();
+          // Software-pipelined over two register sets: the tcgen05.ld of chunk c+1 is in flight while
+          // chunk c is examined (reading a 128 x 256 f32 accumulator out of TMEM takes ~2/3 of the
+          // tile's MMA time by itself; serialised with the ALU work it paced the whole GEMM).
+          auto examine = [&](const uint32_t (&r)[32], int c) {
             float mx = __uint_as_float(r[0]);
 #pragma unroll
             for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
@@ -379,12 +400,35 @@ stb_batch_gemm_kernel(const GemmArgs args) {
                 ++cnt;                                                                 // > cand_cap = overflow marker
               }
             }
+          };
+          const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * STB_B_TILE;
+          uint32_t ra[32], rb[32];
+          tc_ld_32x32b_x32(taddr, ra);
+#pragma unroll 1
+          for (int c = 0; c < STB_B_TILE / STB_SUB; c += 2) {
+            tc_wait_ld();
+            tc_ld_32x32b_x32(taddr + (c + 1) * STB_SUB, rb);
+            examine(ra, c);
+            tc_wait_ld();
+            if (c + 2 < STB_B_TILE / STB_SUB) tc_ld_32x32b_x32(taddr + (c + 2) * STB_SUB, ra);
+            examine(rb, c + 1);
           }
-          if (cnt != cnt0) *cnt_p = cnt;
+          if (reg_state) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) cnt_r[jj] = (m == (uint32_t)jj) ? cnt : cnt_r[jj];
+          } else if (cnt != cnt0) *cnt_p = cnt;
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(d_empty + acc);
+      }
+    }
+    if constexpr (EPI == 1) {
+      if (reg_state) {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)
+          if ((uint32_t)jj < args.m_tiles && cnt_r[jj])
+            args.cand_cnt[(size_t)(jj * STB_A_TILE + quarter * 32 + lane) * gridDim.x + blockIdx.x] = cnt_r[jj];
       }
     }
   }

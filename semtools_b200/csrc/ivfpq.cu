@@ -799,8 +799,8 @@ int stb_ivfpq_search(stb_ivfpq *x, const float *q, uint32_t nprobe, uint32_t top
   cudaStream_t st = ctx->stream;
   memcpy(ctx->q_pin, q, STB_D * sizeof(float));
   STB_CUDA(cudaMemcpyAsync(ctx->q_dev, ctx->q_pin, STB_D * sizeof(float), cudaMemcpyHostToDevice, st));
-  const char *v2_env = getenv("STB_IVFPQ_V2");
-  if (v2_env && v2_env[0] == '1' && rerank <= ADC2_RERANK_CAP && top_k <= 1024) {
+  const char *v1_env = getenv("STB_IVFPQ_V1");            // STB_IVFPQ_V1=1: the round-1 multi-launch search
+  if (!(v1_env && v1_env[0] == '1') && rerank <= ADC2_RERANK_CAP && top_k <= 1024) {
     // fused search: two launches, one synchronisation
     uint32_t npow2 = 1; while (npow2 < x->nlist) npow2 <<= 1;
     if (!(ctx->func_attr_mask & (1u << STB_ATTR_IVF_V2))) {

@@ -21,14 +21,14 @@ std::vector<std::string> rust_lines(const std::string &content) {
   while (pos <= content.size()) {
     size_t nl = content.find('\n', pos);
     if (nl == std::string::npos) {
-      if (pos < content.size()) out.emplace_back(content.substr(pos));
+      if (pos < content.size()) out.emplace_back(content.substr(pos));   // unterminated last line: kept verbatim (a trailing '\r' stays)
       break;
     }
-    out.emplace_back(content.substr(pos, nl - pos));
+    size_t end = nl;
+    if (end > pos && content[end - 1] == '\r') --end;                    // "\r\n" is one terminator
+    out.emplace_back(content.substr(pos, end - pos));
     pos = nl + 1;
   }
-  for (auto &l : out)
-    if (!l.empty() && l.back() == '\r') l.pop_back();
   return out;
 }
 

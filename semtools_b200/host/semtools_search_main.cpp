@@ -123,6 +123,23 @@ int main(int argc, char **argv) {
       const unsigned threads = i + 2 < argc ? (unsigned)std::stoul(argv[i + 2]) : 0;
       return tokenize_bench(n_lines, threads);
     }
+    if (a == "--lines") {                          // test hook: stdin -> rust_lines -> one JSON string per line
+      std::string in;
+      char buf[65536];
+      size_t n;
+      while ((n = fread(buf, 1, sizeof(buf), stdin)) > 0) in.append(buf, n);
+      for (const auto &l : rust_lines(in)) {
+        std::string o = "\"";
+        for (unsigned char ch : l) {
+          if (ch == '"' || ch == '\\') { o.push_back('\\'); o.push_back((char)ch); }
+          else if (ch < 0x20) { char e[8]; snprintf(e, sizeof(e), "\\u%04x", ch); o += e; }
+          else o.push_back((char)ch);
+        }
+        o += "\"\n";
+        fwrite(o.data(), 1, o.size(), stdout);
+      }
+      return 0;
+    }
     if (a == "--lower") {                          // test hook: stdin -> to_lowercase -> stdout
       std::string in, line;
       char buf[65536];
@@ -165,6 +182,17 @@ int main(int argc, char **argv) {
     std::ifstream tf(table, std::ios::binary);
     std::vector<char> raw((std::istreambuf_iterator<char>(tf)), std::istreambuf_iterator<char>());
     if (raw.empty() || raw.size() % (STB_DIM * sizeof(float))) { fprintf(stderr, "Error: bad table file\n"); return 1; }
+    // identity of this host's embedder (WordLevel vocabulary file + table), recorded in the store so its
+    // vectors are never mixed with another host's / model's
+    char fp_buf[96];
+    {
+      std::ifstream vf(vocab, std::ios::binary);
+      std::vector<char> vraw((std::istreambuf_iterator<char>(vf)), std::istreambuf_iterator<char>());
+      const uint64_t hv = stb_fnv1a64(reinterpret_cast<const uint8_t *>(vraw.data()), vraw.size());
+      const uint64_t ht = stb_fnv1a64(reinterpret_cast<const uint8_t *>(raw.data()), std::min<size_t>(raw.size(), 1u << 20));
+      snprintf(fp_buf, sizeof(fp_buf), "wordlevel:%zux256:%016llx", raw.size() / (STB_DIM * sizeof(float)), (unsigned long long)(hv ^ (ht * 0x9E3779B97F4A7C15ull)));
+    }
+    const std::string fingerprint = fp_buf;
     bool in_workspace = false;
     if (!files.empty()) { try { Workspace::active(workspace_name); in_workspace = true; } catch (const std::exception &) {} }
     if (in_workspace) {
@@ -174,7 +202,7 @@ int main(int argc, char **argv) {
       auto ranked = search_with_workspace(
           files, s.encode_single(query, tok),
           [&](const std::vector<std::string> &lines) { return s.embed_lines(lines, tok, cfg.ignore_case); }, cfg, workspace_name,
-          [](const std::string &m) { fprintf(stderr, "%s\n", m.c_str()); });
+          [](const std::string &m) { fprintf(stderr, "%s\n", m.c_str()); }, 0, fingerprint);
       if (json) printf("%s\n", workspace_output_json(ranked, cfg.n_lines).c_str());
       else fputs(format_workspace_search_results(ranked, cfg.n_lines, isatty(1)).c_str(), stdout);
       return 0;

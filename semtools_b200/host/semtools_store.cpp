@@ -1,6 +1,9 @@
 #include "semtools_store.hpp"
 
+#include <fcntl.h>
+#include <sys/file.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -152,60 +155,114 @@ uint64_t DocMeta::id() const { return stb_fnv1a64(reinterpret_cast<const uint8_t
 uint64_t LineEmbedding::id() const { return stb_line_id(reinterpret_cast<const uint8_t *>(path.data()), path.size(), line_number); }
 
 // ------------------------------------------------------------------ Store ----------------
+namespace {
+struct DirLock {                                   // flock(<dir>/.lock), released on scope exit
+  int fd = -1;
+  DirLock(const std::string &dir, bool exclusive) {
+    fd = ::open((dir + "/.lock").c_str(), O_RDWR | O_CREAT, 0644);
+    if (fd < 0 || ::flock(fd, exclusive ? LOCK_EX : LOCK_SH) != 0) { if (fd >= 0) ::close(fd); fd = -1; throw std::runtime_error("cannot lock workspace store " + dir); }
+  }
+  ~DirLock() { if (fd >= 0) { ::flock(fd, LOCK_UN); ::close(fd); } }
+  DirLock(const DirLock &) = delete;
+  DirLock &operator=(const DirLock &) = delete;
+};
+long long file_size(const std::string &p) { struct stat st; return ::stat(p.c_str(), &st) == 0 ? (long long)st.st_size : -1; }
+}  // namespace
+
 Store Store::open(const std::string &workspace_dir) {
   Store s;
   s.dir_ = workspace_dir + "/flat.b200";
   mkdirs(s.dir_);
-  const std::string meta = s.dir_ + "/store.json";
-  if (!exists(meta)) return s;
+  DirLock lk(s.dir_, false);
+  s.load();
+  return s;
+}
+
+uint64_t Store::disk_gen() const {
+  if (!exists(dir_ + "/GEN")) return 0;
+  return std::strtoull(read_file(dir_ + "/GEN").c_str(), nullptr, 10);
+}
+
+void Store::load() {
+  paths_.clear(); path_idx_.clear(); docs_.clear(); rows_.clear(); emb_.clear(); id_row_.clear(); dirty_.clear();
+  gen_ = 0; rows_file_ = "rows.i32"; emb_file_ = "line_embeddings.f32"; stored_model_.clear();
+  n_disk_ = 0; rewrite_ = true;
+  const std::string meta = dir_ + "/store.json";
+  if (!exists(meta)) return;
   Json j = Json::parse(read_file(meta));
   const Json *fmt = j.get("format");
   if (!fmt || fmt->str != "semtools_b200.flat.v1") throw std::runtime_error("unknown store format");
-  for (const auto &p : j.get("paths")->arr) { s.path_idx_[p.str] = (int32_t)s.paths_.size(); s.paths_.push_back(p.str); }
+  for (const auto &p : j.get("paths")->arr) { path_idx_[p.str] = (int32_t)paths_.size(); paths_.push_back(p.str); }
   for (const auto &d : j.get("docs")->arr) {
     DocMeta m;
     m.path = d.get("path")->str;
     m.size_bytes = std::strtoull(d.get("size_bytes")->raw_num.c_str(), nullptr, 10);
     m.mtime = std::strtoll(d.get("mtime")->raw_num.c_str(), nullptr, 10);
     m.version = (uint32_t)d.get("_version")->num;
-    s.docs_.push_back(m);
+    docs_.push_back(m);
   }
-  const std::string rows = read_file(s.dir_ + "/rows.i32"), emb = read_file(s.dir_ + "/line_embeddings.f32");
-  s.rows_.resize(rows.size() / 4);
-  std::memcpy(s.rows_.data(), rows.data(), s.rows_.size() * 4);
-  s.emb_.resize(emb.size() / 4);
-  std::memcpy(s.emb_.data(), emb.data(), s.emb_.size() * 4);
-  if (s.rows_.size() / 2 != s.emb_.size() / LINE_EMBEDDING_SIZE) throw std::runtime_error("store files disagree on the row count");
-  for (size_t r = 0; r < s.rows_.size() / 2; ++r) {
-    LineEmbedding le{s.paths_[s.rows_[2 * r]], s.rows_[2 * r + 1], {}};
-    s.id_row_[le.id()] = r;
+  if (const Json *g = j.get("gen")) gen_ = std::strtoull(g->raw_num.c_str(), nullptr, 10);
+  if (const Json *f = j.get("files"); f && f->type == Json::Obj) {
+    if (const Json *r = f->get("rows")) rows_file_ = r->str;
+    if (const Json *e = f->get("emb")) emb_file_ = e->str;
   }
-  s.n_disk_ = s.rows_.size() / 2;
-  s.rewrite_ = false;
-  return s;
+  if (const Json *m = j.get("model"); m && m->type == Json::Str) stored_model_ = m->str;
+  const std::string rows_p = dir_ + "/" + rows_file_, emb_p = dir_ + "/" + emb_file_;
+  const long long rs = file_size(rows_p), es = file_size(emb_p);
+  const size_t n_rows_file = rs > 0 ? (size_t)rs / 8 : 0, n_emb_file = es > 0 ? (size_t)es / (LINE_EMBEDDING_SIZE * 4) : 0;
+  size_t n = std::min(n_rows_file, n_emb_file);
+  if (const Json *r = j.get("rows")) n = (size_t)std::strtoull(r->raw_num.c_str(), nullptr, 10);
+  if (n_rows_file < n || n_emb_file < n)
+    throw std::runtime_error("workspace store " + dir_ + " is truncated: store.json commits " + std::to_string(n) + " rows, the row files hold " +
+                             std::to_string(n_rows_file) + " / " + std::to_string(n_emb_file) + "; delete the directory to rebuild it");
+  rows_.resize(2 * n); emb_.resize(n * LINE_EMBEDDING_SIZE);
+  if (n) {
+    std::ifstream fr(rows_p, std::ios::binary), fe(emb_p, std::ios::binary);
+    fr.read(reinterpret_cast<char *>(rows_.data()), (std::streamsize)(rows_.size() * 4));
+    fe.read(reinterpret_cast<char *>(emb_.data()), (std::streamsize)(emb_.size() * 4));
+    if (!fr || !fe) throw std::runtime_error("workspace store " + dir_ + ": short read");
+  }
+  for (size_t r = 0; r < n; ++r) {
+    const int32_t pi = rows_[2 * r];
+    if (pi < 0 || (size_t)pi >= paths_.size())
+      throw std::runtime_error("workspace store " + dir_ + " is corrupt: a row refers to path index " + std::to_string(pi) + " but the path table has " +
+                               std::to_string(paths_.size()) + " entries; delete the directory to rebuild it");
+    LineEmbedding le{paths_[pi], rows_[2 * r + 1], {}};
+    id_row_[le.id()] = r;
+  }
+  n_disk_ = n;
+  rewrite_ = false;
 }
 
-void Store::flush() const {
-  const std::string tmp = dir_ + "/store.json.tmp";
-  {
-    std::ofstream f(tmp);
-    f << "{\"format\": \"semtools_b200.flat.v1\", \"dim\": 256, \"rows\": " << rows_.size() / 2 << ", \"paths\": [";
-    for (size_t i = 0; i < paths_.size(); ++i) f << (i ? ", " : "") << json_string(paths_[i]);
-    f << "], \"docs\": [";
-    for (size_t i = 0; i < docs_.size(); ++i)
-      f << (i ? ", " : "") << "{\"path\": " << json_string(docs_[i].path) << ", \"size_bytes\": " << docs_[i].size_bytes
-        << ", \"mtime\": " << docs_[i].mtime << ", \"_version\": " << docs_[i].version << "}";
-    f << "]}";
-  }
-  // the two row files are appended to / patched in place; only deletions rewrite them
-  const std::string rows_p = dir_ + "/rows.i32", emb_p = dir_ + "/line_embeddings.f32";
+template <class F>
+void Store::mutate(F &&apply) {
+  DirLock lk(dir_, true);
+  if (disk_gen() != gen_) load();                  // another process committed since this handle loaded
+  apply();
+  flush();
+}
+
+void Store::flush() {                              // caller holds the exclusive lock
+  const uint64_t gen = gen_ + 1;
+  std::string rows_file = rows_file_, emb_file = emb_file_;
+  std::string rows_p = dir_ + "/" + rows_file, emb_p = dir_ + "/" + emb_file;
   const size_t n = rows_.size() / 2;
-  auto file_size = [](const std::string &p) -> long long { struct stat st; return ::stat(p.c_str(), &st) == 0 ? (long long)st.st_size : -1; };
-  if (rewrite_ || file_size(rows_p) != (long long)(n_disk_ * 8) || file_size(emb_p) != (long long)(n_disk_ * LINE_EMBEDDING_SIZE * 4)) {
+  std::string old_rows, old_emb;
+  const bool have = exists(rows_p) && exists(emb_p);
+  const bool damaged = have && (file_size(rows_p) < (long long)(n_disk_ * 8) || file_size(emb_p) < (long long)(n_disk_ * LINE_EMBEDDING_SIZE * 4));
+  if (rewrite_ || !have || damaged) {
+    if (exists(rows_p) || exists(emb_p)) {         // never overwrite a committed generation in place
+      old_rows = rows_p; old_emb = emb_p;
+      rows_file = "rows." + std::to_string(gen) + ".i32"; emb_file = "line_embeddings." + std::to_string(gen) + ".f32";
+      rows_p = dir_ + "/" + rows_file; emb_p = dir_ + "/" + emb_file;
+    }
     { std::ofstream f(rows_p, std::ios::binary); f.write(reinterpret_cast<const char *>(rows_.data()), (std::streamsize)(rows_.size() * 4)); }
     { std::ofstream f(emb_p, std::ios::binary); f.write(reinterpret_cast<const char *>(emb_.data()), (std::streamsize)(emb_.size() * 4)); }
     ++full_rewrites;
   } else {
+    // anything beyond the committed rows is the debris of an interrupted flush
+    if (::truncate(rows_p.c_str(), (off_t)(n_disk_ * 8)) != 0 || ::truncate(emb_p.c_str(), (off_t)(n_disk_ * LINE_EMBEDDING_SIZE * 4)) != 0)
+      throw std::runtime_error("workspace store " + dir_ + ": cannot truncate the row files");
     std::fstream fr(rows_p, std::ios::in | std::ios::out | std::ios::binary), fe(emb_p, std::ios::in | std::ios::out | std::ios::binary);
     for (size_t r : dirty_) {
       if (r >= n_disk_) continue;
@@ -219,8 +276,28 @@ void Store::flush() const {
       fe.write(reinterpret_cast<const char *>(emb_.data() + n_disk_ * LINE_EMBEDDING_SIZE), (std::streamsize)((n - n_disk_) * LINE_EMBEDDING_SIZE * 4));
     }
   }
+  const std::string tmp = dir_ + "/store.json.tmp";
+  {
+    const std::string &model = model_fingerprint.empty() ? stored_model_ : model_fingerprint;
+    std::ofstream f(tmp);
+    f << "{\"format\": \"semtools_b200.flat.v1\", \"dim\": 256, \"rows\": " << n << ", \"gen\": " << gen
+      << ", \"files\": {\"rows\": " << json_string(rows_file) << ", \"emb\": " << json_string(emb_file) << "}, \"model\": ";
+    if (model.empty()) f << "null"; else f << json_string(model);
+    f << ", \"paths\": [";
+    for (size_t i = 0; i < paths_.size(); ++i) f << (i ? ", " : "") << json_string(paths_[i]);
+    f << "], \"docs\": [";
+    for (size_t i = 0; i < docs_.size(); ++i)
+      f << (i ? ", " : "") << "{\"path\": " << json_string(docs_[i].path) << ", \"size_bytes\": " << docs_[i].size_bytes
+        << ", \"mtime\": " << docs_[i].mtime << ", \"_version\": " << docs_[i].version << "}";
+    f << "]}";
+  }
+  std::rename(tmp.c_str(), (dir_ + "/store.json").c_str());        // the commit
+  { std::ofstream f(dir_ + "/GEN.tmp"); f << gen; }
+  std::rename((dir_ + "/GEN.tmp").c_str(), (dir_ + "/GEN").c_str());
+  if (!old_rows.empty()) { ::unlink(old_rows.c_str()); ::unlink(old_emb.c_str()); }
+  gen_ = gen; rows_file_ = rows_file; emb_file_ = emb_file;
+  if (!model_fingerprint.empty()) stored_model_ = model_fingerprint;
   n_disk_ = n; rewrite_ = false; dirty_.clear();
-  std::rename(tmp.c_str(), (dir_ + "/store.json").c_str());
 }
 
 std::map<std::string, DocMeta> Store::get_existing_docs(const std::vector<std::string> &paths) const {
@@ -240,8 +317,10 @@ std::vector<DocumentState> Store::analyze_document_states(const std::vector<std:
     DocumentState ds;
     ds.filename = fp; ds.meta = cur;
     auto it = existing.find(fp);
+    // a store written by another embedder (both fingerprints known): everything is re-embedded
+    const bool foreign = !model_fingerprint.empty() && !stored_model_.empty() && model_fingerprint != stored_model_;
     if (it != existing.end() && it->second.size_bytes == cur.size_bytes && it->second.mtime == cur.mtime &&
-        it->second.version == CURRENT_EMBEDDING_VERSION) {
+        it->second.version == CURRENT_EMBEDDING_VERSION && !foreign) {
       ds.kind = DocumentState::Unchanged;
     } else {
       ds.kind = it != existing.end() ? DocumentState::Changed : DocumentState::New;
@@ -254,15 +333,17 @@ std::vector<DocumentState> Store::analyze_document_states(const std::vector<std:
 
 void Store::upsert_document_metadata(const std::vector<DocMeta> &metas) {
   if (metas.empty()) return;
-  for (const auto &m : metas) {
-    auto it = std::find_if(docs_.begin(), docs_.end(), [&](const DocMeta &d) { return d.path == m.path; });
-    if (it != docs_.end()) *it = m; else docs_.push_back(m);
-  }
-  flush();
+  mutate([&] {
+    for (const auto &m : metas) {
+      auto it = std::find_if(docs_.begin(), docs_.end(), [&](const DocMeta &d) { return d.path == m.path; });
+      if (it != docs_.end()) *it = m; else docs_.push_back(m);
+    }
+  });
 }
 
 void Store::upsert_line_embeddings(const std::vector<LineEmbedding> &lines) {
   if (lines.empty()) return;
+  mutate([&] {
   for (const auto &le : lines) {
     if (le.embedding.size() != LINE_EMBEDDING_SIZE) throw std::runtime_error("embedding must have 256 floats");
     int32_t pi;
@@ -277,17 +358,20 @@ void Store::upsert_line_embeddings(const std::vector<LineEmbedding> &lines) {
     rows_[2 * row] = pi; rows_[2 * row + 1] = le.line_number;
     std::memcpy(emb_.data() + row * LINE_EMBEDDING_SIZE, le.embedding.data(), LINE_EMBEDDING_SIZE * 4);
   }
-  flush();
+  });
 }
 
 void Store::delete_document_metadata(const std::vector<std::string> &paths) {
-  for (const auto &p : paths)
-    docs_.erase(std::remove_if(docs_.begin(), docs_.end(), [&](const DocMeta &d) { return d.path == p && d.version == CURRENT_EMBEDDING_VERSION; }), docs_.end());
-  if (!paths.empty()) flush();
+  if (paths.empty()) return;
+  mutate([&] {
+    for (const auto &p : paths)
+      docs_.erase(std::remove_if(docs_.begin(), docs_.end(), [&](const DocMeta &d) { return d.path == p && d.version == CURRENT_EMBEDDING_VERSION; }), docs_.end());
+  });
 }
 
 void Store::delete_line_embeddings(const std::vector<std::string> &paths) {
   if (paths.empty()) return;
+  mutate([&] {
   std::vector<char> kill(paths_.size(), 0);
   for (const auto &p : paths) { auto it = path_idx_.find(p); if (it != path_idx_.end()) kill[it->second] = 1; }
   size_t w = 0;
@@ -304,7 +388,7 @@ void Store::delete_line_embeddings(const std::vector<std::string> &paths) {
   if (w != n) rewrite_ = true;                                      // rows moved: the files are rewritten
   id_row_.clear();
   for (size_t r = 0; r < w; ++r) { LineEmbedding le{paths_[rows_[2 * r]], rows_[2 * r + 1], {}}; id_row_[le.id()] = r; }
-  flush();
+  });
 }
 
 void Store::delete_documents(const std::vector<std::string> &paths) {
@@ -361,9 +445,11 @@ std::vector<RankedLine> Store::search_line_embeddings(const std::vector<float> &
 std::vector<RankedLine> search_with_workspace(const std::vector<std::string> &files, const std::vector<float> &query_embedding,
                                               const EmbedLinesFn &embed_lines, const SearchConfig &cfg,
                                               const std::optional<std::string> &workspace_name,
-                                              const std::function<void(const std::string &)> &log, int device) {
+                                              const std::function<void(const std::string &)> &log, int device,
+                                              const std::string &model_fingerprint) {
   Workspace ws = Workspace::open(workspace_name);
   Store store = Store::open(ws.config.root_dir);
+  store.model_fingerprint = model_fingerprint;
   std::vector<LineEmbedding> to_upsert;
   std::vector<DocMeta> docs;
   for (auto &st : store.analyze_document_states(files)) {

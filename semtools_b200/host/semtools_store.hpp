@@ -86,9 +86,25 @@ class Store {
                                                  size_t top_k, std::optional<float> max_distance, int device = 0);
   const std::vector<float> &matrix() const { return emb_; }
 
+  // fingerprint of the embedder (model + tokenizer) whose vectors this handle writes; recorded in
+  // store.json.  A store written with another fingerprint has every document reported Changed.
+  std::string model_fingerprint;
+  const std::string &stored_model_fingerprint() const { return stored_model_; }
+
  private:
-  void flush() const;
+  // Consistency protocol shared with the Python host (workspace.py: Store): store.json is the
+  // commit record ({"rows", "gen", "files", "model"}), replaced atomically after the row files hold
+  // the new state; rows beyond the committed count are debris of an interrupted flush; deletions
+  // write a new generation of row files; flock(<dir>/.lock) shared while loading, exclusive around
+  // every mutation, which first reloads when another process committed in between.
+  void load();
+  void flush();
+  template <class F> void mutate(F &&apply);
+  uint64_t disk_gen() const;
   std::string dir_;
+  uint64_t gen_ = 0;
+  std::string rows_file_ = "rows.i32", emb_file_ = "line_embeddings.f32";
+  std::string stored_model_;
   std::vector<std::string> paths_;
   std::unordered_map<std::string, int32_t> path_idx_;
   std::vector<DocMeta> docs_;                       // insertion order, as the Python dict
@@ -97,11 +113,11 @@ class Store {
   std::unordered_map<uint64_t, size_t> id_row_;
   // persistence bookkeeping (same policy as the Python store): rows [0, n_disk_) are on disk and
   // equal to memory except dirty_; rewrite_ forces a full rewrite (first flush, deletions)
-  mutable size_t n_disk_ = 0;
-  mutable std::set<size_t> dirty_;
-  mutable bool rewrite_ = true;
+  size_t n_disk_ = 0;
+  std::set<size_t> dirty_;
+  bool rewrite_ = true;
  public:
-  mutable unsigned full_rewrites = 0;
+  unsigned full_rewrites = 0;
 };
 
 // search_with_workspace (search/mod.rs:146-216): diff `files` against the store, embed only
@@ -110,7 +126,8 @@ using EmbedLinesFn = std::function<std::vector<float>(const std::vector<std::str
 std::vector<RankedLine> search_with_workspace(const std::vector<std::string> &files, const std::vector<float> &query_embedding,
                                               const EmbedLinesFn &embed_lines, const SearchConfig &cfg,
                                               const std::optional<std::string> &workspace_name,
-                                              const std::function<void(const std::string &)> &log = nullptr, int device = 0);
+                                              const std::function<void(const std::string &)> &log = nullptr, int device = 0,
+                                              const std::string &model_fingerprint = "");
 // print_workspace_search_results (cmds/search.rs:66-110) and the workspace JSON (:208-237)
 std::string format_workspace_search_results(const std::vector<RankedLine> &ranked, size_t n_lines, bool is_tty);
 std::string workspace_output_json(const std::vector<RankedLine> &ranked, size_t n_lines);

@@ -70,6 +70,15 @@ class StaticModel:
             raise ValueError(f"embedding table must be V x {capi.STB_DIM}, got {emb.shape}")
         return cls(tokenizer, emb, weights, mapping, normalize, median, unk_id, ctx)
 
+    def fingerprint(self) -> str:
+        """Identity of the embedder (tokenizer spec + table + pooling flags), recorded in the
+        workspace store so vectors of different models / tokenizers never mix silently."""
+        tok = self.tokenizer.to_str().encode("utf-8") if hasattr(self.tokenizer, "to_str") else repr(self.tokenizer).encode()
+        e = np.ascontiguousarray(self.embeddings)
+        head = e.reshape(-1)[: 262144].tobytes()
+        h = capi.fnv1a64(tok) ^ (capi.fnv1a64(head) * 0x9E3779B97F4A7C15 & 0xFFFFFFFFFFFFFFFF)
+        return f"model2vec:{e.shape[0]}x{e.shape[1]}:n{int(self.normalize)}:{h:016x}"
+
     # -- tokenisation (host) --------------------------------------------------------------------
     @staticmethod
     def truncate_str(text: str, max_tokens: int, median_token_length: int) -> str:

@@ -32,6 +32,8 @@ filter, STB_MODE_STORE_QUERY); nothing here computes a distance on the CPU.
 """
 from __future__ import annotations
 
+import contextlib
+import fcntl
 import json
 import os
 from dataclasses import asdict, dataclass, field
@@ -156,9 +158,15 @@ class WorkspaceStats:                                      # store.rs:98-103
 class Store:
     """Flat-file restatement of store.rs `Store`."""
 
-    def __init__(self, workspace_dir: str, ctx: capi.Context | None = None):
+    def __init__(self, workspace_dir: str, ctx: capi.Context | None = None, _keep=None):
         self.dir = os.path.join(workspace_dir, "flat.b200")
         self.ctx = ctx
+        self.model_fingerprint = getattr(_keep, "model_fingerprint", None)
+        self.stored_model_fingerprint = None
+        self._lock_depth = getattr(_keep, "_lock_depth", 0)
+        self._gen = 0
+        self._files = {"rows": "rows.i32", "emb": "line_embeddings.f32"}
+        self._trailing = False
         self._paths: list = []                 # path table
         self._path_idx: dict = {}
         self._docs: dict = {}                  # path -> DocMeta
@@ -172,64 +180,163 @@ class Store:
         self._n_disk = 0
         self._dirty_rows: set = set()
         self._rewrite = True
-        self.full_rewrites = 0                 # how many flushes rewrote the row files (tests, diagnostics)
+        self.full_rewrites = getattr(_keep, "full_rewrites", 0)   # how many flushes rewrote the row files (tests, diagnostics)
 
     # -- Store::open, store.rs:113-183 (creates the directories on first use)
     @classmethod
-    def open(cls, workspace_dir: str, ctx: capi.Context | None = None) -> "Store":
+    def open(cls, workspace_dir: str, ctx: capi.Context | None = None, model_fingerprint: str | None = None) -> "Store":
         s = cls(workspace_dir, ctx)
+        s.model_fingerprint = model_fingerprint
         os.makedirs(s.dir, exist_ok=True)
-        meta_p = os.path.join(s.dir, "store.json")
-        if os.path.exists(meta_p):
-            with open(meta_p) as f:
-                d = json.load(f)
-            if d.get("format") != FORMAT:
-                raise RuntimeError(f"unknown store format {d.get('format')!r}")
-            s._paths = list(d["paths"])
-            s._path_idx = {p: i for i, p in enumerate(s._paths)}
-            s._docs = {m["path"]: DocMeta(**m) for m in d["docs"]}
-            s._rows = np.fromfile(os.path.join(s.dir, "rows.i32"), dtype=np.int32).reshape(-1, 2)
-            emb_p = os.path.join(s.dir, "line_embeddings.f32")
-            n_emb = os.path.getsize(emb_p) // (LINE_EMBEDDING_SIZE * 4)
-            # copy-on-write map: a query-only process pages the matrix in once, straight into the
-            # chunked GPU upload, instead of holding a second copy in RAM
-            s._emb = np.memmap(emb_p, dtype=np.float32, mode="c", shape=(n_emb, LINE_EMBEDDING_SIZE)) if n_emb \
-                else np.zeros((0, LINE_EMBEDDING_SIZE), dtype=np.float32)
-            if len(s._rows) != len(s._emb):
-                raise RuntimeError("store files disagree on the row count")
-            for r, (pi, ln) in enumerate(s._rows):
-                s._id_row[capi.line_id(s._paths[pi], int(ln))] = r
-            s._n_disk, s._rewrite = len(s._rows), False
+        with s._locked(exclusive=False):
+            s._load()
         return s
+
+    # Consistency protocol (shared with the C++ host, semtools_store.cpp):
+    #  * store.json is the commit record: {"rows": committed row count, "gen": generation,
+    #    "files": the two row files of this generation, "model": fingerprint of the embedder}.  It is
+    #    replaced atomically (write tmp + rename) AFTER the row files hold the new state.
+    #  * appends / in-place patches go to the current row files; rows beyond the committed count
+    #    are garbage from an interrupted flush and are ignored on open (truncated by the next flush).
+    #    A patched row whose commit never happened belongs to a document whose DocMeta is still the
+    #    old one, so the next analyze_document_states sees it as Changed and re-embeds it.
+    #  * anything that moves rows (deletions) writes NEW files (rows.<gen>.i32, ...) and commits
+    #    by naming them in store.json; the old generation is unlinked afterwards.
+    #  * flock(<dir>/.lock): shared while loading, exclusive around every mutation.  A mutation first
+    #    checks the on-disk generation and reloads when another process committed in between, then
+    #    applies itself to the fresh state -- nobody overwrites rows they never saw.
+    @contextlib.contextmanager
+    def _locked(self, exclusive: bool):
+        if self._lock_depth:
+            self._lock_depth += 1
+            try:
+                yield
+            finally:
+                self._lock_depth -= 1
+            return
+        fd = os.open(os.path.join(self.dir, ".lock"), os.O_RDWR | os.O_CREAT, 0o644)
+        try:
+            fcntl.flock(fd, fcntl.LOCK_EX if exclusive else fcntl.LOCK_SH)
+            self._lock_depth = 1
+            yield
+        finally:
+            self._lock_depth = 0
+            try:
+                fcntl.flock(fd, fcntl.LOCK_UN)
+            finally:
+                os.close(fd)
+
+    def _disk_gen(self) -> int:
+        try:
+            with open(os.path.join(self.dir, "GEN")) as f:
+                return int(f.read().strip() or 0)
+        except (OSError, ValueError):
+            return 0
+
+    def _load(self) -> None:
+        """(Re)load the committed state.  Caller holds the lock."""
+        self.__init__(os.path.dirname(self.dir), self.ctx, _keep=self)
+        meta_p = os.path.join(self.dir, "store.json")
+        if not os.path.exists(meta_p):
+            return
+        with open(meta_p) as f:
+            d = json.load(f)
+        if d.get("format") != FORMAT:
+            raise RuntimeError(f"unknown store format {d.get('format')!r}")
+        self._paths = list(d["paths"])
+        self._path_idx = {p: i for i, p in enumerate(self._paths)}
+        self._docs = {m["path"]: DocMeta(**m) for m in d["docs"]}
+        self._gen = int(d.get("gen", 0))
+        self._files = dict(d.get("files") or {"rows": "rows.i32", "emb": "line_embeddings.f32"})
+        self.stored_model_fingerprint = d.get("model")
+        rows_p, emb_p = os.path.join(self.dir, self._files["rows"]), os.path.join(self.dir, self._files["emb"])
+        n_rows_file = os.path.getsize(rows_p) // 8 if os.path.exists(rows_p) else 0
+        n_emb_file = os.path.getsize(emb_p) // (LINE_EMBEDDING_SIZE * 4) if os.path.exists(emb_p) else 0
+        n = int(d["rows"]) if "rows" in d else min(n_rows_file, n_emb_file)
+        if n_rows_file < n or n_emb_file < n:
+            raise RuntimeError(f"workspace store {self.dir} is truncated: store.json commits {n} rows, the row files hold "
+                               f"{n_rows_file} / {n_emb_file}; delete the directory to rebuild it")
+        self._rows = np.fromfile(rows_p, dtype=np.int32, count=2 * n).reshape(-1, 2) if n else np.zeros((0, 2), dtype=np.int32)
+        # copy-on-write map: a query-only process pages the matrix in once, straight into the
+        # chunked GPU upload, instead of holding a second copy in RAM
+        self._emb = np.memmap(emb_p, dtype=np.float32, mode="c", shape=(n, LINE_EMBEDDING_SIZE)) if n \
+            else np.zeros((0, LINE_EMBEDDING_SIZE), dtype=np.float32)
+        if n and (self._rows[:, 0].min() < 0 or self._rows[:, 0].max() >= len(self._paths)):
+            raise RuntimeError(f"workspace store {self.dir} is corrupt: a row refers to path index "
+                               f"{int(self._rows[:, 0].max())} but the path table has {len(self._paths)} entries; "
+                               "delete the directory to rebuild it")
+        if n:
+            ids = capi.line_ids(self._paths, self._rows)                # one native call, not one per row
+            self._id_row = {int(v): r for r, v in enumerate(ids)}
+        self._n_disk, self._rewrite = n, False
+        self._trailing = n_rows_file > n or n_emb_file > n              # garbage of an interrupted flush
+
+    def _mutate(self, apply) -> None:
+        """Run one mutation under the exclusive lock on a state that is current on disk, then commit."""
+        with self._locked(exclusive=True):
+            if self._disk_gen() != self._gen:
+                self._load()                                             # another process committed since we loaded
+            apply()
+            self._flush()
 
     # -- flush_documents / flush_line_embeddings, store.rs:639-648
     def _flush(self) -> None:
         """store.json is rewritten every time (path table + DocMeta: small); the two row files
-        are appended to / patched in place, and only rewritten after deletions -- an upsert of
-        a few files into a multi-GB store writes a few MB."""
-        tmp = os.path.join(self.dir, "store.json.tmp")
-        with open(tmp, "w") as f:
-            json.dump({"format": FORMAT, "dim": LINE_EMBEDDING_SIZE, "rows": int(len(self._rows)),
-                       "paths": self._paths, "docs": [asdict(m) for m in self._docs.values()]}, f)
-        rows_p, emb_p = os.path.join(self.dir, "rows.i32"), os.path.join(self.dir, "line_embeddings.f32")
-        n = len(self._rows)
-        if self._rewrite or not (os.path.exists(rows_p) and os.path.exists(emb_p)) \
-                or os.path.getsize(rows_p) != self._n_disk * 8 or os.path.getsize(emb_p) != self._n_disk * LINE_EMBEDDING_SIZE * 4:
-            self._rows.astype(np.int32).tofile(rows_p)
-            self._emb.astype(np.float32).tofile(emb_p)
-            self.full_rewrites += 1
-        else:
-            with open(rows_p, "r+b") as fr, open(emb_p, "r+b") as fe:
-                for r in sorted(self._dirty_rows):
-                    if r < self._n_disk:
-                        fr.seek(r * 8); fr.write(self._rows[r].astype(np.int32).tobytes())
-                        fe.seek(r * LINE_EMBEDDING_SIZE * 4); fe.write(self._emb[r].astype(np.float32).tobytes())
-                if n > self._n_disk:
-                    fr.seek(0, os.SEEK_END); fr.write(self._rows[self._n_disk:].astype(np.int32).tobytes())
-                    fe.seek(0, os.SEEK_END); fe.write(self._emb[self._n_disk:].astype(np.float32).tobytes())
-        os.replace(tmp, os.path.join(self.dir, "store.json"))
-        self._n_disk, self._rewrite = n, False
-        self._dirty_rows.clear()
+        are appended to / patched in place, and only rewritten (as a new generation) after deletions
+        -- an upsert of a few files into a multi-GB store writes a few MB."""
+        with self._locked(exclusive=True):
+            gen = self._gen + 1
+            files = dict(self._files)
+            rows_p, emb_p = os.path.join(self.dir, files["rows"]), os.path.join(self.dir, files["emb"])
+            n = len(self._rows)
+            old_files = None
+            if self._rewrite or not (os.path.exists(rows_p) and os.path.exists(emb_p)):
+                if os.path.exists(rows_p) or os.path.exists(emb_p):      # never overwrite a committed generation in place
+                    old_files = (rows_p, emb_p)
+                    files = {"rows": f"rows.{gen}.i32", "emb": f"line_embeddings.{gen}.f32"}
+                    rows_p, emb_p = os.path.join(self.dir, files["rows"]), os.path.join(self.dir, files["emb"])
+                self._rows.astype(np.int32).tofile(rows_p)
+                np.asarray(self._emb, dtype=np.float32).tofile(emb_p)
+                self.full_rewrites += 1
+            elif os.path.getsize(rows_p) < self._n_disk * 8 or os.path.getsize(emb_p) < self._n_disk * LINE_EMBEDDING_SIZE * 4:
+                # the committed rows are no longer all there (foreign truncation): memory holds the full
+                # state, so heal by writing a new generation instead of patching a damaged file
+                old_files = (rows_p, emb_p)
+                files = {"rows": f"rows.{gen}.i32", "emb": f"line_embeddings.{gen}.f32"}
+                rows_p, emb_p = os.path.join(self.dir, files["rows"]), os.path.join(self.dir, files["emb"])
+                self._rows.astype(np.int32).tofile(rows_p)
+                np.asarray(self._emb, dtype=np.float32).tofile(emb_p)
+                self.full_rewrites += 1
+            else:
+                with open(rows_p, "r+b") as fr, open(emb_p, "r+b") as fe:
+                    # anything beyond the committed rows is the debris of an interrupted flush
+                    fr.truncate(self._n_disk * 8); fe.truncate(self._n_disk * LINE_EMBEDDING_SIZE * 4)
+                    for r in sorted(self._dirty_rows):
+                        if r < self._n_disk:
+                            fr.seek(r * 8); fr.write(self._rows[r].astype(np.int32).tobytes())
+                            fe.seek(r * LINE_EMBEDDING_SIZE * 4); fe.write(np.asarray(self._emb[r], dtype=np.float32).tobytes())
+                    if n > self._n_disk:
+                        fr.seek(0, os.SEEK_END); fr.write(self._rows[self._n_disk:].astype(np.int32).tobytes())
+                        fe.seek(0, os.SEEK_END); fe.write(np.asarray(self._emb[self._n_disk:], dtype=np.float32).tobytes())
+                    fr.flush(); fe.flush()
+                    os.fsync(fr.fileno()); os.fsync(fe.fileno())
+            tmp = os.path.join(self.dir, "store.json.tmp")
+            with open(tmp, "w") as f:
+                json.dump({"format": FORMAT, "dim": LINE_EMBEDDING_SIZE, "rows": int(n), "gen": gen, "files": files,
+                           "model": self.model_fingerprint or self.stored_model_fingerprint,
+                           "paths": self._paths, "docs": [asdict(m) for m in self._docs.values()]}, f)
+                f.flush(); os.fsync(f.fileno())
+            os.replace(tmp, os.path.join(self.dir, "store.json"))        # the commit
+            with open(os.path.join(self.dir, "GEN.tmp"), "w") as f:
+                f.write(str(gen))
+            os.replace(os.path.join(self.dir, "GEN.tmp"), os.path.join(self.dir, "GEN"))
+            if old_files:
+                for pth in old_files:
+                    if os.path.exists(pth) and os.path.basename(pth) not in files.values():
+                        os.unlink(pth)
+            self._gen, self._files = gen, files
+            self._n_disk, self._rewrite, self._trailing = n, False, False
+            self._dirty_rows.clear()
 
     def flush_documents(self) -> None:
         self._flush()
@@ -240,6 +347,13 @@ class Store:
     # -- store.rs:185-233
     def get_existing_docs(self, paths) -> dict:
         return {p: self._docs[p] for p in paths if p in self._docs}
+
+    def _foreign_model(self) -> bool:
+        """The store's vectors came from another embedder than this handle's (both known): every
+        document counts as Changed, so it is re-embedded instead of being mixed in (no reference
+        analogue -- the reference has one model; here two hosts with different tokenizers share a store)."""
+        return bool(self.model_fingerprint and self.stored_model_fingerprint
+                    and self.model_fingerprint != self.stored_model_fingerprint)
 
     # -- store.rs:549-611
     def analyze_document_states(self, file_paths) -> list:
@@ -253,11 +367,10 @@ class Store:
             cur = DocMeta(fp, st.st_size, int(st.st_mtime), CURRENT_EMBEDDING_VERSION)
             old = existing.get(fp)
             if old is not None and old.size_bytes == cur.size_bytes and old.mtime == cur.mtime \
-                    and old._version == CURRENT_EMBEDDING_VERSION:
+                    and old._version == CURRENT_EMBEDDING_VERSION and not self._foreign_model():
                 states.append(DocumentState("Unchanged", fp))
                 continue
-            with open(fp, encoding="utf-8") as f:                    # read_to_string: invalid UTF-8 is an error
-                content = f.read()
+            content = read_to_string(fp)                             # invalid UTF-8 is an error
             states.append(DocumentState("Changed" if old is not None else "New", fp, DocumentInfo(fp, content, cur)))
         return states
 
@@ -265,14 +378,19 @@ class Store:
     def upsert_document_metadata(self, metas) -> None:
         if not metas:
             return
-        for m in metas:
-            self._docs[m.path] = m                                   # same id (fnv1a(path)) -> replaced
-        self._flush()
+
+        def apply():
+            for m in metas:
+                self._docs[m.path] = m                               # same id (fnv1a(path)) -> replaced
+        self._mutate(apply)
 
     # -- store.rs:402-434
     def upsert_line_embeddings(self, line_embeddings) -> None:
         if not line_embeddings:
             return
+        self._mutate(lambda: self._apply_upsert_lines(line_embeddings))
+
+    def _apply_upsert_lines(self, line_embeddings) -> None:
         new_rows, new_emb = [], []
         for le in line_embeddings:
             emb = np.asarray(le.embedding, dtype=np.float32)
@@ -299,30 +417,34 @@ class Store:
         if new_emb:
             self._emb = np.concatenate([self._emb, np.stack(new_emb)]) if len(self._emb) else np.stack(new_emb)
             self._rows = np.concatenate([self._rows, np.asarray(new_rows, dtype=np.int32).reshape(-1, 2)])
-        self._flush()                                                 # appended rows reach the GPU mirror lazily
+        # appended rows reach the GPU mirror lazily
 
     # -- store.rs:235-296: only metadata of the CURRENT embedding version is deleted
     def delete_document_metadata(self, paths) -> None:
-        for p in paths:
-            m = self._docs.get(p)
-            if m is not None and m._version == CURRENT_EMBEDDING_VERSION:
-                del self._docs[p]
+        def apply():
+            for p in paths:
+                m = self._docs.get(p)
+                if m is not None and m._version == CURRENT_EMBEDDING_VERSION:
+                    del self._docs[p]
         if paths:
-            self._flush()
+            self._mutate(apply)
 
     # -- store.rs:298-357
     def delete_line_embeddings(self, paths) -> None:
         if not paths:
             return
-        kill = {self._path_idx[p] for p in paths if p in self._path_idx}
-        if kill:
-            keep = ~np.isin(self._rows[:, 0], list(kill))
-            self._rows = self._rows[keep]
-            self._emb = np.ascontiguousarray(self._emb[keep])
-            self._id_row = {capi.line_id(self._paths[pi], int(ln)): r for r, (pi, ln) in enumerate(self._rows)}
-            self._corpus = None
-            self._rewrite = True                                      # rows moved: the files are rewritten
-        self._flush()
+
+        def apply():
+            kill = {self._path_idx[p] for p in paths if p in self._path_idx}
+            if kill:
+                keep = ~np.isin(self._rows[:, 0], list(kill))
+                self._rows = self._rows[keep]
+                self._emb = np.ascontiguousarray(self._emb[keep])
+                ids = capi.line_ids(self._paths, self._rows) if len(self._rows) else []
+                self._id_row = {int(v): r for r, v in enumerate(ids)}
+                self._corpus = None
+                self._rewrite = True                                  # rows moved: a new generation of row files
+        self._mutate(apply)
 
     # -- store.rs:360-370
     def delete_documents(self, paths) -> None:
@@ -385,12 +507,12 @@ class Store:
 
 # ------------------------------------------------------------------ search/mod.rs:146-216 ---
 def search_with_workspace(files, query_embedding, embed_lines, config, workspace_name=None, ctx=None,
-                          log=None) -> list:
+                          log=None, model_fingerprint: str | None = None) -> list:
     """search_with_workspace: diff `files` against the store, embed only New/Changed
     documents (`embed_lines(list[str]) -> (n,256) f32`, i.e. create_document_from_content's
     encode_with_args on the caller's tokenizer + K3), upsert, then the filtered query."""
     ws = Workspace.open(workspace_name)
-    store = Store.open(ws.config.root_dir, ctx)
+    store = Store.open(ws.config.root_dir, ctx, model_fingerprint=model_fingerprint)
     to_upsert, docs = [], []
     for st in store.analyze_document_states(files):
         if st.kind == "Unchanged":
@@ -414,12 +536,23 @@ def search_with_workspace(files, query_embedding, embed_lines, config, workspace
     return store.search_line_embeddings(query_embedding, files, config.top_k, max_d)
 
 
+def read_to_string(path: str) -> str:
+    """fs::read_to_string: bytes decoded as UTF-8 (invalid UTF-8 is an error), NO newline
+    translation -- Python's default text mode would turn a bare '\\r' into a line break, which
+    str::lines() does not treat as one."""
+    with open(path, encoding="utf-8", newline="") as f:
+        return f.read()
+
+
 def _rust_lines(content: str) -> list:
-    """str::lines(): split on '\\n', strip one trailing '\\r' per line, no trailing empty
-    line (search/mod.rs:55)."""
+    """str::lines() (search/mod.rs:55): a line ends at '\\n'; a '\\r' directly before that
+    '\\n' belongs to the terminator; no trailing empty line.  A bare '\\r' is ordinary text, and
+    an unterminated last line keeps a trailing '\\r' (current Rust)."""
     if not content:
         return []
     parts = content.split("\n")
-    if parts and parts[-1] == "":
-        parts.pop()
-    return [p[:-1] if p.endswith("\r") else p for p in parts]
+    last = parts.pop()                                   # text after the final '\n' (unterminated line)
+    out = [p[:-1] if p.endswith("\r") else p for p in parts]
+    if last != "":
+        out.append(last)
+    return out

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_contract_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                        "--warmup", "1", "--cpu-sample-rows", "20000", "--rows", "100000"],
+                        "--warmup", "1", "--rows", "100000"],
                        capture_output=True, text=True, cwd=ROOT, timeout=300)
     assert r.returncode == 0, r.stderr
     d = json.loads(r.stdout.strip().splitlines()[-1])
@@ -21,6 +21,17 @@ def test_reference_arm_prints_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
     assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["value"] > 0 and d["config"]["rows"] == 100000
+    assert d["steps"] == 1 and d["cpu_baseline"]["sample"].startswith("all 100000 rows")     # same workload, same step count
+    assert len(r.stdout.strip().splitlines()[-1]) < 1500
+
+
+def test_reference_arm_can_bound_its_sample():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
+                        "--warmup", "0", "--rows", "100000", "--ref-rows", "20000"],
+                       capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert r.returncode == 0, r.stderr
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["steps"] == 2 and "scaled x5" in d["cpu_baseline"]["sample"]
 
 
 def test_reference_arm_non_zero_ranks_exit_quietly():

@@ -52,14 +52,11 @@ def test_ivfpq_recall_and_exact_distances(ctx):
 
 
 # ------------------------------------------------------------------------------------------
-# Fused search (v2: two launches, one sync).  Opt-in in the library (STB_IVFPQ_V2=1) and in this
-# suite (STB_TEST_V2=1) until validated on hardware.
+# Fused search (v2: two launches, one sync) is the default since round 2; STB_IVFPQ_V1=1 selects
+# the round-1 multi-launch search, which this test uses as the comparator.
 import os
 
-v2 = pytest.mark.skipif(os.environ.get("STB_TEST_V2") != "1", reason="fused IVF-PQ search is opt-in (STB_TEST_V2=1)")
 
-
-@v2
 def test_v2_fused_search_matches_v1_candidates_and_exact_distances(ctx):
     rng = np.random.default_rng(6)
     n = 200_000
@@ -69,9 +66,9 @@ def test_v2_fused_search_matches_v1_candidates_and_exact_distances(ctx):
     c.append(rows)
     idx = capi.IvfPq(c, nlist=256, train_rows=65536, iters=6)
     queries = clustered(rng, centers, 30)
-    os.environ.pop("STB_IVFPQ_V2", None)
+    os.environ["STB_IVFPQ_V1"] = "1"
     v1 = [idx.search(q, nprobe=32, top_k=10, rerank=512) for q in queries]
-    os.environ["STB_IVFPQ_V2"] = "1"
+    os.environ.pop("STB_IVFPQ_V1", None)
     try:
         recalls = []
         for i, q in enumerate(queries):
@@ -96,5 +93,5 @@ def test_v2_fused_search_matches_v1_candidates_and_exact_distances(ctx):
         got, _ = idx.search(np.zeros(256, np.float32), nprobe=4, top_k=5, rerank=64)
         assert len(got) == 5 and np.all(got["distance"] == 1.0)
     finally:
-        os.environ.pop("STB_IVFPQ_V2", None)
+        os.environ.pop("STB_IVFPQ_V1", None)
         idx.close()

@@ -129,9 +129,12 @@ def test_cpp_store_and_python_store_write_the_same_files(binary, tmp_path):
     assert r2.returncode == 0, r2.stderr
     assert r.stdout == r2.stdout
     assert "documents 3" in r.stdout and "line_embeddings 8" in r.stdout
-    for name in ("rows.i32", "line_embeddings.f32"):
+    mc, mp = (json.loads((d / "flat.b200" / "store.json").read_text()) for d in (dc, dp))
+    assert mc == mp                                                  # same commit record: rows, gen, files, paths, docs
+    assert mc["rows"] == 8 and mc["files"]["rows"] != "rows.i32"     # the deletions committed a new generation of row files
+    for name in mc["files"].values():
         assert (dc / "flat.b200" / name).read_bytes() == (dp / "flat.b200" / name).read_bytes()
-    assert json.loads((dc / "flat.b200" / "store.json").read_text()) == json.loads((dp / "flat.b200" / "store.json").read_text())
+    assert sorted(p.name for p in (dc / "flat.b200").iterdir()) == sorted(p.name for p in (dp / "flat.b200").iterdir())
     s = Store.open(str(dc))                                                               # Python reads C++'s files
     assert s.get_all_document_paths() == ["a.txt", "cé.txt", "old.txt"]
     assert s.count_line_embeddings() == 8
@@ -183,6 +186,18 @@ def test_cpp_workspace_commands_match_python_mirror(binary, tmp_path):
             os.environ["SEMTOOLS_WORKSPACE"] = old_ws
 
 
+def test_cpp_rust_lines_equals_python_mirror_including_bare_cr(binary):
+    """the Python host used to split on a bare CR, the C++ host did not; both now follow
+    str::lines() (search/mod.rs:55) and share one store, so they must agree byte for byte."""
+    import json as _json
+    from semtools_b200.workspace import _rust_lines
+    for text in ["one\rstill one\ntwo\r\nthree", "a\r", "a\r\n", "a\r\r\nb", "", "\n", "x\n\n", "t\tab \"q\" \\ z\n", "\r\n\r\n", "é\rü\n"]:
+        r = subprocess.run([binary, "--lines"], input=text.encode("utf-8"), capture_output=True)
+        assert r.returncode == 0
+        got = [_json.loads(l) for l in r.stdout.decode("utf-8").splitlines()]
+        assert got == _rust_lines(text), (text, got)
+
+
 def test_cpp_to_lowercase_is_full_unicode(binary):
     """str::to_lowercase (mod.rs:63-67): full mapping, multi-char expansions, Final_Sigma,
     case-ignorable skipping -- byte-identical to Python's str.lower() (same UCD algorithm)."""
@@ -228,7 +243,6 @@ def test_cpp_workspace_renderers_match_python(binary, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("STB_TEST_V2") != "1", reason="written after the last GPU session of round 1; enable with STB_TEST_V2=1")
 def test_cpp_cli_workspace_mode_equals_python_mirror(binary, tmp_path, ctx, monkeypatch):
     """search with an active workspace (search/mod.rs:146-216 + cmds/search.rs:194-241): the C++ CLI
     and the Python mirror build their own workspaces over the same files and print the same

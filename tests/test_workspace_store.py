@@ -6,6 +6,8 @@ import json
 import os
 import time
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 import numpy as np
 import pytest
 
@@ -156,6 +158,24 @@ def test_rust_lines_semantics():                          # search/mod.rs:55 str
     assert _rust_lines("a\r\nb\n") == ["a", "b"]
     assert _rust_lines("a\n\nb\n\n") == ["a", "", "b", ""]
     assert _rust_lines("\n") == [""]
+    # a bare CR is text, not a line break; only "\r\n" / "\n" terminate; an unterminated last
+    # line keeps its trailing CR (Python text mode used to split on the bare CR)
+    assert _rust_lines("one\rstill one\ntwo\r\nthree") == ["one\rstill one", "two", "three"]
+    assert _rust_lines("a\r") == ["a\r"]
+    assert _rust_lines("a\r\n") == ["a"]
+    assert _rust_lines("a\r\r\n") == ["a\r"]
+
+
+def test_read_to_string_does_not_translate_newlines(tmp_path):
+    from semtools_b200.workspace import read_to_string
+    p = tmp_path / "cr.txt"
+    p.write_bytes(b"one\rstill one\ntwo\r\nthree")
+    assert read_to_string(str(p)) == "one\rstill one\ntwo\r\nthree"
+    assert len(_rust_lines(read_to_string(str(p)))) == 3
+    bad = tmp_path / "bad.txt"
+    bad.write_bytes(b"\xff\xfe")
+    with pytest.raises(UnicodeDecodeError):
+        read_to_string(str(bad))
 
 
 # ------------------------------------------------------------------ GPU query tests ------
@@ -246,9 +266,99 @@ def test_incremental_flush_appends_and_patches_in_place(tmp_path):
     assert s2.full_rewrites == 1
     s3 = Store.open(str(tmp_path))
     assert s3.count_line_embeddings() == 5 and s3._emb[:, 0].tolist() == [0, 1, 99, 3, 20]
-    # a truncated / foreign row file is detected by its size and rewritten instead of appended to
-    with open(d / "rows.i32", "ab") as f:
-        f.write(b"\0" * 8)
+    # deletions commit a NEW generation of row files; the old one is gone
+    meta = json.load(open(d / "store.json"))
+    assert meta["files"]["rows"] != "rows.i32" and not (d / "rows.i32").exists() and meta["rows"] == 5
+    # debris behind the committed rows (an interrupted flush) is cut off, not appended to
+    with open(d / meta["files"]["rows"], "ab") as f:
+        f.write(b"\x07" * 8)
     s3.upsert_line_embeddings([LineEmbedding("d.txt", 0, emb(30))])
-    assert s3.full_rewrites == 1
-    assert Store.open(str(tmp_path)).count_line_embeddings() == 6
+    assert s3.full_rewrites == 0
+    s4 = Store.open(str(tmp_path))
+    assert s4.count_line_embeddings() == 6 and s4._emb[:, 0].tolist() == [0, 1, 99, 3, 20, 30]
+    assert s4._rows[-1].tolist() == [s4._path_idx["d.txt"], 0]
+
+
+def test_store_is_crash_consistent_and_validates_what_it_loads(tmp_path):
+    """rows reach the files before store.json is replaced, so a crash in between must
+    leave a store that opens (the uncommitted rows are ignored), and a row file that lost
+    committed rows or points outside the path table must fail with a clear error, not IndexError."""
+    def emb(v):
+        return np.full(256, v, dtype=np.float32)
+    s = Store.open(str(tmp_path))
+    s.upsert_line_embeddings([LineEmbedding("a.txt", i, emb(i)) for i in range(3)])
+    s.upsert_document_metadata([DocMeta("a.txt", 1, 2)])
+    d = tmp_path / "flat.b200"
+    # "crash" after appending two rows of a NEW path (index 1) but before the commit
+    with open(d / "rows.i32", "ab") as f:
+        f.write(np.array([[1, 0], [1, 1]], dtype=np.int32).tobytes())
+    with open(d / "line_embeddings.f32", "ab") as f:
+        f.write(np.stack([emb(7), emb(8)]).tobytes())
+    t = Store.open(str(tmp_path))
+    assert t.count_line_embeddings() == 3 and t._paths == ["a.txt"]
+    t.upsert_line_embeddings([LineEmbedding("b.txt", 0, emb(50))])
+    u = Store.open(str(tmp_path))
+    assert u._emb[:, 0].tolist() == [0, 1, 2, 50] and u._paths == ["a.txt", "b.txt"]
+    assert os.path.getsize(d / "rows.i32") == 4 * 8
+    # committed rows missing -> clear error
+    with open(d / "rows.i32", "r+b") as f:
+        f.truncate(2 * 8)
+    with pytest.raises(RuntimeError, match="truncated"):
+        Store.open(str(tmp_path))
+    # path index outside the table -> clear error
+    np.array([[0, 0], [0, 1], [0, 2], [9, 0]], dtype=np.int32).tofile(d / "rows.i32")
+    with pytest.raises(RuntimeError, match="corrupt"):
+        Store.open(str(tmp_path))
+
+
+def test_two_writers_do_not_drop_each_others_rows(tmp_path):
+    """two `search -w` processes used to overwrite each other.  Every mutation now runs
+    under an exclusive flock and first reloads when the on-disk generation moved."""
+    def emb(v):
+        return np.full(256, v, dtype=np.float32)
+    a, b = Store.open(str(tmp_path)), Store.open(str(tmp_path))        # both loaded the same (empty) state
+    a.upsert_line_embeddings([LineEmbedding("a.txt", i, emb(i)) for i in range(3)])
+    a.upsert_document_metadata([DocMeta("a.txt", 1, 2)])
+    b.upsert_line_embeddings([LineEmbedding("b.txt", i, emb(10 + i)) for i in range(2)])   # stale handle: reloads first
+    b.upsert_document_metadata([DocMeta("b.txt", 3, 4)])
+    a.upsert_line_embeddings([LineEmbedding("a.txt", 1, emb(77))])      # stale again: patch lands on the merged state
+    c = Store.open(str(tmp_path))
+    assert sorted(c.get_all_document_paths()) == ["a.txt", "b.txt"]
+    assert c._emb[:, 0].tolist() == [0, 77, 2, 10, 11]
+    assert [c._paths[i] for i in c._rows[:, 0]] == ["a.txt"] * 3 + ["b.txt"] * 2
+    # separate processes, same protocol
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, %r)
+        from semtools_b200.workspace import Store, LineEmbedding
+        s = Store.open(%r)
+        tag = int(sys.argv[1])
+        for j in range(20):
+            s.upsert_line_embeddings([LineEmbedding("p%%d.txt" %% tag, j, np.full(256, tag * 100 + j, dtype=np.float32))])
+    """) % (ROOT, str(tmp_path))
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(t)]) for t in (1, 2, 3)]
+    assert all(p.wait(timeout=120) == 0 for p in procs)
+    e = Store.open(str(tmp_path))
+    assert e.count_line_embeddings() == 5 + 60
+    vals = sorted(e._emb[5:, 0].tolist())
+    assert vals == sorted(t * 100 + j for t in (1, 2, 3) for j in range(20))
+
+
+def test_store_records_the_embedder_and_re_embeds_foreign_vectors(tmp_path):
+    """ADVICE r1: the C++ host (WordLevel stand-in) and the Python host (HF tokenizer) share one store;
+    change detection alone (size, mtime, _version) would silently mix their vectors."""
+    f = tmp_path / "doc.txt"; f.write_text("hello\nworld\n")
+    st = os.stat(f)
+    a = Store.open(str(tmp_path), model_fingerprint="model2vec:A")
+    a.upsert_line_embeddings([LineEmbedding(str(f), 0, np.ones(256, np.float32))])
+    a.upsert_document_metadata([DocMeta(str(f), st.st_size, int(st.st_mtime))])
+    assert json.load(open(tmp_path / "flat.b200" / "store.json"))["model"] == "model2vec:A"
+    same = Store.open(str(tmp_path), model_fingerprint="model2vec:A")
+    assert [s.kind for s in same.analyze_document_states([str(f)])] == ["Unchanged"]
+    other = Store.open(str(tmp_path), model_fingerprint="wordlevel:B")
+    assert [s.kind for s in other.analyze_document_states([str(f)])] == ["Changed"]
+    anon = Store.open(str(tmp_path))                                  # no fingerprint given: reference behaviour
+    assert [s.kind for s in anon.analyze_document_states([str(f)])] == ["Unchanged"]
+    other.upsert_document_metadata([DocMeta(str(f), st.st_size, int(st.st_mtime))])    # re-embedded by B: the store is B's now
+    assert json.load(open(tmp_path / "flat.b200" / "store.json"))["model"] == "wordlevel:B"
