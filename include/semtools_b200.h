@@ -269,6 +269,17 @@ int stb_ivfpq_search(stb_ivfpq *index, const float *q, uint32_t nprobe, uint32_t
 int stb_search_xchg(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint32_t top_k,
                     stb_xchg *x, stb_hit *out_hits, uint32_t *out_n, int *out_complete);
 
+/* Many independent single queries, one synchronisation (a host that has several queries in hand:
+ * an agent's tool calls, a batch of CLI invocations).  q: nq x 256 f32 (host); out_hits: nq x top_k
+ * (entry i*top_k.. of query i), out_n: nq counts.  Each query is its own scan (use stb_search_batch
+ * when nq is in the hundreds: one pass over the corpus for all of them); the kernels are enqueued
+ * back to back, so every tail overlaps the next scan, and hits are written straight to pinned host
+ * memory.  x == NULL: results are exactly stb_search's (an unproven query is re-run through it).
+ * x != NULL: the sharded form of stb_search_xchg -- out_complete[i] = 0 marks a query some rank could
+ * not prove (every rank sees the same flags).  out_complete may be NULL when x is NULL. */
+int stb_search_many(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint32_t nq, uint32_t top_k,
+                    stb_xchg *x, stb_hit *out_hits, uint32_t *out_n, uint8_t *out_complete);
+
 /* ---- K4: merge per-shard hit lists -----------------------------------------------
  * The final sort_by + take of src/search/mod.rs:107-119 applied across row
  * shards: `lists_dev` holds n_lists x per_list hits (e.g. the all-gathered

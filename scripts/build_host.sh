@@ -5,6 +5,7 @@ set -euo pipefail
 cd "$(dirname "$0")/.."
 /usr/bin/g++ -std=c++17 -O2 -Wall -Wextra -o semtools_b200/lib/semtools_b200_search \
   semtools_b200/host/semtools_search_main.cpp semtools_b200/host/semtools_host.cpp semtools_b200/host/semtools_store.cpp \
+  semtools_b200/host/semtools_tokenizer.cpp \
   -Lsemtools_b200/lib -lsemtools_b200 -Wl,-rpath,'$ORIGIN'
 /usr/bin/g++ -std=c++17 -O2 -Wall -Wextra -o semtools_b200/lib/semtools_b200_workspace \
   semtools_b200/host/semtools_workspace_main.cpp semtools_b200/host/semtools_store.cpp semtools_b200/host/semtools_host.cpp \

@@ -25,7 +25,7 @@ SYMBOLS = [
     "stb_embed_status", "stb_search",
     "stb_search_topk_dev", "stb_corpus_prepare", "stb_corpus_tier_stats", "stb_corpus_prepare_batch", "stb_search_batch", "stb_search_batch_dev",
     "stb_xchg_create", "stb_xchg_destroy", "stb_xchg_local_handle",
-    "stb_xchg_connect", "stb_xchg_connect_local", "stb_search_topk_xchg", "stb_search_xchg", "stb_ivfpq_build",
+    "stb_xchg_connect", "stb_xchg_connect_local", "stb_search_topk_xchg", "stb_search_xchg", "stb_search_many", "stb_ivfpq_build",
     "stb_ivfpq_destroy", "stb_ivfpq_stats", "stb_ivfpq_search", "stb_hits_merge_dev", "stb_hits_merge_batch_dev", "stb_hits_merge", "stb_fnv1a64", "stb_line_id", "stb_line_ids",
     "stb_ctx_counters", "stb_debug_ticket_check", "stb_debug_timestamps", "stb_debug_batch_gemm", "stb_debug_batch_params",
 ]
@@ -94,6 +94,7 @@ def lib() -> C.CDLL:
     L.stb_xchg_connect_local.argtypes = [vp, C.POINTER(vp)]
     L.stb_search_topk_xchg.argtypes = [vp, vp, vp, u32, vp, vp, vp]
     L.stb_search_xchg.argtypes = [vp, vp, vp, u32, vp, vp, C.POINTER(u32), C.POINTER(i32)]
+    L.stb_search_many.argtypes = [vp, vp, vp, u32, u32, vp, vp, vp, vp]
     L.stb_ivfpq_build.argtypes = [vp, vp, u32, u32, u32, C.POINTER(vp)]
     L.stb_ivfpq_destroy.argtypes = [vp]
     L.stb_ivfpq_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)]
@@ -310,6 +311,21 @@ class Corpus:
                 cap = int(n.value)
                 continue
             return out[: int(n.value)]
+
+    def search_many(self, queries, top_k: int = 10, xchg=None):
+        """stb_search_many: nq independent single queries, one synchronisation.  Returns a list of
+        HIT_DTYPE arrays (x is None) or (list, complete flags) for the sharded form."""
+        queries = np.ascontiguousarray(queries, dtype=np.float32)
+        if queries.ndim != 2 or queries.shape[1] != STB_DIM:
+            raise StbError(STB_ERR_ARG, f"queries must be (nq,{STB_DIM}) f32")
+        nq = queries.shape[0]
+        out = np.zeros((nq, max(top_k, 1)), dtype=HIT_DTYPE)
+        cnt = np.zeros(max(nq, 1), dtype=np.uint32)
+        ok = np.ones(max(nq, 1), dtype=np.uint8)
+        _check(lib().stb_search_many(self.ctx._h, self._h, _np_ptr(queries), nq, top_k, xchg._h if xchg is not None else None,
+                                     _np_ptr(out), _np_ptr(cnt), _np_ptr(ok)))
+        res = [out[i, : cnt[i]] for i in range(nq)]
+        return res if xchg is None else (res, ok[:nq].astype(bool))
 
     # -- K2 -----------------------------------------------------------------
     def prepare(self, what: int = 3):

@@ -148,6 +148,8 @@ int stb_ctx_destroy(stb_ctx *c) {
   if (c->q_pin) cudaFreeHost(c->q_pin);
   if (c->hits_pin) cudaFreeHost(c->hits_pin);
   if (c->status_pin) cudaFreeHost(c->status_pin);
+  if (c->many_q_pin) cudaFreeHost(c->many_q_pin);
+  if (c->many_status_pin) cudaFreeHost(c->many_status_pin);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   cudaGetLastError();
   delete c;
@@ -1049,6 +1051,85 @@ int stb_search_xchg(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint
   *out_n = n;
   *out_complete = ctx->status_pin[1] ? 1 : 0;
   if (ctx->status_pin[2] == 0xfffffffeu) { stb_set_error("search_xchg: a peer rank never arrived (timeout)"); return STB_ERR_STATE; }
+  return STB_OK;
+}
+
+// Many independent single queries with ONE synchronisation: queries are staged through pinned
+// memory in one H2D copy, the nq scan kernels are enqueued back to back (PDL overlaps each tail
+// with the next scan) and every kernel's final CTA stores its hits + status straight into pinned
+// host memory.  Unproven queries are re-run through stb_search (x == NULL) or reported
+// (x != NULL: all ranks see the same flag and fall back together).
+int stb_search_many(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint32_t nq, uint32_t top_k, stb_xchg *x,
+                    stb_hit *out_hits, uint32_t *out_n, uint8_t *out_complete) {
+  int rc = ctx_use(ctx);
+  if (rc) return rc;
+  if (!corpus || !q || !out_hits || !out_n) { stb_set_error("search_many: null argument"); return STB_ERR_ARG; }
+  if (corpus->ctx != ctx || (x && x->ctx != ctx)) { stb_set_error("search_many: handles belong to another context"); return STB_ERR_ARG; }
+  if (nq == 0) return STB_OK;
+  for (uint32_t i = 0; i < nq; ++i) { out_n[i] = 0; if (out_complete) out_complete[i] = 1; }
+  if (top_k == 0 || corpus->n == 0) {
+    if (x && corpus->n == 0) { stb_set_error("search_many: empty shard in a sharded search"); return STB_ERR_STATE; }
+    return STB_OK;
+  }
+  if (top_k > (x ? x->max_k : stb_scan_topk_max_k())) {
+    if (x) { stb_set_error("search_many: top_k must be 1..%u", x->max_k); return STB_ERR_ARG; }
+    for (uint32_t i = 0; i < nq; ++i) {                    // beyond the register lists: the general path, query by query
+      uint64_t n = 0;
+      rc = stb_search(ctx, corpus, q + (size_t)i * STB_D, top_k, 0, 0.0, STB_MODE_SEARCH_DOCUMENTS, nullptr, 0,
+                      out_hits + (size_t)i * top_k, top_k, &n);
+      if (rc != STB_OK) return rc;
+      out_n[i] = (uint32_t)n;
+    }
+    return STB_OK;
+  }
+  // many queries amortise the reduced-width copy: build it now (same size rule as the lazy build)
+  stb_corpus *cm = const_cast<stb_corpus *>(corpus);
+  if (nq >= 2 && cm->n >= 32768 && stb_env_max_tier() >= STB_TIER_Q8 && top_k <= STB_Q8_MAX_K && !(cm->q8 && cm->q8_rows == cm->n)) {
+    rc = corpus_ensure_q8(ctx, cm);
+    if (rc != STB_OK && rc != STB_ERR_STATE) return rc;
+  }
+  if ((rc = dev_reserve(&ctx->bq_dev, &ctx->bq_dev_cap, (size_t)nq * STB_D)) != STB_OK) return rc;
+  if ((rc = ensure_hits_pin(ctx, (size_t)nq * top_k)) != STB_OK) return rc;
+  if ((size_t)nq * STB_D > ctx->many_q_pin_cap) {
+    float *np = nullptr; uint32_t *ns = nullptr;
+    const size_t cap = std::max<size_t>((size_t)nq, 64);
+    if (cudaMallocHost((void **)&np, cap * STB_D * sizeof(float)) != cudaSuccess ||
+        cudaMallocHost((void **)&ns, cap * 4 * sizeof(uint32_t)) != cudaSuccess) {
+      cudaGetLastError(); if (np) cudaFreeHost(np);
+      stb_set_error("search_many: pinned staging allocation failed"); return STB_ERR_NOMEM;
+    }
+    if (ctx->many_q_pin) cudaFreeHost(ctx->many_q_pin);
+    if (ctx->many_status_pin) cudaFreeHost(ctx->many_status_pin);
+    ctx->many_q_pin = np; ctx->many_status_pin = ns; ctx->many_q_pin_cap = cap * STB_D;
+  }
+  memcpy(ctx->many_q_pin, q, (size_t)nq * STB_D * sizeof(float));
+  STB_CUDA(cudaMemcpyAsync(ctx->bq_dev, ctx->many_q_pin, (size_t)nq * STB_D * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  const int tier = best_built_tier(corpus, top_k);
+  for (uint32_t i = 0; i < nq; ++i) {
+    stb_hit *oh = ctx->hits_pin + (size_t)i * top_k;
+    uint32_t *os = ctx->many_status_pin + 4 * (size_t)i;
+    if (x) rc = stb_search_topk_xchg(ctx, corpus, ctx->bq_dev + (size_t)i * STB_D, top_k, x, oh, os);
+    else rc = stb_launch_scan_topk(ctx, corpus, tier, ctx->bq_dev + (size_t)i * STB_D, top_k, nullptr, 0, corpus->n, oh, os, nullptr);
+    if (rc != STB_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
+  }
+  STB_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (uint32_t i = 0; i < nq; ++i) {
+    const uint32_t *st = ctx->many_status_pin + 4 * (size_t)i;
+    if (x && st[2] == 0xfffffffeu) { stb_set_error("search_many: a peer rank never arrived (timeout)"); return STB_ERR_STATE; }
+    if (st[1]) {
+      const uint32_t n = std::min<uint32_t>(st[0], top_k);
+      memcpy(out_hits + (size_t)i * top_k, ctx->hits_pin + (size_t)i * top_k, n * sizeof(stb_hit));
+      out_n[i] = n;
+    } else if (x) {
+      if (out_complete) out_complete[i] = 0;               // every rank sees the same flag: fall back together
+    } else {
+      uint64_t n = 0;                                      // tier ladder / collect path
+      rc = stb_search(ctx, corpus, q + (size_t)i * STB_D, top_k, 0, 0.0, STB_MODE_SEARCH_DOCUMENTS, nullptr, 0,
+                      out_hits + (size_t)i * top_k, top_k, &n);
+      if (rc != STB_OK) return rc;
+      out_n[i] = (uint32_t)n;
+    }
+  }
   return STB_OK;
 }
 

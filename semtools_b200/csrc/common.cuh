@@ -116,6 +116,9 @@ struct stb_ctx {
   stb_hit *hits_pin;
   size_t hits_pin_cap;
   uint32_t *status_pin;
+  float *many_q_pin;          // stb_search_many: queries / per-query status (kernels write the latter directly)
+  uint32_t *many_status_pin;
+  size_t many_q_pin_cap;      // in floats
   // --- counters ---
   uint64_t kernel_launches;
   uint64_t fallback_searches;

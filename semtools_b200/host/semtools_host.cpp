@@ -83,7 +83,13 @@ void encode(uint32_t c, std::string &out) {
 }
 }  // namespace
 
-std::string to_lowercase(const std::string &s) {
+static std::string to_lowercase_impl(const std::string &s, bool final_sigma);
+std::string to_lowercase(const std::string &s) { return to_lowercase_impl(s, true); }
+// char::to_lowercase applied per character (what the tokenizers Lowercase normalizer does): the same
+// mapping WITHOUT the context-sensitive Final_Sigma rule of str::to_lowercase
+std::string to_lowercase_per_char(const std::string &s) { return to_lowercase_impl(s, false); }
+
+static std::string to_lowercase_impl(const std::string &s, bool final_sigma) {
   std::vector<uint32_t> cps;
   cps.reserve(s.size());
   for (size_t i = 0; i < s.size();) cps.push_back(decode(s, i));
@@ -93,6 +99,7 @@ std::string to_lowercase(const std::string &s) {
   for (size_t i = 0; i < cps.size(); ++i) {
     const uint32_t c = cps[i];
     if (c < 0x80) { out += (char)((c >= 'A' && c <= 'Z') ? c + 32 : c); continue; }
+    if (c == 0x3A3 && !final_sigma) { encode(0x3C3, out); continue; }   // char::to_lowercase: always the medial form
     if (c == 0x3A3) {
       // Final_Sigma: preceded by a cased letter (skipping case-ignorables) and not followed by one
       size_t j = i;
@@ -232,8 +239,21 @@ void tokenize_to_csr(const std::vector<std::string> &lines, const Tokenizer &tok
   auto work = [&](unsigned t) {
     const size_t lo = n * t / threads, hi = n * (t + 1) / threads;
     auto &out = part[t];
+    const size_t max_chars = tok.median_token_length() ? max_len * tok.median_token_length() : 0;
     for (size_t i = lo; i < hi; ++i) {
-      auto v = tok.encode(lines[i]);
+      // truncate_str(line, max_tokens, median_token_length): cut at max_tokens * median CHARACTERS first
+      const std::string *line = &lines[i];
+      std::string cut;
+      if (max_chars && line->size() > max_chars) {              // bytes >= chars: only then can it be too long
+        size_t pos = 0, chars = 0;
+        while (pos < line->size() && chars < max_chars) {
+          const unsigned char c = (unsigned char)(*line)[pos];
+          pos += c < 0x80 ? 1 : (c >> 5) == 6 ? 2 : (c >> 4) == 14 ? 3 : (c >> 3) == 30 ? 4 : 1;
+          ++chars;
+        }
+        if (pos < line->size()) { cut = line->substr(0, pos); line = &cut; }
+      }
+      auto v = tok.encode(*line);
       if (v.size() > max_len) v.resize(max_len);               // truncate(max_length)
       offsets[i + 1] = v.size();                               // per-line count; prefix-summed below
       out.insert(out.end(), v.begin(), v.end());

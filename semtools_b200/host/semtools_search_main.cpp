@@ -19,7 +19,10 @@
 #include <iostream>
 #include <iterator>
 
+#include <memory>
+
 #include "semtools_store.hpp"
+#include "semtools_tokenizer.hpp"
 
 using namespace semtools;
 
@@ -109,7 +112,7 @@ static int selftest() {
 }
 
 int main(int argc, char **argv) {
-  std::string vocab, table, query;
+  std::string vocab, tokenizer_json, table, query;
   std::vector<std::string> files;
   SearchConfig cfg;
   bool json = false, have_query = false;
@@ -122,6 +125,24 @@ int main(int argc, char **argv) {
       const size_t n_lines = i + 1 < argc ? std::stoul(argv[i + 1]) : 1000000;
       const unsigned threads = i + 2 < argc ? (unsigned)std::stoul(argv[i + 2]) : 0;
       return tokenize_bench(n_lines, threads);
+    }
+    if (a == "--encode") {                         // test hook: --encode tokenizer.json: stdin lines -> "raw ids | ids without unk"
+      HfTokenizer tk(next());
+      std::string in;
+      char buf[65536];
+      size_t n;
+      while ((n = fread(buf, 1, sizeof(buf), stdin)) > 0) in.append(buf, n);
+      printf("median_token_length %zu vocab %zu\n", tk.median_token_length(), tk.vocab_size());
+      for (const auto &l : rust_lines(in)) {
+        try {
+          std::string o;
+          for (uint32_t id : tk.encode_raw(l)) o += std::to_string(id) + " ";
+          o += "|";
+          for (uint32_t id : tk.encode(l)) o += " " + std::to_string(id);
+          puts(o.c_str());
+        } catch (const std::exception &e) { printf("ERROR %s\n", e.what()); }
+      }
+      return 0;
     }
     if (a == "--lines") {                          // test hook: stdin -> rust_lines -> one JSON string per line
       std::string in;
@@ -150,6 +171,7 @@ int main(int argc, char **argv) {
       return 0;
     }
     else if (a == "--vocab") vocab = next();
+    else if (a == "--tokenizer") tokenizer_json = next();
     else if (a == "--table") table = next();
     else if (a == "-n" || a == "--n-lines" || a == "--context") cfg.n_lines = std::stoul(next());
     else if (a == "--top-k") cfg.top_k = std::stoul(next());
@@ -160,8 +182,10 @@ int main(int argc, char **argv) {
     else if (!have_query) { query = a; have_query = true; }
     else files.push_back(a);
   }
-  if (!have_query || vocab.empty() || table.empty()) {
-    fprintf(stderr, "usage: semtools_b200_search --vocab V --table T QUERY [FILES...] [-n N] [--top-k K] [-m D] [-i] [-j] [-w WORKSPACE]\n");
+  if (!have_query || (vocab.empty() == tokenizer_json.empty()) || table.empty()) {
+    fprintf(stderr, "usage: semtools_b200_search (--tokenizer tokenizer.json | --vocab V) --table T QUERY [FILES...] [-n N] [--top-k K] [-m D] [-i] [-j] [-w WORKSPACE]\n"
+                    "  --tokenizer: the model's HF tokenizer.json (Unigram + Metaspace subset, see semtools_tokenizer.hpp)\n"
+                    "  --vocab:     whitespace WordLevel vocabulary, one token per line (synthetic models)\n");
     return 2;
   }
   try {
@@ -178,7 +202,10 @@ int main(int argc, char **argv) {
       else fprintf(stderr, "Error: %s\n", msg);
       return 1;
     }
-    WordLevelTokenizer tok(vocab);
+    std::unique_ptr<Tokenizer> tok_owner;
+    if (!tokenizer_json.empty()) tok_owner.reset(new HfTokenizer(tokenizer_json));
+    else tok_owner.reset(new WordLevelTokenizer(vocab));
+    const Tokenizer &tok = *tok_owner;
     std::ifstream tf(table, std::ios::binary);
     std::vector<char> raw((std::istreambuf_iterator<char>(tf)), std::istreambuf_iterator<char>());
     if (raw.empty() || raw.size() % (STB_DIM * sizeof(float))) { fprintf(stderr, "Error: bad table file\n"); return 1; }
@@ -186,11 +213,11 @@ int main(int argc, char **argv) {
     // vectors are never mixed with another host's / model's
     char fp_buf[96];
     {
-      std::ifstream vf(vocab, std::ios::binary);
+      std::ifstream vf(tokenizer_json.empty() ? vocab : tokenizer_json, std::ios::binary);
       std::vector<char> vraw((std::istreambuf_iterator<char>(vf)), std::istreambuf_iterator<char>());
       const uint64_t hv = stb_fnv1a64(reinterpret_cast<const uint8_t *>(vraw.data()), vraw.size());
       const uint64_t ht = stb_fnv1a64(reinterpret_cast<const uint8_t *>(raw.data()), std::min<size_t>(raw.size(), 1u << 20));
-      snprintf(fp_buf, sizeof(fp_buf), "wordlevel:%zux256:%016llx", raw.size() / (STB_DIM * sizeof(float)), (unsigned long long)(hv ^ (ht * 0x9E3779B97F4A7C15ull)));
+      snprintf(fp_buf, sizeof(fp_buf), "%s:%zux256:%016llx", tokenizer_json.empty() ? "wordlevel" : "hf-unigram", raw.size() / (STB_DIM * sizeof(float)), (unsigned long long)(hv ^ (ht * 0x9E3779B97F4A7C15ull)));
     }
     const std::string fingerprint = fp_buf;
     bool in_workspace = false;

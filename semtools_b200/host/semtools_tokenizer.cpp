@@ -1,0 +1,284 @@
+// HfTokenizer: tokenizer.json (Unigram + Metaspace subset) on the host.  See semtools_tokenizer.hpp.
+// Semantics follow HF `tokenizers` 0.21/0.22 (the crate model2vec-rs 0.1.3 links; Cargo.lock:4375):
+//   normalizers/{utils.rs,replace.rs,strip.rs,prepend.rs}, pre_tokenizers/metaspace.rs,
+//   models/unigram/model.rs (encode_optimized, fuse_unk = true, K_UNK_PENALTY = 10).
+#include "semtools_tokenizer.hpp"
+
+#include <algorithm>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
+
+extern "C" uint64_t stb_fnv1a64(const uint8_t *bytes, uint64_t len);
+
+namespace semtools {
+
+namespace {
+enum { N_LOWER = 0, N_REPLACE_STR, N_REPLACE_MULTISPACE, N_STRIP, N_PREPEND, N_UNICODE_ASCII_ONLY };
+enum { P_METASPACE = 0, P_WHITESPACE_SPLIT };
+enum { PREPEND_ALWAYS = 0, PREPEND_FIRST, PREPEND_NEVER };
+
+std::string slurp(const std::string &p) {
+  std::ifstream f(p, std::ios::binary);
+  if (!f) throw std::runtime_error("cannot read " + p);
+  std::stringstream ss; ss << f.rdbuf(); return ss.str();
+}
+const Json &need(const Json &j, const char *key, const char *where) {
+  const Json *v = j.get(key);
+  if (!v) throw std::runtime_error(std::string("tokenizer.json: ") + where + " lacks \"" + key + "\"");
+  return *v;
+}
+std::string type_of(const Json &j) {
+  const Json *t = j.get("type");
+  return (t && t->type == Json::Str) ? t->str : "";
+}
+inline size_t utf8_len(unsigned char c) { return c < 0x80 ? 1 : (c >> 5) == 6 ? 2 : (c >> 4) == 14 ? 3 : (c >> 3) == 30 ? 4 : 1; }
+// Unicode White_Space (what Rust's char::is_whitespace tests)
+bool is_space_at(const std::string &s, size_t i, size_t *len) {
+  const unsigned char c = (unsigned char)s[i];
+  if (c < 0x80) { *len = 1; return c == ' ' || (c >= 9 && c <= 13); }
+  const size_t n = utf8_len(c);
+  *len = n;
+  if (i + n > s.size()) return false;
+  uint32_t cp = 0;
+  if (n == 2) cp = ((c & 0x1F) << 6) | ((unsigned char)s[i + 1] & 0x3F);
+  else if (n == 3) cp = ((c & 0x0F) << 12) | (((unsigned char)s[i + 1] & 0x3F) << 6) | ((unsigned char)s[i + 2] & 0x3F);
+  else return false;
+  return cp == 0x85 || cp == 0xA0 || cp == 0x1680 || (cp >= 0x2000 && cp <= 0x200A) || cp == 0x2028 || cp == 0x2029 || cp == 0x202F ||
+         cp == 0x205F || cp == 0x3000;
+}
+}  // namespace
+
+void HfTokenizer::add_norm(const Json &j) {
+  if (j.type == Json::Null) return;
+  const std::string t = type_of(j);
+  if (t == "Sequence") { for (const auto &n : need(j, "normalizers", "Sequence normalizer").arr) add_norm(n); return; }
+  if (t == "Lowercase") { norm_.push_back({N_LOWER, "", ""}); return; }
+  if (t == "Replace") {
+    const Json &pat = need(j, "pattern", "Replace normalizer");
+    const std::string content = need(j, "content", "Replace normalizer").str;
+    if (const Json *s = pat.get("String")) { if (!s->str.empty()) norm_.push_back({N_REPLACE_STR, s->str, content}); return; }
+    if (const Json *r = pat.get("Regex")) {
+      if (r->str == " {2,}") { norm_.push_back({N_REPLACE_MULTISPACE, "", content}); return; }
+      throw std::runtime_error("tokenizer.json: Replace normalizer with regex /" + r->str + "/ is not supported by the C++ host (only \" {2,}\")");
+    }
+    throw std::runtime_error("tokenizer.json: Replace normalizer without pattern");
+  }
+  if (t == "Strip") {
+    NormStep s{N_STRIP, "", ""};
+    if (const Json *l = j.get("strip_left")) s.left = l->b;
+    if (const Json *r = j.get("strip_right")) s.right = r->b;
+    norm_.push_back(s); return;
+  }
+  if (t == "Prepend") { norm_.push_back({N_PREPEND, need(j, "prepend", "Prepend normalizer").str, ""}); return; }
+  if (t == "NFC" || t == "NFD" || t == "NFKC" || t == "NFKD" || t == "Precompiled" || t == "Nmt") {
+    norm_.push_back({N_UNICODE_ASCII_ONLY, t, ""}); return;
+  }
+  throw std::runtime_error("tokenizer.json: normalizer \"" + t + "\" is not supported by the C++ host");
+}
+
+void HfTokenizer::add_pre(const Json &j) {
+  if (j.type == Json::Null) return;
+  const std::string t = type_of(j);
+  if (t == "Sequence") { for (const auto &n : need(j, "pretokenizers", "Sequence pre_tokenizer").arr) add_pre(n); return; }
+  if (t == "Metaspace") {
+    PreStep p{P_METASPACE, "\xE2\x96\x81", PREPEND_ALWAYS, true};
+    if (const Json *r = j.get("replacement")) p.replacement = r->str;
+    if (const Json *s = j.get("prepend_scheme")) p.prepend = s->str == "first" ? PREPEND_FIRST : s->str == "never" ? PREPEND_NEVER : PREPEND_ALWAYS;
+    else if (const Json *a = j.get("add_prefix_space")) p.prepend = a->b ? PREPEND_ALWAYS : PREPEND_NEVER;   // pre-0.15 files
+    if (const Json *s = j.get("split")) p.split = s->b;
+    pre_.push_back(p); return;
+  }
+  if (t == "WhitespaceSplit") { pre_.push_back({P_WHITESPACE_SPLIT, "", 0, true}); return; }
+  throw std::runtime_error("tokenizer.json: pre_tokenizer \"" + t + "\" is not supported by the C++ host");
+}
+
+HfTokenizer::HfTokenizer(const std::string &path) {
+  const std::string text = slurp(path);
+  file_hash_ = stb_fnv1a64(reinterpret_cast<const uint8_t *>(text.data()), text.size());
+  const Json j = Json::parse(text);
+  if (const Json *n = j.get("normalizer")) add_norm(*n);
+  if (const Json *p = j.get("pre_tokenizer")) add_pre(*p);
+  const Json &model = need(j, "model", "the file");
+  if (type_of(model) != "Unigram") throw std::runtime_error("tokenizer.json: model \"" + type_of(model) + "\" is not supported by the C++ host (Unigram only)");
+  if (const Json *bf = model.get("byte_fallback"); bf && bf->b) throw std::runtime_error("tokenizer.json: Unigram byte_fallback is not supported by the C++ host");
+  if (const Json *u = model.get("unk_id"); u && u->type == Json::Num) { has_unk_ = true; unk_id_ = (uint32_t)u->num; }
+  const Json &vocab = need(model, "vocab", "Unigram model");
+  tokens_.reserve(vocab.arr.size()); scores_.reserve(vocab.arr.size());
+  for (const auto &e : vocab.arr) {
+    if (e.type != Json::Arr || e.arr.size() != 2) throw std::runtime_error("tokenizer.json: malformed Unigram vocab entry");
+    tokens_.push_back(e.arr[0].str);
+    scores_.push_back(e.arr[1].num);
+  }
+  if (tokens_.empty()) throw std::runtime_error("tokenizer.json: empty vocabulary");
+  if (has_unk_ && unk_id_ >= tokens_.size()) throw std::runtime_error("tokenizer.json: unk_id outside the vocabulary");
+  min_score_ = *std::min_element(scores_.begin(), scores_.end());
+  // byte trie; a token that occurs twice keeps the LAST id (tokenizers builds token_to_ids by insertion)
+  terminal_.push_back(-1);
+  for (size_t id = 0; id < tokens_.size(); ++id) {
+    uint32_t node = 0;
+    for (unsigned char c : tokens_[id]) {
+      const uint64_t key = ((uint64_t)node << 8) | c;
+      auto it = edges_.find(key);
+      if (it == edges_.end()) { it = edges_.emplace(key, (uint32_t)terminal_.size()).first; terminal_.push_back(-1); }
+      node = it->second;
+    }
+    if (!tokens_[id].empty()) terminal_[node] = (int32_t)id;
+  }
+  // median token length in BYTES over the vocabulary (model2vec: `tk.len()` of every vocab key)
+  std::vector<size_t> lens;
+  lens.reserve(tokens_.size());
+  for (const auto &t : tokens_) lens.push_back(t.size());
+  std::sort(lens.begin(), lens.end());
+  median_len_ = std::max<size_t>(1, lens[lens.size() / 2]);
+}
+
+std::string HfTokenizer::normalize(const std::string &in) const {
+  std::string s = in;
+  for (const auto &st : norm_) {
+    switch (st.kind) {
+      case N_LOWER: s = to_lowercase_per_char(s); break;
+      case N_REPLACE_STR: {
+        std::string o; size_t pos = 0, f;
+        while ((f = s.find(st.a, pos)) != std::string::npos) { o.append(s, pos, f - pos); o += st.b; pos = f + st.a.size(); }
+        o.append(s, pos, std::string::npos); s.swap(o); break;
+      }
+      case N_REPLACE_MULTISPACE: {
+        std::string o; size_t i = 0;
+        while (i < s.size()) {
+          if (s[i] == ' ') { size_t e = i; while (e < s.size() && s[e] == ' ') ++e; if (e - i >= 2) o += st.b; else o += ' '; i = e; }
+          else o += s[i++];
+        }
+        s.swap(o); break;
+      }
+      case N_STRIP: {
+        size_t b = 0, e = s.size(), l;
+        if (st.left) while (b < e && is_space_at(s, b, &l)) b += l;
+        if (st.right) {
+          for (;;) {                                   // step back one UTF-8 character at a time
+            if (e <= b) break;
+            size_t k = e - 1;
+            while (k > b && ((unsigned char)s[k] & 0xC0) == 0x80) --k;
+            if (is_space_at(s, k, &l) && k + l == e) e = k; else break;
+          }
+        }
+        s = s.substr(b, e - b); break;
+      }
+      case N_PREPEND: if (!s.empty()) s = st.a + s; break;
+      case N_UNICODE_ASCII_ONLY:
+        for (unsigned char c : s)
+          if (c >= 0x80 || (c < 0x20 && c != '\t' && c != '\n' && c != '\r'))
+            throw std::runtime_error("the C++ host applies the " + st.a + " normalizer to printable ASCII only; this line needs the Python host");
+        break;
+    }
+  }
+  return s;
+}
+
+void HfTokenizer::pre_tokenize(const std::string &normalized, std::vector<std::string> &pieces) const {
+  pieces.clear();
+  pieces.push_back(normalized);
+  bool first_step = true;
+  for (const auto &p : pre_) {
+    std::vector<std::string> next;
+    size_t piece_no = 0;
+    for (const auto &piece : pieces) {
+      if (p.kind == P_WHITESPACE_SPLIT) {
+        size_t i = 0, l;
+        while (i < piece.size()) {
+          while (i < piece.size() && is_space_at(piece, i, &l)) i += l;
+          size_t b = i;
+          while (i < piece.size() && !is_space_at(piece, i, &l)) i += l;
+          if (i > b) next.push_back(piece.substr(b, i - b));
+        }
+      } else {
+        // Metaspace: ' ' -> replacement; prepend (always | first: only the piece that starts the
+        // original string | never) unless already there; split MergedWithNext on the replacement
+        std::string s;
+        for (char c : piece) { if (c == ' ') s += p.replacement; else s += c; }
+        const bool starts = s.compare(0, p.replacement.size(), p.replacement) == 0;
+        const bool at_origin = first_step && piece_no == 0;
+        if (!starts && (p.prepend == PREPEND_ALWAYS || (p.prepend == PREPEND_FIRST && at_origin))) s = p.replacement + s;
+        if (!p.split) { if (!s.empty()) next.push_back(s); }
+        else {
+          size_t b = 0, pos = p.replacement.empty() ? std::string::npos : s.find(p.replacement, 0);
+          // every delimiter starts a new piece that runs up to the next delimiter
+          if (pos != 0 && !s.empty()) { const size_t e = pos == std::string::npos ? s.size() : pos; next.push_back(s.substr(0, e)); b = e; }
+          while (b < s.size()) {
+            const size_t nxt = s.find(p.replacement, b + p.replacement.size());
+            const size_t e = nxt == std::string::npos ? s.size() : nxt;
+            next.push_back(s.substr(b, e - b));
+            b = e;
+          }
+        }
+      }
+      ++piece_no;
+    }
+    pieces.swap(next);
+    first_step = false;
+  }
+}
+
+// models/unigram/model.rs: encode_optimized + tokenize (string -> id, unknown strings -> unk_id)
+void HfTokenizer::unigram(const std::string &s, std::vector<uint32_t> &out) const {
+  const size_t size = s.size();
+  if (size == 0) return;
+  struct Node { uint32_t id = 0; double score = 0.0; int64_t starts_at = -1; };
+  std::vector<Node> best(size + 1);
+  const double unk_score = min_score_ - 10.0;
+  size_t at = 0;
+  while (at < size) {
+    const double here = best[at].score;
+    bool has_single = false;
+    const size_t mblen = std::min(utf8_len((unsigned char)s[at]), size - at);
+    uint32_t node = 0;
+    for (size_t k = at; k < size; ++k) {
+      auto it = edges_.find(((uint64_t)node << 8) | (unsigned char)s[k]);
+      if (it == edges_.end()) break;
+      node = it->second;
+      const int32_t id = terminal_[node];
+      if (id < 0) continue;
+      const size_t key_pos = k + 1;
+      Node &t = best[key_pos];
+      const double cand = scores_[id] + here;
+      if (t.starts_at < 0 || cand > t.score) { t.score = cand; t.starts_at = (int64_t)at; t.id = (uint32_t)id; }
+      if (!has_single && key_pos - at == mblen) has_single = true;
+    }
+    if (!has_single) {
+      if (!has_unk_) throw std::runtime_error("tokenizer: a character is not in the vocabulary and the model has no unk_id");
+      Node &t = best[at + mblen];
+      const double cand = unk_score + here;
+      if (t.starts_at < 0 || cand > t.score) { t.score = cand; t.starts_at = (int64_t)at; t.id = unk_id_; }
+    }
+    at += mblen;
+  }
+  // backtrack; consecutive unknown characters fuse into ONE unk token (fuse_unk)
+  std::vector<uint32_t> rev;
+  size_t ends = size;
+  bool in_unk = false;
+  while (ends > 0) {
+    const Node &n = best[ends];
+    if (has_unk_ && n.id == unk_id_) { if (!in_unk) { rev.push_back(unk_id_); in_unk = true; } }
+    else { rev.push_back(n.id); in_unk = false; }
+    ends = (size_t)n.starts_at;
+  }
+  out.insert(out.end(), rev.rbegin(), rev.rend());
+}
+
+std::vector<uint32_t> HfTokenizer::encode_raw(const std::string &text) const {
+  std::vector<std::string> pieces;
+  std::vector<uint32_t> ids;
+  const std::string normalized = normalize(text);
+  if (normalized.empty()) return ids;       // AddedVocabulary::extract_and_normalize yields no split for an empty string
+  pre_tokenize(normalized, pieces);
+  for (const auto &p : pieces) unigram(p, ids);
+  return ids;
+}
+
+std::vector<uint32_t> HfTokenizer::encode(const std::string &text) const {
+  std::vector<uint32_t> ids = encode_raw(text);
+  if (has_unk_) ids.erase(std::remove(ids.begin(), ids.end(), unk_id_), ids.end());    // encode_with_args drops unk ids
+  return ids;
+}
+
+}  // namespace semtools

@@ -1,0 +1,66 @@
+// Host tokenizer of the C++ layer: the `tokenizer.json` pipeline the reference runs through the
+// HF `tokenizers` crate inside model2vec-rs (encode_with_args -> tokenizer.encode_batch_fast(..,
+// add_special_tokens = false), reference call site src/search/mod.rs:69), restated for the subset of
+// components a SentencePiece-style static-embedding model uses:
+//   normalizer     Sequence | Lowercase | Replace (string pattern, or the regex " {2,}") | Strip |
+//                  Prepend | NFC/NFD/NFKC/NFKD/Precompiled (identity on printable ASCII; a line with
+//                  other characters is REFUSED with an error -- the composition tables are not
+//                  restated here; use the Python host for such text)
+//   pre_tokenizer  Metaspace (replacement, prepend_scheme always|first|never, split) | WhitespaceSplit |
+//                  Sequence of those
+//   model          Unigram (vocab [[token, score]...], unk_id, byte_fallback = false): Viterbi over a
+//                  byte trie exactly as tokenizers' `encode_optimized` (f64 scores, strict > on ties,
+//                  unknown characters at min_score - 10, consecutive unknowns fused into one token)
+// Anything else in tokenizer.json fails the constructor with a clear message.  Output ids are
+// checked token for token against HF `tokenizers` on synthetic vocabularies (tests/test_host_cpp.py);
+// the real model's tokenizer.json is not available offline (parity unpinned for it).
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "semtools_host.hpp"
+#include "semtools_store.hpp"   // Json
+
+namespace semtools {
+
+class HfTokenizer : public Tokenizer {
+ public:
+  explicit HfTokenizer(const std::string &tokenizer_json_path);
+  // ids of one line with unknown tokens DROPPED (model2vec's encode_with_args removes unk ids)
+  std::vector<uint32_t> encode(const std::string &text) const override;
+  // ids exactly as tokenizer.encode(text, add_special_tokens = false).ids
+  std::vector<uint32_t> encode_raw(const std::string &text) const;
+  size_t median_token_length() const override { return median_len_; }
+  size_t vocab_size() const { return tokens_.size(); }
+  bool has_unk() const { return has_unk_; }
+  uint32_t unk_id() const { return unk_id_; }
+  // fnv1a64 of the file: part of the store's model fingerprint
+  uint64_t fingerprint() const { return file_hash_; }
+
+ private:
+  struct NormStep { int kind; std::string a, b; bool left = true, right = true; };
+  struct PreStep { int kind; std::string replacement; int prepend = 0; bool split = true; };
+  std::string normalize(const std::string &text) const;
+  void pre_tokenize(const std::string &normalized, std::vector<std::string> &pieces) const;
+  void unigram(const std::string &piece, std::vector<uint32_t> &out) const;
+  void add_norm(const Json &j);
+  void add_pre(const Json &j);
+
+  std::vector<NormStep> norm_;
+  std::vector<PreStep> pre_;
+  std::vector<std::string> tokens_;
+  std::vector<double> scores_;
+  double min_score_ = 0.0;
+  bool has_unk_ = false;
+  uint32_t unk_id_ = 0;
+  size_t median_len_ = 1;
+  uint64_t file_hash_ = 0;
+  // byte trie: edge (node << 8 | byte) -> child node; terminal_[node] = token id or -1
+  std::unordered_map<uint64_t, uint32_t> edges_;
+  std::vector<int32_t> terminal_;
+};
+
+}  // namespace semtools

@@ -43,13 +43,30 @@ class ShardedCorpus:
     all_gather: Callable        # (k,) HIT_DTYPE -> (world, k) HIT_DTYPE
 
     def search(self, q, top_k: int, max_distance=None, mode=capi.STB_MODE_STORE_QUERY):
-        """Global top_k.  (Threshold-lifts-top_k mode is shard-local by nature: its
-        result size is unbounded; callers concatenate shard results instead.)"""
-        if top_k == 0:
+        """Global result of one query over all shards.
+
+        top_k caps the result (STORE_QUERY always; SEARCH_DOCUMENTS without a threshold): ONE
+        exchange of k hits per rank, then the K4 merge.
+        SEARCH_DOCUMENTS with `max_distance` lifts the cap (src/search/mod.rs:115-116: every line
+        under the threshold is returned): the per-shard result size is data-dependent, so the ranks
+        first all-gather their COUNTS, then a payload padded to the largest count, and
+        every rank merges by (distance,row) -- the reference's stable sort over (doc,line) order."""
+        threshold_all = mode == capi.STB_MODE_SEARCH_DOCUMENTS and max_distance is not None
+        if top_k == 0 and not threshold_all:
             return np.zeros(0, dtype=capi.HIT_DTYPE)
-        local = pad_hits(self.local_search(q, top_k, max_distance, mode), top_k)
-        lists = self.all_gather(local)
-        return self.merge(lists, top_k)
+        if not threshold_all:
+            local = pad_hits(self.local_search(q, top_k, max_distance, mode), top_k)
+            lists = self.all_gather(local)
+            return self.merge(lists, top_k)
+        local = np.ascontiguousarray(self.local_search(q, top_k, max_distance, mode), dtype=capi.HIT_DTYPE)
+        cnt = np.zeros(1, dtype=capi.HIT_DTYPE)
+        cnt["row"] = len(local)                                   # counts ride in the row field of one 16-byte hit
+        counts = self.all_gather(cnt)["row"].reshape(-1).astype(np.int64)
+        widest = int(counts.max())
+        if widest == 0:
+            return np.zeros(0, dtype=capi.HIT_DTYPE)
+        lists = self.all_gather(pad_hits(local, widest))          # (world, widest), padding = (+inf, PAD_ROW)
+        return self.merge(lists, int(counts.sum()))
 
     def search_batch(self, queries, top_k: int, local_search_batch: Callable):
         """Batched queries (K2) over the row shards: every rank answers all nq queries on its
@@ -70,7 +87,16 @@ class ShardedCorpus:
         def local_search(q, top_k, max_distance, mode):
             return corpus.search(q, top_k, max_distance, mode)
 
-        return cls(dist.get_rank(), dist.get_world_size(), local_search, ctx.hits_merge, _device_all_gather(dist, device))
+        def merge(lists, top_k):
+            # the K4 kernel sorts up to 4096 hits in shared memory; threshold-mode results beyond that
+            # are ordered on the host (ordering bookkeeping, no distance is computed here)
+            if lists.size <= 4096:
+                return ctx.hits_merge(lists, top_k)
+            flat = lists.reshape(-1)
+            flat = flat[flat["row"] != PAD_ROW]
+            return flat[np.lexsort((flat["row"], flat["distance"]))][:top_k]
+
+        return cls(dist.get_rank(), dist.get_world_size(), local_search, merge, _device_all_gather(dist, device))
 
     @classmethod
     def on_gpu_ivfpq(cls, ctx: capi.Context, index: "capi.IvfPq", dist, device, nprobe: int = 64, rerank: int = 256):

@@ -622,3 +622,89 @@ def test_ticket_schedule_stays_consistent_and_order_independent(ctx, monkeypatch
             got = np.ascontiguousarray(raw[i]).view(capi.HIT_DTYPE).reshape(-1)[: st[i, 0]]
             assert st[i, 1] == 1, (n, i, st[i])
             check(got, r, dd)
+
+
+def test_search_many_equals_search_one_by_one(ctx, monkeypatch):
+    """stb_search_many: nq queries enqueued back to back, one synchronisation, hits stored straight
+    into pinned host memory; unproven queries (zero query) go through stb_search.  Same hits as
+    the oracle for every query, for k inside and beyond the register lists."""
+    monkeypatch.delenv("STB_SCAN_TIER", raising=False)
+    rng = np.random.default_rng(515)
+    rows = unit_rows(rng, 80_000)
+    rows[70_000] = rows[9]
+    c = make_corpus(ctx, rows)
+    qs = unit_rows(rng, 37)
+    qs[3] = 0.0                                                     # everything ties: fallback
+    qs[5] = rows[9]                                                 # exact duplicate pair -> tie by row
+    for k in (1, 10, 96, 200):
+        got = c.search_many(qs, top_k=k)
+        assert len(got) == len(qs)
+        for i, q in enumerate(qs):
+            r, d = oracle.search_rows(rows, q, top_k=k)
+            check(got[i], r, d)
+    assert c.tier_stats()["q8"]["built_rows"] == 80_000             # many queries amortise the int8 copy: built eagerly
+    assert len(c.search_many(np.zeros((0, 256), np.float32), top_k=3)) == 0
+    d, h = ctx.ticket_check()
+    assert d == h
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_threshold_mode_counts_then_padded_payload(world):
+    """SURVEY 8e / VERDICT r1 #9: search_documents with max_distance returns ALL lines under the
+    threshold (mod.rs:115-116); across shards the ranks exchange counts, then a payload padded to the
+    largest count, and merge by (distance,row).  `world` contexts on cuda:0 in threads stand in for
+    ranks; the all-gather is a barrier-synchronised list (the NCCL one is exercised by bench.py)."""
+    import threading
+    from semtools_b200.sharded import ShardedCorpus, shard_bounds
+    rng = np.random.default_rng(world)
+    n = 50_000 + world
+    rows = unit_rows(rng, n)
+    rows[n - 1] = rows[11]
+    q = rows[11].copy()
+    barrier, slots = threading.Barrier(world), [None] * world
+    results, errors = [None] * world, []
+
+    def run(rank):
+        try:
+            c_ctx = capi.Context(0)
+            lo, hi = shard_bounds(n, world, rank)
+            c = capi.Corpus(c_ctx, hi - lo, row_base=lo)
+            c.append(rows[lo:hi])
+
+            def all_gather(local):
+                slots[rank] = local.copy()
+                barrier.wait(timeout=60)
+                out = np.stack(slots)
+                barrier.wait(timeout=60)
+                return out
+
+            sc = ShardedCorpus(rank, world, lambda qv, k, md, mode: c.search(qv, k, md, mode),
+                               lambda lists, k: c_ctx.hits_merge(lists, k) if lists.size <= 4096 else
+                               np.sort(lists.reshape(-1)[lists.reshape(-1)["row"] != np.uint64(0xFFFFFFFFFFFFFFFF)], order=["distance", "row"])[:k],
+                               all_gather)
+            out = {}
+            for thr in (0.0, 0.78, 0.9, 1.0000001):
+                out[thr] = sc.search(q, 3, max_distance=thr, mode=capi.STB_MODE_SEARCH_DOCUMENTS)
+            out["topk"] = sc.search(q, 5, mode=capi.STB_MODE_SEARCH_DOCUMENTS)
+            results[rank] = out
+            c.close(); c_ctx.close()
+        except Exception as e:                                  # noqa: BLE001
+            errors.append((rank, repr(e)))
+            barrier.abort()
+
+    ths = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join(timeout=180)
+    assert not errors, errors
+    for thr in (0.0, 0.78, 0.9, 1.0000001):
+        r, d = oracle.search_rows(rows, q, top_k=3, max_distance=thr)
+        for rank in range(world):
+            got = results[rank][thr]
+            assert got["row"].tolist() == [int(x) for x in r], (thr, rank, len(got), len(r))
+            assert np.array_equal(got["distance"], d)
+    r, d = oracle.search_rows(rows, q, top_k=5)
+    for rank in range(world):
+        check(results[rank]["topk"], r, d)
+    assert len(results[0][0.78]) > 3 and len(results[0][1.0000001]) > 40_000       # really lifted the cap, really > 4096 hits

@@ -300,3 +300,79 @@ def test_cpp_tokenize_bench_hook_runs(binary):
     rows = [json.loads(l) for l in r.stdout.strip().splitlines()]
     assert [x["threads"] for x in rows] == [1, 2]
     assert rows[0]["tokens"] == rows[1]["tokens"] > 100_000 and rows[0]["lines"] == 20000
+
+
+def _synthetic_unigram(tmp_path, seed, normalizer, prepend_scheme="always", with_unk=True):
+    """A SentencePiece-style tokenizer.json built with HF `tokenizers`: single characters plus random
+    multi-character pieces with random log-probabilities, Metaspace pre-tokenizer."""
+    import random
+    from tokenizers import Tokenizer, models, normalizers, pre_tokenizers
+    rnd = random.Random(seed)
+    alphabet = list("abcdefghijklmnopqrstuvwxyz0123456789.,-") + ["é", "ü", "ß", "λ", "σ", "ς", "中", "文", "▁"]
+    vocab = [("<unk>", 0.0)] if with_unk else []
+    seen = {"<unk>"}
+    for ch in alphabet[:-6] + ["▁"]:                      # some characters stay OUT of the vocabulary (-> unk)
+        vocab.append((ch, -rnd.uniform(4.0, 9.0))); seen.add(ch)
+    while len(vocab) < 1500:
+        n = rnd.choice([2, 2, 3, 3, 4, 5, 6])
+        tok = ("▁" if rnd.random() < 0.35 else "") + "".join(rnd.choice(alphabet[:-3]) for _ in range(n))
+        if tok not in seen:
+            seen.add(tok); vocab.append((tok, -rnd.uniform(2.0, 14.0)))
+    vocab.append(("▁the", -2.5)); vocab.append(("ing", -3.0)); vocab.append(("ab", -3.25)); vocab.append(("abab", -6.5))   # exact score ties on purpose
+    tk = Tokenizer(models.Unigram(vocab, unk_id=0 if with_unk else None, byte_fallback=False))
+    if normalizer is not None:
+        tk.normalizer = normalizer
+    tk.pre_tokenizer = pre_tokenizers.Metaspace(replacement="▁", prepend_scheme=prepend_scheme, split=True)
+    path = tmp_path / f"tokenizer_{seed}.json"
+    tk.save(str(path))
+    return tk, path, alphabet
+
+
+@pytest.mark.parametrize("case", ["lower+multispace", "plain_first", "strip_prepend", "nfkc_ascii"])
+def test_cpp_unigram_tokenizer_matches_hf_tokenizers_id_for_id(binary, tmp_path, case):
+    """the C++ host tokenises with the model's tokenizer.json (Unigram + Metaspace
+    subset) instead of a WordLevel stand-in.  Token ids -- with and without the unk-drop of
+    encode_with_args (mod.rs:69) -- must equal HF `tokenizers` on random text, including unknown
+    characters (fused unk), score ties, multiple spaces and non-ASCII lowercase."""
+    import random
+    from tokenizers import Regex, normalizers
+    norm = {"lower+multispace": normalizers.Sequence([normalizers.Lowercase(), normalizers.Replace(Regex(" {2,}"), " ")]),
+            "plain_first": None,
+            "strip_prepend": normalizers.Sequence([normalizers.Strip(), normalizers.Replace("--", "-")]),
+            "nfkc_ascii": normalizers.Sequence([normalizers.NFKC(), normalizers.Lowercase()])}[case]
+    tk, path, alphabet = _synthetic_unigram(tmp_path, seed=len(case), normalizer=norm,
+                                            prepend_scheme="first" if case == "plain_first" else "always")
+    rnd = random.Random(99)
+    ascii_only = case == "nfkc_ascii"
+    pool = [a for a in alphabet if (ord(a[0]) < 128 or not ascii_only)] + ["X", "Q", "THE", "Σ", "ΑΣ", "ab", "abab", "ing"]
+    if ascii_only:
+        pool = [p for p in pool if all(ord(c) < 128 for c in p)]
+    lines = ["", " ", "the thing", "  leading and   multiple   spaces  ", "abab abababab", "ΑΣ ΣΑΣ σας" if not ascii_only else "AS SAS sas"]
+    for _ in range(300):
+        words = ["".join(rnd.choice(pool) for _ in range(rnd.randint(1, 9))) for _ in range(rnd.randint(0, 12))]
+        lines.append((" " * rnd.randint(0, 3)).join(words) if rnd.random() < 0.2 else " ".join(words))
+    lines = [l for l in lines if "\n" not in l and "\r" not in l]
+    r = subprocess.run([binary, "--encode", str(path)], input=("\n".join(lines) + "\n").encode("utf-8"), capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    out = r.stdout.decode().splitlines()
+    lens = sorted(len(t.encode("utf-8")) for t in tk.get_vocab(False).keys())
+    assert out[0] == f"median_token_length {lens[len(lens) // 2]} vocab {tk.get_vocab_size()}"
+    assert len(out) == len(lines) + 1
+    unk = 0
+    for line, got in zip(lines, out[1:]):
+        want = tk.encode(line, add_special_tokens=False).ids
+        raw, dropped = got.split("|")
+        assert [int(x) for x in raw.split()] == want, (case, line)
+        assert [int(x) for x in dropped.split()] == [i for i in want if i != unk], (case, line)
+    if ascii_only:      # non-ASCII text under NFKC is refused, not silently mis-normalised
+        r = subprocess.run([binary, "--encode", str(path)], input="café\n".encode("utf-8"), capture_output=True)
+        assert "ERROR" in r.stdout.decode() and "Python host" in r.stdout.decode()
+
+
+def test_cpp_tokenizer_rejects_what_it_does_not_implement(binary, tmp_path):
+    from tokenizers import Tokenizer, models, pre_tokenizers
+    tk = Tokenizer(models.WordPiece({"[UNK]": 0, "a": 1}, unk_token="[UNK]"))
+    tk.pre_tokenizer = pre_tokenizers.Whitespace()
+    p = tmp_path / "wp.json"; tk.save(str(p))
+    r = subprocess.run([binary, "--encode", str(p)], input=b"a\n", capture_output=True)
+    assert r.returncode != 0 and b"not supported by the C++ host" in r.stderr

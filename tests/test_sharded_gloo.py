@@ -31,7 +31,13 @@ def _worker(rank, world, port, q_out):
     lo, hi = shard_bounds(1003, world, rank)
 
     def local_search(qv, top_k, max_distance, mode):
-        r, d = oracle.search_rows(rows[lo:hi], qv, top_k=top_k)
+        if mode == capi.STB_MODE_SEARCH_DOCUMENTS and max_distance is not None:
+            r, d = oracle.search_rows(rows[lo:hi], qv, top_k=top_k, max_distance=max_distance)    # threshold lifts top_k
+        else:
+            r, d = oracle.search_rows(rows[lo:hi], qv, top_k=top_k)
+            if max_distance is not None:
+                keep = d < max_distance
+                r, d = r[keep], d[keep]
         out = np.zeros(len(r), dtype=capi.HIT_DTYPE)
         out["row"], out["distance"] = r + lo, d
         return out
@@ -54,6 +60,14 @@ def _worker(rank, world, port, q_out):
         r, d = oracle.search_rows(rows, q, top_k=k)
         res[k] = bool(got["row"].tolist() == [int(x) for x in r] and np.array_equal(got["distance"], d))
     res["tie"] = sc.search(q, 2)["row"].tolist() == [5, 1000]
+    # threshold mode (mod.rs:115-116): counts all-gather, then a payload padded to the largest count
+    thr_ok = True
+    for thr in (0.0, 0.3, 0.93, 1.0, 1.5):
+        got = sc.search(q, 3, max_distance=thr, mode=capi.STB_MODE_SEARCH_DOCUMENTS)
+        r, d = oracle.search_rows(rows, q, top_k=3, max_distance=thr)
+        thr_ok = thr_ok and got["row"].tolist() == [int(x) for x in r] and np.array_equal(got["distance"], d)
+    res["threshold"] = bool(thr_ok)
+    res["threshold_sizes"] = [len(sc.search(q, 3, max_distance=t, mode=capi.STB_MODE_SEARCH_DOCUMENTS)) for t in (0.0, 0.93, 1.5)]
 
     # an APPROXIMATE shard-local search (IVF-PQ sharded by row: each shard may miss rows) --
     # the global answer must be exactly the (distance,row)-ordered union of the shard lists
@@ -107,6 +121,8 @@ def test_sharded_search_gloo(world):
         for k in (1, 3, 10, 600):
             assert res[k], (rank, k)
         assert res["tie"]
+        assert res["threshold"], f"rank {rank}: sharded threshold-mode search differs from the oracle"
+        assert res["threshold_sizes"][0] == 0 and res["threshold_sizes"][2] == 1003 and 0 < res["threshold_sizes"][1] < 1003
 
 
 def test_shard_bounds_cover_and_are_contiguous():
