@@ -245,7 +245,9 @@ def timed_queries(E, corpus, q_dev, k, steps, warm, xchg=None):
         step(i)
     e1.record(stream)
     E.barrier()
-    ms = E.max_over_ranks(e0.elapsed_time(e1)) / steps
+    mine = e0.elapsed_time(e1) / steps
+    E.last_per_rank_ms = E.gather_over_ranks(mine)
+    ms = max(E.last_per_rank_ms)
     return ms, st[warm:].cpu().numpy(), hits[warm:]
 
 
@@ -314,31 +316,53 @@ def side_config2(E, k):
     return out
 
 
-def side_batch(E, corpus, rows, k, nq=1024, iters=5):
+def side_batch(E, corpus, rows, k, nq=1024, iters=5, make_xchg=None):
     """BASELINE configs[2]: 10M-line corpus, batch of 1024 queries, top-k=10 through the tcgen05
-    path.  Sharded (N>1): K2 per shard, local K1 fallback for unproven queries, then the nq x k
-    hits are all-gathered (NCCL) and merged per query.  Unproven queries are re-run INSIDE the
-    timed region (round 1 left them out)."""
-    torch, dev, stream, dist, world = E.torch, E.dev, E.stream, E.dist, E.world
+    path.  Sharded (N>1): K2 per shard, then ONE exchange of the nq x k hits over NVLink peer memory
+    inside two small kernels (stb_search_batch_xchg_dev: push + wait/merge; NCCL all-gather + merge
+    kernel with --exchange nccl).  Unproven queries are re-run INSIDE the timed region (round 1 left
+    them out): N=1 through the single-query path, N>1 through the fused single-query exchange on
+    every rank (all ranks see the same proof flags)."""
+    torch, dev, stream, dist, world, capi = E.torch, E.dev, E.stream, E.dist, E.world, E.capi
     qh = gen_queries(nq + 64)[64:]
     q_dev = torch.from_numpy(qh).to(dev)
     hits = torch.zeros((nq, k, 2), dtype=torch.float64, device=dev)
     st = torch.zeros((nq, 2), dtype=torch.int32, device=dev)
     st1 = torch.zeros((4,), dtype=torch.int32, device=dev)
-    gathered = torch.zeros((world, nq, k, 2), dtype=torch.float64, device=dev) if world > 1 else None
     merged = torch.zeros((nq, k, 2), dtype=torch.float64, device=dev)
+    gathered = st_all = None
+    xb = None
+    if world > 1 and make_xchg is not None:
+        xb = make_xchg(max_nq=nq)
+    elif world > 1:
+        gathered = torch.zeros((world, nq, k, 2), dtype=torch.float64, device=dev)
+        st_all = torch.zeros((world, nq, 2), dtype=torch.int32, device=dev)
     corpus.prepare()
     fallbacks = []
 
     def one():
-        corpus.search_batch_dev(q_dev.data_ptr(), nq, k, hits.data_ptr(), st.data_ptr())
-        bad = (st[:, 1] != 1).nonzero().flatten().tolist()          # synchronises: the product path does too
-        for i in bad:                                                # exact single-query path for the unproven
-            corpus.search_topk_dev(q_dev[i].data_ptr(), k, hits[i].data_ptr(), st1.data_ptr())
-        fallbacks.append(len(bad))
-        if world > 1:
+        if world == 1:
+            corpus.search_batch_dev(q_dev.data_ptr(), nq, k, hits.data_ptr(), st.data_ptr())
+            bad = (st[:, 1] != 1).nonzero().flatten().tolist()          # synchronises: the product path does too
+            for i in bad:                                                # exact single-query path for the unproven
+                corpus.search_topk_dev(q_dev[i].data_ptr(), k, hits[i].data_ptr(), st1.data_ptr())
+        elif xb is not None:
+            xb.search_batch_dev(corpus, q_dev.data_ptr(), nq, k, merged.data_ptr(), st.data_ptr())
+            bad = (st[:, 1] != 1).nonzero().flatten().tolist()          # identical on every rank
+            for i in bad:
+                xb.search_topk(corpus, q_dev[i].data_ptr(), k, merged[i].data_ptr(), st1.data_ptr())
+        else:
+            corpus.search_batch_dev(q_dev.data_ptr(), nq, k, hits.data_ptr(), st.data_ptr())
             dist.all_gather_into_tensor(gathered, hits)
+            dist.all_gather_into_tensor(st_all, st)
             E.ctx.hits_merge_batch_dev(gathered.data_ptr(), world, nq, k, k, merged.data_ptr())
+            bad = (st_all[:, :, 1].min(dim=0).values != 1).nonzero().flatten().tolist()
+            for i in bad:                                                # every rank re-runs its shard, then one more exchange
+                corpus.search_topk_dev(q_dev[i].data_ptr(), k, hits[i].data_ptr(), st1.data_ptr())
+            if bad:
+                dist.all_gather_into_tensor(gathered, hits)
+                E.ctx.hits_merge_batch_dev(gathered.data_ptr(), world, nq, k, k, merged.data_ptr())
+        fallbacks.append(len(bad))
 
     for _ in range(2):
         one()
@@ -353,7 +377,7 @@ def side_batch(E, corpus, rows, k, nq=1024, iters=5):
     ms = E.max_over_ranks(e0.elapsed_time(e1)) / iters
     out = {"workload": f"{rows}-line corpus{'' if world == 1 else f' row-sharded x{world}'}, batch of {nq} queries, top-k={k} (BASELINE configs[2])",
            "value": nq / ms * 1e3, "unit": "queries/s", "ms_per_batch": ms, "dtype": "fp16 candidates (tcgen05 kind::f16, f32 TMEM) + f64 exact re-rank",
-           "TFLOPs_pipeline": 2.0 * nq * rows * 256 / ms / 1e9, "fallback_queries_per_batch_this_rank": float(np.mean(fallbacks)),
+           "TFLOPs_pipeline": 2.0 * nq * rows * 256 / ms / 1e9, "fallback_queries_per_batch": float(np.mean(fallbacks)),
            "fallbacks_timed": True}
     out["frac_of_bf16_peak_pipeline"] = out["TFLOPs_pipeline"] / (E.peak_tf * world)
     if world == 1:
@@ -369,7 +393,18 @@ def side_batch(E, corpus, rows, k, nq=1024, iters=5):
         agree = torch.tensor([int(torch.equal(ref.view(torch.int64), merged.view(torch.int64)))], device=dev)
         dist.all_reduce(agree, op=dist.ReduceOp.MIN)
         out["ranks_agree"] = bool(agree.item())
-        out["exchange"] = "nccl all_gather of nq x k hits + stb_hits_merge_batch_dev"
+        out["exchange"] = ("fused: push + wait/merge kernels over NVLink peer memory (stb_search_batch_xchg_dev)" if xb is not None
+                           else "nccl all_gather of nq x k hits + stb_hits_merge_batch_dev")
+        # spot-check against the single-query fused path (exact by its own proof)
+        chk = torch.zeros((k, 2), dtype=torch.float64, device=dev)
+        same = True
+        if xb is not None:
+            for i in (0, nq // 2, nq - 1):
+                xb.search_topk(corpus, q_dev[i].data_ptr(), k, chk.data_ptr(), st1.data_ptr())
+                torch.cuda.synchronize(dev)
+                same = same and bool(torch.equal(chk.view(torch.int64), merged[i].view(torch.int64)))
+            out["agrees_with_single_query_path"] = same
+            xb.close()
     return out
 
 
@@ -585,6 +620,14 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def gather_over_ranks(v):
+        if world == 1:
+            return [float(v)]
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        out = torch.zeros(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(out, t)
+        return [float(x) for x in out.cpu()]
+
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -593,7 +636,8 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy, burst)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     E = Env(torch=torch, dist=dist, capi=capi, dev=dev, stream=stream, ctx=ctx, world=world, rank=rank,
-            barrier=barrier, max_over_ranks=max_over_ranks, peak_gbs=peak, peak_tf=float(peaks.get("bf16_tflops", 1590.0)))
+            barrier=barrier, max_over_ranks=max_over_ranks, gather_over_ranks=gather_over_ranks, last_per_rank_ms=None,
+            peak_gbs=peak, peak_tf=float(peaks.get("bf16_tflops", 1590.0)))
 
     # ---- corpus shard of this rank (strong scaling: the SAME global corpus) + candidate copies --------
     corpus, lo, hi = fill_shard(torch, dev, capi, ctx, args.rows, world, rank)
@@ -609,8 +653,8 @@ def run_ours(args):
     # ---- exchange wiring (N > 1) ---------------------------------------------------------
     exchange = "none"
 
-    def make_xchg():
-        x = capi.Exchange(ctx, world, rank, k)
+    def make_xchg(max_nq=0):
+        x = capi.Exchange(ctx, world, rank, k, max_nq=max_nq)
         handles = [None] * world
         dist.all_gather_object(handles, x.local_handle())
         x.connect(handles)
@@ -657,12 +701,14 @@ def run_ours(args):
             step(i)
         ev1.record(stream)
         barrier()
-        ms_step = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+        per_rank_ms = gather_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+        ms_step = max(per_rank_ms)
         st = status[args.warmup:].cpu().numpy()
         hits_t = final_hits[args.warmup:]
     else:
         # warm-up launches are counted out below
         ms_step, st, hits_t = timed_queries(E, corpus, q_dev, k, args.steps, args.warmup, xchg=xchg)
+        per_rank_ms = E.last_per_rank_ms
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.counters()["kernel_launches"] - launches0 - (args.warmup if (world == 1 or xchg is not None) else 0)
     n_expect = min(k, args.rows) if xchg is not None else min(k, hi - lo)
@@ -742,7 +788,7 @@ def run_ours(args):
             except Exception as e:                                     # noqa: BLE001
                 cpu_base = {"error": f"{type(e).__name__}: {e}"}
         else:
-            side("batch1024", side_batch, E, corpus, args.rows, k, collective=True)
+            side("batch1024", side_batch, E, corpus, args.rows, k, make_xchg=make_xchg if xchg is not None else None, collective=True)
     tier_stats = corpus.tier_stats()
     corpus.close()
     torch.cuda.empty_cache()
@@ -776,7 +822,7 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": r5(1e3 / e2e_ms), "unit": "queries/s", "h2d_bytes_per_step": 1024, "d2h_bytes_per_step": 16 * k + 16,
                     "steps": e2e_steps, "ms_per_step": r5(e2e_ms)},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "per_rank_ms_per_step": [r5(v) for v in per_rank_ms],
             "roofline": {"bound": "hbm", "kernel": f"stb_scan_topk_kernel/{tier}", "achieved": r5(achieved), "peak": peak, "unit": "GB/s",
                          "frac": r5(achieved / peak), "traffic": traffic, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
                          "algorithmic_bytes": rows_per_gpu * 1024, "bytes_read": rows_per_gpu * TIER_BYTES[tier],

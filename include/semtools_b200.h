@@ -243,6 +243,19 @@ int stb_xchg_connect_local(stb_xchg *x, stb_xchg *const *peers);
 int stb_search_topk_xchg(stb_ctx *ctx, const stb_corpus *corpus, const float *q_dev,
                          uint32_t top_k, stb_xchg *x, stb_hit *out_hits_dev,
                          uint32_t *out_status_dev);
+/* Sharded K2 over the same peer-memory exchange.  stb_xchg_create_batch allocates, behind the single-query
+ * area, two batch slots of world x max_nq x max_k hits (+ flags and per-query proof bits); everything else
+ * (handles, connect, destroy, stb_search_topk_xchg) works as with stb_xchg_create.
+ * stb_search_batch_xchg_dev = stb_search_batch_dev on the local shard, then a push kernel (this rank's
+ * nq x k hits into every peer's slot over NVLink, release-stored sequence flag) and a merge kernel (waits
+ * for every peer's flag, merges each query's world x k hits by (distance,row)): two launches, no NCCL.
+ *   out_status_dev[2q] = hits of query q, [2q+1] = 1 iff every rank proved its part (0: re-run query q
+ *   through stb_search_xchg / stb_search_many on every rank; 2: a peer never arrived).
+ * All ranks must issue the same sequence of calls. */
+int stb_xchg_create_batch(stb_ctx *ctx, uint32_t world, uint32_t rank, uint32_t max_k, uint32_t max_nq,
+                          stb_xchg **out);
+int stb_search_batch_xchg_dev(stb_ctx *ctx, const stb_corpus *corpus, const float *q_dev, uint32_t nq,
+                              uint32_t top_k, stb_xchg *x, stb_hit *out_hits_dev, uint32_t *out_status_dev);
 
 /* ---- K5: IVF-PQ index (approximate) ------------------------------------------------------
  * NOT a replacement of any reference code: this snapshot of semtools has no IVF_PQ (the

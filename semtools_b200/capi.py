@@ -25,7 +25,7 @@ SYMBOLS = [
     "stb_embed_status", "stb_search",
     "stb_search_topk_dev", "stb_corpus_prepare", "stb_corpus_tier_stats", "stb_corpus_prepare_batch", "stb_search_batch", "stb_search_batch_dev",
     "stb_xchg_create", "stb_xchg_destroy", "stb_xchg_local_handle",
-    "stb_xchg_connect", "stb_xchg_connect_local", "stb_search_topk_xchg", "stb_search_xchg", "stb_search_many", "stb_ivfpq_build",
+    "stb_xchg_connect", "stb_xchg_connect_local", "stb_search_topk_xchg", "stb_search_xchg", "stb_search_many", "stb_xchg_create_batch", "stb_search_batch_xchg_dev", "stb_ivfpq_build",
     "stb_ivfpq_destroy", "stb_ivfpq_stats", "stb_ivfpq_search", "stb_hits_merge_dev", "stb_hits_merge_batch_dev", "stb_hits_merge", "stb_fnv1a64", "stb_line_id", "stb_line_ids",
     "stb_ctx_counters", "stb_debug_ticket_check", "stb_debug_timestamps", "stb_debug_batch_gemm", "stb_debug_batch_params",
 ]
@@ -95,6 +95,8 @@ def lib() -> C.CDLL:
     L.stb_search_topk_xchg.argtypes = [vp, vp, vp, u32, vp, vp, vp]
     L.stb_search_xchg.argtypes = [vp, vp, vp, u32, vp, vp, C.POINTER(u32), C.POINTER(i32)]
     L.stb_search_many.argtypes = [vp, vp, vp, u32, u32, vp, vp, vp, vp]
+    L.stb_xchg_create_batch.argtypes = [vp, u32, u32, u32, u32, C.POINTER(vp)]
+    L.stb_search_batch_xchg_dev.argtypes = [vp, vp, vp, u32, u32, vp, vp, vp]
     L.stb_ivfpq_build.argtypes = [vp, vp, u32, u32, u32, C.POINTER(vp)]
     L.stb_ivfpq_destroy.argtypes = [vp]
     L.stb_ivfpq_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)]
@@ -401,10 +403,14 @@ class Exchange:
     """stb_xchg: peer-memory exchange buffers for the fused multi-GPU search."""
     HANDLE_BYTES = 64
 
-    def __init__(self, ctx: Context, world: int, rank: int, max_k: int):
-        self.ctx, self.world, self.rank, self.max_k = ctx, world, rank, max_k
+    def __init__(self, ctx: Context, world: int, rank: int, max_k: int, max_nq: int = 0):
+        """max_nq > 0 also allocates the batch area for the sharded K2 exchange (stb_xchg_create_batch)."""
+        self.ctx, self.world, self.rank, self.max_k, self.max_nq = ctx, world, rank, max_k, max_nq
         self._h = vp()
-        _check(lib().stb_xchg_create(ctx._h, world, rank, max_k, C.byref(self._h)))
+        if max_nq:
+            _check(lib().stb_xchg_create_batch(ctx._h, world, rank, max_k, max_nq, C.byref(self._h)))
+        else:
+            _check(lib().stb_xchg_create(ctx._h, world, rank, max_k, C.byref(self._h)))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h and _lib is not None:
@@ -438,6 +444,11 @@ class Exchange:
         _check(lib().stb_search_xchg(self.ctx._h, corpus._h, _np_ptr(q), top_k, self._h, _np_ptr(out), C.byref(n),
                                      C.byref(ok)))
         return out[: n.value], bool(ok.value)
+
+    def search_batch_dev(self, corpus: "Corpus", q_dev: int, nq: int, top_k: int, out_hits_dev: int, out_status_dev: int):
+        """stb_search_batch_xchg_dev: K2 on the local shard + fused NVLink exchange + per-query merge."""
+        _check(lib().stb_search_batch_xchg_dev(self.ctx._h, corpus._h, vp(q_dev), nq, top_k, self._h, vp(out_hits_dev),
+                                               vp(out_status_dev)))
 
     def search_topk(self, corpus: "Corpus", q_dev: int, top_k: int, out_hits_dev: int, out_status_dev: int):
         """stb_search_topk_xchg: one kernel = scan + NVLink exchange + global merge."""

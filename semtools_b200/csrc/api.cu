@@ -668,25 +668,43 @@ static size_t xchg_bytes(uint32_t world, uint32_t max_k) {
   return (size_t)STB_XCHG_SLOTS * world * 16 + (size_t)STB_XCHG_SLOTS * world * max_k * sizeof(stb_hit);
 }
 
-int stb_xchg_create(stb_ctx *ctx, uint32_t world, uint32_t rank, uint32_t max_k, stb_xchg **out) {
+static size_t xchg_batch_slot_bytes(uint32_t world, uint32_t max_nq, uint32_t max_k) {
+  const size_t head = ((size_t)world * 8 + (size_t)world * max_nq * 4 + 15) & ~(size_t)15;   // flags | status, 16-byte aligned
+  return ((head + (size_t)world * max_nq * max_k * sizeof(stb_hit)) + 255) & ~(size_t)255;
+}
+
+static int xchg_create_impl(stb_ctx *ctx, uint32_t world, uint32_t rank, uint32_t max_k, uint32_t max_nq, stb_xchg **out) {
   int rc = ctx_use(ctx);
   if (rc) return rc;
   if (!out) { stb_set_error("xchg_create: out is null"); return STB_ERR_ARG; }
   if (world < 1 || world > STB_XCHG_MAX_WORLD || rank >= world) { stb_set_error("xchg_create: world must be 1..%d and rank < world", STB_XCHG_MAX_WORLD); return STB_ERR_ARG; }
   if (max_k < 1 || max_k > stb_scan_topk_max_k()) { stb_set_error("xchg_create: max_k must be 1..%u", stb_scan_topk_max_k()); return STB_ERR_ARG; }
+  if (max_nq > 65536 || (uint64_t)world * max_k > 2048) { stb_set_error("xchg_create: batch area too large (max_nq <= 65536, world * max_k <= 2048)"); return STB_ERR_ARG; }
   stb_xchg *x = new (std::nothrow) stb_xchg();
   if (!x) { stb_set_error("out of host memory"); return STB_ERR_NOMEM; }
   memset(x, 0, sizeof(*x));
-  x->ctx = ctx; x->world = world; x->rank = rank; x->max_k = max_k;
-  x->bytes = xchg_bytes(world, max_k);
+  x->ctx = ctx; x->world = world; x->rank = rank; x->max_k = max_k; x->max_nq = max_nq;
+  x->batch_off = (xchg_bytes(world, max_k) + 255) & ~(size_t)255;
+  x->batch_slot_bytes = max_nq ? xchg_batch_slot_bytes(world, max_nq, max_k) : 0;
+  x->bytes = x->batch_off + 2 * x->batch_slot_bytes;
   // plain cudaMalloc memory: required for cudaIpcGetMemHandle
   cudaError_t e = cudaMalloc((void **)&x->local, x->bytes);
   if (e == cudaSuccess) e = cudaMemset(x->local, 0, x->bytes);
-  if (e != cudaSuccess) { cudaGetLastError(); stb_set_error("xchg_create: %s", cudaGetErrorString(e)); delete x; return STB_ERR_NOMEM; }
+  if (e == cudaSuccess) e = cudaMalloc((void **)&x->batch_ticket, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(x->batch_ticket, 0, sizeof(unsigned int));
+  if (e != cudaSuccess) { cudaGetLastError(); cudaFree(x->local); stb_set_error("xchg_create: %s", cudaGetErrorString(e)); delete x; return STB_ERR_NOMEM; }
   x->peers[rank] = x->local;
   x->connected = (world == 1);
   *out = x;
   return STB_OK;
+}
+
+int stb_xchg_create(stb_ctx *ctx, uint32_t world, uint32_t rank, uint32_t max_k, stb_xchg **out) {
+  return xchg_create_impl(ctx, world, rank, max_k, 0, out);
+}
+int stb_xchg_create_batch(stb_ctx *ctx, uint32_t world, uint32_t rank, uint32_t max_k, uint32_t max_nq, stb_xchg **out) {
+  if (max_nq == 0) { stb_set_error("xchg_create_batch: max_nq must be > 0"); return STB_ERR_ARG; }
+  return xchg_create_impl(ctx, world, rank, max_k, max_nq, out);
 }
 
 int stb_xchg_destroy(stb_xchg *x) {
@@ -695,6 +713,7 @@ int stb_xchg_destroy(stb_xchg *x) {
   else cudaDeviceSynchronize();
   for (uint32_t r = 0; r < x->world; ++r)
     if (x->ipc_opened[r] && x->peers[r]) cudaIpcCloseMemHandle(x->peers[r]);
+  cudaFree(x->batch_ticket);
   cudaFree(x->local);
   cudaGetLastError();
   delete x;
@@ -740,7 +759,7 @@ int stb_xchg_connect_local(stb_xchg *x, stb_xchg *const *peers) {
   if (rc) return rc;
   for (uint32_t r = 0; r < x->world; ++r) {
     if (r == x->rank) continue;
-    if (!peers[r] || peers[r]->world != x->world || peers[r]->rank != r || peers[r]->max_k != x->max_k) { stb_set_error("xchg_connect_local: peer %u mismatched", r); return STB_ERR_ARG; }
+    if (!peers[r] || peers[r]->world != x->world || peers[r]->rank != r || peers[r]->max_k != x->max_k || peers[r]->max_nq != x->max_nq) { stb_set_error("xchg_connect_local: peer %u mismatched", r); return STB_ERR_ARG; }
     const int pd = peers[r]->ctx->device;
     if (pd != x->ctx->device) {
       int can = 0;
@@ -977,6 +996,33 @@ int stb_search_batch(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uin
     for (uint64_t j = n; j < top_k; ++j) { out_hits[(size_t)i * top_k + j].distance = INFINITY; out_hits[(size_t)i * top_k + j].row = 0xffffffffffffffffull; }
   }
   return STB_OK;
+}
+
+// Sharded K2: every rank answers the nq queries on its shard (stb_search_batch_dev), then ONE exchange over
+// NVLink peer memory -- each rank stores its nq x k hits + per-query proof flags into every peer's batch slot
+// (push kernel), waits for all peers' sequence flags and merges per query (merge kernel).  Two launches, no
+// NCCL call.  out_status_dev[2q] = hits of query q, [2q+1] = 1 iff EVERY rank proved its part, 2 = a peer
+// never arrived.  Unproven queries: re-run them with stb_search_xchg / stb_search_many(x) (collective: every
+// rank sees the same flags).
+int stb_search_batch_xchg_dev(stb_ctx *ctx, const stb_corpus *corpus, const float *q_dev, uint32_t nq, uint32_t top_k,
+                              stb_xchg *x, stb_hit *out_hits_dev, uint32_t *out_status_dev) {
+  int rc = ctx_use(ctx);
+  if (rc) return rc;
+  if (!corpus || !q_dev || !x || !out_hits_dev || !out_status_dev) { stb_set_error("search_batch_xchg_dev: null argument"); return STB_ERR_ARG; }
+  if (corpus->ctx != ctx || x->ctx != ctx) { stb_set_error("search_batch_xchg_dev: handles belong to another context"); return STB_ERR_ARG; }
+  if (!x->connected) { stb_set_error("search_batch_xchg_dev: exchange not connected"); return STB_ERR_STATE; }
+  if (nq == 0) return STB_OK;
+  if (x->max_nq == 0 || nq > x->max_nq || top_k == 0 || top_k > x->max_k) { stb_set_error("search_batch_xchg_dev: needs stb_xchg_create_batch with max_nq >= %u, max_k >= %u", nq, top_k); return STB_ERR_ARG; }
+  if ((rc = dev_reserve(&ctx->bh_dev, &ctx->bh_dev_cap, (size_t)nq * top_k)) != STB_OK) return rc;
+  if ((rc = dev_reserve(&ctx->bs_dev, &ctx->bs_dev_cap, (size_t)nq * 2)) != STB_OK) return rc;
+  if ((rc = stb_search_batch_dev(ctx, corpus, q_dev, nq, top_k, ctx->bh_dev, ctx->bs_dev)) != STB_OK) return rc;
+  StbBatchXchgArgs a;
+  memset(&a, 0, sizeof(a));
+  a.world = x->world; a.rank = x->rank; a.max_nq = x->max_nq; a.max_k = x->max_k; a.nq = nq; a.top_k = top_k;
+  a.seq = ++x->batch_seq;
+  a.ticket = x->batch_ticket;
+  for (uint32_t r = 0; r < x->world; ++r) a.slot[r] = x->peers[r] + x->batch_off + (size_t)(a.seq & 1) * x->batch_slot_bytes;
+  return stb_launch_batch_xchg(ctx, a, ctx->bh_dev, ctx->bs_dev, out_hits_dev, out_status_dev);
 }
 
 int stb_debug_batch_params(int *shadow_is_f16, double *eps) {

@@ -141,6 +141,12 @@ struct stb_xchg {
   bool ipc_opened[STB_XCHG_MAX_WORLD];
   bool connected;
   unsigned long long seq;
+  // batch area (stb_xchg_create_batch; sharded K2): 2 slots x { flags[world] u64 | status[world][max_nq] u32 |
+  // hits[world][max_nq][max_k] } behind the single-query area
+  uint32_t max_nq;
+  size_t batch_off, batch_slot_bytes;
+  unsigned long long batch_seq;
+  unsigned int *batch_ticket;                // device: arrival counter of the push kernel
 };
 
 struct stb_table {
@@ -216,6 +222,16 @@ int stb_launch_hits_merge(stb_ctx *ctx, const stb_hit *lists_dev, uint32_t n_lis
 
 int stb_launch_hits_merge_batch(stb_ctx *ctx, const stb_hit *lists_dev, uint32_t n_lists, uint32_t nq,
                                 uint32_t per_list, uint32_t top_k, stb_hit *out_dev);
+// sharded K2 exchange over peer memory: push this rank's nq x k hits + per-query status into every
+// peer's batch slot, then (second launch) wait for all peers and merge per query
+struct StbBatchXchgArgs {
+  unsigned char *slot[STB_XCHG_MAX_WORLD];   // batch slot of every rank (peer-mapped), this batch's parity
+  uint32_t world, rank, max_nq, max_k, nq, top_k;
+  unsigned long long seq;
+  unsigned int *ticket;
+};
+int stb_launch_batch_xchg(stb_ctx *ctx, const StbBatchXchgArgs &a, const stb_hit *local_hits, const uint32_t *local_status,
+                          stb_hit *out_hits, uint32_t *out_status);
 
 // opt-in to > 48 KiB dynamic shared memory (or another function attribute) once per context
 enum { STB_ATTR_GEMM0 = 0, STB_ATTR_GEMM1, STB_ATTR_MERGE, STB_ATTR_IVF_PROBE, STB_ATTR_IVF_V2, STB_ATTR_FINISH2 };

@@ -815,8 +815,18 @@ stb_scan_topk_kernel(const TopkArgs args) {
     for (int i = 0; i < STB_D; ++i) q2 = fma(sqd[i], sqd[i], q2);
     s_q2 = q2;
   }
+  // Candidates are sorted by approximate score (or upper bound) best-first and re-scored 32 at a
+  // time.  After the first 32 the k-th best EXACT cosine c_k among them is known; a later
+  // candidate whose score + eps is below c_k cannot enter the top-k, and neither can anything
+  // after it -- with K' = 128 (q8) this usually ends the re-rank after one pass instead of four.
+  __shared__ double s_cthr;
+  __shared__ int s_done;
+  if (threadIdx.x == 0) { s_cthr = -CUDART_INF; s_done = 0; }
   for (int chunk = 0; chunk < EF; ++chunk) {
-    if (chunk > 0 && skeys[chunk * 32] == STB_KEY_INVALID) break;     // sorted: nothing valid beyond (uniform)
+    if (chunk > 0) {
+      const uint64_t nk = skeys[chunk * 32];                            // uniform
+      if (nk == STB_KEY_INVALID || (double)stb_key_score(nk) + kScoreEps < s_cthr) break;
+    }
     {
       constexpr int PER = 32 * STB_ROW_F4 / STB_SCAN_THREADS;   // float4 per thread
       float4 v[PER];
@@ -858,12 +868,37 @@ stb_scan_topk_kernel(const TopkArgs args) {
       }
     }
     __syncthreads();
+    if (threadIdx.x == 0) s_done = chunk + 1;
+    if (chunk == 0 && EF > 1 && args.top_k <= 32) {
+      if (threadIdx.x < 32) {
+        const uint64_t key = skeys[lane];
+        double dist = CUDART_INF;
+        if (key != STB_KEY_INVALID) {
+          const double ab = s_d[lane], r2 = s_r2[lane], q2 = s_q2;
+          if (q2 == 0.0 && r2 == 0.0) dist = 0.0;
+          else if (ab == 0.0) dist = 1.0;
+          else { const double t = 1.0 - ab / (sqrt(q2) * sqrt(r2)); dist = t > 0.0 ? t : 0.0; }
+          if (!(dist < 100.0)) dist = CUDART_INF;
+        }
+        int rank = 0;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const double dj = __shfl_sync(0xffffffffu, dist, jj);
+          rank += (dj < dist || (dj == dist && jj < lane)) ? 1 : 0;
+        }
+        const unsigned passing = __ballot_sync(0xffffffffu, dist < CUDART_INF);
+        if ((uint32_t)__popc(passing) >= args.top_k && rank == (int)args.top_k - 1) s_cthr = 1.0 - dist;
+      }
+      __syncthreads();
+    }
   }
+  __syncthreads();
   if (threadIdx.x < KF) {
     const uint64_t key = skeys[threadIdx.x];
     double d = CUDART_INF;
     uint64_t grow = 0xffffffffffffffffull;
-    if (key != STB_KEY_INVALID) {
+    if (key != STB_KEY_INVALID) atomicAdd(&s_nv[0], 1);     // valid candidates (re-scored or provably outside the top-k)
+    if (key != STB_KEY_INVALID && (int)threadIdx.x < 32 * s_done) {
       const double ab = s_d[threadIdx.x], r2 = s_r2[threadIdx.x], q2 = s_q2;
       double dist;
       if (q2 == 0.0 && r2 == 0.0) dist = 0.0;
@@ -872,7 +907,6 @@ stb_scan_topk_kernel(const TopkArgs args) {
         double t = 1.0 - ab / (sqrt(q2) * sqrt(r2));
         dist = t > 0.0 ? t : 0.0;
       }
-      atomicAdd(&s_nv[0], 1);                     // valid candidates
       if (dist < 100.0) {                         // max_distance.unwrap_or(100.0), strict
         d = dist;
         grow = args.row_base + (uint64_t)stb_key_row(key);

@@ -223,3 +223,62 @@ def test_v2_ties_zero_rows_dense_neighbourhoods(ctx, batch_v2):
     one = c.search_batch(queries[2:3], top_k=10)
     assert np.array_equal(one[0], res[2])
     assert ctx.counters()["fallback_searches"] == before
+
+
+@pytest.mark.parametrize("world,nq,k", [(3, 24, 10), (2, 9, 1)])
+def test_sharded_batch_search_with_fused_peer_memory_exchange(world, nq, k):
+    """stb_search_batch_xchg_dev: K2 per shard, then push + merge kernels over peer memory (no NCCL).
+    `world` contexts on cuda:0 stand in for the ranks (same-process peer buffers); every rank must end
+    up with the unsharded oracle answer for every query, twice in a row (slot parity / sequence reuse).
+    (nq stays small here: on ONE GPU a rank's spinning merge CTAs share the SMs with its peers' GEMMs.)"""
+    torch = pytest.importorskip("torch")
+    from semtools_b200.sharded import shard_bounds
+    rng = np.random.default_rng(world * 10 + nq)
+    n = 45_000 + world
+    rows = unit_rows(rng, n)
+    rows[n - 1] = rows[5]                       # cross-shard exact tie
+    queries = unit_rows(rng, nq)
+    queries[0] = rows[5]
+    dev = torch.device("cuda:0")
+    ctxs = [capi.Context(0) for _ in range(world)]
+    corpora, xs = [], []
+    for r in range(world):
+        lo, hi = shard_bounds(n, world, r)
+        c = capi.Corpus(ctxs[r], hi - lo, row_base=lo)
+        c.append(rows[lo:hi])
+        c.prepare()
+        corpora.append(c)
+        xs.append(capi.Exchange(ctxs[r], world, r, max(k, 10), max_nq=32))
+    for x in xs:
+        x.connect_local(xs)
+    q_dev = torch.from_numpy(queries).to(dev)
+    out = torch.zeros((world, nq, k, 2), dtype=torch.float64, device=dev)
+    status = torch.zeros((world, nq, 2), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    for rep in range(3):
+        out.zero_(); status.zero_(); torch.cuda.synchronize()
+        for r in range(world):
+            xs[r].search_batch_dev(corpora[r], q_dev.data_ptr(), nq, k, out[r].data_ptr(), status[r].data_ptr())
+        for c in ctxs:
+            c.sync()
+        raw, st = out.cpu().numpy(), status.cpu().numpy()
+        assert (st[:, :, 1] <= 1).all(), "a rank timed out waiting for a peer"
+        for r in range(world):
+            assert np.array_equal(st[r], st[0])                      # every rank sees the same proof flags
+            got = np.ascontiguousarray(raw[r]).view(capi.HIT_DTYPE).reshape(nq, k)
+            for i in range(nq):
+                if st[r, i, 1] != 1:
+                    continue
+                rr, dd = oracle.search_rows(rows, queries[i], top_k=k)
+                assert got[i]["row"].tolist() == [int(v) for v in rr], (rep, r, i)
+                assert np.array_equal(got[i]["distance"], dd)
+        assert st[0, :, 1].mean() >= 0.8
+        if st[0, 0, 1] == 1 and k >= 2:
+            first = np.ascontiguousarray(raw[0]).view(capi.HIT_DTYPE).reshape(nq, k)[0]
+            assert first["row"][:2].tolist() == [5, n - 1]
+    for x in xs:
+        x.close()
+    for c in corpora:
+        c.close()
+    for c in ctxs:
+        c.close()

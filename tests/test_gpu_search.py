@@ -707,4 +707,4 @@ def test_sharded_threshold_mode_counts_then_padded_payload(world):
     r, d = oracle.search_rows(rows, q, top_k=5)
     for rank in range(world):
         check(results[rank]["topk"], r, d)
-    assert len(results[0][0.78]) > 3 and len(results[0][1.0000001]) > 40_000       # really lifted the cap, really > 4096 hits
+    assert len(results[0][0.78]) > 3 and len(results[0][1.0000001]) > 20_000       # really lifted the cap, really > 4096 hits (about half the rows have cosine > 0)
