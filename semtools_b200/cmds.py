@@ -35,14 +35,14 @@ def rust_display_f32(x: float) -> str:
 
 
 def _json_f64(x: float) -> str:
-    """serde_json (ryu): shortest round-trip; positional for 1e-5 <= |x| < 1e21 with a
-    trailing ".0" on integral values; exponent form `1e-7` / `1.5e22` outside."""
+    """serde_json (ryu): shortest round-trip; positional for 1e-5 <= |x| < 1e16 (ryu: -5 < kk <= 16) with a
+    trailing ".0" on integral values; exponent form `1e-7` / `1.5e16` outside."""
     if x != x or x in (float("inf"), float("-inf")):
         return "null"                                     # serde_json writes non-finite floats as null
     if x == 0:
         return "-0.0" if str(x).startswith("-") else "0.0"
     a = abs(x)
-    if 1e-5 <= a < 1e21:
+    if 1e-5 <= a < 1e16:
         s = np.format_float_positional(np.float64(x), unique=True, trim="-")
         return s if "." in s else s + ".0"
     m, e = np.format_float_scientific(np.float64(x), unique=True, trim="-").split("e")

@@ -302,10 +302,11 @@ int stb_corpus_destroy(stb_corpus *c) {
   return STB_OK;
 }
 
-// the reduced-width copies (K2 shadow, K1 tiers) are rebuilt lazily after any change
-static void corpus_changed(stb_corpus *c) {
-  c->shadow_rows = 0;
-  c->q8_rows = 0;
+// The reduced-width copies (K2 shadow, K1 tiers) cover a PREFIX of the rows: an append leaves the
+// prefix valid and the next query / prepare only converts the new rows (q8_rows / shadow_rows < n);
+// anything else (clear) drops them.
+static void corpus_changed(stb_corpus *c, bool appended_only = false) {
+  if (!appended_only) { c->shadow_rows = 0; c->q8_rows = 0; }
   c->searches_since_change = 0;
   memset(c->tier_tries, 0, sizeof(c->tier_tries));
   memset(c->tier_proven, 0, sizeof(c->tier_proven));
@@ -321,7 +322,7 @@ static int corpus_append_impl(stb_corpus *c, const float *rows, uint64_t n, cuda
   STB_CUDA(cudaMemcpyAsync(c->rows + c->n * STB_D, rows, n * STB_D * sizeof(float), kind, c->ctx->stream));
   STB_CUDA(cudaStreamSynchronize(c->ctx->stream));
   c->n += n;
-  corpus_changed(c);
+  corpus_changed(c, true);
   return STB_OK;
 }
 
@@ -393,7 +394,7 @@ int stb_embed(stb_ctx *ctx, const stb_table *table, const uint64_t *offsets, con
   if (out) STB_CUDA(cudaMemcpyAsync(out, dst, n_lines * STB_D * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   STB_CUDA(cudaStreamSynchronize(ctx->stream));
   if (flag) { stb_set_error("embed: a token id maps outside the %llu-row table", (unsigned long long)table->V); return STB_ERR_RANGE; }
-  if (append_to) { append_to->n += n_lines; corpus_changed(append_to); }
+  if (append_to) { append_to->n += n_lines; corpus_changed(append_to, true); }
   return STB_OK;
 }
 
@@ -575,7 +576,10 @@ int stb_search(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint32_t 
       if (tier == STB_TIER_Q8 && top_k > STB_Q8_MAX_K) continue;
       if (cm->tier_tries[tier] >= 8 && 2 * cm->tier_proven[tier] < cm->tier_tries[tier]) continue;
       const bool built = (tier == STB_TIER_Q8) ? (cm->q8 && cm->q8_rows == cm->n) : (cm->shadow && cm->shadow_rows == cm->n);
-      if (!built && !lazy_ok) continue;
+      // a copy that covers a prefix (rows were appended since) is extended right away: converting the
+      // new rows costs far less than scanning everything at 1 KiB/row
+      const bool extendable = (tier == STB_TIER_Q8) ? (cm->q8 && cm->q8_rows > 0 && !cm->q8_bad) : (cm->shadow && cm->shadow_rows > 0 && !cm->shadow_bad);
+      if (!built && !lazy_ok && !extendable) continue;
       const int src = (tier == STB_TIER_Q8) ? corpus_ensure_q8(ctx, cm) : corpus_ensure_shadow(ctx, cm);
       if (src == STB_ERR_STATE) continue;                  // rows that cannot be normalised in fp32
       if (src != STB_OK) return src;
@@ -800,24 +804,29 @@ static int corpus_ensure_shadow(stb_ctx *ctx, stb_corpus *c) {
     return STB_OK;
   }
   const uint64_t tiles = (c->n + 255) / 256;
+  uint64_t first = (c->shadow && c->shadow_rows < c->n && !c->shadow_bad) ? (c->shadow_rows / 256) * 256 : 0;   // valid prefix, whole tiles
   if (tiles > c->shadow_cap_tiles || !c->shadow) {
     uint8_t *np = nullptr;
-    cudaError_t e = cudaMalloc((void **)&np, tiles * 131072ull);
-    if (e != cudaSuccess) { cudaGetLastError(); stb_set_error("search_batch: cannot allocate the %llu MiB bf16 shadow", (unsigned long long)(tiles >> 3)); return STB_ERR_NOMEM; }
+    const uint64_t cap_tiles = std::max<uint64_t>(tiles, (c->capacity + 255) / 256);
+    cudaError_t e = cudaMalloc((void **)&np, cap_tiles * 131072ull);
+    if (e != cudaSuccess) { cudaGetLastError(); stb_set_error("search_batch: cannot allocate the %llu MiB 16-bit shadow", (unsigned long long)(cap_tiles >> 3)); return STB_ERR_NOMEM; }
+    if (c->shadow && first) STB_CUDA(cudaMemcpyAsync(np, c->shadow, (first / 256) * 131072ull, cudaMemcpyDeviceToDevice, ctx->stream));
+    else first = 0;
+    STB_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaFree(c->shadow);
     c->shadow = np;
-    c->shadow_cap_tiles = tiles;
+    c->shadow_cap_tiles = cap_tiles;
   }
   int rc;
   STB_CUDA(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), ctx->stream));
-  if ((rc = stb_launch_shadow_build(ctx, c->rows, c->n, 256, c->shadow, ctx->err_flag)) != STB_OK) return rc;
+  if ((rc = stb_launch_shadow_build(ctx, c->rows, c->n, 256, c->shadow, ctx->err_flag, first)) != STB_OK) return rc;
   int flag = 0;
   STB_CUDA(cudaMemcpyAsync(&flag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   STB_CUDA(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), ctx->stream));
   STB_CUDA(cudaStreamSynchronize(ctx->stream));
   c->shadow_rows = c->n;
-  c->shadow_bad = flag;
-  if (flag) { stb_set_error("search_batch: corpus holds rows whose norm is not a normal fp32 number; use stb_search"); return STB_ERR_STATE; }
+  c->shadow_bad = (first ? c->shadow_bad : 0) | flag;
+  if (c->shadow_bad) { stb_set_error("search_batch: corpus holds rows whose norm is not a normal fp32 number; use stb_search"); return STB_ERR_STATE; }
   return STB_OK;
 }
 
@@ -826,6 +835,7 @@ static int corpus_ensure_q8(stb_ctx *ctx, stb_corpus *c) {
     if (c->q8_bad) { stb_set_error("q8 tier: corpus holds rows whose norm is not a normal fp32 number"); return STB_ERR_STATE; }
     return STB_OK;
   }
+  uint64_t first = (c->q8 && c->q8_rows < c->n && !c->q8_bad) ? c->q8_rows : 0;      // valid prefix: convert only the new rows
   if (c->n > c->q8_cap_rows || !c->q8) {
     uint8_t *np = nullptr;
     float *ns = nullptr;
@@ -833,19 +843,24 @@ static int corpus_ensure_q8(stb_ctx *ctx, stb_corpus *c) {
     cudaError_t e = cudaMalloc((void **)&np, cap * 256ull);
     if (e == cudaSuccess) e = cudaMalloc((void **)&ns, cap * sizeof(float));
     if (e != cudaSuccess) { cudaGetLastError(); cudaFree(np); stb_set_error("q8 tier: cannot allocate %llu MiB", (unsigned long long)(cap * 260 >> 20)); return STB_ERR_NOMEM; }
+    if (c->q8 && first) {
+      STB_CUDA(cudaMemcpyAsync(np, c->q8, first * 256ull, cudaMemcpyDeviceToDevice, ctx->stream));
+      STB_CUDA(cudaMemcpyAsync(ns, c->q8_scale, first * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+      STB_CUDA(cudaStreamSynchronize(ctx->stream));
+    } else first = 0;
     cudaFree(c->q8); cudaFree(c->q8_scale);
     c->q8 = np; c->q8_scale = ns; c->q8_cap_rows = cap;
   }
   int rc;
   STB_CUDA(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), ctx->stream));
-  if ((rc = stb_launch_q8_build(ctx, c->rows, 0, c->n, c->q8, c->q8_scale, ctx->err_flag)) != STB_OK) return rc;
+  if ((rc = stb_launch_q8_build(ctx, c->rows, first, c->n, c->q8, c->q8_scale, ctx->err_flag)) != STB_OK) return rc;
   int flag = 0;
   STB_CUDA(cudaMemcpyAsync(&flag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   STB_CUDA(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), ctx->stream));
   STB_CUDA(cudaStreamSynchronize(ctx->stream));
   c->q8_rows = c->n;
-  c->q8_bad = flag;
-  if (flag) { stb_set_error("q8 tier: corpus holds rows whose norm is not a normal fp32 number"); return STB_ERR_STATE; }
+  c->q8_bad = (first ? c->q8_bad : 0) | flag;
+  if (c->q8_bad) { stb_set_error("q8 tier: corpus holds rows whose norm is not a normal fp32 number"); return STB_ERR_STATE; }
   return STB_OK;
 }
 
@@ -870,7 +885,7 @@ int stb_corpus_tier_stats(const stb_corpus *corpus, uint32_t tries[3], uint32_t 
   }
   if (built_rows) {
     built_rows[STB_TIER_F32] = corpus->n;
-    built_rows[STB_TIER_H16] = (corpus->shadow && !corpus->shadow_bad) ? corpus->shadow_rows : 0;
+    built_rows[STB_TIER_H16] = (corpus->shadow && !corpus->shadow_bad) ? corpus->shadow_rows : 0;   // < n after an append: a valid prefix
     built_rows[STB_TIER_Q8] = (corpus->q8 && !corpus->q8_bad) ? corpus->q8_rows : 0;
   }
   return STB_OK;

@@ -250,7 +250,7 @@ int stb_launch_embed(stb_ctx *ctx, const stb_table *t, const uint64_t *offsets_d
 
 // ---- batch_scan.cu (K2) ------------------------------------------------------------------
 int stb_launch_shadow_build(stb_ctx *ctx, const float *rows_dev, uint64_t n_rows, int tile,
-                            uint8_t *out, int *bad_flag_dev);
+                            uint8_t *out, int *bad_flag_dev, uint64_t first_row = 0);
 int stb_launch_batch_gemm(stb_ctx *ctx, const uint8_t *a_tiles, uint32_t m_tiles,
                           const uint8_t *b_tiles, uint32_t n_tiles, float *submax,
                           float *tilemax, float *full_out);

@@ -162,7 +162,7 @@ std::string rust_display_f32(float x) {
 std::string json_f64(double x) {
   if (std::isnan(x) || std::isinf(x)) return "null";
   const double a = std::fabs(x);
-  if (x == 0.0 || (a >= 1e-5 && a < 1e21)) return positional(x, true);
+  if (x == 0.0 || (a >= 1e-5 && a < 1e16)) return positional(x, true);   // ryu: positional while -5 < kk <= 16
   std::string d;
   int e;
   shortest_digits(a, d, e);

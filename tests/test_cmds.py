@@ -66,6 +66,7 @@ def test_serde_json_pretty_shapes():                       # json_mode.rs + serd
     assert cmds.to_string_pretty({"results": []}) == '{\n  "results": []\n}'
     assert cmds.to_string_pretty({"error": "m", "error_type": "NoInput"}) == '{\n  "error": "m",\n  "error_type": "NoInput"\n}'
     assert cmds._json_f64(1.0) == "1.0" and cmds._json_f64(0.00001) == "0.00001" and cmds._json_f64(0.000001) == "1e-6"
+    assert cmds._json_f64(1e15) == "1000000000000000.0" and cmds._json_f64(1e16) == "1e16" and cmds._json_f64(1.5e16) == "1.5e16"   # ryu switches at 1e16
 
 
 def test_workspace_result_rendering(tmp_path):             # cmds/search.rs:66-110,208-237

@@ -584,7 +584,14 @@ def test_lazy_tier_build_waits_for_the_second_query(ctx, monkeypatch):
     check(c.search(q, top_k=10), r, d)
     st = c.tier_stats()
     assert st["q8"]["built_rows"] == 40_000 and st["q8"]["proven"] == 1, st
-    c.append(rows[:10])                                                 # any change drops the copies
+    c.append(rows[:10])                                                 # an append leaves a valid PREFIX ...
+    assert c.tier_stats()["q8"]["built_rows"] == 40_000
+    rows2 = np.concatenate([rows, rows[:10]])
+    r2, d2 = oracle.search_rows(rows2, rows[3], top_k=10)               # rows[3] now has an exact duplicate at row 40003
+    check(c.search(rows[3], top_k=10), r2, d2)                          # ... which the next query extends (only the new rows are converted)
+    st = c.tier_stats()
+    assert st["q8"]["built_rows"] == 40_010 and st["q8"]["tries"] == 1, st
+    c.clear()                                                           # anything else drops the copies
     assert c.tier_stats()["q8"]["built_rows"] == 0
     small = make_corpus(ctx, rows[:5000])
     small.search(q, top_k=3); small.search(q, top_k=3)
