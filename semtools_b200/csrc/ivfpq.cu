@@ -417,7 +417,7 @@ __global__ void ivf_pick_rows_kernel(const stb_hit *cand, uint32_t r, const uint
 // Opt-in (STB_IVFPQ_V2=1) until validated on hardware.
 #define ADC2_THREADS 512
 #define ADC2_MAX_CTAS 32
-#define ADC2_KEEP 256
+#define ADC2_KEEP 64        // per CTA; chunks are dealt round-robin over the 32 CTAs, so each sees a uniform sample: ~16 of the best 512 land in one CTA
 #define ADC2_RERANK_CAP 1024
 #define ADC2_SMEM 65536
 
@@ -470,14 +470,18 @@ ivf_coarse_probe_kernel(const Probe2Args a) {
       }
       __syncthreads();
     }
+  // list sizes in parallel (one thread per probed list), then a serial prefix over shared memory:
+  // a single thread chasing 2 x nprobe dependent global loads cost ~20 us of this kernel's 62
+  __shared__ uint32_t s_sz[1024];
+  if (threadIdx.x < a.nprobe) {
+    const uint32_t l = stb_key_row(p2_keys[threadIdx.x]);
+    a.probe[threadIdx.x] = l;
+    s_sz[threadIdx.x] = __ldg(a.list_off + l + 1) - __ldg(a.list_off + l);
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t acc = 0;
-    for (uint32_t p = 0; p < a.nprobe; ++p) {
-      const uint32_t l = stb_key_row(p2_keys[p]);
-      a.probe[p] = l;
-      a.probe[a.nprobe + p] = acc;
-      acc += a.list_off[l + 1] - a.list_off[l];
-    }
+    for (uint32_t p = 0; p < a.nprobe; ++p) { a.probe[a.nprobe + p] = acc; acc += s_sz[p]; }
     a.probe[2 * a.nprobe] = acc;
     *a.ticket = 0;                                   // ready for the next query (stream-ordered)
   }
