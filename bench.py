@@ -222,6 +222,41 @@ class Env:
         self.__dict__.update(kw)
 
 
+class Dist:
+    """torch.distributed with one switch: STB_BENCH_ONE_GPU=1 puts every rank on cuda:0 (NCCL refuses two
+    ranks on one device) and runs the few collectives bench.py needs on gloo through CPU copies.  That
+    mode validates the N>1 code path on a single-GPU box -- its timings mean nothing and the line says so."""
+    def __init__(self, dist, torch, dev, one_gpu):
+        self.d, self.torch, self.dev, self.one_gpu = dist, torch, dev, one_gpu
+        self.ReduceOp = dist.ReduceOp
+
+    def __getattr__(self, name):                                  # barrier, all_gather_object, get_rank, ...
+        return getattr(self.d, name)
+
+    def _cpu(self, t):
+        return t.detach().cpu() if self.one_gpu else t
+
+    def all_reduce(self, t, op=None):
+        c = self._cpu(t)
+        self.d.all_reduce(c, op=op)
+        if self.one_gpu:
+            t.copy_(c)
+
+    def broadcast(self, t, src=0):
+        c = self._cpu(t)
+        self.d.broadcast(c, src=src)
+        if self.one_gpu:
+            t.copy_(c)
+
+    def all_gather_into_tensor(self, out, t):
+        if not self.one_gpu:
+            return self.d.all_gather_into_tensor(out, t)
+        self.torch.cuda.synchronize(self.dev)
+        parts = [self.torch.empty_like(t, device="cpu") for _ in range(self.d.get_world_size())]
+        self.d.all_gather(parts, t.detach().cpu())
+        out.copy_(self.torch.stack(parts).reshape(out.shape))
+
+
 def timed_queries(E, corpus, q_dev, k, steps, warm, xchg=None):
     """Pipelined device-timed top-k queries (stb_search_topk_dev / stb_search_topk_xchg).
     Returns (ms per query [max over ranks], status array of the timed steps, hits tensor)."""
@@ -595,11 +630,18 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world == 1 and args.gpus > 1:
         raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    one_gpu = os.environ.get("STB_BENCH_ONE_GPU") == "1" and world > 1
+    if one_gpu:
+        local_rank = 0
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        if one_gpu:
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=dev)
+    dist = Dist(dist, torch, dev, one_gpu)
 
     # a dedicated non-default stream shared by torch (events, NCCL ordering) and the library
     stream = torch.cuda.Stream(dev)
@@ -817,7 +859,8 @@ def run_ours(args):
             "dtype": {"q8": "s8 dp4a scan + f64 exact re-rank", "h16": "f16 scan + f64 exact re-rank", "f32": "f32 scan + f64 exact re-rank"}[tier],
             "data": "synthetic",
             "config": {"workload": workload_name(args.rows, k), "rows": args.rows, "rows_per_gpu": rows_per_gpu, "top_k": k,
-                       "tier": tier, "parallelism": f"row-shard x{world}", "exchange": exchange,
+                       "tier": tier, "parallelism": f"row-shard x{world}" + (" ON ONE GPU (functional check, timings void)" if one_gpu else ""),
+                       "exchange": exchange,
                        "l2": "scanned copy >> 126 MB L2, no flush" if rows_per_gpu * TIER_BYTES[tier] > 4 * 126e6 else "WARNING scanned copy fits partly in L2"},
             "clocks": clocks,
             "e2e": {"value": r5(1e3 / e2e_ms), "unit": "queries/s", "h2d_bytes_per_step": 1024, "d2h_bytes_per_step": 16 * k + 16,

@@ -15,13 +15,14 @@ for i in range(0, rows, 1_000_000):
     torch.cuda.synchronize(); c.append_dev(x.data_ptr(), n)
 q = torch.randn((8, 256), generator=g, device=dev); q /= q.norm(dim=1, keepdim=True)
 qh = q.cpu().numpy()
+c.prepare()                                  # q8 + h16 copies; STB_SCAN_TIER=f32 in the environment pins the f32 rows
 
 def timeit(fn, reps=8):
     fn(0); t0 = time.perf_counter()
     for i in range(reps): r = fn(i % 8)
     return (time.perf_counter() - t0) / reps * 1e3, r
 
-out = {"rows": rows}
+out = {"rows": rows, "tier": os.environ.get("STB_SCAN_TIER", "q8 (default)")}
 ms, r = timeit(lambda i: c.search(qh[i], top_k=10)); out["topk10_ms"] = ms
 ms, r = timeit(lambda i: c.search(qh[i], top_k=10, mode=capi.STB_MODE_STORE_QUERY, row_ranges=[[0, rows]])); out["store_1_range_ms"] = ms
 rng = np.random.default_rng(0)

@@ -463,12 +463,12 @@ static int ensure_hits_pin(stb_ctx *ctx, size_t need) {
 // On return ctx->collect_hits holds the sorted hits and *n_pass their count.
 static int collect_exact_sorted(stb_ctx *ctx, const stb_corpus *c, float cos_floor, double limit,
                                 const uint64_t *ranges_dev, uint32_t n_ranges, uint64_t n_virtual,
-                                uint64_t *n_pass) {
+                                uint64_t *n_pass, int tier = STB_TIER_F32) {
   int rc;
   unsigned long long count = 0;
   if ((rc = dev_reserve(&ctx->collect_rows, &ctx->collect_cap, 1, 1u << 20)) != STB_OK) return rc;
   for (int attempt = 0; attempt < 3; ++attempt) {
-    if ((rc = stb_launch_scan_collect(ctx, c->rows, c->n, ctx->q_dev, cos_floor, ranges_dev, n_ranges, n_virtual)) != STB_OK) return rc;
+    if ((rc = stb_launch_scan_collect(ctx, c, tier, ctx->q_dev, cos_floor, ranges_dev, n_ranges, n_virtual)) != STB_OK) return rc;
     STB_CUDA(cudaMemcpyAsync(&count, ctx->collect_count, sizeof(count), cudaMemcpyDeviceToHost, ctx->stream));
     STB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (count <= ctx->collect_cap) break;
@@ -615,12 +615,35 @@ int stb_search(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint32_t 
     total = std::min<uint64_t>(n_pass, top_k);
     src_dev = ctx->collect_hits;
   } else {
+    // ---- threshold mode / top_k beyond the register lists: collect -> exact -> sort --------------
+    // When the int8 copy exists (or may be built: same lazy rule as the top-k tiers) the streaming
+    // passes read it instead of the f32 rows: its scores are upper bounds u >= c - 2e-5 of the exact
+    // cosine, so "u >= floor" collects a superset of "c >= floor" at a quarter of the bytes.
+    stb_corpus *cm = const_cast<stb_corpus *>(corpus);
+    const bool lazy_ok = cm->searches_since_change >= 1 && cm->n >= 32768;
+    cm->searches_since_change++;
+    bool use_q8 = stb_env_max_tier() >= STB_TIER_Q8;
+    if (use_q8) {
+      const bool built = cm->q8 && cm->q8_rows == cm->n;
+      const bool extendable = cm->q8 && cm->q8_rows > 0 && !cm->q8_bad;
+      if (!built && !lazy_ok && !extendable) use_q8 = false;
+      else {
+        const int src = corpus_ensure_q8(ctx, cm);
+        if (src == STB_ERR_STATE) use_q8 = false;
+        else if (src != STB_OK) return src;
+      }
+    }
     float floor_cos = -INFINITY;
     double limit = 100.0;
+    uint64_t n_pass = 0;
+    bool done = false;
     if (threshold_all) {
       limit = max_distance;
-      floor_cos = (float)(1.0 - max_distance - STB_SCORE_EPS);
+      floor_cos = (float)(1.0 - max_distance - (use_q8 ? 2.0 * STB_Q8_SCAN_EPS : STB_SCORE_EPS));
       if (!(max_distance == max_distance)) floor_cos = INFINITY;   // NaN threshold: nothing passes
+      if ((rc = collect_exact_sorted(ctx, corpus, floor_cos, limit, ranges_dev, n_loc, n_virtual, &n_pass,
+                                     use_q8 ? STB_TIER_Q8 : STB_TIER_F32)) != STB_OK) return rc;
+      done = true;
     } else {
       if (has_max) {
         limit = std::min(max_distance, 100.0);
@@ -628,17 +651,43 @@ int stb_search(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint32_t 
       }
       // top_k beyond the register lists: histogram pass to find the score bin of the k-th
       // best, then collect only rows at or above that bin (instead of the whole shard)
-      if ((rc = stb_launch_scan_hist(ctx, corpus->rows, ctx->q_dev, ranges_dev, n_loc, n_virtual, ctx->hist_dev)) != STB_OK) return rc;
       std::vector<unsigned int> hist(4096);
-      STB_CUDA(cudaMemcpyAsync(hist.data(), ctx->hist_dev, 4096 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
-      STB_CUDA(cudaStreamSynchronize(ctx->stream));
-      uint64_t cum = 0;
-      int b = 0;
-      for (; b < 4096; ++b) { cum += hist[b]; if (cum >= top_k) break; }
-      if (b < 4095) floor_cos = (float)(1.0 - (double)(b + 1) / 2048.0 - 2.0 * STB_SCORE_EPS);   // else: fewer than k rows, take all
+      auto kth_bin = [&](int tier, int *bin) -> int {
+        int r;
+        if ((r = stb_launch_scan_hist(ctx, corpus, tier, ctx->q_dev, ranges_dev, n_loc, n_virtual, ctx->hist_dev)) != STB_OK) return r;
+        STB_CUDA(cudaMemcpyAsync(hist.data(), ctx->hist_dev, 4096 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+        STB_CUDA(cudaStreamSynchronize(ctx->stream));
+        uint64_t cum = 0;
+        int b = 0;
+        for (; b < 4096; ++b) { cum += hist[b]; if (cum >= top_k) break; }
+        *bin = b;
+        return STB_OK;
+      };
+      if (use_q8) {
+        // q8: the histogram is over UPPER BOUNDS, which sit up to ~0.02-0.04 above the exact cosines, so the
+        // floor is put 0.04 below the k-th best bound and the result is PROVEN afterwards: every row that
+        // was not collected has c < floor + 2e-5; if the k-th exact distance found is below
+        // 1 - floor - 2e-5 nothing outside can enter or tie.  Otherwise the f32 passes below answer.
+        int b = 0;
+        if ((rc = kth_bin(STB_TIER_Q8, &b)) != STB_OK) return rc;
+        floor_cos = (b < 4095) ? (float)(1.0 - (double)(b + 1) / 2048.0 - 0.04) : -INFINITY;
+        if ((rc = collect_exact_sorted(ctx, corpus, floor_cos, limit, ranges_dev, n_loc, n_virtual, &n_pass, STB_TIER_Q8)) != STB_OK) return rc;
+        if (floor_cos == -INFINITY) done = true;             // everything was collected
+        else if (n_pass >= top_k) {
+          stb_hit kth;
+          STB_CUDA(cudaMemcpyAsync(&kth, ctx->collect_hits + (top_k - 1), sizeof(kth), cudaMemcpyDeviceToHost, ctx->stream));
+          STB_CUDA(cudaStreamSynchronize(ctx->stream));
+          done = kth.distance < 1.0 - (double)floor_cos - 2.0 * STB_Q8_SCAN_EPS;
+        }
+        if (!done) ctx->fallback_searches++;
+      }
+      if (!done) {
+        int b = 0;
+        if ((rc = kth_bin(STB_TIER_F32, &b)) != STB_OK) return rc;
+        floor_cos = (b < 4095) ? (float)(1.0 - (double)(b + 1) / 2048.0 - 2.0 * STB_SCORE_EPS) : -INFINITY;   // else: fewer than k rows, take all
+        if ((rc = collect_exact_sorted(ctx, corpus, floor_cos, limit, ranges_dev, n_loc, n_virtual, &n_pass)) != STB_OK) return rc;
+      }
     }
-    uint64_t n_pass = 0;
-    if ((rc = collect_exact_sorted(ctx, corpus, floor_cos, limit, ranges_dev, n_loc, n_virtual, &n_pass)) != STB_OK) return rc;
     total = threshold_all ? n_pass : std::min<uint64_t>(n_pass, top_k);
     src_dev = ctx->collect_hits;
   }

@@ -199,13 +199,14 @@ int stb_launch_q8_build(stb_ctx *ctx, const float *rows_dev, uint64_t first_row,
 uint32_t stb_scan_topk_max_k(void);
 // Collect path: every row whose approximate cosine >= cos_floor (or that cannot be
 // scored safely) is appended to ctx->collect_rows; total count -> collect_count.
-int stb_launch_scan_collect(stb_ctx *ctx, const float *rows, uint64_t n_rows,
+// tier: STB_TIER_F32 (approximate cosine of the f32 rows) or STB_TIER_Q8 (upper bounds from the int8 copy)
+int stb_launch_scan_collect(stb_ctx *ctx, const stb_corpus *c, int tier,
                             const float *q_dev, float cos_floor,
                             const uint64_t *ranges_dev, uint32_t n_ranges,
                             uint64_t n_virtual);
 // Large-k support: 4096-bin histogram of the approximate cosine over the scanned rows
 // (bin b: cos in (1-(b+1)/2048, 1-b/2048]).  hist_dev: 4096 u32 on device.
-int stb_launch_scan_hist(stb_ctx *ctx, const float *rows, const float *q_dev, const uint64_t *ranges_dev,
+int stb_launch_scan_hist(stb_ctx *ctx, const stb_corpus *c, int tier, const float *q_dev, const uint64_t *ranges_dev,
                          uint32_t n_ranges, uint64_t n_virtual, unsigned int *hist_dev);
 // Exact canonical distances of m collected rows -> hits (invalid/failing rows get
 // distance=+inf,row=UINT64_MAX); counts passing rows into pass_count.

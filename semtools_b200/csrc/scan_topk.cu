@@ -1191,22 +1191,25 @@ struct CollectArgs {
   uint32_t *out;
   unsigned long long *count;
   uint64_t cap;
+  const uint8_t *q8;         // SRC == 2: scores are the q8 tier's upper bounds of the exact cosine
+  const float *q8_scale;
 };
 
-template <int U, bool RANGES>
+template <int U, bool RANGES, int SRC = 0>
 __global__ void __launch_bounds__(STB_SCAN_THREADS, STB_SCAN_MINB)
 stb_scan_collect_kernel(const CollectArgs args) {
   CollectSink sink{args.cos_floor, args.out, args.count, args.cap};
-  stb_scan_rows<U, RANGES>(args.scan, sink);
+  if constexpr (SRC == 2) stb_scan_q8<U, RANGES>(args.scan, args.q8, args.q8_scale, sink);
+  else stb_scan_rows<U, RANGES>(args.scan, sink);
 }
 
-int stb_launch_scan_collect(stb_ctx *ctx, const float *rows, uint64_t n_rows,
+int stb_launch_scan_collect(stb_ctx *ctx, const stb_corpus *c, int tier,
                             const float *q_dev, float cos_floor,
                             const uint64_t *ranges_dev, uint32_t n_ranges,
                             uint64_t n_virtual) {
-  (void)n_rows;
   CollectArgs a;
-  a.scan.rows = reinterpret_cast<const float4 *>(rows);
+  a.scan.rows = reinterpret_cast<const float4 *>(c->rows);
+  a.q8 = c->q8; a.q8_scale = c->q8_scale;
   a.scan.n_virtual = n_virtual;
   a.scan.q = q_dev;
   a.scan.vstart = ranges_dev;
@@ -1218,11 +1221,16 @@ int stb_launch_scan_collect(stb_ctx *ctx, const float *rows, uint64_t n_rows,
   a.count = ctx->collect_count;
   a.cap = ctx->collect_cap;
   STB_CUDA(cudaMemsetAsync(ctx->collect_count, 0, sizeof(unsigned long long), ctx->stream));
-  uint64_t tiles = (n_virtual + 4 * STB_SCAN_U - 1) / (4 * STB_SCAN_U);
+  const int u = tier == STB_TIER_Q8 ? STB_Q8_SCAN_U : STB_SCAN_U;
+  uint64_t tiles = (n_virtual + 4 * u - 1) / (4 * u);
   uint64_t want = (tiles + STB_SCAN_WARPS - 1) / STB_SCAN_WARPS;
   uint64_t grid = (uint64_t)ctx->sm_count * STB_SCAN_MINB;
   if (want < grid) grid = want < 1 ? 1 : want;
-  if (n_ranges > 0)
+  if (tier == STB_TIER_Q8) {
+    if (!c->q8) { stb_set_error("scan_collect: q8 tier unavailable"); return STB_ERR_STATE; }
+    if (n_ranges > 0) stb_scan_collect_kernel<STB_Q8_SCAN_U, true, 2><<<(unsigned)grid, STB_SCAN_THREADS, 0, ctx->stream>>>(a);
+    else stb_scan_collect_kernel<STB_Q8_SCAN_U, false, 2><<<(unsigned)grid, STB_SCAN_THREADS, 0, ctx->stream>>>(a);
+  } else if (n_ranges > 0)
     stb_scan_collect_kernel<STB_SCAN_U, true><<<(unsigned)grid, STB_SCAN_THREADS, 0, ctx->stream>>>(a);
   else
     stb_scan_collect_kernel<STB_SCAN_U, false><<<(unsigned)grid, STB_SCAN_THREADS, 0, ctx->stream>>>(a);
@@ -1249,23 +1257,24 @@ struct HistSink {
   }
 };
 
-template <int U, bool RANGES>
+template <int U, bool RANGES, int SRC = 0>
 __global__ void __launch_bounds__(STB_SCAN_THREADS, STB_SCAN_MINB)
-stb_scan_hist_kernel(const ScanArgs scan, unsigned int *global_hist) {
+stb_scan_hist_kernel(const ScanArgs scan, unsigned int *global_hist, const uint8_t *q8, const float *q8_scale) {
   __shared__ unsigned int s_hist[STB_HIST_BINS];
   for (int i = threadIdx.x; i < STB_HIST_BINS; i += blockDim.x) s_hist[i] = 0u;
   __syncthreads();
   HistSink sink{s_hist};
-  stb_scan_rows<U, RANGES>(scan, sink);
+  if constexpr (SRC == 2) stb_scan_q8<U, RANGES>(scan, q8, q8_scale, sink);
+  else stb_scan_rows<U, RANGES>(scan, sink);
   __syncthreads();
   for (int i = threadIdx.x; i < STB_HIST_BINS; i += blockDim.x)
     if (s_hist[i]) atomicAdd(global_hist + i, s_hist[i]);
 }
 
-int stb_launch_scan_hist(stb_ctx *ctx, const float *rows, const float *q_dev, const uint64_t *ranges_dev,
+int stb_launch_scan_hist(stb_ctx *ctx, const stb_corpus *c, int tier, const float *q_dev, const uint64_t *ranges_dev,
                          uint32_t n_ranges, uint64_t n_virtual, unsigned int *hist_dev) {
   ScanArgs a;
-  a.rows = reinterpret_cast<const float4 *>(rows);
+  a.rows = reinterpret_cast<const float4 *>(c->rows);
   a.n_virtual = n_virtual;
   a.q = q_dev;
   a.vstart = ranges_dev;
@@ -1273,14 +1282,19 @@ int stb_launch_scan_hist(stb_ctx *ctx, const float *rows, const float *q_dev, co
   a.n_ranges = n_ranges;
   a.tickets = nullptr; a.t_base = 0; a.t_bulk = 0;
   STB_CUDA(cudaMemsetAsync(hist_dev, 0, STB_HIST_BINS * sizeof(unsigned int), ctx->stream));
-  uint64_t tiles = (n_virtual + 4 * STB_SCAN_U - 1) / (4 * STB_SCAN_U);
+  const int u = tier == STB_TIER_Q8 ? STB_Q8_SCAN_U : STB_SCAN_U;
+  uint64_t tiles = (n_virtual + 4 * u - 1) / (4 * u);
   uint64_t want = (tiles + STB_SCAN_WARPS - 1) / STB_SCAN_WARPS;
   uint64_t grid = (uint64_t)ctx->sm_count * STB_SCAN_MINB;
   if (want < grid) grid = want < 1 ? 1 : want;
-  if (n_ranges > 0)
-    stb_scan_hist_kernel<STB_SCAN_U, true><<<(unsigned)grid, STB_SCAN_THREADS, 0, ctx->stream>>>(a, hist_dev);
+  if (tier == STB_TIER_Q8) {
+    if (!c->q8) { stb_set_error("scan_hist: q8 tier unavailable"); return STB_ERR_STATE; }
+    if (n_ranges > 0) stb_scan_hist_kernel<STB_Q8_SCAN_U, true, 2><<<(unsigned)grid, STB_SCAN_THREADS, 0, ctx->stream>>>(a, hist_dev, c->q8, c->q8_scale);
+    else stb_scan_hist_kernel<STB_Q8_SCAN_U, false, 2><<<(unsigned)grid, STB_SCAN_THREADS, 0, ctx->stream>>>(a, hist_dev, c->q8, c->q8_scale);
+  } else if (n_ranges > 0)
+    stb_scan_hist_kernel<STB_SCAN_U, true><<<(unsigned)grid, STB_SCAN_THREADS, 0, ctx->stream>>>(a, hist_dev, nullptr, nullptr);
   else
-    stb_scan_hist_kernel<STB_SCAN_U, false><<<(unsigned)grid, STB_SCAN_THREADS, 0, ctx->stream>>>(a, hist_dev);
+    stb_scan_hist_kernel<STB_SCAN_U, false><<<(unsigned)grid, STB_SCAN_THREADS, 0, ctx->stream>>>(a, hist_dev, nullptr, nullptr);
   STB_CUDA(cudaGetLastError());
   ctx->kernel_launches++;
   return STB_OK;

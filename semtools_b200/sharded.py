@@ -118,9 +118,16 @@ def _device_all_gather(dist, device):
     world = dist.get_world_size()
 
     def all_gather(local):
-        t = torch.from_numpy(local.view(np.float64).reshape(-1, 2).copy()).to(device)
-        out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=device)
-        dist.all_gather_into_tensor(out, t)
-        return np.ascontiguousarray(out.cpu().numpy()).view(capi.HIT_DTYPE).reshape(world, -1)
+        t = torch.from_numpy(local.view(np.float64).reshape(-1, 2).copy())
+        if dist.get_backend() == "gloo":                   # CPU collectives (tests; bench.py's one-GPU functional mode)
+            parts = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(parts, t)
+            out = torch.stack(parts)
+        else:
+            t = t.to(device)
+            out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=device)
+            dist.all_gather_into_tensor(out, t)
+            out = out.cpu()
+        return np.ascontiguousarray(out.numpy()).view(capi.HIT_DTYPE).reshape(world, -1)
 
     return all_gather

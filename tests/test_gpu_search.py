@@ -715,3 +715,35 @@ def test_sharded_threshold_mode_counts_then_padded_payload(world):
     for rank in range(world):
         check(results[rank]["topk"], r, d)
     assert len(results[0][0.78]) > 3 and len(results[0][1.0000001]) > 20_000       # really lifted the cap, really > 4096 hits (about half the rows have cosine > 0)
+
+
+@pytest.mark.parametrize("tier", ["q8", "f32"])
+def test_threshold_mode_and_large_k_read_the_narrowest_copy(ctx, monkeypatch, tier):
+    """Threshold mode (mod.rs:115-116) and top_k beyond the register lists run collect -> exact -> sort.
+    With the int8 copy built the streaming passes read it (upper bounds of the cosine: a superset is
+    collected; the large-k floor is proven afterwards) -- a quarter of the bytes, the same hits."""
+    monkeypatch.setenv("STB_SCAN_TIER", tier)
+    rng = np.random.default_rng(808)
+    n = 120_000
+    rows = unit_rows(rng, n)
+    rows[rng.integers(0, n, 40)] = rows[rng.integers(0, n, 40)]
+    rows[[7, n // 2]] = 0.0
+    q = unit_rows(rng, 1)[0]
+    rows[4321] = q
+    c = make_corpus(ctx, rows)
+    c.prepare()
+    before = ctx.counters()["fallback_searches"]
+    for thr in (0.0, 0.5, 0.8, 0.93, 1.0, 1.0000001):
+        r, d = oracle.search_rows(rows, q, top_k=3, max_distance=thr)
+        check(c.search(q, top_k=3, max_distance=thr), r, d)
+    for k in (97, 1000, 5000):
+        r, d = oracle.search_rows(rows, q, top_k=k)
+        check(c.search(q, top_k=k), r, d)
+    ranges = [[10, n // 2], [n // 2 + 5, n - 3]]
+    r2, d2 = oracle.store_search(rows, ranges, q, 300)
+    got = c.search(q, top_k=300, mode=capi.STB_MODE_STORE_QUERY, row_ranges=ranges)
+    assert got["row"].tolist() == [int(x) for x in r2]
+    zq = np.zeros(256, np.float32)                                   # zero query: every bound is +inf -> everything collected
+    r, d = oracle.search_rows(rows, zq, top_k=3, max_distance=0.5)
+    check(c.search(zq, top_k=3, max_distance=0.5), r, d)
+    assert ctx.counters()["fallback_searches"] == before             # random data: the q8 floor proves itself
