@@ -78,16 +78,26 @@ struct ScanArgs {
 template <int RANGES, int WB, class Body>
 __device__ __forceinline__ void stb_for_each_tile(const ScanArgs &args, uint64_t n_tiles, Body &&body) {
   if (args.tickets) {
+    // The next ticket is drawn BEFORE the current one is processed, so the atomic's L2 round trip
+    // (~1 us under load) overlaps a ticket's worth of loads instead of stalling the warp 4-6 times per
+    // query (at 1.25M rows per GPU that was ~10 % of the scan).  A warp stops drawing at its first
+    // failing draw, so the "exactly one failing draw per warp" bookkeeping holds.
     const int lane = threadIdx.x & 31;
-    for (;;) {
+    auto draw = [&]() -> unsigned long long {
       unsigned long long t = 0;
       if (lane == 0) t = atomicAdd(args.tickets, 1ull);
-      t = __shfl_sync(0xffffffffu, t, 0) - args.t_base;
-      uint64_t t0, t1;
-      if (t < args.t_bulk) { t0 = t * STB_TICKET_TILES; t1 = t0 + STB_TICKET_TILES; }
-      else { t0 = args.t_bulk * STB_TICKET_TILES + (t - args.t_bulk); t1 = t0 + 1; }
-      if (t0 >= n_tiles) break;
+      return __shfl_sync(0xffffffffu, t, 0) - args.t_base;
+    };
+    auto first_tile = [&](unsigned long long t) -> uint64_t {
+      return t < args.t_bulk ? t * STB_TICKET_TILES : args.t_bulk * STB_TICKET_TILES + (t - args.t_bulk);
+    };
+    unsigned long long cur = draw();
+    while (first_tile(cur) < n_tiles) {
+      const unsigned long long nxt = draw();
+      const uint64_t t0 = first_tile(cur);
+      const uint64_t t1 = cur < args.t_bulk ? t0 + STB_TICKET_TILES : t0 + 1;
       for (uint64_t tile = t0; tile < t1; ++tile) body(tile, tile == t0);
+      cur = nxt;
     }
     return;
   }

@@ -298,18 +298,47 @@ static void to_csr(const std::vector<std::string> &lines, const Tokenizer &tok, 
   tokenize_to_csr(lines, tok, max_len, offsets, ids);
 }
 
+// encode_with_args(lines, Some(2048), 16384) (mod.rs:69): batches of 16384 lines.  A producer thread
+// tokenises batch i+1 (itself multi-threaded, tokenize_to_csr) while this thread has K3 embed batch i
+// (stb_embed: CSR H2D + kernel + optional D2H), so host tokenisation and the GPU overlap; the result is
+// identical to one big batch because lines are independent.  `out` (n x 256) and `append_to` may be null.
+static const size_t kEmbedBatchLines = 16384;
+static void embed_batched(stb_ctx *ctx, stb_table *table, const std::vector<std::string> &lines, const Tokenizer &tok,
+                          float *out, stb_corpus *append_to) {
+  const size_t n = lines.size(), n_batches = (n + kEmbedBatchLines - 1) / kEmbedBatchLines;
+  struct Batch { std::vector<uint64_t> offsets; std::vector<uint32_t> ids; size_t first = 0, count = 0; };
+  auto tokenise = [&](size_t b, Batch &dst) {
+    dst.first = b * kEmbedBatchLines;
+    dst.count = std::min(kEmbedBatchLines, n - dst.first);
+    std::vector<std::string> part(lines.begin() + dst.first, lines.begin() + dst.first + dst.count);
+    tokenize_to_csr(part, tok, 2048, dst.offsets, dst.ids);
+  };
+  auto embed = [&](const Batch &b) {
+    uint32_t dummy = 0;
+    check(stb_embed(ctx, table, b.offsets.data(), b.ids.empty() ? &dummy : b.ids.data(), b.count,
+                    out ? out + b.first * STB_DIM : nullptr, append_to));
+  };
+  Batch cur, nxt;
+  tokenise(0, cur);
+  for (size_t b = 0; b < n_batches; ++b) {
+    std::thread producer;
+    std::exception_ptr perr;
+    if (b + 1 < n_batches) producer = std::thread([&] { try { tokenise(b + 1, nxt); } catch (...) { perr = std::current_exception(); } });
+    try { embed(cur); } catch (...) { if (producer.joinable()) producer.join(); throw; }
+    if (producer.joinable()) producer.join();
+    if (perr) std::rethrow_exception(perr);
+    std::swap(cur, nxt);
+  }
+}
+
 bool Searcher::add_document(const std::string &filename, const std::string &content, const Tokenizer &tok, bool ignore_case) {
   auto lines = rust_lines(content);
   if (lines.empty()) return false;                             // mod.rs:57-59
   if (!table_) throw std::runtime_error("load_table first");
   std::vector<std::string> emb_lines = lines;
   if (ignore_case) for (auto &l : emb_lines) l = to_lowercase(l);
-  std::vector<uint64_t> offsets;
-  std::vector<uint32_t> ids;
-  to_csr(emb_lines, tok, 2048, offsets, ids);                  // encode_with_args(.., Some(2048), 16384), mod.rs:69
   Document d{filename, std::move(lines), rows()};
-  uint32_t dummy = 0;
-  check(stb_embed(ctx_, table_, offsets.data(), ids.empty() ? &dummy : ids.data(), d.lines.size(), nullptr, corpus_));
+  embed_batched(ctx_, table_, emb_lines, tok, nullptr, corpus_);   // rows go straight into the corpus in HBM
   docs_.push_back(std::move(d));
   return true;
 }
@@ -320,11 +349,7 @@ std::vector<float> Searcher::embed_lines(const std::vector<std::string> &lines, 
   if (lines.empty()) return out;
   std::vector<std::string> emb_lines = lines;
   if (ignore_case) for (auto &l : emb_lines) l = to_lowercase(l);
-  std::vector<uint64_t> offsets;
-  std::vector<uint32_t> ids;
-  to_csr(emb_lines, tok, 2048, offsets, ids);
-  uint32_t dummy = 0;
-  check(stb_embed(ctx_, table_, offsets.data(), ids.empty() ? &dummy : ids.data(), lines.size(), out.data(), nullptr));
+  embed_batched(ctx_, table_, emb_lines, tok, out.data(), nullptr);
   return out;
 }
 

@@ -28,11 +28,16 @@ using namespace semtools;
 
 // Synthetic ingestion batch of SURVEY 8d: V = 500k words, line lengths ~ LogNormal(2.5, 0.8)
 // clipped to [0, 2048], word ranks ~ Zipf(1.1); reports lines/s and tokens/s of tokenize_to_csr.
-static int tokenize_bench(size_t n_lines, unsigned threads) {
+static int tokenize_bench(size_t n_lines, unsigned threads, const std::string &tokenizer_json = "") {
   std::vector<std::string> words;
   words.reserve(500000);
   for (uint64_t i = 0; i < 500000; ++i) words.push_back("t" + std::to_string(i * 7919 % 1000003));
-  WordLevelTokenizer tok(words);
+  // with a tokenizer.json: the same synthetic lines go through the Unigram pipeline (the words are
+  // then segmented into whatever pieces its vocabulary offers); without: the WordLevel tokenizer
+  std::unique_ptr<Tokenizer> owner;
+  if (!tokenizer_json.empty()) owner.reset(new HfTokenizer(tokenizer_json));
+  else owner.reset(new WordLevelTokenizer(words));
+  const Tokenizer &tok = *owner;
   std::mt19937_64 rng(12345);
   std::lognormal_distribution<double> len(2.5, 0.8);
   std::vector<double> cdf(500000);
@@ -124,7 +129,7 @@ int main(int argc, char **argv) {
     if (a == "--tokenize-bench") {                 // host tokenisation throughput: LINES THREADS
       const size_t n_lines = i + 1 < argc ? std::stoul(argv[i + 1]) : 1000000;
       const unsigned threads = i + 2 < argc ? (unsigned)std::stoul(argv[i + 2]) : 0;
-      return tokenize_bench(n_lines, threads);
+      return tokenize_bench(n_lines, threads, i + 3 < argc ? argv[i + 3] : "");
     }
     if (a == "--encode") {                         // test hook: --encode tokenizer.json: stdin lines -> "raw ids | ids without unk"
       HfTokenizer tk(next());
