@@ -114,17 +114,28 @@ HfTokenizer::HfTokenizer(const std::string &path) {
   if (has_unk_ && unk_id_ >= tokens_.size()) throw std::runtime_error("tokenizer.json: unk_id outside the vocabulary");
   min_score_ = *std::min_element(scores_.begin(), scores_.end());
   // byte trie; a token that occurs twice keeps the LAST id (tokenizers builds token_to_ids by insertion)
+  std::unordered_map<uint64_t, uint32_t> edges;             // (node << 8 | byte) -> child, construction only
   terminal_.push_back(-1);
   for (size_t id = 0; id < tokens_.size(); ++id) {
     uint32_t node = 0;
     for (unsigned char c : tokens_[id]) {
       const uint64_t key = ((uint64_t)node << 8) | c;
-      auto it = edges_.find(key);
-      if (it == edges_.end()) { it = edges_.emplace(key, (uint32_t)terminal_.size()).first; terminal_.push_back(-1); }
+      auto it = edges.find(key);
+      if (it == edges.end()) { it = edges.emplace(key, (uint32_t)terminal_.size()).first; terminal_.push_back(-1); }
       node = it->second;
     }
     if (!tokens_[id].empty()) terminal_[node] = (int32_t)id;
   }
+  // flatten: children of a node contiguous and sorted by byte (cache-friendly Viterbi walks)
+  std::vector<std::pair<uint64_t, uint32_t>> flat(edges.begin(), edges.end());
+  std::sort(flat.begin(), flat.end());
+  first_child_.assign(terminal_.size() + 1, 0);
+  child_byte_.resize(flat.size()); child_node_.resize(flat.size());
+  for (const auto &e : flat) first_child_[(e.first >> 8) + 1]++;
+  for (size_t i = 1; i < first_child_.size(); ++i) first_child_[i] += first_child_[i - 1];
+  for (size_t i = 0; i < flat.size(); ++i) { child_byte_[i] = (uint8_t)(flat[i].first & 0xff); child_node_[i] = flat[i].second; }
+  for (int b = 0; b < 256; ++b) root_[b] = UINT32_MAX;
+  for (uint32_t i = first_child_[0]; i < first_child_[1]; ++i) root_[child_byte_[i]] = child_node_[i];
   // median token length in BYTES over the vocabulary (model2vec: `tk.len()` of every vocab key)
   std::vector<size_t> lens;
   lens.reserve(tokens_.size());
@@ -219,6 +230,14 @@ void HfTokenizer::pre_tokenize(const std::string &normalized, std::vector<std::s
   }
 }
 
+uint32_t HfTokenizer::step(uint32_t node, unsigned char c) const {
+  if (node == 0) return root_[c];
+  uint32_t lo = first_child_[node], hi = first_child_[node + 1];
+  if (hi - lo <= 8) { for (; lo < hi; ++lo) if (child_byte_[lo] == c) return child_node_[lo]; return UINT32_MAX; }
+  while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (child_byte_[mid] < c) lo = mid + 1; else hi = mid; }
+  return (lo < first_child_[node + 1] && child_byte_[lo] == c) ? child_node_[lo] : UINT32_MAX;
+}
+
 // models/unigram/model.rs: encode_optimized + tokenize (string -> id, unknown strings -> unk_id)
 void HfTokenizer::unigram(const std::string &s, std::vector<uint32_t> &out) const {
   const size_t size = s.size();
@@ -233,9 +252,8 @@ void HfTokenizer::unigram(const std::string &s, std::vector<uint32_t> &out) cons
     const size_t mblen = std::min(utf8_len((unsigned char)s[at]), size - at);
     uint32_t node = 0;
     for (size_t k = at; k < size; ++k) {
-      auto it = edges_.find(((uint64_t)node << 8) | (unsigned char)s[k]);
-      if (it == edges_.end()) break;
-      node = it->second;
+      node = step(node, (unsigned char)s[k]);
+      if (node == UINT32_MAX) break;
       const int32_t id = terminal_[node];
       if (id < 0) continue;
       const size_t key_pos = k + 1;

@@ -58,8 +58,13 @@ class HfTokenizer : public Tokenizer {
   uint32_t unk_id_ = 0;
   size_t median_len_ = 1;
   uint64_t file_hash_ = 0;
-  // byte trie: edge (node << 8 | byte) -> child node; terminal_[node] = token id or -1
-  std::unordered_map<uint64_t, uint32_t> edges_;
+  // byte trie, flattened after construction: node n's children are child_byte_/child_node_
+  // [first_child_[n], first_child_[n + 1]) sorted by byte (the root has a direct 256-entry table);
+  // terminal_[node] = token id or -1
+  uint32_t step(uint32_t node, unsigned char c) const;      // child or UINT32_MAX
+  std::vector<uint32_t> first_child_, child_node_;
+  std::vector<uint8_t> child_byte_;
+  uint32_t root_[256];
   std::vector<int32_t> terminal_;
 };
 
