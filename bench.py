@@ -493,7 +493,7 @@ def clustered_shard(E, rows_total, lo, hi, n_centers, spread=0.6):
     return c, q.cpu().numpy()
 
 
-def side_ivfpq(E, args, nlist=4096, nprobe=64):
+def side_ivfpq(E, args, nlist=4096, nprobe=64, make_xchg=None):
     """BASELINE configs[4] (IVF-PQ; self-specified: the reference has no IVF_PQ, so no parity --
     recall@10 against the exact scan of the same rows is the quality metric).  N=1: --ivfpq-rows
     clustered rows on one GPU.  N>1: --ivfpq-rows-per-gpu rows per GPU, sharded by ROW (one index
@@ -509,27 +509,46 @@ def side_ivfpq(E, args, nlist=4096, nprobe=64):
     index = capi.IvfPq(c, nlist=nlist, train_rows=262144, iters=8)
     E.torch.cuda.synchronize(dev)
     build_s = E.max_over_ranks(time.perf_counter() - t0)
+    xq = None
     if E.world == 1:
-        search_exact = lambda q: c.search(q, top_k=10)
-        search_ivf = lambda q: index.search(q, nprobe=nprobe, top_k=10, rerank=512)
+        search_exact = lambda i: c.search(qh[i], top_k=10)
+        search_ivf = lambda i: index.search(qh[i], nprobe=nprobe, top_k=10, rerank=512)
     else:
-        exact = ShardedCorpus.on_gpu(E.ctx, c, dist, dev)
-        approx = ShardedCorpus.on_gpu_ivfpq(E.ctx, index, dist, dev, nprobe=nprobe, rerank=512)
-        scanned_box = [0]
+        # exact comparator: the fused single-query exchange (stb_search_xchg) over the same shards;
+        # IVF-PQ: stb_ivfpq_search_dev per rank -> all-gather of the k hits -> stb_hits_merge_dev -> one D2H
+        c.prepare(1)
+        xq = make_xchg() if make_xchg is not None else None
+        exact_sc = ShardedCorpus.on_gpu(E.ctx, c, dist, dev)
+        search_exact = (lambda i: xq.search(c, qh[i], 10)[0]) if xq is not None else (lambda i: exact_sc.search(qh[i], 10))
+        q_pin = torch.from_numpy(qh).pin_memory()
+        q_d = torch.empty(256, dtype=torch.float32, device=dev)
+        loc = torch.zeros((10, 2), dtype=torch.float64, device=dev)
+        st2 = torch.zeros(2, dtype=torch.int32, device=dev)
+        gat = torch.zeros((E.world, 10, 2), dtype=torch.float64, device=dev)
+        mer = torch.zeros((10, 2), dtype=torch.float64, device=dev)
+        out_pin = torch.zeros((10, 2), dtype=torch.float64).pin_memory()
 
-        def search_ivf(q):
-            return approx.search(q, 10), scanned_box[0]
-        search_exact = lambda q: exact.search(q, 10)
-    want = [search_exact(qh[i]) for i in range(64)]
+        def search_ivf(i):
+            q_d.copy_(q_pin[i], non_blocking=True)
+            index.search_dev(q_d.data_ptr(), nprobe, 10, 512, loc.data_ptr(), st2.data_ptr())
+            dist.all_gather_into_tensor(gat, loc)
+            E.ctx.hits_merge_dev(gat.data_ptr(), E.world, 10, 10, mer.data_ptr())
+            out_pin.copy_(mer, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            h = np.ascontiguousarray(out_pin.numpy()).view(capi.HIT_DTYPE).reshape(-1).copy()
+            return h[h["row"] != np.uint64(0xFFFFFFFFFFFFFFFF)], 0
+    want = [search_exact(i) for i in range(64)]
     E.barrier()
     t0 = time.perf_counter()
     for i in range(64):
-        search_exact(qh[i])
+        search_exact(i)
     exact_ms = E.max_over_ranks(time.perf_counter() - t0) / 64 * 1e3
     rec, scanned = [], []
+    for i in range(3):
+        search_ivf(i)
     E.barrier()
     t0 = time.perf_counter()
-    got = [search_ivf(qh[i]) for i in range(64)]
+    got = [search_ivf(i) for i in range(64)]
     ms = E.max_over_ranks(time.perf_counter() - t0) / 64 * 1e3
     for i in range(64):
         rec.append(len(set(got[i][0]["row"].tolist()) & set(want[i]["row"].tolist())) / 10.0)
@@ -540,6 +559,8 @@ def side_ivfpq(E, args, nlist=4096, nprobe=64):
     loc = [index.search(qh[i], nprobe=nprobe, top_k=10, rerank=512) for i in range(64)]
     local_ms = E.max_over_ranks(time.perf_counter() - t0) / 64 * 1e3
     local_scanned = float(np.mean([x[1] for x in loc]))
+    if xq is not None:
+        xq.close()
     index.close(); c.close()
     torch.cuda.empty_cache()
     return {"workload": f"{rows} clustered rows{'' if E.world == 1 else f' row-sharded x{E.world}'}, nlist={nlist}{'' if E.world == 1 else ' per shard'}, nprobe={nprobe}, m=32x8bit, rerank=512, top-k=10"
@@ -550,7 +571,8 @@ def side_ivfpq(E, args, nlist=4096, nprobe=64):
             "local_probe_ms_per_query": local_ms, "scanned_rows_per_query_per_gpu": local_scanned,
             "code_bytes_per_query_per_gpu": local_scanned * 32 + nlist * 1024 + 32768,
             "index_bytes_per_gpu": stt["index_bytes"], "max_list": stt["max_list"],
-            "exchange": None if E.world == 1 else "nccl all_gather of k hits + stb_hits_merge"}
+            "exchange": None if E.world == 1 else "stb_ivfpq_search_dev per rank -> nccl all_gather of k hits -> stb_hits_merge_dev -> one D2H; "
+                                                   "exact comparator: fused stb_search_xchg (q8 tier)"}
 
 
 def side_embed(E, V=500_000, n_lines=1_000_000):
@@ -838,7 +860,7 @@ def run_ours(args):
         if args.config4_rows:
             side("config4_100M", side_config4, E, args, k, make_xchg, collective=world > 1)
         if world > 1 and args.ivfpq_rows_per_gpu:
-            side("ivfpq_sharded", side_ivfpq, E, args, collective=True)
+            side("ivfpq_sharded", side_ivfpq, E, args, make_xchg=make_xchg if exchange == "p2p" else None, collective=True)
 
     if rank == 0:
         traffic = None

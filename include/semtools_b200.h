@@ -274,6 +274,12 @@ int stb_ivfpq_stats(const stb_ivfpq *index, uint64_t *rows, uint32_t *nlist, uin
                     uint64_t *index_bytes);
 int stb_ivfpq_search(stb_ivfpq *index, const float *q, uint32_t nprobe, uint32_t top_k,
                      uint32_t rerank, stb_hit *out_hits, uint32_t *out_n, uint64_t *out_scanned);
+/* Asynchronous device-resident form (query, hits and status stay in HBM, nothing synchronises): the
+ * sharded index is one of these per rank, an all-gather of the k hits and stb_hits_merge_dev.
+ * out_hits_dev: top_k entries (unused tail +inf / UINT64_MAX); out_status_dev[0] = hits, [1] = codes
+ * scanned.  rerank is capped at 1024. */
+int stb_ivfpq_search_dev(stb_ivfpq *index, const float *q_dev, uint32_t nprobe, uint32_t top_k,
+                         uint32_t rerank, stb_hit *out_hits_dev, uint32_t *out_status_dev);
 
 /* Host-buffer form of the fused multi-GPU search (the call a sharded host makes per query):
  * pinned H2D of the query, ONE kernel (scan + NVLink exchange + merge), D2H of the merged

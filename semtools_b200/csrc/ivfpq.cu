@@ -646,8 +646,10 @@ ivf_adc_finish_kernel(const Adc2Args a) {
       __syncthreads();
     }
   const uint32_t n_out = min((uint32_t)s_pass, a.top_k);
-  for (uint32_t i = tid; i < n_out; i += ADC2_THREADS) {
-    stb_hit h; h.distance = sd[i]; h.row = sr[i];
+  for (uint32_t i = tid; i < a.top_k; i += ADC2_THREADS) {          // unused tail: (+inf, UINT64_MAX), mergeable as-is
+    stb_hit h;
+    h.distance = (i < n_out) ? sd[i] : CUDART_INF;
+    h.row = (i < n_out) ? sr[i] : 0xffffffffffffffffull;
     a.out_hits[i] = h;
   }
   if (tid == 0) { a.out_status[0] = n_out; a.out_status[1] = total; *a.ticket = 0; }
@@ -791,6 +793,45 @@ int stb_ivfpq_stats(const stb_ivfpq *x, uint64_t *rows, uint32_t *nlist, uint32_
 // Approximate top-k: probe `nprobe` lists, keep the `rerank` best ADC scores, re-score those
 // rows exactly (canonical f64 distance on the f32 corpus rows), return the best top_k by
 // (distance,row).  q_dev: 256 f32 on device.  Synchronous (returns host hits).
+// fused search (coarse probe + ADC/finish), asynchronous: q, hits and status on the device
+static int ivf_fused_launch(stb_ivfpq *x, const float *q_dev, uint32_t nprobe, uint32_t top_k, uint32_t rerank,
+                            stb_hit *out_hits_dev, uint32_t *out_status_dev) {
+  stb_ctx *ctx = x->ctx;
+  cudaStream_t st = ctx->stream;
+  uint32_t npow2 = 1; while (npow2 < x->nlist) npow2 <<= 1;
+  if (!(ctx->func_attr_mask & (1u << STB_ATTR_IVF_V2))) {
+    STB_CUDA(cudaFuncSetAttribute(ivf_coarse_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+    STB_CUDA(cudaFuncSetAttribute(ivf_adc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ADC2_SMEM));
+    ctx->func_attr_mask |= 1u << STB_ATTR_IVF_V2;
+  }
+  Probe2Args pa;
+  pa.C = x->centroids; pa.nlist = x->nlist; pa.nprobe = nprobe; pa.q = q_dev; pa.coarse = x->coarse;
+  pa.list_off = x->list_off; pa.cb = x->codebooks; pa.probe = x->probe; pa.lut = x->lut; pa.ticket = x->tickets;
+  ivf_coarse_probe_kernel<<<(x->nlist + 31) / 32, 1024, npow2 * 8, st>>>(pa);
+  STB_CUDA(cudaGetLastError());
+  Adc2Args aa;
+  aa.codes = x->codes; aa.list_off = x->list_off; aa.probe = x->probe; aa.nprobe = nprobe; aa.coarse = x->coarse;
+  aa.lut = x->lut; aa.order = x->order; aa.keys2 = x->keys2; aa.ticket = x->tickets + 1;
+  aa.rows = reinterpret_cast<const float4 *>(x->corpus->rows); aa.row_base = x->corpus->row_base; aa.q = q_dev;
+  aa.top_k = top_k; aa.rerank = rerank; aa.out_hits = out_hits_dev; aa.out_status = out_status_dev;
+  ivf_adc_finish_kernel<<<ADC2_MAX_CTAS, ADC2_THREADS, ADC2_SMEM, st>>>(aa);
+  STB_CUDA(cudaGetLastError());
+  ctx->kernel_launches += 2;
+  return STB_OK;
+}
+
+// Asynchronous device-resident form (sharded use: per-rank probe -> all-gather of k hits -> stb_hits_merge_dev).
+// out_hits_dev receives top_k entries (unused tail: +inf / UINT64_MAX), out_status_dev[0] = hits, [1] = codes scanned.
+int stb_ivfpq_search_dev(stb_ivfpq *x, const float *q_dev, uint32_t nprobe, uint32_t top_k, uint32_t rerank,
+                         stb_hit *out_hits_dev, uint32_t *out_status_dev) {
+  if (!x || !q_dev || !out_hits_dev || !out_status_dev) { stb_set_error("ivfpq_search_dev: null argument"); return STB_ERR_ARG; }
+  if (cudaSetDevice(x->ctx->device) != cudaSuccess) { stb_set_error("cudaSetDevice failed"); return STB_ERR_CUDA; }
+  if (top_k == 0 || top_k > 1024) { stb_set_error("ivfpq_search_dev: top_k must be 1..1024"); return STB_ERR_ARG; }
+  nprobe = std::max(1u, std::min(std::min(nprobe, x->nlist), 1024u));
+  rerank = std::max(top_k, std::min(rerank, (uint32_t)ADC2_RERANK_CAP));
+  return ivf_fused_launch(x, q_dev, nprobe, top_k, rerank, out_hits_dev, out_status_dev);
+}
+
 int stb_ivfpq_search(stb_ivfpq *x, const float *q, uint32_t nprobe, uint32_t top_k, uint32_t rerank,
                      stb_hit *out_hits, uint32_t *out_n, uint64_t *out_scanned) {
   if (!x || !q || !out_hits || !out_n) { stb_set_error("ivfpq_search: null argument"); return STB_ERR_ARG; }
@@ -806,24 +847,8 @@ int stb_ivfpq_search(stb_ivfpq *x, const float *q, uint32_t nprobe, uint32_t top
   const char *v1_env = getenv("STB_IVFPQ_V1");            // STB_IVFPQ_V1=1: the round-1 multi-launch search
   if (!(v1_env && v1_env[0] == '1') && rerank <= ADC2_RERANK_CAP && top_k <= 1024) {
     // fused search: two launches, one synchronisation
-    uint32_t npow2 = 1; while (npow2 < x->nlist) npow2 <<= 1;
-    if (!(ctx->func_attr_mask & (1u << STB_ATTR_IVF_V2))) {
-      STB_CUDA(cudaFuncSetAttribute(ivf_coarse_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
-      STB_CUDA(cudaFuncSetAttribute(ivf_adc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ADC2_SMEM));
-      ctx->func_attr_mask |= 1u << STB_ATTR_IVF_V2;
-    }
-    Probe2Args pa;
-    pa.C = x->centroids; pa.nlist = x->nlist; pa.nprobe = nprobe; pa.q = ctx->q_dev; pa.coarse = x->coarse;
-    pa.list_off = x->list_off; pa.cb = x->codebooks; pa.probe = x->probe; pa.lut = x->lut; pa.ticket = x->tickets;
-    ivf_coarse_probe_kernel<<<(x->nlist + 31) / 32, 1024, npow2 * 8, st>>>(pa);
-    STB_CUDA(cudaGetLastError());
-    Adc2Args aa;
-    aa.codes = x->codes; aa.list_off = x->list_off; aa.probe = x->probe; aa.nprobe = nprobe; aa.coarse = x->coarse;
-    aa.lut = x->lut; aa.order = x->order; aa.keys2 = x->keys2; aa.ticket = x->tickets + 1;
-    aa.rows = reinterpret_cast<const float4 *>(x->corpus->rows); aa.row_base = x->corpus->row_base; aa.q = ctx->q_dev;
-    aa.top_k = top_k; aa.rerank = rerank; aa.out_hits = ctx->hits_dev; aa.out_status = ctx->status_dev;
-    ivf_adc_finish_kernel<<<ADC2_MAX_CTAS, ADC2_THREADS, ADC2_SMEM, st>>>(aa);
-    STB_CUDA(cudaGetLastError());
+    int frc = ivf_fused_launch(x, ctx->q_dev, nprobe, top_k, rerank, ctx->hits_dev, ctx->status_dev);
+    if (frc != STB_OK) return frc;
     STB_CUDA(cudaMemcpyAsync(ctx->status_pin, ctx->status_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     STB_CUDA(cudaMemcpyAsync(ctx->hits_pin, ctx->hits_dev, top_k * sizeof(stb_hit), cudaMemcpyDeviceToHost, st));
     STB_CUDA(cudaStreamSynchronize(st));
@@ -831,7 +856,6 @@ int stb_ivfpq_search(stb_ivfpq *x, const float *q, uint32_t nprobe, uint32_t top
     memcpy(out_hits, ctx->hits_pin, n_out * sizeof(stb_hit));
     *out_n = n_out;
     if (out_scanned) *out_scanned = ctx->status_pin[1];
-    ctx->kernel_launches += 2;
     return STB_OK;
   }
   ivf_coarse_kernel<<<(x->nlist + 7) / 8, 256, 0, st>>>(x->centroids, x->nlist, ctx->q_dev, x->coarse);

@@ -95,3 +95,33 @@ def test_v2_fused_search_matches_v1_candidates_and_exact_distances(ctx):
     finally:
         os.environ.pop("STB_IVFPQ_V1", None)
         idx.close()
+
+
+def test_device_resident_search_equals_the_host_call(ctx):
+    """stb_ivfpq_search_dev (asynchronous, query / hits / status in HBM; what the sharded index runs per
+    rank) returns exactly the hits of stb_ivfpq_search, padded with (+inf, UINT64_MAX)."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(8)
+    n = 120_000
+    centers = make_centers(rng)
+    rows = clustered(rng, centers, n)
+    c = capi.Corpus(ctx, n, row_base=1_000_000)
+    c.append(rows)
+    idx = capi.IvfPq(c, nlist=128, train_rows=65536, iters=6)
+    queries = clustered(rng, centers, 12)
+    dev = torch.device("cuda:0")
+    q_dev = torch.from_numpy(queries).to(dev)
+    hits = torch.zeros((12, 20, 2), dtype=torch.float64, device=dev)
+    st = torch.zeros((12, 2), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    for i in range(12):
+        idx.search_dev(q_dev[i].data_ptr(), 16, 20, 256, hits[i].data_ptr(), st[i].data_ptr())
+    ctx.sync()
+    raw, sth = hits.cpu().numpy(), st.cpu().numpy()
+    for i in range(12):
+        want, n_scan = idx.search(queries[i], nprobe=16, top_k=20, rerank=256)
+        got = np.ascontiguousarray(raw[i]).view(capi.HIT_DTYPE).reshape(-1)
+        assert sth[i, 0] == len(want) and sth[i, 1] == n_scan
+        assert np.array_equal(got[: len(want)], want)
+        assert np.all(np.isinf(got["distance"][len(want):]))
+    idx.close()
