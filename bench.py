@@ -503,6 +503,9 @@ def side_ivfpq(E, args, nlist=4096, nprobe=64, make_xchg=None):
     capi, torch, dev, dist = E.capi, E.torch, E.dev, E.dist
     rows = args.ivfpq_rows if E.world == 1 else args.ivfpq_rows_per_gpu * E.world
     lo, hi = shard_bounds(rows, E.world, E.rank)
+    # exact re-scores per query per shard: the PQ ranking gets noisier as the lists grow (12.5M-row shards scan
+    # ~195k codes per query), so the large configuration re-ranks the kernel's maximum
+    rerank = 512 if (hi - lo) <= 5_000_000 else 1024
     torch.cuda.empty_cache()
     c, qh = clustered_shard(E, rows, lo, hi, max(rows // 100, 1000))
     t0 = time.perf_counter()
@@ -512,7 +515,7 @@ def side_ivfpq(E, args, nlist=4096, nprobe=64, make_xchg=None):
     xq = None
     if E.world == 1:
         search_exact = lambda i: c.search(qh[i], top_k=10)
-        search_ivf = lambda i: index.search(qh[i], nprobe=nprobe, top_k=10, rerank=512)
+        search_ivf = lambda i: index.search(qh[i], nprobe=nprobe, top_k=10, rerank=rerank)
     else:
         # exact comparator: the fused single-query exchange (stb_search_xchg) over the same shards;
         # IVF-PQ: stb_ivfpq_search_dev per rank -> all-gather of the k hits -> stb_hits_merge_dev -> one D2H
@@ -530,7 +533,7 @@ def side_ivfpq(E, args, nlist=4096, nprobe=64, make_xchg=None):
 
         def search_ivf(i):
             q_d.copy_(q_pin[i], non_blocking=True)
-            index.search_dev(q_d.data_ptr(), nprobe, 10, 512, loc.data_ptr(), st2.data_ptr())
+            index.search_dev(q_d.data_ptr(), nprobe, 10, rerank, loc.data_ptr(), st2.data_ptr())
             dist.all_gather_into_tensor(gat, loc)
             E.ctx.hits_merge_dev(gat.data_ptr(), E.world, 10, 10, mer.data_ptr())
             out_pin.copy_(mer, non_blocking=True)
@@ -556,14 +559,14 @@ def side_ivfpq(E, args, nlist=4096, nprobe=64, make_xchg=None):
     stt = index.stats()
     # local probe alone (no exchange): what one rank's ADC kernel pair costs per query
     t0 = time.perf_counter()
-    loc = [index.search(qh[i], nprobe=nprobe, top_k=10, rerank=512) for i in range(64)]
+    loc = [index.search(qh[i], nprobe=nprobe, top_k=10, rerank=rerank) for i in range(64)]
     local_ms = E.max_over_ranks(time.perf_counter() - t0) / 64 * 1e3
     local_scanned = float(np.mean([x[1] for x in loc]))
     if xq is not None:
         xq.close()
     index.close(); c.close()
     torch.cuda.empty_cache()
-    return {"workload": f"{rows} clustered rows{'' if E.world == 1 else f' row-sharded x{E.world}'}, nlist={nlist}{'' if E.world == 1 else ' per shard'}, nprobe={nprobe}, m=32x8bit, rerank=512, top-k=10"
+    return {"workload": f"{rows} clustered rows{'' if E.world == 1 else f' row-sharded x{E.world}'}, nlist={nlist}{'' if E.world == 1 else ' per shard'}, nprobe={nprobe}, m=32x8bit, rerank={rerank}, top-k=10"
                         + (" (BASELINE configs[4])" if rows == 100_000_000 and E.world == 8 else ""),
             "parity": "unpinned (no IVF_PQ exists in the reference); quality = recall vs exact scan",
             "recall_at_10": float(np.mean(rec)), "min_recall": float(np.min(rec)), "build_s": build_s,
