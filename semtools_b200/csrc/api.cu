@@ -111,11 +111,11 @@ int stb_ctx_create(int device, void *cuda_stream, stb_ctx **out) {
     one = 0;
     if ((rc = dev_reserve(&c->hist_dev, &one, 4096)) != STB_OK) goto fail;
     one = 0;
-    if ((rc = dev_reserve(&c->tickets, &one, 1)) != STB_OK) goto fail;
+    if ((rc = dev_reserve(&c->tickets, &one, STB_TICKET_SLOTS)) != STB_OK) goto fail;
   }
   if ((rc = dev_reserve(&c->hits_dev, &c->hits_cap, 1024)) != STB_OK) goto fail;
   if (cudaMemset(c->counters, 0, c->counters_cap * sizeof(unsigned int)) != cudaSuccess ||
-      cudaMemset(c->tickets, 0, sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMemset(c->tickets, 0, STB_TICKET_SLOTS * sizeof(unsigned long long)) != cudaSuccess ||
       cudaMemset(c->err_flag, 0, sizeof(int)) != cudaSuccess ||
       cudaMallocHost((void **)&c->q_pin, STB_D * sizeof(float)) != cudaSuccess ||
       cudaMallocHost((void **)&c->status_pin, 8 * sizeof(uint32_t)) != cudaSuccess ||
@@ -186,12 +186,15 @@ int stb_debug_timestamps(stb_ctx *ctx, int reset, uint64_t out[8]) {
 int stb_debug_ticket_check(stb_ctx *ctx, uint64_t *device_value, uint64_t *host_value) {
   int rc = ctx_use(ctx);
   if (rc) return rc;
-  unsigned long long v = 0;
+  unsigned long long v[STB_TICKET_SLOTS];
   STB_CUDA(cudaStreamSynchronize(ctx->stream));
-  STB_CUDA(cudaMemcpy(&v, ctx->tickets, sizeof(v), cudaMemcpyDeviceToHost));
-  if (device_value) *device_value = v;
-  if (host_value) *host_value = ctx->ticket_next;
-  if (v != ctx->ticket_next) { stb_set_error("ticket counter %llu, host expects %llu", v, ctx->ticket_next); return STB_ERR_STATE; }
+  STB_CUDA(cudaMemcpy(v, ctx->tickets, sizeof(v), cudaMemcpyDeviceToHost));
+  unsigned long long dsum = 0, hsum = 0;
+  int bad = -1;
+  for (int i = 0; i < STB_TICKET_SLOTS; ++i) { dsum += v[i]; hsum += ctx->ticket_next[i]; if (v[i] != ctx->ticket_next[i] && bad < 0) bad = i; }
+  if (device_value) *device_value = dsum;          // sums over the counter ring
+  if (host_value) *host_value = hsum;
+  if (bad >= 0) { stb_set_error("ticket counter %d is %llu, host expects %llu", bad, v[bad], ctx->ticket_next[bad]); return STB_ERR_STATE; }
   return STB_OK;
 }
 
@@ -431,6 +434,13 @@ static int stb_env_max_tier() {
   if (e[0] == 'f') return STB_TIER_F32;
   if (e[0] == 'h') return STB_TIER_H16;
   return STB_TIER_Q8;
+}
+// STB_SCAN_OVERLAP=1 (opt-in until timed on hardware): the asynchronous entry points (stb_search_topk_dev,
+// stb_search_topk_xchg, stb_search_many) use the overlapped launch mode (one CTA per SM, dependent released
+// at kernel start); default: they launch like the synchronous ones (full grid, dependent released after the scan).
+static bool stb_env_overlap() {
+  const char *e = getenv("STB_SCAN_OVERLAP");
+  return e && e[0] == '1';
 }
 static bool stb_env_direct_out() {
   const char *e = getenv("STB_DIRECT_OUT");
@@ -713,7 +723,7 @@ int stb_search_topk_dev(stb_ctx *ctx, const stb_corpus *corpus, const float *q_d
   // builds one: stb_corpus_prepare does); status[1] says whether the result is proven, the
   // caller's fallback is unchanged
   return stb_launch_scan_topk(ctx, corpus, best_built_tier(corpus, top_k), q_dev, top_k, nullptr, 0, corpus->n,
-                              out_hits_dev, out_status_dev, nullptr);
+                              out_hits_dev, out_status_dev, nullptr, stb_env_overlap());
 }
 
 // ------------------------------------------------------------ peer-memory exchange ---
@@ -828,8 +838,8 @@ int stb_xchg_connect_local(stb_xchg *x, stb_xchg *const *peers) {
   return STB_OK;
 }
 
-int stb_search_topk_xchg(stb_ctx *ctx, const stb_corpus *corpus, const float *q_dev, uint32_t top_k,
-                         stb_xchg *x, stb_hit *out_hits_dev, uint32_t *out_status_dev) {
+static int search_topk_xchg_impl(stb_ctx *ctx, const stb_corpus *corpus, const float *q_dev, uint32_t top_k,
+                                 stb_xchg *x, stb_hit *out_hits_dev, uint32_t *out_status_dev, bool overlapped) {
   int rc = ctx_use(ctx);
   if (rc) return rc;
   if (!corpus || !q_dev || !x || !out_hits_dev || !out_status_dev) { stb_set_error("search_topk_xchg: null argument"); return STB_ERR_ARG; }
@@ -843,7 +853,12 @@ int stb_search_topk_xchg(stb_ctx *ctx, const stb_corpus *corpus, const float *q_
   a.seq = ++x->seq;
   a.slot = (uint32_t)(a.seq % STB_XCHG_SLOTS);
   return stb_launch_scan_topk(ctx, corpus, best_built_tier(corpus, top_k), q_dev, top_k, nullptr, 0, corpus->n,
-                              out_hits_dev, out_status_dev, &a);
+                              out_hits_dev, out_status_dev, &a, overlapped);
+}
+
+int stb_search_topk_xchg(stb_ctx *ctx, const stb_corpus *corpus, const float *q_dev, uint32_t top_k,
+                         stb_xchg *x, stb_hit *out_hits_dev, uint32_t *out_status_dev) {
+  return search_topk_xchg_impl(ctx, corpus, q_dev, top_k, x, out_hits_dev, out_status_dev, stb_env_overlap());
 }
 
 // ----------------------------------------------------------------- K2 batched search ---
@@ -1142,9 +1157,9 @@ int stb_search_xchg(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint
   memcpy(ctx->q_pin, q, STB_D * sizeof(float));
   STB_CUDA(cudaMemcpyAsync(ctx->q_dev, ctx->q_pin, STB_D * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   if (stb_env_direct_out()) {        // the merge CTA stores the hits + status straight into pinned host memory
-    if ((rc = stb_search_topk_xchg(ctx, corpus, ctx->q_dev, top_k, x, ctx->hits_pin, ctx->status_pin)) != STB_OK) return rc;
+    if ((rc = search_topk_xchg_impl(ctx, corpus, ctx->q_dev, top_k, x, ctx->hits_pin, ctx->status_pin, false)) != STB_OK) return rc;
   } else {
-    if ((rc = stb_search_topk_xchg(ctx, corpus, ctx->q_dev, top_k, x, ctx->hits_dev, ctx->status_dev)) != STB_OK) return rc;
+    if ((rc = search_topk_xchg_impl(ctx, corpus, ctx->q_dev, top_k, x, ctx->hits_dev, ctx->status_dev, false)) != STB_OK) return rc;
     STB_CUDA(cudaMemcpyAsync(ctx->status_pin, ctx->status_dev, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     STB_CUDA(cudaMemcpyAsync(ctx->hits_pin, ctx->hits_dev, top_k * sizeof(stb_hit), cudaMemcpyDeviceToHost, ctx->stream));
   }
@@ -1218,8 +1233,9 @@ int stb_search_many(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint
   for (uint32_t i = 0; i < nq; ++i) {
     stb_hit *oh = ctx->hits_pin + (size_t)i * top_k;
     uint32_t *os = ctx->many_status_pin + 4 * (size_t)i;
-    if (x) rc = stb_search_topk_xchg(ctx, corpus, ctx->bq_dev + (size_t)i * STB_D, top_k, x, oh, os);
-    else rc = stb_launch_scan_topk(ctx, corpus, tier, ctx->bq_dev + (size_t)i * STB_D, top_k, nullptr, 0, corpus->n, oh, os, nullptr);
+    if (x) rc = search_topk_xchg_impl(ctx, corpus, ctx->bq_dev + (size_t)i * STB_D, top_k, x, oh, os, nq > 1 && stb_env_overlap());
+    else rc = stb_launch_scan_topk(ctx, corpus, tier, ctx->bq_dev + (size_t)i * STB_D, top_k, nullptr, 0, corpus->n, oh, os, nullptr,
+                                   nq > 1 && stb_env_overlap());
     if (rc != STB_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
   }
   STB_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -74,8 +74,12 @@ struct stb_ctx {
   size_t block_keys_cap;    // in keys
   unsigned int *counters;   // tree arrival counters (zeroed; kernels re-zero)
   size_t counters_cap;
-  unsigned long long *tickets;      // K1 tile-ticket counter (monotonic; scan_topk.cu: stb_for_each_tile)
-  unsigned long long ticket_next;   // its value when the next top-k launch starts
+  // K1 tile-ticket counters (monotonic; scan_topk.cu: stb_for_each_tile).  A ring of STB_TICKET_SLOTS
+  // counters, one per launch in turn: with the overlapped launch mode two consecutive scans run
+  // concurrently and must not draw from the same counter.
+  unsigned long long *tickets;
+  unsigned long long ticket_next[8];   // per slot: its value when the next launch using it starts
+  unsigned long long topk_launches;    // picks the slot
   float *q_dev;             // 256 f32 staging for host queries
   stb_hit *hits_dev;        // result hits (top-k path)
   size_t hits_cap;
@@ -124,6 +128,7 @@ struct stb_ctx {
   uint64_t fallback_searches;
 };
 
+#define STB_TICKET_SLOTS 8
 #define STB_XCHG_SLOTS 4
 #define STB_XCHG_MAX_WORLD 8
 struct StbXchgArgs {
@@ -188,10 +193,13 @@ struct stb_corpus {
 // exact f64 re-rank + completeness check.  q_dev: 256 f32 on device.
 // n_ranges > 0: ranges_dev holds local [begin,end,vstart] triples.
 // tier: STB_TIER_* -- which copy of `c` the streaming pass reads (must exist and be current).
+// overlapped: the launch is one of a pipelined series (asynchronous entry points): the grid is sized
+// for ONE CTA per SM and releases its dependent at its START, so the next query's scan co-runs with
+// this one instead of waiting for it to drain (scan_topk.cu: "overlapped launches").
 int stb_launch_scan_topk(stb_ctx *ctx, const stb_corpus *c, int tier, const float *q_dev, uint32_t top_k,
                          const uint64_t *ranges_dev, uint32_t n_ranges,
                          uint64_t n_virtual, stb_hit *out_hits_dev,
-                         uint32_t *out_status_dev, const StbXchgArgs *xchg = nullptr);
+                         uint32_t *out_status_dev, const StbXchgArgs *xchg = nullptr, bool overlapped = false);
 // int8 codes + scales of rows [first_row, n_rows) (q8 tier)
 int stb_launch_q8_build(stb_ctx *ctx, const float *rows_dev, uint64_t first_row, uint64_t n_rows, uint8_t *out,
                         float *scale, int *bad_flag_dev);

@@ -607,6 +607,7 @@ struct TopkArgs {
   StbXchgArgs xchg;          // world == 0: no cross-GPU exchange
   unsigned long long *dbg;   // STB_TAIL_TIMING builds only: phase timestamps (ns)
   const uint8_t *shadow;     // SRC == 1: 16-bit normalised corpus shadow (UMMA tile layout)
+  uint32_t early_trigger;    // overlapped launch: release the dependent launch at kernel start
   const uint8_t *q8;         // SRC == 2: int8 codes [n][256] ...
   const float *q8_scale;     //           ... and per-row scales [n]
 };
@@ -688,6 +689,11 @@ stb_scan_topk_kernel(const TopkArgs args) {
   __shared__ int s_nv[2];
 
   STB_T_MIN(0);                      // first CTA starts
+  // Overlapped launches (asynchronous entry points): the grid is sized for one CTA per SM and lets the
+  // NEXT query's grid in right away, so two scans share the SMs and the ~10 us in which a draining
+  // grid leaves HBM idle (CTA merge before exit, launch, ramp-up) are covered by the other scan.
+  // Tails stay ordered: everything after the scan sits behind griddepcontrol.wait.
+  if (args.early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   TopSink<E> sink;
   sink.init();
   if constexpr (SRC == 2) stb_scan_q8<U, RANGES>(args.scan, args.q8, args.q8_scale, sink);
@@ -1076,7 +1082,7 @@ static int stb_scan_ctas_per_sm_override() {
 }
 
 template <int E, int RANGES, int SRC = 0, int EF = E>
-static int stb_launch_topk_t(stb_ctx *ctx, const TopkArgs &a_in) {
+static int stb_launch_topk_t(stb_ctx *ctx, const TopkArgs &a_in, bool overlapped) {
   constexpr int kU = SRC == 2 ? STB_Q8_SCAN_U : (SRC == 1 ? STB_SHADOW_SCAN_U : STB_SCAN_U);
   auto kern = stb_scan_topk_kernel<E, kU, RANGES, SRC, EF>;
   int occ = 0;
@@ -1085,6 +1091,10 @@ static int stb_launch_topk_t(stb_ctx *ctx, const TopkArgs &a_in) {
   const int ovr = stb_scan_ctas_per_sm_override();
   if (ovr >= 1 && ovr < occ) occ = ovr;
   TopkArgs a = a_in;
+  const bool use_tickets = stb_scan_tickets_enabled();
+  overlapped = overlapped && use_tickets && occ >= 2;
+  if (overlapped) occ = 1;                 // two consecutive grids co-reside, one CTA per SM each
+  a.early_trigger = overlapped ? 1u : 0u;
   const uint64_t tiles = (a.scan.n_virtual + 4 * kU - 1) / (4 * kU);
   uint64_t want = (tiles + STB_SCAN_WARPS - 1) / STB_SCAN_WARPS;
   uint64_t grid = (uint64_t)ctx->sm_count * occ;
@@ -1098,14 +1108,14 @@ static int stb_launch_topk_t(stb_ctx *ctx, const TopkArgs &a_in) {
   // tile tickets (stb_for_each_tile): bulk tickets of STB_TICKET_TILES tiles, then the last ~2 tiles
   // per warp one by one.  The launch advances the counter by n_tickets + total_warps exactly.
   const uint64_t warps_total = grid * STB_SCAN_WARPS;
-  const bool use_tickets = stb_scan_tickets_enabled();
   if (use_tickets) {
     const uint64_t single = std::min<uint64_t>(tiles, 2 * warps_total);
     a.scan.t_bulk = (tiles - single) / STB_TICKET_TILES;
     const uint64_t n_tickets = a.scan.t_bulk + (tiles - a.scan.t_bulk * STB_TICKET_TILES);
-    a.scan.tickets = ctx->tickets;
-    a.scan.t_base = ctx->ticket_next;
-    ctx->ticket_next += n_tickets + warps_total;
+    const int slot = (int)(ctx->topk_launches++ % STB_TICKET_SLOTS);     // at most ~3 grids are ever in flight
+    a.scan.tickets = ctx->tickets + slot;
+    a.scan.t_base = ctx->ticket_next[slot];
+    ctx->ticket_next[slot] += n_tickets + warps_total;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -1125,28 +1135,28 @@ static int stb_launch_topk_t(stb_ctx *ctx, const TopkArgs &a_in) {
 }
 
 template <int RANGES>
-static int stb_launch_topk_r(stb_ctx *ctx, const TopkArgs &a, int tier, uint32_t top_k) {
+static int stb_launch_topk_r(stb_ctx *ctx, const TopkArgs &a, int tier, uint32_t top_k, bool ov) {
   const int e = stb_pick_e(top_k);
   // q8: 32-key lists below the root, 128 candidates re-ranked at the root (see stb_scan_q8)
-  if (tier == STB_TIER_Q8) return stb_launch_topk_t<1, RANGES, 2, 4>(ctx, a);
+  if (tier == STB_TIER_Q8) return stb_launch_topk_t<1, RANGES, 2, 4>(ctx, a, ov);
   if (tier == STB_TIER_H16) {
     switch (e) {
-      case 1: return stb_launch_topk_t<1, RANGES, 1>(ctx, a);
-      case 2: return stb_launch_topk_t<2, RANGES, 1>(ctx, a);
-      default: return stb_launch_topk_t<4, RANGES, 1>(ctx, a);
+      case 1: return stb_launch_topk_t<1, RANGES, 1>(ctx, a, ov);
+      case 2: return stb_launch_topk_t<2, RANGES, 1>(ctx, a, ov);
+      default: return stb_launch_topk_t<4, RANGES, 1>(ctx, a, ov);
     }
   }
   switch (e) {
-    case 1: return stb_launch_topk_t<1, RANGES, 0>(ctx, a);
-    case 2: return stb_launch_topk_t<2, RANGES, 0>(ctx, a);
-    default: return stb_launch_topk_t<4, RANGES, 0>(ctx, a);
+    case 1: return stb_launch_topk_t<1, RANGES, 0>(ctx, a, ov);
+    case 2: return stb_launch_topk_t<2, RANGES, 0>(ctx, a, ov);
+    default: return stb_launch_topk_t<4, RANGES, 0>(ctx, a, ov);
   }
 }
 
 int stb_launch_scan_topk(stb_ctx *ctx, const stb_corpus *c, int tier, const float *q_dev, uint32_t top_k,
                          const uint64_t *ranges_dev, uint32_t n_ranges,
                          uint64_t n_virtual, stb_hit *out_hits_dev,
-                         uint32_t *out_status_dev, const StbXchgArgs *xchg) {
+                         uint32_t *out_status_dev, const StbXchgArgs *xchg, bool overlapped) {
   TopkArgs a;
   a.scan.rows = reinterpret_cast<const float4 *>(c->rows);
   a.scan.n_virtual = n_virtual;
@@ -1163,12 +1173,13 @@ int stb_launch_scan_topk(stb_ctx *ctx, const stb_corpus *c, int tier, const floa
   a.top_k = top_k;
   if (xchg) a.xchg = *xchg; else memset(&a.xchg, 0, sizeof(a.xchg));
   a.dbg = ctx->dbg_dev;
+  a.early_trigger = 0;
   a.shadow = c->shadow;
   a.q8 = c->q8;
   a.q8_scale = c->q8_scale;
   if (tier == STB_TIER_Q8 && (top_k > STB_Q8_MAX_K || !c->q8)) { stb_set_error("scan_topk: q8 tier unavailable"); return STB_ERR_STATE; }
   if (tier == STB_TIER_H16 && !c->shadow) { stb_set_error("scan_topk: h16 tier unavailable"); return STB_ERR_STATE; }
-  return n_ranges > 0 ? stb_launch_topk_r<1>(ctx, a, tier, top_k) : stb_launch_topk_r<0>(ctx, a, tier, top_k);
+  return n_ranges > 0 ? stb_launch_topk_r<1>(ctx, a, tier, top_k, overlapped) : stb_launch_topk_r<0>(ctx, a, tier, top_k, overlapped);
 }
 
 // ------------------------------------------------------------------ collect path ---
