@@ -11,8 +11,8 @@ ctx = capi.Context(0, s.cuda_stream)
 g = torch.Generator(device=dev); g.manual_seed(1)
 x = torch.randn((rows, 256), generator=g, device=dev); x /= x.norm(dim=1, keepdim=True)
 c = capi.Corpus(ctx, rows); torch.cuda.synchronize(); c.append_dev(x.data_ptr(), rows)
-if os.environ.get("STB_PROBE_PREPARE") == "1":      # build the 16-bit shadow (STB_SCAN_SHADOW=1 then scans it)
-    c.prepare_batch()
+if os.environ.get("STB_PROBE_PREPARE", "1") == "1":  # build the q8 / h16 copies (STB_SCAN_TIER picks the tier that is scanned)
+    c.prepare()
 q = torch.randn((16, 256), generator=g, device=dev); q /= q.norm(dim=1, keepdim=True)
 hits = torch.zeros((16, 10, 2), dtype=torch.float64, device=dev); st = torch.zeros((16, 4), dtype=torch.int32, device=dev)
 for i in range(iters):
@@ -24,8 +24,8 @@ for i in range(iters):
     c.search_topk_dev(q[i % 16].data_ptr(), 10, hits[i % 16].data_ptr(), st[i % 16].data_ptr())
 e1.record(s); torch.cuda.synchronize()
 h32 = None
-if os.environ.get("STB_SCAN_SHADOW") == "1":        # cross-check the shadow scan against the f32 scan
-    got = hits.clone(); os.environ.pop("STB_SCAN_SHADOW")
+if os.environ.get("STB_SCAN_TIER", "q8") != "f32":   # cross-check the reduced-width scan against the f32 scan
+    got = hits.clone(); os.environ["STB_SCAN_TIER"] = "f32"
     for i in range(16):
         c.search_topk_dev(q[i].data_ptr(), 10, hits[i].data_ptr(), st[i].data_ptr())
     torch.cuda.synchronize()

@@ -414,7 +414,7 @@ __global__ void ivf_pick_rows_kernel(const stb_hit *cand, uint32_t r, const uint
 //                            CTA); each CTA keeps its ADC2_KEEP best; the LAST CTA sorts the
 //                            <= 8192 survivors, re-scores the best `rerank` rows exactly
 //                            (canonical f64, as K1) and writes the top-k hits.
-// Opt-in (STB_IVFPQ_V2=1) until validated on hardware.
+// Default since round 2 (validated on hardware); STB_IVFPQ_V1=1 selects the multi-launch search above.
 #define ADC2_THREADS 512
 #define ADC2_MAX_CTAS 32
 #define ADC2_KEEP 64        // per CTA; chunks are dealt round-robin over the 32 CTAs, so each sees a uniform sample: ~16 of the best 512 land in one CTA

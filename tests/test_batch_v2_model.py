@@ -82,7 +82,7 @@ def test_fp16_shadow_bound():
 
 @pytest.mark.parametrize("dtype,eps", [("bfloat16", 0.0040), ("float16", 0.00052)])
 def test_shadow_scan_margin_with_f32_query(dtype, eps):
-    """K1's half-width scan (STB_SCAN_SHADOW=1) rounds only the ROW; the query stays f32:
+    """K1's half-width scan (tier h16) rounds only the ROW; the query stays f32:
     |q^ . round(x^) - exact cosine| <= STB_SHADOW_SCAN_EPS."""
     torch = pytest.importorskip("torch")
     rng = np.random.default_rng(21)
