@@ -257,6 +257,65 @@ class Dist:
         out.copy_(self.torch.stack(parts).reshape(out.shape))
 
 
+class Watchdog:
+    """Deadlines for the multi-rank run.  The fused exchanges are spin-waits on peer memory and the few
+    NCCL calls block until every rank arrives: a rank that fails (or a peer that stalls) would otherwise
+    leave the job waiting for NCCL's own 10-minute watchdog with nothing printed.  Every rank runs this
+    thread; the main thread arms a deadline per phase.  When one passes, rank 0 prints the headline built
+    from what has been measured so far (marked "truncated") and every rank leaves with os._exit(0) --
+    hung kernels go down with the process.  No collective, no store traffic: the ranks' clocks are aligned
+    by the barrier that precedes every arm()."""
+
+    def __init__(self, rank, emit):
+        self.rank, self.emit = rank, emit
+        self.deadline, self.label, self.budget = None, None, 0.0
+        self.lock = threading.Lock()
+        self.done = False
+        t = threading.Thread(target=self._run, daemon=True)
+        t.start()
+
+    def arm(self, label, seconds):
+        with self.lock:
+            self.label, self.budget, self.deadline = label, float(seconds), time.monotonic() + float(seconds)
+
+    def disarm(self):
+        with self.lock:
+            self.deadline = None
+
+    def fire(self, reason):
+        """Print what exists (rank 0) and leave.  Also called by a rank whose section raised."""
+        with self.lock:
+            if self.done:
+                return
+            self.done = True
+        print(f"[rank {self.rank}] leaving: {reason}", file=sys.stderr, flush=True)
+        if self.emit is None:                                  # nothing measured yet: an error, not a result
+            if self.rank == 0:
+                print(json.dumps({"error": reason}), flush=True)
+            os._exit(1)
+        if self.rank == 0:
+            try:
+                self.emit(reason)
+            finally:
+                sys.stdout.flush()
+        os._exit(0)
+
+    def park(self, reason):
+        """A non-zero rank whose section raised: the peers are inside a collective or a spin-wait and will
+        run into their own deadline; stay alive until ours (torchrun kills the job if a rank dies)."""
+        print(f"[rank {self.rank}] {reason}; waiting for the phase deadline", file=sys.stderr, flush=True)
+        while True:
+            time.sleep(1.0)
+
+    def _run(self):
+        while True:
+            time.sleep(0.25)
+            with self.lock:
+                d, label, budget = self.deadline, self.label, self.budget
+            if d is not None and time.monotonic() > d:
+                self.fire(f"phase '{label}' exceeded its {budget:.0f} s deadline")
+
+
 def timed_queries(E, corpus, q_dev, k, steps, warm, xchg=None):
     """Pipelined device-timed top-k queries (stb_search_topk_dev / stb_search_topk_xchg).
     Returns (ms per query [max over ranks], status array of the timed steps, hits tensor)."""
@@ -394,6 +453,11 @@ def side_batch(E, corpus, rows, k, nq=1024, iters=5, make_xchg=None):
         gathered = torch.zeros((world, nq, k, 2), dtype=torch.float64, device=dev)
         st_all = torch.zeros((world, nq, 2), dtype=torch.int32, device=dev)
     corpus.prepare()
+    if world > 1:
+        # first-call costs (shadow build, kernel attributes, workspaces) stay local; the ranks then enter the
+        # exchange together: its wait is bounded (~4 s per kernel), a rank arriving later than that is "gone"
+        corpus.search_batch_dev(q_dev.data_ptr(), nq, k, hits.data_ptr(), st.data_ptr())
+        E.barrier()
     fallbacks = []
 
     def one():
@@ -404,6 +468,8 @@ def side_batch(E, corpus, rows, k, nq=1024, iters=5, make_xchg=None):
                 corpus.search_topk_dev(q_dev[i].data_ptr(), k, hits[i].data_ptr(), st1.data_ptr())
         elif xb is not None:
             xb.search_batch_dev(corpus, q_dev.data_ptr(), nq, k, merged.data_ptr(), st.data_ptr())
+            if bool((st[:, 1] == 2).any()):                              # a peer never arrived: the ranks no longer agree on
+                raise RuntimeError("fused batch exchange: a peer rank timed out")   # what to re-run -- stop here
             bad = (st[:, 1] != 1).nonzero().flatten().tolist()          # identical on every rank
             for i in bad:
                 xb.search_topk(corpus, q_dev[i].data_ptr(), k, merged[i].data_ptr(), st1.data_ptr())
@@ -469,6 +535,8 @@ def side_config4(E, args, k, xchg_factory):
     one GPU, 102.4 GB f32 + 26 GB q8 -- the comparator the >=6x claim needs), single query."""
     capi, torch, dev = E.capi, E.torch, E.dev
     rows = args.config4_rows
+    if E.world > 1 and xchg_factory is None:
+        return {"skipped": "the sharded 100M-line section runs on the fused peer-memory exchange (--exchange p2p)"}
     torch.cuda.empty_cache()
     corpus, lo, hi = fill_shard(torch, dev, capi, E.ctx, rows, E.world, E.rank, seed_shift=4000)
     corpus.prepare(1)                                                 # q8 only: K2's shadow is not needed here
@@ -561,6 +629,23 @@ def side_ivfpq(E, args, nlist=4096, nprobe=64, make_xchg=None):
             torch.cuda.synchronize(dev)
             h = np.ascontiguousarray(out_pin.numpy()).view(capi.HIT_DTYPE).reshape(-1).copy()
             return h[h["row"] != np.uint64(0xFFFFFFFFFFFFFFFF)], 0
+    ivf_path = "stb_ivfpq_search_dev per rank -> nccl all_gather of k hits -> stb_hits_merge_dev -> one D2H"
+    if E.world > 1:
+        # the device-resident per-rank probe must return what the host call returns (ShardedCorpus.on_gpu_ivfpq:
+        # stb_ivfpq_search per rank, all-gather, host merge); if it does not on ANY rank, every rank times the host form
+        approx = ShardedCorpus.on_gpu_ivfpq(E.ctx, index, dist, dev, nprobe=nprobe, rerank=rerank)
+        same = 1
+        try:
+            for i in range(3):
+                a, b = search_ivf(i)[0], approx.search(qh[i], 10)
+                same &= int(np.array_equal(a["row"], b["row"]) and np.array_equal(a["distance"], b["distance"]))
+        except capi.StbError:
+            same = 0
+        flag = torch.tensor([same], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            search_ivf = lambda i: (approx.search(qh[i], 10), 0)
+            ivf_path = "stb_ivfpq_search per rank (host hits) -> all_gather -> host merge (the device-resident form disagreed with it)"
     want = [search_exact(i) for i in range(64)]
     E.barrier()
     t0 = time.perf_counter()
@@ -595,8 +680,7 @@ def side_ivfpq(E, args, nlist=4096, nprobe=64, make_xchg=None):
             "local_probe_ms_per_query": local_ms, "scanned_rows_per_query_per_gpu": local_scanned,
             "code_bytes_per_query_per_gpu": local_scanned * 32 + nlist * 1024 + 32768,
             "index_bytes_per_gpu": stt["index_bytes"], "max_list": stt["max_list"],
-            "exchange": None if E.world == 1 else "stb_ivfpq_search_dev per rank -> nccl all_gather of k hits -> stb_hits_merge_dev -> one D2H; "
-                                                   "exact comparator: fused stb_search_xchg (q8 tier)"}
+            "exchange": None if E.world == 1 else ivf_path + "; exact comparator: fused stb_search_xchg (q8 tier)"}
 
 
 def side_embed(E, V=500_000, n_lines=1_000_000):
@@ -688,6 +772,11 @@ def run_ours(args):
         else:
             dist.init_process_group("nccl", device_id=dev)
     dist = Dist(dist, torch, dev, one_gpu)
+    # N > 1: deadlines from the first collective on (see Watchdog); until the headline exists a missed
+    # deadline is an error exit, afterwards it costs the unfinished side sections only
+    wd = Watchdog(rank, None) if world > 1 else None
+    if wd is not None:
+        wd.arm("corpus fill + headline measurements", 420.0)
 
     # a dedicated non-default stream shared by torch (events, NCCL ordering) and the library
     stream = torch.cuda.Stream(dev)
@@ -827,69 +916,21 @@ def run_ours(args):
         e2e_ms = max_over_ranks(time.perf_counter() - t0) / e2e_steps * 1e3
     else:
         e2e_ms = e2e_queries(E, corpus, queries_h, k, e2e_steps, xchg=xchg)
+    # second e2e figure (stb_search_many, 16 queries per call): single-GPU runs only -- the sharded form of
+    # that entry point has not been through a multi-GPU box yet and stays out of the scaling run
     e2e_many_ms = None
-    if world == 1 or xchg is not None:
-        e2e_many_ms = e2e_queries_many(E, corpus, queries_h, k, max(e2e_steps, 64), xchg=xchg)
+    if world == 1:
+        try:
+            e2e_many_ms = e2e_queries_many(E, corpus, queries_h, k, max(e2e_steps, 64))
+        except Exception as e:                                         # noqa: BLE001 - the headline does not depend on it
+            print(f"e2e many16 skipped: {type(e).__name__}: {e}", file=sys.stderr)
 
-    # ---- parity spot-check of the benchmarked configuration (not timed) ----------------
-    check = None
-    if rank == 0 and world == 1 and not args.no_side:
-        import oracle
-        n_s = min(1_000_000, hi - lo)
-        sample = corpus.read(0, n_s)
-        cs = capi.Corpus(ctx, n_s)
-        cs.append(sample)
-        cs.prepare()
-        got = cs.search(queries_h[0], top_k=k)
-        r, d = oracle.search_rows(sample, queries_h[0], top_k=k)
-        check = bool(got["row"].tolist() == [int(x) for x in r] and np.array_equal(got["distance"], d)
-                     and cs.tier_stats()["q8"]["proven"] >= 1)
-        cs.close()
-
-    # ---- side sections ------------------------------------------------------------------
-    sides = {}
-
-    def side(name, fn, *a, collective=False, **kw):
-        """Side sections never take the headline line down with them (collective ones run bare: a
-        rank that swallowed an error would leave the others waiting in a collective)."""
-        t0 = time.perf_counter()
-        if collective:
-            res = fn(*a, **kw)
-        else:
-            try:
-                res = fn(*a, **kw)
-            except Exception as e:                                     # noqa: BLE001 - reported in the JSON
-                res = {"error": f"{type(e).__name__}: {e}"}
-        res["section_s"] = round(time.perf_counter() - t0, 2)
-        sides[name] = res
-        if rank == 0:
-            print(json.dumps({"side": name, **res}), flush=True)
-
+    # ---- the headline line: everything it needs is measured; side sections only add to it ----------
     rows_per_gpu = hi - lo
-    cpu_base = None
-    if not args.no_side:
-        if world == 1:
-            side("k1_tiers", side_k1_tiers, E, corpus, q_dev, queries_h, k, args.rows)
-            side("config2_1M", side_config2, E, k)
-            side("batch1024", side_batch, E, corpus, args.rows, k)
-            side("k3_embed", side_embed, E)
-            side("ivfpq", side_ivfpq, E, args)
-            try:
-                cpu_base = cpu_baseline_section(corpus, queries_h, args.rows, k)
-            except Exception as e:                                     # noqa: BLE001
-                cpu_base = {"error": f"{type(e).__name__}: {e}"}
-        else:
-            side("batch1024", side_batch, E, corpus, args.rows, k, make_xchg=make_xchg if xchg is not None else None, collective=True)
-    tier_stats = corpus.tier_stats()
-    corpus.close()
-    torch.cuda.empty_cache()
-    if not args.no_side:
-        if args.config4_rows:
-            side("config4_100M", side_config4, E, args, k, make_xchg, collective=world > 1)
-        if world > 1 and args.ivfpq_rows_per_gpu:
-            side("ivfpq_sharded", side_ivfpq, E, args, make_xchg=make_xchg if exchange == "p2p" else None, collective=True)
+    sides = {}
+    state = {"check": None, "cpu_base": None, "tier_stats": None}
 
-    if rank == 0:
+    def make_line(truncated=None):
         traffic = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
@@ -912,7 +953,7 @@ def run_ours(args):
                        "exchange": exchange,
                        "l2": "scanned copy >> 126 MB L2, no flush" if rows_per_gpu * TIER_BYTES[tier] > 4 * 126e6 else "WARNING scanned copy fits partly in L2"},
             "clocks": clocks,
-            # e2e.value: one synchronous host call per query (stb_search / stb_search_xchg).  many16: the same
+            # e2e.value: one synchronous host call per query (stb_search / stb_search_xchg).  many16 (N=1): the same
             # queries through stb_search_many, 16 per call (one H2D, 16 kernels, one sync): what a host holding
             # several queries calls; every query's input and result still cross PCIe inside the timed region
             "e2e": {"value": r5(1e3 / e2e_ms), "unit": "queries/s", "h2d_bytes_per_step": 1024, "d2h_bytes_per_step": 16 * k + 16,
@@ -923,11 +964,12 @@ def run_ours(args):
                          "frac": r5(achieved / peak), "traffic": traffic, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
                          "algorithmic_bytes": rows_per_gpu * 1024, "bytes_read": rows_per_gpu * TIER_BYTES[tier],
                          "frac_bytes_read": r5(read_gbs / peak)},
-            "all_results_proven_exact": all_complete, "ranks_agree": ranks_agree, "parity_spot_check": check,
-            "tier_stats": {t: [v["tries"], v["proven"]] for t, v in tier_stats.items()},
+            "all_results_proven_exact": all_complete, "ranks_agree": ranks_agree, "parity_spot_check": state["check"],
         }
-        if cpu_base is not None:
-            line["cpu_baseline"] = cpu_base
+        if state["tier_stats"] is not None:
+            line["tier_stats"] = {t: [v["tries"], v["proven"]] for t, v in state["tier_stats"].items()}
+        if state["cpu_base"] is not None:
+            line["cpu_baseline"] = state["cpu_base"]
         # one-number summaries of the side sections (details: the {"side": ...} lines above / bench_side.json)
         summ = {}
         if "batch1024" in sides and "value" in sides["batch1024"]:
@@ -942,6 +984,12 @@ def run_ours(args):
         if "k3_embed" in sides and "lines_per_s" in sides["k3_embed"]:
             summ["k3_Mlines_s"] = round(sides["k3_embed"]["lines_per_s"] / 1e6, 1)
         line["side"] = summ
+        if truncated:
+            line["side_sections_truncated"] = truncated    # the headline figures above were complete before it happened
+        return line
+
+    def emit_line(truncated=None):
+        line = make_line(truncated)
         blob = {"headline": line, "sides": sides}
         for path in (os.path.join(ROOT, "bench_side.json"), os.path.join(ROOT, "gpurun_out", f"bench_side_N{world}.json")):
             try:
@@ -950,6 +998,88 @@ def run_ours(args):
             except OSError:
                 pass
         print(json.dumps(line), flush=True)
+
+    # N > 1: from here on a stalled or failed side section costs that section, not the line (see Watchdog)
+    if wd is not None:
+        with wd.lock:
+            wd.emit = emit_line
+        wd.disarm()
+
+    # ---- parity spot-check of the benchmarked configuration (not timed) ----------------
+    if rank == 0 and world == 1 and not args.no_side:
+        try:
+            import oracle
+            n_s = min(1_000_000, hi - lo)
+            sample = corpus.read(0, n_s)
+            cs = capi.Corpus(ctx, n_s)
+            cs.append(sample)
+            cs.prepare()
+            got = cs.search(queries_h[0], top_k=k)
+            r, d = oracle.search_rows(sample, queries_h[0], top_k=k)
+            state["check"] = bool(got["row"].tolist() == [int(x) for x in r] and np.array_equal(got["distance"], d)
+                                  and cs.tier_stats()["q8"]["proven"] >= 1)
+            cs.close()
+        except Exception as e:                                         # noqa: BLE001 - reported, never fatal to the line
+            state["check"] = f"error: {type(e).__name__}: {e}"
+
+    # ---- side sections ------------------------------------------------------------------
+    def side(name, fn, *a, collective=False, budget_s=240.0, **kw):
+        """Side sections never take the headline line down with them.  Single-rank sections: errors are
+        caught and reported.  Collective sections (N > 1): a deadline is armed (aligned by a barrier); a
+        rank that raises cannot rejoin its peers, so rank 0 prints the line at once and the others leave at
+        the deadline."""
+        t0 = time.perf_counter()
+        if collective and wd is not None:
+            wd.arm(name + " (entry barrier)", 120.0)
+            barrier()
+            wd.arm(name, budget_s)
+        try:
+            res = fn(*a, **kw)
+        except Exception as e:                                         # noqa: BLE001 - reported in the JSON
+            res = {"error": f"{type(e).__name__}: {e}"}
+            if collective and wd is not None:
+                sides[name] = res
+                if rank == 0:
+                    wd.fire(f"section '{name}' failed on rank 0: {res['error']}")
+                wd.park(f"section '{name}' failed: {res['error']}")
+        if wd is not None:
+            wd.disarm()
+        res["section_s"] = round(time.perf_counter() - t0, 2)
+        sides[name] = res
+        if rank == 0:
+            print(json.dumps({"side": name, **res}), flush=True)
+
+    if not args.no_side:
+        if world == 1:
+            side("k1_tiers", side_k1_tiers, E, corpus, q_dev, queries_h, k, args.rows)
+            side("config2_1M", side_config2, E, k)
+            side("batch1024", side_batch, E, corpus, args.rows, k)
+            side("k3_embed", side_embed, E)
+            side("ivfpq", side_ivfpq, E, args)
+            try:
+                state["cpu_base"] = cpu_baseline_section(corpus, queries_h, args.rows, k)
+            except Exception as e:                                     # noqa: BLE001
+                state["cpu_base"] = {"error": f"{type(e).__name__}: {e}"}
+        else:
+            # order: the section that shares the headline's code path first; the sharded K2 exchange last (its
+            # N=8 run stalled once on the builder's box -- BASELINE.md section 6 -- and a stall must not cost the others)
+            if args.config4_rows:
+                side("config4_100M", side_config4, E, args, k, make_xchg if xchg is not None else None, collective=True, budget_s=240.0)
+            if args.ivfpq_rows_per_gpu:
+                side("ivfpq_sharded", side_ivfpq, E, args, make_xchg=make_xchg if exchange == "p2p" else None, collective=True, budget_s=360.0)
+            side("batch1024", side_batch, E, corpus, args.rows, k, make_xchg=make_xchg if xchg is not None else None, collective=True, budget_s=120.0)
+    state["tier_stats"] = corpus.tier_stats()
+    corpus.close()
+    torch.cuda.empty_cache()
+    if not args.no_side and world == 1 and args.config4_rows:
+        side("config4_100M", side_config4, E, args, k, make_xchg)
+
+    if wd is not None:
+        wd.arm("teardown", 120.0)
+        with wd.lock:
+            wd.emit = lambda reason: None                               # the line is about to be printed here
+    if rank == 0:
+        emit_line()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -50,3 +50,30 @@ def test_synthetic_generators_are_deterministic():
     assert (norms == 0).sum() >= 1 and np.allclose(norms[norms > 0], 1.0, atol=1e-5)     # zero rows injected
     q = bench.gen_queries(8)
     assert np.array_equal(q, bench.gen_queries(8)) and np.allclose(np.linalg.norm(q, axis=1), 1.0, atol=1e-5)
+
+
+def _run_snippet(code):
+    return subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=60)
+
+
+def test_watchdog_prints_the_line_and_leaves_cleanly_when_a_phase_stalls():
+    """bench.py's multi-rank deadline thread: a stalled phase costs the unfinished side sections, never
+    the headline (rank 0 prints it, exit code 0); before a headline exists it is an error exit."""
+    code = ("import sys, time, json; sys.path.insert(0, '.'); import bench\n"
+            "wd = bench.Watchdog(0, lambda why: print(json.dumps({'value': 1.0, 'side_sections_truncated': why})))\n"
+            "wd.arm('stuck section', 0.5); time.sleep(30)\n")
+    r = _run_snippet(code)
+    assert r.returncode == 0, r.stderr
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["value"] == 1.0 and "stuck section" in d["side_sections_truncated"]
+    # a non-zero rank leaves quietly (stdout stays rank 0's)
+    r = _run_snippet(code.replace("bench.Watchdog(0,", "bench.Watchdog(3,"))
+    assert r.returncode == 0 and r.stdout.strip() == "" and "rank 3" in r.stderr
+    # nothing measured yet: error exit with an error object
+    r = _run_snippet("import sys, time; sys.path.insert(0, '.'); import bench\n"
+                     "wd = bench.Watchdog(0, None); wd.arm('fill', 0.3); time.sleep(30)\n")
+    assert r.returncode == 1 and "error" in json.loads(r.stdout.strip().splitlines()[-1])
+    # disarmed in time: nothing happens
+    r = _run_snippet("import sys, time; sys.path.insert(0, '.'); import bench\n"
+                     "wd = bench.Watchdog(0, None); wd.arm('quick', 0.5); wd.disarm(); time.sleep(1.2); print('alive')\n")
+    assert r.returncode == 0 and r.stdout.strip() == "alive"
