@@ -1068,9 +1068,12 @@ def run_ours(args):
             if args.ivfpq_rows_per_gpu:
                 side("ivfpq_sharded", side_ivfpq, E, args, make_xchg=make_xchg if exchange == "p2p" else None, collective=True, budget_s=360.0)
             side("batch1024", side_batch, E, corpus, args.rows, k, make_xchg=make_xchg if xchg is not None else None, collective=True, budget_s=120.0)
-    state["tier_stats"] = corpus.tier_stats()
-    corpus.close()
-    torch.cuda.empty_cache()
+    try:                                                               # nothing after the measurements may cost the line
+        state["tier_stats"] = corpus.tier_stats()
+        corpus.close()
+        torch.cuda.empty_cache()
+    except Exception as e:                                             # noqa: BLE001
+        print(f"[rank {rank}] closing the corpus: {type(e).__name__}: {e}", file=sys.stderr)
     if not args.no_side and world == 1 and args.config4_rows:
         side("config4_100M", side_config4, E, args, k, make_xchg)
 
