@@ -266,9 +266,10 @@ class Watchdog:
     hung kernels go down with the process.  No collective, no store traffic: the ranks' clocks are aligned
     by the barrier that precedes every arm()."""
 
-    def __init__(self, rank, emit):
+    def __init__(self, rank, emit, total_s=720.0):
         self.rank, self.emit = rank, emit
         self.deadline, self.label, self.budget = None, None, 0.0
+        self.total_s, self.t_end = float(total_s), time.monotonic() + float(total_s)   # the whole run, whatever the phases do
         self.lock = threading.Lock()
         self.done = False
         t = threading.Thread(target=self._run, daemon=True)
@@ -314,6 +315,8 @@ class Watchdog:
                 d, label, budget = self.deadline, self.label, self.budget
             if d is not None and time.monotonic() > d:
                 self.fire(f"phase '{label}' exceeded its {budget:.0f} s deadline")
+            if time.monotonic() > self.t_end:
+                self.fire(f"the run exceeded {self.total_s:.0f} s (phase '{label}')")
 
 
 def timed_queries(E, corpus, q_dev, k, steps, warm, xchg=None):
@@ -455,7 +458,7 @@ def side_batch(E, corpus, rows, k, nq=1024, iters=5, make_xchg=None):
     corpus.prepare()
     if world > 1:
         # first-call costs (shadow build, kernel attributes, workspaces) stay local; the ranks then enter the
-        # exchange together: its wait is bounded (~4 s per kernel), a rank arriving later than that is "gone"
+        # exchange together: its wait is bounded (STB_XCHG_TIMEOUT_CYCLES), a rank arriving later than that is "gone"
         corpus.search_batch_dev(q_dev.data_ptr(), nq, k, hits.data_ptr(), st.data_ptr())
         E.barrier()
     fallbacks = []

@@ -228,7 +228,10 @@ int stb_search_batch_dev(stb_ctx *ctx, const stb_corpus *corpus, const float *q_
  * Within one process (several contexts), use stb_xchg_connect_local instead of IPC.
  *   out_status_dev[0] = hits, [1] = 1 iff every rank proved its shard result exact
  *   (0 -> run the per-shard stb_search + stb_hits_merge path), [2] = 0xfffffffe if a
- *   peer never arrived (timeout). */
+ *   peer never arrived.  The wait is bounded (~15 s of SM cycles): ranks may enter a call seconds
+ *   apart, not more.  After a timeout the ranks no longer agree on what was exchanged: stop using
+ *   the exchange (destroy it on every rank); do NOT re-run queries on it, a surplus call waits a
+ *   full bound for peers that will not come. */
 typedef struct stb_xchg stb_xchg;
 #define STB_IPC_HANDLE_BYTES 64
 #define STB_XCHG_MAX_RANKS 8
@@ -250,7 +253,8 @@ int stb_search_topk_xchg(stb_ctx *ctx, const stb_corpus *corpus, const float *q_
  * nq x k hits into every peer's slot over NVLink, release-stored sequence flag) and a merge kernel (waits
  * for every peer's flag, merges each query's world x k hits by (distance,row)): two launches, no NCCL.
  *   out_status_dev[2q] = hits of query q, [2q+1] = 1 iff every rank proved its part (0: re-run query q
- *   through stb_search_xchg / stb_search_many on every rank; 2: a peer never arrived).
+ *   through stb_search_xchg / stb_search_many on every rank; 2: a peer never arrived -- see above:
+ *   treat the exchange as dead, the flags of this batch are not the same on every rank).
  * All ranks must issue the same sequence of calls. */
 int stb_xchg_create_batch(stb_ctx *ctx, uint32_t world, uint32_t rank, uint32_t max_k, uint32_t max_nq,
                           stb_xchg **out);

@@ -755,6 +755,9 @@ static int xchg_create_impl(stb_ctx *ctx, uint32_t world, uint32_t rank, uint32_
   if (e == cudaSuccess) e = cudaMemset(x->local, 0, x->bytes);
   if (e == cudaSuccess) e = cudaMalloc((void **)&x->batch_ticket, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMemset(x->batch_ticket, 0, sizeof(unsigned int));
+  // cudaMemset on device memory may return before it ran (legacy default stream, which a non-blocking
+  // stream does not order against): the zeroed flags must be in place before any peer can store to them
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { cudaGetLastError(); cudaFree(x->local); stb_set_error("xchg_create: %s", cudaGetErrorString(e)); delete x; return STB_ERR_NOMEM; }
   x->peers[rank] = x->local;
   x->connected = (world == 1);

@@ -129,6 +129,11 @@ struct stb_ctx {
 };
 
 #define STB_TICKET_SLOTS 8
+// Spin-wait bound of the peer-memory exchanges (SM cycles, ~15 s): long enough that ranks entering a sharded
+// search a few seconds apart (first-call allocations, a busy host) still meet; a peer that is really gone
+// costs one bound, the call reports it (status 0xfffffffe / 2) and the caller must stop using the exchange:
+// ranks that disagree on whether an exchange happened no longer issue the same sequence of calls.
+#define STB_XCHG_TIMEOUT_CYCLES 30000000000ll
 #define STB_XCHG_SLOTS 4
 #define STB_XCHG_MAX_WORLD 8
 struct StbXchgArgs {

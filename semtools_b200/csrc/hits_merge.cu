@@ -139,7 +139,7 @@ stb_batch_xchg_merge_kernel(const StbBatchXchgArgs a, uint32_t n_sort, stb_hit *
       unsigned long long v;
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
       if (v == a.seq) break;
-      if (clock64() - t0 > 8000000000ll) { s_timeout = 1u; break; }    // ~4 s: a peer is gone
+      if (clock64() - t0 > STB_XCHG_TIMEOUT_CYCLES) { s_timeout = 1u; break; }    // a peer is gone
     }
   }
   __syncthreads();

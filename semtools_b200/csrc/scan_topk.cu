@@ -999,7 +999,7 @@ stb_scan_topk_kernel(const TopkArgs args) {
     const unsigned long long *f = stb_x_flags(X, me) + (size_t)X.slot * world + threadIdx.x;
     const long long t0 = clock64();
     while (stb_ld_acquire_sys(f) != X.seq) {
-      if (clock64() - t0 > 8000000000ll) { s_timeout = 1u; break; }   // ~4 s: a peer is gone
+      if (clock64() - t0 > STB_XCHG_TIMEOUT_CYCLES) { s_timeout = 1u; break; }   // a peer is gone
     }
   }
   __syncthreads();
