@@ -56,6 +56,10 @@ def parse_args():
     p.add_argument("--no-side", action="store_true", help="headline only (no side sections, no cpu_baseline)")
     p.add_argument("--no-cpu-baseline", action="store_true", help="alias of --no-side (round-1 name)")
     p.add_argument("--config4-rows", type=int, default=100_000_000, help="BASELINE configs[3]: rows of the sharded 100M-line section (0 = skip)")
+    p.add_argument("--config2-rows", type=int, default=1_000_000, help="BASELINE configs[1]: rows of the 1M-line section")
+    p.add_argument("--embed-lines", type=int, default=1_000_000, help="K3 side section: lines of the synthetic ingestion batch")
+    p.add_argument("--embed-vocab", type=int, default=500_000, help="K3 side section: rows of the embedding table")
+    p.add_argument("--batch-queries", type=int, default=1024, help="K2 side section: queries per batch (BASELINE configs[2]: 1024)")
     p.add_argument("--ivfpq-rows", type=int, default=4_000_000, help="N=1 IVF-PQ side section rows")
     p.add_argument("--ivfpq-rows-per-gpu", type=int, default=12_500_000, help="N>1: clustered rows per GPU of the IVF-PQ section (x8 = configs[4])")
     p.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
@@ -257,6 +261,30 @@ class Dist:
         out.copy_(self.torch.stack(parts).reshape(out.shape))
 
 
+# The stdout line must stay below 1.5 kB (the driver keeps a bounded tail of stdout).  The full line always
+# goes to bench_side.json; on stdout the least important keys are dropped, in this order, until it fits.
+LINE_LIMIT = 1480
+DROPPABLE = (("tier_stats",), ("roofline", "algorithmic_bytes"), ("cpu_baseline", "all_cores_threads"), ("cpu_baseline", "host_cores"),
+             ("e2e", "steps"), ("roofline", "peak_source"), ("config", "rows"), ("e2e", "ms_per_step"), ("cpu_baseline", "gpu_rows_equal_cpu_rows"),
+             ("per_rank_ms_per_step",), ("clocks", "samples"), ("roofline", "bytes_read"), ("cpu_baseline", "all_cores_value"),
+             ("cpu_baseline", "isa"), ("side",))
+
+
+def shrink_line(full):
+    line = json.loads(json.dumps(full))
+    for k in [k for k, v in line.items() if v is None and k not in ("vs_baseline",)]:
+        del line[k]                                                   # ranks_agree at N=1, parity_spot_check at N>1, ...
+    for path in DROPPABLE:
+        if len(json.dumps(line)) <= LINE_LIMIT:
+            break
+        d = line
+        for key in path[:-1]:
+            d = d.get(key, {}) if isinstance(d, dict) else {}
+        if isinstance(d, dict):
+            d.pop(path[-1], None)
+    return line
+
+
 class Watchdog:
     """Deadlines for the multi-rank run.  The fused exchanges are spin-waits on peer memory and the few
     NCCL calls block until every rank arrives: a rank that fails (or a peer that stalls) would otherwise
@@ -276,6 +304,7 @@ class Watchdog:
         t.start()
 
     def arm(self, label, seconds):
+        seconds = float(seconds) * float(os.environ.get("STB_BENCH_DEADLINE_SCALE", "1"))   # tests shrink the deadlines
         with self.lock:
             self.label, self.budget, self.deadline = label, float(seconds), time.monotonic() + float(seconds)
 
@@ -409,17 +438,16 @@ def side_k1_tiers(E, corpus, q_dev, queries_h, k, rows):
     return out
 
 
-def side_config2(E, k):
+def side_config2(E, k, n=1_000_000):
     """BASELINE configs[1]: 1M-line corpus, single query, top-k=10, 1xB200."""
     capi, torch, dev = E.capi, E.torch, E.dev
-    n = 1_000_000
     x = gen_chunk_torch(torch, dev, 2002, n)
     c = capi.Corpus(E.ctx, n)
     torch.cuda.synchronize(dev); c.append_dev(x.data_ptr(), n); del x
     c.prepare()
     qh = gen_queries(96)[64:]
     q_dev = torch.from_numpy(qh).to(dev)
-    out = {"workload": "1M-line corpus, single query, top-k=%d (BASELINE configs[1])" % k}
+    out = {"workload": "%d-line corpus, single query, top-k=%d (BASELINE configs[1])" % (n, k)}
     for tier in ("q8", "f32"):
         os.environ["STB_SCAN_TIER"] = tier
         try:
@@ -717,7 +745,7 @@ def side_embed(E, V=500_000, n_lines=1_000_000):
     capi.embed(E.ctx, table, offsets, ids, out=False, append_to=corpus)       # host CSR in, rows stay in HBM
     e2e_s = time.perf_counter() - t0
     import oracle
-    n_chk = 2000
+    n_chk = min(2000, n_lines)
     exp = oracle.embed_csr(Emb, offsets[:n_chk + 1], ids[:int(offsets[n_chk])])
     bit_exact = bool(np.array_equal(corpus.read(0, n_chk).view(np.uint32), exp.view(np.uint32)))
     corpus.close(); table.close()
@@ -992,8 +1020,9 @@ def run_ours(args):
         return line
 
     def emit_line(truncated=None):
-        line = make_line(truncated)
-        blob = {"headline": line, "sides": sides}
+        full = make_line(truncated)
+        line = shrink_line(full)
+        blob = {"headline": full, "sides": sides}
         for path in (os.path.join(ROOT, "bench_side.json"), os.path.join(ROOT, "gpurun_out", f"bench_side_N{world}.json")):
             try:
                 if os.path.isdir(os.path.dirname(path)):
@@ -1055,9 +1084,9 @@ def run_ours(args):
     if not args.no_side:
         if world == 1:
             side("k1_tiers", side_k1_tiers, E, corpus, q_dev, queries_h, k, args.rows)
-            side("config2_1M", side_config2, E, k)
-            side("batch1024", side_batch, E, corpus, args.rows, k)
-            side("k3_embed", side_embed, E)
+            side("config2_1M", side_config2, E, k, n=args.config2_rows)
+            side("batch1024", side_batch, E, corpus, args.rows, k, nq=args.batch_queries)
+            side("k3_embed", side_embed, E, V=args.embed_vocab, n_lines=args.embed_lines)
             side("ivfpq", side_ivfpq, E, args)
             try:
                 state["cpu_base"] = cpu_baseline_section(corpus, queries_h, args.rows, k)
@@ -1070,7 +1099,8 @@ def run_ours(args):
                 side("config4_100M", side_config4, E, args, k, make_xchg if xchg is not None else None, collective=True, budget_s=240.0)
             if args.ivfpq_rows_per_gpu:
                 side("ivfpq_sharded", side_ivfpq, E, args, make_xchg=make_xchg if exchange == "p2p" else None, collective=True, budget_s=360.0)
-            side("batch1024", side_batch, E, corpus, args.rows, k, make_xchg=make_xchg if xchg is not None else None, collective=True, budget_s=120.0)
+            side("batch1024", side_batch, E, corpus, args.rows, k, nq=args.batch_queries, make_xchg=make_xchg if xchg is not None else None,
+                 collective=True, budget_s=120.0)
     try:                                                               # nothing after the measurements may cost the line
         state["tier_stats"] = corpus.tier_stats()
         corpus.close()
