@@ -231,7 +231,9 @@ int stb_search_batch_dev(stb_ctx *ctx, const stb_corpus *corpus, const float *q_
  *   peer never arrived.  The wait is bounded (~15 s of SM cycles): ranks may enter a call seconds
  *   apart, not more.  After a timeout the ranks no longer agree on what was exchanged: stop using
  *   the exchange (destroy it on every rank); do NOT re-run queries on it, a surplus call waits a
- *   full bound for peers that will not come. */
+ *   full bound for peers that will not come.  The synchronous entry points (stb_search_xchg,
+ *   stb_search_many) mark the exchange dead when they see the timeout: every later call on it
+ *   returns STB_ERR_STATE at once. */
 typedef struct stb_xchg stb_xchg;
 #define STB_IPC_HANDLE_BYTES 64
 #define STB_XCHG_MAX_RANKS 8

@@ -848,6 +848,7 @@ static int search_topk_xchg_impl(stb_ctx *ctx, const stb_corpus *corpus, const f
   if (!corpus || !q_dev || !x || !out_hits_dev || !out_status_dev) { stb_set_error("search_topk_xchg: null argument"); return STB_ERR_ARG; }
   if (corpus->ctx != ctx || x->ctx != ctx) { stb_set_error("search_topk_xchg: handles belong to another context"); return STB_ERR_ARG; }
   if (!x->connected) { stb_set_error("search_topk_xchg: exchange not connected"); return STB_ERR_STATE; }
+  if (x->dead) { stb_set_error("search_topk_xchg: this exchange saw a peer time-out; destroy it on every rank"); return STB_ERR_STATE; }
   if (top_k == 0 || top_k > x->max_k) { stb_set_error("search_topk_xchg: top_k must be 1..%u", x->max_k); return STB_ERR_ARG; }
   StbXchgArgs a;
   memset(&a, 0, sizeof(a));
@@ -1093,6 +1094,7 @@ int stb_search_batch_xchg_dev(stb_ctx *ctx, const stb_corpus *corpus, const floa
   if (!corpus || !q_dev || !x || !out_hits_dev || !out_status_dev) { stb_set_error("search_batch_xchg_dev: null argument"); return STB_ERR_ARG; }
   if (corpus->ctx != ctx || x->ctx != ctx) { stb_set_error("search_batch_xchg_dev: handles belong to another context"); return STB_ERR_ARG; }
   if (!x->connected) { stb_set_error("search_batch_xchg_dev: exchange not connected"); return STB_ERR_STATE; }
+  if (x->dead) { stb_set_error("search_batch_xchg_dev: this exchange saw a peer time-out; destroy it on every rank"); return STB_ERR_STATE; }
   if (nq == 0) return STB_OK;
   if (x->max_nq == 0 || nq > x->max_nq || top_k == 0 || top_k > x->max_k) { stb_set_error("search_batch_xchg_dev: needs stb_xchg_create_batch with max_nq >= %u, max_k >= %u", nq, top_k); return STB_ERR_ARG; }
   if ((rc = dev_reserve(&ctx->bh_dev, &ctx->bh_dev_cap, (size_t)nq * top_k)) != STB_OK) return rc;
@@ -1178,7 +1180,7 @@ int stb_search_xchg(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint
   memcpy(out_hits, ctx->hits_pin, n * sizeof(stb_hit));
   *out_n = n;
   *out_complete = ctx->status_pin[1] ? 1 : 0;
-  if (ctx->status_pin[2] == 0xfffffffeu) { stb_set_error("search_xchg: a peer rank never arrived (timeout)"); return STB_ERR_STATE; }
+  if (ctx->status_pin[2] == 0xfffffffeu) { x->dead = true; stb_set_error("search_xchg: a peer rank never arrived (timeout)"); return STB_ERR_STATE; }
   return STB_OK;
 }
 
@@ -1244,7 +1246,7 @@ int stb_search_many(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint
   STB_CUDA(cudaStreamSynchronize(ctx->stream));
   for (uint32_t i = 0; i < nq; ++i) {
     const uint32_t *st = ctx->many_status_pin + 4 * (size_t)i;
-    if (x && st[2] == 0xfffffffeu) { stb_set_error("search_many: a peer rank never arrived (timeout)"); return STB_ERR_STATE; }
+    if (x && st[2] == 0xfffffffeu) { x->dead = true; stb_set_error("search_many: a peer rank never arrived (timeout)"); return STB_ERR_STATE; }
     if (st[1]) {
       const uint32_t n = std::min<uint32_t>(st[0], top_k);
       memcpy(out_hits + (size_t)i * top_k, ctx->hits_pin + (size_t)i * top_k, n * sizeof(stb_hit));

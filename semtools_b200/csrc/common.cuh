@@ -157,6 +157,7 @@ struct stb_xchg {
   size_t batch_off, batch_slot_bytes;
   unsigned long long batch_seq;
   unsigned int *batch_ticket;                // device: arrival counter of the push kernel
+  bool dead;                                 // a synchronous call saw a peer time-out: every later call is refused
 };
 
 struct stb_table {
