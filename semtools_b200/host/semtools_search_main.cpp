@@ -149,6 +149,31 @@ int main(int argc, char **argv) {
       }
       return 0;
     }
+    if (a == "--normalize") {                      // test hook: --normalize tokenizer.json: stdin lines -> normalizer output, one per line
+      HfTokenizer tk(next());
+      std::string in;
+      char buf[65536];
+      size_t n;
+      while ((n = fread(buf, 1, sizeof(buf), stdin)) > 0) in.append(buf, n);
+      for (const auto &l : rust_lines(in)) {
+        try { const std::string o = tk.normalize_str(l); fwrite(o.data(), 1, o.size(), stdout); fputc('\n', stdout); }
+        catch (const std::exception &e) { printf("ERROR %s\n", e.what()); }
+      }
+      return 0;
+    }
+    if (a == "--graphemes") {                      // test hook: stdin lines -> byte lengths of the extended grapheme clusters
+      std::string in;
+      char buf[65536];
+      size_t n;
+      while ((n = fread(buf, 1, sizeof(buf), stdin)) > 0) in.append(buf, n);
+      for (const auto &l : rust_lines(in)) {
+        std::string o;
+        size_t b = 0;
+        for (size_t e : grapheme_ends(l)) { o += std::to_string(e - b) + " "; b = e; }
+        puts(o.c_str());
+      }
+      return 0;
+    }
     if (a == "--lines") {                          // test hook: stdin -> rust_lines -> one JSON string per line
       std::string in;
       char buf[65536];

@@ -1,7 +1,9 @@
 // HfTokenizer: tokenizer.json (Unigram + Metaspace subset) on the host.  See semtools_tokenizer.hpp.
 // Semantics follow HF `tokenizers` 0.21/0.22 (the crate model2vec-rs 0.1.3 links; Cargo.lock:4375):
-//   normalizers/{utils.rs,replace.rs,strip.rs,prepend.rs}, pre_tokenizers/metaspace.rs,
-//   models/unigram/model.rs (encode_optimized, fuse_unk = true, K_UNK_PENALTY = 10).
+//   normalizers/{utils.rs,replace.rs,strip.rs,prepend.rs,precompiled.rs}, pre_tokenizers/metaspace.rs,
+//   models/unigram/model.rs (encode_optimized, fuse_unk = true, K_UNK_PENALTY = 10);
+//   Precompiled: crate spm_precompiled 0.1 (darts-clone unit layout, common_prefix_search) over
+//   unicode_segmentation's extended grapheme clusters.
 #include "semtools_tokenizer.hpp"
 
 #include <algorithm>
@@ -14,7 +16,7 @@ extern "C" uint64_t stb_fnv1a64(const uint8_t *bytes, uint64_t len);
 namespace semtools {
 
 namespace {
-enum { N_LOWER = 0, N_REPLACE_STR, N_REPLACE_MULTISPACE, N_STRIP, N_PREPEND, N_UNICODE_ASCII_ONLY };
+enum { N_LOWER = 0, N_REPLACE_STR, N_REPLACE_MULTISPACE, N_STRIP, N_PREPEND, N_UNICODE_ASCII_ONLY, N_PRECOMPILED };
 enum { P_METASPACE = 0, P_WHITESPACE_SPLIT };
 enum { PREPEND_ALWAYS = 0, PREPEND_FIRST, PREPEND_NEVER };
 
@@ -47,7 +49,174 @@ bool is_space_at(const std::string &s, size_t i, size_t *len) {
   return cp == 0x85 || cp == 0xA0 || cp == 0x1680 || (cp >= 0x2000 && cp <= 0x200A) || cp == 0x2028 || cp == 0x2029 || cp == 0x202F ||
          cp == 0x205F || cp == 0x3000;
 }
+
+// ---- extended grapheme clusters (UAX #29) -------------------------------------------------------
+struct GbRange { uint32_t a, b; uint8_t v; };
+#include "grapheme_break.inc"
+enum { GB_OTHER = 0, GB_CR, GB_LF, GB_CONTROL, GB_EXTEND, GB_ZWJ, GB_RI, GB_PREPEND, GB_SPACINGMARK, GB_L, GB_V, GB_T, GB_LV, GB_LVT };
+enum { INCB_NONE = 0, INCB_CONSONANT, INCB_EXTEND, INCB_LINKER };
+
+template <size_t N>
+uint8_t gb_lookup(const GbRange (&t)[N], uint32_t cp) {
+  size_t lo = 0, hi = N;
+  while (lo < hi) { const size_t mid = (lo + hi) >> 1; if (t[mid].b < cp) lo = mid + 1; else hi = mid; }
+  return (lo < N && t[lo].a <= cp) ? t[lo].v : 0;
+}
+inline uint8_t gcb_of(uint32_t cp) {
+  if (cp >= 0xAC00 && cp <= 0xD7A3) return (cp - 0xAC00) % 28 == 0 ? GB_LV : GB_LVT;
+  return gb_lookup(kGcbRanges, cp);
+}
+// one scalar value at s[i]; malformed sequences yield the single byte as an (unassigned-looking) code point
+inline uint32_t decode_at(const std::string &s, size_t i, size_t *len) {
+  const unsigned char c = (unsigned char)s[i];
+  size_t n = utf8_len(c);
+  if (c < 0x80) { *len = 1; return c; }
+  if (n == 1 || i + n > s.size()) { *len = 1; return 0xFFFD; }
+  uint32_t cp = n == 2 ? (c & 0x1F) : n == 3 ? (c & 0x0F) : (c & 0x07);
+  for (size_t k = 1; k < n; ++k) {
+    const unsigned char d = (unsigned char)s[i + k];
+    if ((d & 0xC0) != 0x80) { *len = 1; return 0xFFFD; }
+    cp = (cp << 6) | (d & 0x3F);
+  }
+  *len = n;
+  return cp;
+}
+
+std::string b64_decode(const std::string &in) {
+  static int8_t T[256]; static bool init = false;
+  if (!init) {
+    for (int i = 0; i < 256; ++i) T[i] = -1;
+    const char *A = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+    for (int i = 0; i < 64; ++i) T[(unsigned char)A[i]] = (int8_t)i;
+    init = true;
+  }
+  std::string out;
+  out.reserve(in.size() * 3 / 4);
+  uint32_t acc = 0; int bits = 0;
+  for (unsigned char c : in) {
+    if (c == '=') break;
+    if (T[c] < 0) { if (c == '\n' || c == '\r' || c == ' ') continue; throw std::runtime_error("tokenizer.json: precompiled_charsmap is not base64"); }
+    acc = (acc << 6) | (uint32_t)T[c]; bits += 6;
+    if (bits >= 8) { bits -= 8; out.push_back((char)((acc >> bits) & 0xFF)); }
+  }
+  return out;
+}
 }  // namespace
+
+std::vector<size_t> grapheme_ends(const std::string &s) {
+  std::vector<size_t> ends;
+  size_t i = 0, len = 0;
+  int prev = -1, ri_run = 0, ep_state = 0, incb_state = 0;   // ep: 1 = ExtPict Extend*, 2 = ... ZWJ; incb: 1 = Consonant [Extend|Linker]*, 2 = with a Linker
+  while (i < s.size()) {
+    const uint32_t cp = decode_at(s, i, &len);
+    const int c = gcb_of(cp);
+    const bool ep = gb_lookup(kExtPictRanges, cp) != 0;
+    const int incb = gb_lookup(kInCbRanges, cp);
+    if (prev >= 0) {
+      bool brk;
+      if (prev == GB_CR && c == GB_LF) brk = false;                                              // GB3
+      else if (prev == GB_CONTROL || prev == GB_CR || prev == GB_LF) brk = true;                 // GB4
+      else if (c == GB_CONTROL || c == GB_CR || c == GB_LF) brk = true;                          // GB5
+      else if (prev == GB_L && (c == GB_L || c == GB_V || c == GB_LV || c == GB_LVT)) brk = false;   // GB6
+      else if ((prev == GB_LV || prev == GB_V) && (c == GB_V || c == GB_T)) brk = false;         // GB7
+      else if ((prev == GB_LVT || prev == GB_T) && c == GB_T) brk = false;                       // GB8
+      else if (c == GB_EXTEND || c == GB_ZWJ) brk = false;                                       // GB9
+      else if (c == GB_SPACINGMARK) brk = false;                                                 // GB9a
+      else if (prev == GB_PREPEND) brk = false;                                                  // GB9b
+      else if (incb_state == 2 && incb == INCB_CONSONANT) brk = false;                           // GB9c
+      else if (ep_state == 2 && ep) brk = false;                                                 // GB11
+      else if (prev == GB_RI && c == GB_RI && (ri_run & 1)) brk = false;                         // GB12, GB13
+      else brk = true;                                                                           // GB999
+      if (brk) ends.push_back(i);
+    }
+    ri_run = c == GB_RI ? ri_run + 1 : 0;
+    if (ep) ep_state = 1;
+    else if (ep_state == 1 && c == GB_EXTEND) ep_state = 1;
+    else if (ep_state == 1 && c == GB_ZWJ) ep_state = 2;
+    else ep_state = 0;
+    if (incb == INCB_CONSONANT) incb_state = 1;
+    else if (incb_state >= 1 && incb == INCB_EXTEND) { /* keeps its state */ }
+    else if (incb_state >= 1 && incb == INCB_LINKER) incb_state = 2;
+    else incb_state = 0;
+    prev = c;
+    i += len;
+  }
+  if (!s.empty()) ends.push_back(s.size());
+  return ends;
+}
+
+// darts-clone unit layout (sentencepiece third_party/darts_clone, restated by spm_precompiled)
+int64_t HfTokenizer::Charsmap::first_prefix(const char *p, size_t n) const {
+  if (trie.empty()) return -1;
+  auto has_leaf = [](uint32_t u) { return ((u >> 8) & 1u) == 1u; };
+  auto value = [](uint32_t u) { return u & ((1u << 31) - 1u); };
+  auto label = [](uint32_t u) { return u & ((1u << 31) | 0xFFu); };
+  auto offset = [](uint32_t u) { return (size_t)(u >> 10) << ((u & (1u << 9)) >> 6); };
+  size_t node = 0;
+  uint32_t unit = trie[0];
+  node ^= offset(unit);
+  for (size_t i = 0; i < n; ++i) {
+    const unsigned char c = (unsigned char)p[i];
+    if (c == 0) break;
+    node ^= c;
+    if (node >= trie.size()) return -1;
+    unit = trie[node];
+    if (label(unit) != c) return -1;
+    node ^= offset(unit);
+    if (has_leaf(unit)) {
+      if (node >= trie.size()) return -1;
+      return (int64_t)value(trie[node]);
+    }
+  }
+  return -1;
+}
+
+// normalizers/precompiled.rs: every grapheme shorter than 6 bytes is looked up WHOLE first (the first,
+// i.e. shortest, key that is a prefix of it replaces the whole grapheme); otherwise character by character
+std::string HfTokenizer::apply_charsmap(const Charsmap &m, const std::string &s) const {
+  if (m.trie.empty()) return s;
+  std::string o;
+  o.reserve(s.size());
+  auto emit = [&](int64_t at) { for (size_t k = (size_t)at; k < m.normalized.size() && m.normalized[k] != 0; ++k) o.push_back(m.normalized[k]); };
+  auto slow = [&](const std::string &seg) {
+    size_t b = 0;
+    for (size_t e : grapheme_ends(seg)) {
+      bool done = false;
+      if (e - b < 6) {
+        const int64_t at = m.first_prefix(seg.data() + b, e - b);
+        if (at >= 0) { emit(at); done = true; }
+      }
+      if (!done) {
+        size_t i = b, len = 0;
+        while (i < e) {
+          decode_at(seg, i, &len);
+          const int64_t at = m.first_prefix(seg.data() + i, len);
+          if (at >= 0) emit(at); else o.append(seg, i, len);
+          i += len;
+        }
+      }
+      b = e;
+    }
+  };
+  // Fast path: a printable ASCII character between ASCII neighbours is a grapheme of its own (it is neither
+  // Extend / SpacingMark / ZWJ nor preceded by a Prepend character, and no ASCII character is
+  // Extended_Pictographic or an Indic consonant), so cluster boundaries on both sides are certain; if the map
+  // leaves it alone it is copied.  Everything else goes through the grapheme walk, one maximal segment at a time.
+  const size_t n = s.size();
+  auto fast = [&](size_t i) {
+    const unsigned char c = (unsigned char)s[i];
+    return c >= 0x20 && c < 0x7F && m.ascii_plain[c] && (i + 1 == n || (unsigned char)s[i + 1] < 0x80) && (i == 0 || (unsigned char)s[i - 1] < 0x80);
+  };
+  size_t i = 0;
+  while (i < n) {
+    if (fast(i)) { o.push_back(s[i]); ++i; continue; }
+    size_t j = i + 1;
+    while (j < n && !fast(j)) ++j;
+    slow(s.substr(i, j - i));
+    i = j;
+  }
+  return o;
+}
 
 void HfTokenizer::add_norm(const Json &j) {
   if (j.type == Json::Null) return;
@@ -71,7 +240,27 @@ void HfTokenizer::add_norm(const Json &j) {
     norm_.push_back(s); return;
   }
   if (t == "Prepend") { norm_.push_back({N_PREPEND, need(j, "prepend", "Prepend normalizer").str, ""}); return; }
-  if (t == "NFC" || t == "NFD" || t == "NFKC" || t == "NFKD" || t == "Precompiled" || t == "Nmt") {
+  if (t == "Precompiled") {
+    Charsmap m;
+    const Json *c = j.get("precompiled_charsmap");
+    if (c && c->type == Json::Str && !c->str.empty()) {
+      const std::string blob = b64_decode(c->str);
+      if (blob.size() < 4) throw std::runtime_error("tokenizer.json: precompiled_charsmap is truncated");
+      auto u32_at = [&](size_t o) { return (uint32_t)(unsigned char)blob[o] | ((uint32_t)(unsigned char)blob[o + 1] << 8) |
+                                           ((uint32_t)(unsigned char)blob[o + 2] << 16) | ((uint32_t)(unsigned char)blob[o + 3] << 24); };
+      const size_t trie_bytes = u32_at(0);
+      if (trie_bytes % 4 != 0 || 4 + trie_bytes > blob.size()) throw std::runtime_error("tokenizer.json: precompiled_charsmap has a bad trie size");
+      m.trie.resize(trie_bytes / 4);
+      for (size_t k = 0; k < m.trie.size(); ++k) m.trie[k] = u32_at(4 + 4 * k);
+      m.normalized = blob.substr(4 + trie_bytes);
+      for (int ch = 0x20; ch < 0x7F; ++ch) { const char b1 = (char)ch; m.ascii_plain[ch] = m.first_prefix(&b1, 1) < 0; }
+    }                                                        // null / empty charsmap: identity
+    NormStep st{N_PRECOMPILED, "", ""};
+    st.map = (int)maps_.size();
+    maps_.push_back(std::move(m));
+    norm_.push_back(st); return;
+  }
+  if (t == "NFC" || t == "NFD" || t == "NFKC" || t == "NFKD" || t == "Nmt") {
     norm_.push_back({N_UNICODE_ASCII_ONLY, t, ""}); return;
   }
   throw std::runtime_error("tokenizer.json: normalizer \"" + t + "\" is not supported by the C++ host");
@@ -176,6 +365,7 @@ std::string HfTokenizer::normalize(const std::string &in) const {
         s = s.substr(b, e - b); break;
       }
       case N_PREPEND: if (!s.empty()) s = st.a + s; break;
+      case N_PRECOMPILED: s = apply_charsmap(maps_[st.map], s); break;
       case N_UNICODE_ASCII_ONLY:
         for (unsigned char c : s)
           if (c >= 0x80 || (c < 0x20 && c != '\t' && c != '\n' && c != '\r'))

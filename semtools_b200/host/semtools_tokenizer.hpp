@@ -3,9 +3,13 @@
 // add_special_tokens = false), reference call site src/search/mod.rs:69), restated for the subset of
 // components a SentencePiece-style static-embedding model uses:
 //   normalizer     Sequence | Lowercase | Replace (string pattern, or the regex " {2,}") | Strip |
-//                  Prepend | NFC/NFD/NFKC/NFKD/Precompiled (identity on printable ASCII; a line with
-//                  other characters is REFUSED with an error -- the composition tables are not
-//                  restated here; use the Python host for such text)
+//                  Prepend | Precompiled (the SentencePiece charsmap carried by tokenizer.json --
+//                  nmt_nfkc for the XLM-R family the reference's model uses: double-array trie +
+//                  replacement blob, applied grapheme by grapheme exactly as tokenizers'
+//                  normalizers/precompiled.rs does, quirks included; extended grapheme clusters per
+//                  UAX #29 from generated property tables, grapheme_break.inc) |
+//                  NFC/NFD/NFKC/NFKD/Nmt (identity on printable ASCII; a line with other characters
+//                  is REFUSED with an error -- those composition tables are not restated here)
 //   pre_tokenizer  Metaspace (replacement, prepend_scheme always|first|never, split) | WhitespaceSplit |
 //                  Sequence of those
 //   model          Unigram (vocab [[token, score]...], unk_id, byte_fallback = false): Viterbi over a
@@ -33,6 +37,8 @@ class HfTokenizer : public Tokenizer {
   std::vector<uint32_t> encode(const std::string &text) const override;
   // ids exactly as tokenizer.encode(text, add_special_tokens = false).ids
   std::vector<uint32_t> encode_raw(const std::string &text) const;
+  // the normalizer alone (tokenizer.normalizer.normalize_str)
+  std::string normalize_str(const std::string &text) const { return normalize(text); }
   size_t median_token_length() const override { return median_len_; }
   size_t vocab_size() const { return tokens_.size(); }
   bool has_unk() const { return has_unk_; }
@@ -41,7 +47,17 @@ class HfTokenizer : public Tokenizer {
   uint64_t fingerprint() const { return file_hash_; }
 
  private:
-  struct NormStep { int kind; std::string a, b; bool left = true, right = true; };
+  struct NormStep { int kind; std::string a, b; bool left = true, right = true; int map = -1; };
+  // SentencePiece precompiled charsmap: darts-clone double array + NUL-separated replacement strings
+  struct Charsmap {
+    std::vector<uint32_t> trie;
+    std::string normalized;
+    // offset of the replacement of the SHORTEST key that is a prefix of p[0..n), or -1
+    // (spm_precompiled: common_prefix_search(...)[0])
+    int64_t first_prefix(const char *p, size_t n) const;
+    bool ascii_plain[128] = {};   // printable ASCII bytes the map leaves alone when they stand alone
+  };
+  std::string apply_charsmap(const Charsmap &m, const std::string &s) const;
   struct PreStep { int kind; std::string replacement; int prepend = 0; bool split = true; };
   std::string normalize(const std::string &text) const;
   void pre_tokenize(const std::string &normalized, std::vector<std::string> &pieces) const;
@@ -50,6 +66,7 @@ class HfTokenizer : public Tokenizer {
   void add_pre(const Json &j);
 
   std::vector<NormStep> norm_;
+  std::vector<Charsmap> maps_;
   std::vector<PreStep> pre_;
   std::vector<std::string> tokens_;
   std::vector<double> scores_;
@@ -67,5 +84,10 @@ class HfTokenizer : public Tokenizer {
   uint32_t root_[256];
   std::vector<int32_t> terminal_;
 };
+
+// Extended grapheme clusters (UAX #29, GB1-GB13 including GB9c and GB11) of a UTF-8 string: the END offset
+// of every cluster, in order (what unicode_segmentation::graphemes(true) yields).  Bytes that are not valid
+// UTF-8 stand alone.
+std::vector<size_t> grapheme_ends(const std::string &s);
 
 }  // namespace semtools

@@ -376,3 +376,120 @@ def test_cpp_tokenizer_rejects_what_it_does_not_implement(binary, tmp_path):
     p = tmp_path / "wp.json"; tk.save(str(p))
     r = subprocess.run([binary, "--encode", str(p)], input=b"a\n", capture_output=True)
     assert r.returncode != 0 and b"not supported by the C++ host" in r.stderr
+
+
+def _u(s):
+    return s.encode("ascii").decode("unicode_escape")
+
+
+def test_cpp_grapheme_clusters_match_uax29(binary):
+    """HF tokenizers' Precompiled normalizer walks `graphemes(true)`; the C++ host cuts extended grapheme
+    clusters with generated Unicode property tables (host/grapheme_break.inc).  Checked against the `regex`
+    module's \\X on random strings over every break class (CR/LF/Control, Extend, ZWJ, regional indicators,
+    Prepend, SpacingMark, Hangul jamo and syllables, emoji ZWJ sequences, Indic conjuncts)."""
+    regex = pytest.importorskip("regex")
+    import random
+    rnd = random.Random(5)
+    cands = [0x61, 0x41, 0x20, 0x0D, 0x09, 0x301, 0x302, 0x308, 0x200D, 0x200C, 0x1F1E6, 0x1F1FA, 0x1F1F8, 0x600, 0x110BD, 0x903, 0x93E, 0x915, 0x937,
+             0x94D, 0x1100, 0x1161, 0x11A8, 0xAC00, 0xAC01, 0x1F468, 0x1F469, 0x1F466, 0x2764, 0xFE0F, 0x1F3FB, 0x1F600, 0xE0020, 0xE007F, 0x0E01, 0x0E33,
+             0x0E48, 0x0BA8, 0x0BBF, 0x0D15, 0x0D4D, 0x0D30, 0x0A95, 0x0ACD, 0x0AB7, 0xFF21, 0x3042, 0x4E2D, 0x00E9, 0x1E9E, 0xFB01, 0x2122, 0x00AD, 0x061C,
+             0x180E, 0x1F9D1, 0x1F91D, 0x2640, 0x1F3F4, 0xE0067, 0x0C15, 0x0C4D, 0x0C37, 0x1B05, 0x1B44, 0x11F02, 0x0D4E, 0x1193F, 0x11941, 0xA9, 0x3030]
+    lines = ["".join(chr(rnd.choice(cands)) for _ in range(rnd.randint(1, 12))) for _ in range(3000)]
+    lines += [_u(x) for x in ("e\\u0301\\u0302", "\\U0001f468\\u200d\\U0001f469\\u200d\\U0001f467\\u200d\\U0001f466", "\\U0001f1fa\\U0001f1f8\\U0001f1e6",
+                              "\\u0915\\u094d\\u0937", "\\u0915\\u094d\\u200d\\u0937", "\\u1100\\u1161\\u11a8", "\\r\\rx", "a\\rb")]
+    lines = [l for l in lines if "\n" not in l and not l.endswith("\r")]       # rust_lines strips a final \r
+    r = subprocess.run([binary, "--graphemes"], input=("\n".join(lines) + "\n").encode("utf-8"), capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    got = r.stdout.decode().split("\n")[:-1]
+    assert len(got) == len(lines)
+    for line, g in zip(lines, got):
+        assert [int(x) for x in g.split()] == [len(x.encode("utf-8")) for x in regex.findall(r"\X", line)], [hex(ord(c)) for c in line]
+
+
+@pytest.fixture(scope="module")
+def nmt_nfkc_tokenizer(tmp_path_factory):
+    """A tokenizer.json of the XLM-R family shape (what minishlab/potion-multilingual-128M carries): Unigram +
+    Metaspace + Sequence[Precompiled(nmt_nfkc charsmap), Replace(" {2,}")].  The charsmap is the REAL one:
+    sentencepiece writes it into any model trained with normalization_rule_name=nmt_nfkc."""
+    spm = pytest.importorskip("sentencepiece")
+    pb = pytest.importorskip("sentencepiece.sentencepiece_model_pb2")
+    import random
+    from tokenizers import Regex, Tokenizer
+    from tokenizers.models import Unigram
+    from tokenizers.normalizers import Precompiled, Replace, Sequence
+    from tokenizers.pre_tokenizers import Metaspace
+    d = tmp_path_factory.mktemp("spm")
+    rnd = random.Random(3)
+    words = _u("the quick brown fox na\\u00efve caf\\u00e9 stra\\u00dfe \\u00fcber \\u043f\\u0440\\u0438\\u0432\\u0435\\u0442 \\u043c\\u0438\\u0440 \\u0451\\u0436\\u0438\\u043a "
+               "\\u03ba\\u03b1\\u03bb\\u03b7\\u03bc\\u03ad\\u03c1\\u03b1 \\u1f48\\u03b4\\u03c5\\u03c3\\u03c3\\u03b5\\u03cd\\u03c2 \\u3053\\u3093\\u306b\\u3061\\u306f \\u4e16\\u754c "
+               "\\uff76\\uff9e\\uff77\\uff9e \\uff83\\uff7d\\uff84 \\u30d1\\u30fc\\u30c6\\u30a3\\u30fc \\u4f60\\u597d \\u6e2c\\u8a66 \\uc548\\ub155\\ud558\\uc138\\uc694 \\ud55c\\uad6d\\uc5b4 "
+               "\\u0928\\u092e\\u0938\\u094d\\u0924\\u0947 \\u0915\\u094d\\u0937\\u0924\\u094d\\u0930\\u093f\\u092f \\u0645\\u0631\\u062d\\u0628\\u0627 \\u0634\\u0643\\u0631\\u0627 "
+               "\\u0e2a\\u0e27\\u0e31\\u0e2a\\u0e14\\u0e35 \\u0e19\\u0e49\\u0e33 \\uff21\\uff22\\uff23 \\uff11\\uff12\\uff13 \\ufb01ne \\ufb02ow \\u2122 \\u00b2 \\u2462 \\u2167 \\u338f").split()
+    lines = [" ".join(rnd.choice(words) for _ in range(rnd.randint(3, 12))) for _ in range(4000)]
+    (d / "corpus.txt").write_text("\n".join(lines) + "\n", encoding="utf-8")
+    spm.SentencePieceTrainer.train(input=str(d / "corpus.txt"), model_prefix=str(d / "m"), vocab_size=400, model_type="unigram",
+                                   normalization_rule_name="nmt_nfkc", character_coverage=1.0, hard_vocab_limit=False, minloglevel=2)
+    mp = pb.ModelProto()
+    mp.ParseFromString((d / "m.model").read_bytes())
+    charsmap = mp.normalizer_spec.precompiled_charsmap
+    assert len(charsmap) > 100_000                                            # the nmt_nfkc table, not an empty one
+    tk = Tokenizer(Unigram([(p.piece, p.score) for p in mp.pieces], unk_id=next(i for i, p in enumerate(mp.pieces) if p.type == 2), byte_fallback=False))
+    tk.normalizer = Sequence([Precompiled(charsmap), Replace(Regex(" {2,}"), " ")])
+    tk.pre_tokenizer = Metaspace(replacement=_u("\\u2581"), prepend_scheme="always")
+    tk.save(str(d / "tokenizer.json"))
+    return tk, str(d / "tokenizer.json"), lines
+
+
+def test_cpp_precompiled_normalizer_and_ids_match_hf_tokenizers(binary, nmt_nfkc_tokenizer):
+    """The C++ host applies the SentencePiece charsmap (double-array trie, grapheme by grapheme, the crate's
+    quirks included) and then tokenises: normalizer output AND token ids must equal HF tokenizers' on
+    multilingual text -- composed / decomposed accents, full- and half-width forms, ligatures, compatibility
+    symbols, zero-width and control characters, NBSP / ideographic space, emoji sequences, Indic conjuncts,
+    Hangul jamo, NUL."""
+    import random
+    tk, path, corpus_lines = nmt_nfkc_tokenizer
+    rnd = random.Random(11)
+    extra = ["e\\u0301\\u0302 cafe\\u0301", "\\ufb01\\ufb02 \\uff21\\uff22\\uff23\\uff11\\uff12\\uff13", "\\uff76\\uff9e \\uff8a\\uff9f \\uff73\\uff9e", "\\u3000ideographic\\u3000space",
+             "a\\u00a0b\\u2009c\\u200bd\\u200ce", "tab\\there", "ctl\\x01\\x02x", "\\u00bd \\u00bc \\u2460 \\u3231 \\u337b \\u2103 \\u212b \\u2126",
+             "\\U0001f1fa\\U0001f1f8\\U0001f1e6 \\U0001f468\\u200d\\U0001f469\\u200d\\U0001f467\\u200d\\U0001f466 \\u2764\\ufe0f \\U0001f44d\\U0001f3fd",
+             "\\u0915\\u094d\\u0937 \\u0924\\u094d\\u0930 \\u091c\\u094d\\u091e", "\\uac01 \\u1100 \\u1161 \\u11a8 \\u1100\\u1161\\u11a8", "\\u01c4 \\u01c5 \\u01c6 \\u01c8", "\\u017f \\u1e9b \\ufb05",
+             "e\\u0301\\u0301\\u0301\\u0301", "a\\u0300\\u0301\\u0302\\u0303b", "x\\rz", "  multiple   spaces  ", "\\u2460\\u2461 \\u00b2\\u00b3 \\u2122", "\\uff21\\u0301", "\\uff76\\uff9e\\uff76",
+             "\\ufdfa \\ufdf2", "\\u1e9b\\u0323", "\\u0958 \\u0915\\u093c", "\\u314f \\u3131 \\u3132", "\\ufb2c \\ufb49", "\\U0001d400\\U0001d401\\U0001d402 \\U0001d7d8\\U0001d7d9", "\\u3300 \\u3301",
+             "\\u0300\\u0301 \\u0343 \\u0344", "\\u00ad soft\\u00adhyphen", "\\ufeff bom", "\\u2028ls\\u2029", "\\u0085nel", "\\u212b \\u00c5", "\\u0e33 \\u0eb3", "\\u0f77 \\u0f79",
+             "\\u2026  \\u2025 \\u2024", "\\ufe30 \\ufe50 \\ufe52", "\\u0000nul", "a\\u0000b", ""]
+    tests = corpus_lines[:300] + [_u(x) for x in extra]
+    cps = [0x65, 0x301, 0x302, 0xFB01, 0xFF21, 0xFF9E, 0xFF76, 0x3000, 0xA0, 0x200B, 0x200D, 0x1F468, 0x915, 0x94D, 0x937, 0x1100, 0x1161, 0x11A8, 0xAC00, 0x20, 0x20,
+           0x61, 0x2122, 0xB2, 0x1E9B, 0x323, 0x9, 0x1, 0x7F, 0xAD, 0x2460, 0x3300, 0x1D400]
+    tests += ["".join(chr(rnd.choice(cps)) for _ in range(rnd.randint(1, 14))) for _ in range(600)]
+    tests = [t for t in tests if "\n" not in t and not t.endswith("\r")]
+    blob = ("\n".join(tests) + "\n").encode("utf-8")
+    r = subprocess.run([binary, "--normalize", path], input=blob, capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    got = r.stdout.decode("utf-8").split("\n")[:-1]
+    assert len(got) == len(tests)
+    changed = 0
+    for t, g in zip(tests, got):
+        want = tk.normalizer.normalize_str(t)
+        assert g == want, ([hex(ord(c)) for c in t], [hex(ord(c)) for c in want], [hex(ord(c)) for c in g])
+        changed += want != t
+    assert changed > 300                                                       # the charsmap really was exercised
+    r = subprocess.run([binary, "--encode", path], input=blob, capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    out = r.stdout.decode().split("\n")[1:-1]
+    assert len(out) == len(tests)
+    for t, g in zip(tests, out):
+        assert [int(x) for x in g.split("|")[0].split()] == tk.encode(t, add_special_tokens=False).ids, [hex(ord(c)) for c in t]
+
+
+def test_cpp_precompiled_with_an_empty_charsmap_is_the_identity(binary, tmp_path):
+    from tokenizers import Tokenizer, models, pre_tokenizers
+    tk = Tokenizer(models.Unigram([("<unk>", 0.0), (_u("\\u2581"), -2.0), ("a", -3.0), (_u("\\u00e9"), -3.5)], unk_id=0, byte_fallback=False))
+    tk.pre_tokenizer = pre_tokenizers.Metaspace(replacement=_u("\\u2581"), prepend_scheme="always")
+    p = tmp_path / "t.json"
+    tk.save(str(p))
+    j = json.loads(p.read_text(encoding="utf-8"))
+    j["normalizer"] = {"type": "Precompiled", "precompiled_charsmap": None}     # what some exported tokenizer.json files carry
+    p.write_text(json.dumps(j), encoding="utf-8")
+    r = subprocess.run([binary, "--encode", str(p)], input=_u("a\\u00e9 a\n").encode("utf-8"), capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    assert r.stdout.decode().splitlines()[1].split("|")[0].split() == ["1", "2", "3", "1", "2"]
