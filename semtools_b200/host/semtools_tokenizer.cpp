@@ -325,6 +325,22 @@ HfTokenizer::HfTokenizer(const std::string &path) {
   for (size_t i = 0; i < flat.size(); ++i) { child_byte_[i] = (uint8_t)(flat[i].first & 0xff); child_node_[i] = flat[i].second; }
   for (int b = 0; b < 256; ++b) root_[b] = UINT32_MAX;
   for (uint32_t i = first_child_[0]; i < first_child_[1]; ++i) root_[child_byte_[i]] = child_node_[i];
+  // added tokens (added_vocabulary.rs): matched before the model; normalized ones are matched in normalised text
+  if (const Json *at = j.get("added_tokens"); at && at->type == Json::Arr) {
+    for (const auto &e : at->arr) {
+      Added a;
+      a.content = need(e, "content", "added token").str;
+      a.id = (uint32_t)need(e, "id", "added token").num;
+      bool normalized = false;
+      if (const Json *v = e.get("lstrip")) a.lstrip = v->b;
+      if (const Json *v = e.get("rstrip")) a.rstrip = v->b;
+      if (const Json *v = e.get("normalized")) normalized = v->b;
+      if (const Json *v = e.get("single_word"); v && v->b) throw std::runtime_error("tokenizer.json: added token \"" + a.content + "\" has single_word = true, which the C++ host does not support");
+      if (a.content.empty()) continue;
+      if (normalized) { a.content = normalize(a.content); if (!a.content.empty()) added_norm_.push_back(a); }
+      else added_raw_.push_back(a);
+    }
+  }
   // median token length in BYTES over the vocabulary (model2vec: `tk.len()` of every vocab key)
   std::vector<size_t> lens;
   lens.reserve(tokens_.size());
@@ -376,10 +392,42 @@ std::string HfTokenizer::normalize(const std::string &in) const {
   return s;
 }
 
-void HfTokenizer::pre_tokenize(const std::string &normalized, std::vector<std::string> &pieces) const {
+// AddedVocabulary::find_matches: leftmost-longest matches of the set's contents, lstrip / rstrip widening
+// the match over neighbouring whitespace; the text between matches stays plain (id -1)
+void HfTokenizer::split_added(const std::string &s, const std::vector<Added> &set, std::vector<Seg> &out) const {
+  out.clear();
+  if (set.empty() || s.empty()) { out.push_back({-1, s, 0}); return; }
+  size_t pos = 0, start_offset = 0;
+  while (pos < s.size()) {
+    const Added *best = nullptr;
+    for (const auto &a : set)
+      if (a.content.size() <= s.size() - pos && (!best || a.content.size() > best->content.size()) && s.compare(pos, a.content.size(), a.content) == 0) best = &a;
+    if (!best) { ++pos; continue; }
+    size_t start = pos, stop = pos + best->content.size(), l;
+    const size_t mat_end = stop;
+    if (best->lstrip) {                                      // the run of whitespace that ends at `start`
+      size_t k = start;
+      for (;;) {
+        if (k == 0) break;
+        size_t c = k - 1;
+        while (c > 0 && ((unsigned char)s[c] & 0xC0) == 0x80) --c;
+        if (is_space_at(s, c, &l) && c + l == k) k = c; else break;
+      }
+      start = std::max(k, start_offset);
+    }
+    if (best->rstrip) while (stop < s.size() && is_space_at(s, stop, &l)) stop += l;
+    if (start_offset < start) out.push_back({-1, s.substr(start_offset, start - start_offset), start_offset});
+    out.push_back({(int64_t)best->id, s.substr(start, stop - start), start});
+    start_offset = stop;
+    pos = mat_end;
+  }
+  if (start_offset < s.size()) out.push_back({-1, s.substr(start_offset), start_offset});
+}
+
+void HfTokenizer::pre_tokenize(const std::string &normalized, std::vector<std::string> &pieces, bool at_origin_in) const {
   pieces.clear();
   pieces.push_back(normalized);
-  bool first_step = true;
+  bool first_step = at_origin_in;
   for (const auto &p : pre_) {
     std::vector<std::string> next;
     size_t piece_no = 0;
@@ -476,10 +524,20 @@ void HfTokenizer::unigram(const std::string &s, std::vector<uint32_t> &out) cons
 std::vector<uint32_t> HfTokenizer::encode_raw(const std::string &text) const {
   std::vector<std::string> pieces;
   std::vector<uint32_t> ids;
-  const std::string normalized = normalize(text);
-  if (normalized.empty()) return ids;       // AddedVocabulary::extract_and_normalize yields no split for an empty string
-  pre_tokenize(normalized, pieces);
-  for (const auto &p : pieces) unigram(p, ids);
+  std::vector<Seg> raw, sub;
+  split_added(text, added_raw_, raw);                       // 1. non-normalised added tokens, on the text as given
+  for (const auto &seg : raw) {
+    if (seg.id >= 0) { ids.push_back((uint32_t)seg.id); continue; }
+    const std::string normalized = normalize(seg.text);     // 2. normalise what is left, then the normalised added tokens
+    if (normalized.empty()) continue;                       // an empty split yields no token
+    split_added(normalized, added_norm_, sub);
+    for (const auto &part : sub) {
+      if (part.id >= 0) { ids.push_back((uint32_t)part.id); continue; }
+      if (part.text.empty()) continue;
+      pre_tokenize(part.text, pieces, seg.start == 0 && part.start == 0);   // Metaspace "first": only the split that starts the input
+      for (const auto &p : pieces) unigram(p, ids);
+    }
+  }
   return ids;
 }
 

@@ -12,6 +12,10 @@
 //                  is REFUSED with an error -- those composition tables are not restated here)
 //   pre_tokenizer  Metaspace (replacement, prepend_scheme always|first|never, split) | WhitespaceSplit |
 //                  Sequence of those
+//   added_tokens   split out of the text before the model sees it, as AddedVocabulary::extract_and_normalize does:
+//                  normalized = false tokens on the raw text, normalized = true tokens on the normalised
+//                  pieces; leftmost-longest, lstrip / rstrip honoured; single_word = true is refused.
+//                  (A document line that contains "<s>" or "<mask>" literally gets that token's id.)
 //   model          Unigram (vocab [[token, score]...], unk_id, byte_fallback = false): Viterbi over a
 //                  byte trie exactly as tokenizers' `encode_optimized` (f64 scores, strict > on ties,
 //                  unknown characters at min_score - 10, consecutive unknowns fused into one token)
@@ -59,14 +63,18 @@ class HfTokenizer : public Tokenizer {
   };
   std::string apply_charsmap(const Charsmap &m, const std::string &s) const;
   struct PreStep { int kind; std::string replacement; int prepend = 0; bool split = true; };
+  struct Added { std::string content; uint32_t id = 0; bool lstrip = false, rstrip = false; };
+  struct Seg { int64_t id; std::string text; size_t start; };          // id < 0: plain text
+  void split_added(const std::string &s, const std::vector<Added> &set, std::vector<Seg> &out) const;
   std::string normalize(const std::string &text) const;
-  void pre_tokenize(const std::string &normalized, std::vector<std::string> &pieces) const;
+  void pre_tokenize(const std::string &normalized, std::vector<std::string> &pieces, bool at_origin = true) const;
   void unigram(const std::string &piece, std::vector<uint32_t> &out) const;
   void add_norm(const Json &j);
   void add_pre(const Json &j);
 
   std::vector<NormStep> norm_;
   std::vector<Charsmap> maps_;
+  std::vector<Added> added_raw_, added_norm_;                          // normalized = false / true
   std::vector<PreStep> pre_;
   std::vector<std::string> tokens_;
   std::vector<double> scores_;

@@ -493,3 +493,48 @@ def test_cpp_precompiled_with_an_empty_charsmap_is_the_identity(binary, tmp_path
     r = subprocess.run([binary, "--encode", str(p)], input=_u("a\\u00e9 a\n").encode("utf-8"), capture_output=True)
     assert r.returncode == 0, r.stderr.decode()
     assert r.stdout.decode().splitlines()[1].split("|")[0].split() == ["1", "2", "3", "1", "2"]
+
+
+@pytest.mark.parametrize("scheme", ["always", "first"])
+def test_cpp_tokenizer_splits_added_tokens_like_hf(binary, tmp_path, scheme):
+    """AddedVocabulary::extract_and_normalize: special / added tokens that occur literally in a line ("<s>" in an
+    HTML document, "<mask>") become their ids before the model runs -- non-normalised ones matched on the raw
+    text, normalised ones on the normalised text, leftmost-longest, lstrip / rstrip widening the match."""
+    import random
+    from tokenizers import AddedToken, Regex, Tokenizer, models, normalizers, pre_tokenizers
+    rnd = random.Random(7)
+    sp = _u("\\u2581")
+    alphabet = list("abcdefghijklmnopqrstuvwxyz<>/") + [sp]
+    vocab, seen = [("<unk>", 0.0)], {"<unk>"}
+    for ch in alphabet:
+        vocab.append((ch, -rnd.uniform(4, 9))); seen.add(ch)
+    while len(vocab) < 600:
+        t = (sp if rnd.random() < 0.35 else "") + "".join(rnd.choice(alphabet[:26]) for _ in range(rnd.choice([2, 3, 4, 5])))
+        if t not in seen:
+            seen.add(t); vocab.append((t, -rnd.uniform(2, 14)))
+    tk = Tokenizer(models.Unigram(vocab, unk_id=0, byte_fallback=False))
+    tk.normalizer = normalizers.Sequence([normalizers.Lowercase(), normalizers.Replace(Regex(" {2,}"), " ")])
+    tk.pre_tokenizer = pre_tokenizers.Metaspace(replacement=sp, prepend_scheme=scheme, split=True)
+    tk.add_special_tokens(["<s>", "</s>", "<pad>", AddedToken("<mask>", lstrip=True, special=True)])
+    tk.add_tokens([AddedToken("Foo Bar", normalized=True), AddedToken("<x>", lstrip=True, rstrip=True, normalized=False), AddedToken("<s>>", normalized=False)])
+    path = tmp_path / "added.json"
+    tk.save(str(path))
+    pool = ["<s>", "</s>", "<pad>", "<mask>", "foo bar", "FOO BAR", "Foo  Bar", "<x>", "<s>>", "<", ">", "abc", "the", " ", "  ", "x", "<unk>", "<S>", "</s", "s>"]
+    lines = ["<s>hello</s>", "a <mask> b", "a  <mask>  b", "<x>", " <x> ", "a<x>b", "a  <x>   b", "foo bar", "xfoo bary", "<s>><s>", "<pad><pad>", "", "<s>", " <s>",
+             "<s> ", "<mask><mask>", "a <mask>", "<mask> a"]
+    lines += ["".join(rnd.choice(pool) for _ in range(rnd.randint(1, 8))) for _ in range(400)]
+    r = subprocess.run([binary, "--encode", str(path)], input=("\n".join(lines) + "\n").encode("utf-8"), capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    out = r.stdout.decode().split("\n")[1:-1]
+    assert len(out) == len(lines)
+    hit = 0
+    for line, g in zip(lines, out):
+        want = tk.encode(line, add_special_tokens=False).ids
+        assert [int(x) for x in g.split("|")[0].split()] == want, (scheme, line)
+        hit += any(i >= len(vocab) for i in want)
+    assert hit > 200                                                           # added-token ids really occur
+    j = json.loads(path.read_text(encoding="utf-8"))
+    j["added_tokens"][0]["single_word"] = True                                  # not restated: refused, not mis-tokenised
+    path.write_text(json.dumps(j), encoding="utf-8")
+    r = subprocess.run([binary, "--encode", str(path)], input=b"a\n", capture_output=True)
+    assert r.returncode != 0 and b"single_word" in r.stderr
