@@ -1,4 +1,9 @@
 #include "semtools_host.hpp"
+#include "semtools_store.hpp"   // Json
+
+#include <cstring>
+#include <fstream>
+#include <iterator>
 
 #include <algorithm>
 #include <charconv>
@@ -282,9 +287,88 @@ Searcher::~Searcher() {
   stb_ctx_destroy(ctx_);
 }
 
-void Searcher::load_table(const float *E, uint64_t V, bool normalize) {
+void Searcher::load_table(const float *E, uint64_t V, bool normalize, const float *weights, uint64_t n_weights,
+                          const uint32_t *mapping, uint64_t n_mapping) {
   if (table_) { stb_table_destroy(table_); table_ = nullptr; }
-  check(stb_table_load(ctx_, E, V, STB_DIM, nullptr, 0, nullptr, 0, normalize ? 1 : 0, &table_));
+  check(stb_table_load(ctx_, E, V, STB_DIM, n_weights ? weights : nullptr, n_weights, n_mapping ? mapping : nullptr, n_mapping,
+                       normalize ? 1 : 0, &table_));
+}
+
+// ---- model directory (safetensors) ---------------------------------------------------------------
+namespace {
+float half_to_float(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+  uint32_t exp = (h >> 10) & 0x1Fu, man = h & 0x3FFu, bits;
+  if (exp == 0) {
+    if (man == 0) bits = sign;
+    else { int e = -1; do { ++e; man <<= 1; } while (!(man & 0x400u)); bits = sign | ((uint32_t)(127 - 15 - e) << 23) | ((man & 0x3FFu) << 13); }
+  } else if (exp == 31) bits = sign | 0x7F800000u | (man << 13);
+  else bits = sign | ((exp + 112u) << 23) | (man << 13);
+  float f; memcpy(&f, &bits, 4); return f;
+}
+std::string read_all(const std::string &p) {
+  std::ifstream f(p, std::ios::binary);
+  if (!f) throw std::runtime_error("cannot read " + p);
+  return std::string((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+}
+struct StTensor { std::string dtype; std::vector<uint64_t> shape; const unsigned char *data = nullptr; uint64_t bytes = 0; uint64_t count = 0; };
+bool st_find(const Json &hdr, const std::string &blob, uint64_t base, const char *name, StTensor &t) {
+  const Json *e = hdr.get(name);
+  if (!e || e->type != Json::Obj) return false;
+  const Json *dt = e->get("dtype"), *sh = e->get("shape"), *off = e->get("data_offsets");
+  if (!dt || !sh || !off || off->arr.size() != 2) throw std::runtime_error(std::string("model.safetensors: malformed entry for ") + name);
+  t.dtype = dt->str;
+  t.count = 1;
+  for (const auto &d : sh->arr) { t.shape.push_back((uint64_t)d.num); t.count *= (uint64_t)d.num; }
+  const uint64_t a = (uint64_t)off->arr[0].num, b = (uint64_t)off->arr[1].num;
+  if (b < a || base + b > blob.size()) throw std::runtime_error(std::string("model.safetensors: data of ") + name + " lies outside the file");
+  t.data = reinterpret_cast<const unsigned char *>(blob.data()) + base + a;
+  t.bytes = b - a;
+  return true;
+}
+template <class T> T load_le(const unsigned char *p) { T v; memcpy(&v, p, sizeof(T)); return v; }
+void to_f32(const StTensor &t, const char *name, std::vector<float> &out) {
+  out.resize(t.count);
+  const uint64_t w = t.dtype == "F32" ? 4 : t.dtype == "F16" ? 2 : t.dtype == "I8" ? 1 : t.dtype == "F64" ? 8 : 0;
+  if (!w || t.bytes != t.count * w) throw std::runtime_error(std::string("model.safetensors: ") + name + " has dtype " + t.dtype + " / a size the host does not read");
+  for (uint64_t i = 0; i < t.count; ++i) {
+    const unsigned char *p = t.data + i * w;
+    out[i] = w == 4 ? load_le<float>(p) : w == 2 ? half_to_float(load_le<uint16_t>(p)) : w == 1 ? (float)(int8_t)p[0] : (float)load_le<double>(p);
+  }
+}
+}  // namespace
+
+ModelDir load_model_dir(const std::string &dir) {
+  ModelDir m;
+  m.tokenizer_path = dir + "/tokenizer.json";
+  const std::string tok = read_all(m.tokenizer_path);
+  const Json cfg = Json::parse(read_all(dir + "/config.json"));
+  if (const Json *n = cfg.get("normalize"); n && n->type == Json::Bool) m.normalize = n->b;
+  const std::string blob = read_all(dir + "/model.safetensors");
+  if (blob.size() < 8) throw std::runtime_error("model.safetensors: truncated");
+  const uint64_t hlen = load_le<uint64_t>(reinterpret_cast<const unsigned char *>(blob.data()));
+  if (8 + hlen > blob.size()) throw std::runtime_error("model.safetensors: header longer than the file");
+  const Json hdr = Json::parse(blob.substr(8, hlen));
+  StTensor e, w, mp;
+  if (!st_find(hdr, blob, 8 + hlen, "embeddings", e)) throw std::runtime_error("model.safetensors: no \"embeddings\" tensor");
+  if (e.shape.size() != 2 || e.shape[1] != STB_DIM) throw std::runtime_error("model.safetensors: the embedding table must be V x 256");
+  m.V = e.shape[0];
+  to_f32(e, "embeddings", m.E);
+  if (st_find(hdr, blob, 8 + hlen, "weights", w)) to_f32(w, "weights", m.weights);
+  if (st_find(hdr, blob, 8 + hlen, "mapping", mp)) {
+    const uint64_t width = mp.dtype == "I64" || mp.dtype == "U64" ? 8 : mp.dtype == "I32" || mp.dtype == "U32" ? 4 : 0;
+    if (!width || mp.bytes != mp.count * width) throw std::runtime_error("model.safetensors: mapping has dtype " + mp.dtype + " / a size the host does not read");
+    m.mapping.resize(mp.count);
+    for (uint64_t i = 0; i < mp.count; ++i) m.mapping[i] = width == 8 ? (uint32_t)load_le<uint64_t>(mp.data + 8 * i) : load_le<uint32_t>(mp.data + 4 * i);
+  }
+  // model.py StaticModel.fingerprint: fnv1a64(tokenizer.json bytes) ^ (fnv1a64(first 1 MiB of the f32 table) * golden ratio)
+  const uint64_t ht = stb_fnv1a64(reinterpret_cast<const uint8_t *>(tok.data()), tok.size());
+  const uint64_t he = stb_fnv1a64(reinterpret_cast<const uint8_t *>(m.E.data()), std::min<uint64_t>(m.E.size() * sizeof(float), 1u << 20));
+  char buf[96];
+  snprintf(buf, sizeof(buf), "model2vec:%llux%d:n%d:%016llx", (unsigned long long)m.V, STB_DIM, m.normalize ? 1 : 0,
+           (unsigned long long)(ht ^ (he * 0x9E3779B97F4A7C15ull)));
+  m.fingerprint = buf;
+  return m;
 }
 
 uint64_t Searcher::rows() const {

@@ -117,7 +117,7 @@ static int selftest() {
 }
 
 int main(int argc, char **argv) {
-  std::string vocab, tokenizer_json, table, query;
+  std::string vocab, tokenizer_json, table, model_dir, query;
   std::vector<std::string> files;
   SearchConfig cfg;
   bool json = false, have_query = false;
@@ -174,6 +174,16 @@ int main(int argc, char **argv) {
       }
       return 0;
     }
+    if (a == "--model-info") {                     // test hook: what load_model_dir read (no GPU needed)
+      ModelDir m;
+      try { m = load_model_dir(next()); } catch (const std::exception &e) { fprintf(stderr, "Error: %s\n", e.what()); return 1; }
+      auto h = [](const void *p, size_t n) { return (unsigned long long)stb_fnv1a64(reinterpret_cast<const uint8_t *>(p), n); };
+      printf("{\"V\": %llu, \"normalize\": %s, \"n_weights\": %zu, \"n_mapping\": %zu, \"fingerprint\": \"%s\", \"table_fnv\": \"%016llx\", "
+             "\"weights_fnv\": \"%016llx\", \"mapping_fnv\": \"%016llx\"}\n",
+             (unsigned long long)m.V, m.normalize ? "true" : "false", m.weights.size(), m.mapping.size(), m.fingerprint.c_str(),
+             h(m.E.data(), m.E.size() * 4), h(m.weights.data(), m.weights.size() * 4), h(m.mapping.data(), m.mapping.size() * 4));
+      return 0;
+    }
     if (a == "--lines") {                          // test hook: stdin -> rust_lines -> one JSON string per line
       std::string in;
       char buf[65536];
@@ -203,6 +213,7 @@ int main(int argc, char **argv) {
     else if (a == "--vocab") vocab = next();
     else if (a == "--tokenizer") tokenizer_json = next();
     else if (a == "--table") table = next();
+    else if (a == "--model") model_dir = next();
     else if (a == "-n" || a == "--n-lines" || a == "--context") cfg.n_lines = std::stoul(next());
     else if (a == "--top-k") cfg.top_k = std::stoul(next());
     else if (a == "-m" || a == "--max-distance" || a == "--threshold") cfg.max_distance = std::stod(next());
@@ -212,8 +223,11 @@ int main(int argc, char **argv) {
     else if (!have_query) { query = a; have_query = true; }
     else files.push_back(a);
   }
-  if (!have_query || (vocab.empty() == tokenizer_json.empty()) || table.empty()) {
-    fprintf(stderr, "usage: semtools_b200_search (--tokenizer tokenizer.json | --vocab V) --table T QUERY [FILES...] [-n N] [--top-k K] [-m D] [-i] [-j] [-w WORKSPACE]\n"
+  if (!model_dir.empty() && vocab.empty() && tokenizer_json.empty() && table.empty()) tokenizer_json = model_dir + "/tokenizer.json";
+  else if (!model_dir.empty()) { fprintf(stderr, "Error: --model replaces --tokenizer / --vocab / --table\n"); return 2; }
+  if (!have_query || (vocab.empty() == tokenizer_json.empty()) || (table.empty() && model_dir.empty())) {
+    fprintf(stderr, "usage: semtools_b200_search (--model DIR | (--tokenizer tokenizer.json | --vocab V) --table T) QUERY [FILES...] [-n N] [--top-k K] [-m D] [-i] [-j] [-w WORKSPACE]\n"
+                    "  --model:     a local model2vec directory (tokenizer.json, model.safetensors, config.json), as StaticModel::from_pretrained reads it\n"
                     "  --tokenizer: the model's HF tokenizer.json (Unigram + Metaspace subset, see semtools_tokenizer.hpp)\n"
                     "  --vocab:     whitespace WordLevel vocabulary, one token per line (synthetic models)\n");
     return 2;
@@ -236,13 +250,24 @@ int main(int argc, char **argv) {
     if (!tokenizer_json.empty()) tok_owner.reset(new HfTokenizer(tokenizer_json));
     else tok_owner.reset(new WordLevelTokenizer(vocab));
     const Tokenizer &tok = *tok_owner;
-    std::ifstream tf(table, std::ios::binary);
-    std::vector<char> raw((std::istreambuf_iterator<char>(tf)), std::istreambuf_iterator<char>());
-    if (raw.empty() || raw.size() % (STB_DIM * sizeof(float))) { fprintf(stderr, "Error: bad table file\n"); return 1; }
-    // identity of this host's embedder (WordLevel vocabulary file + table), recorded in the store so its
-    // vectors are never mixed with another host's / model's
+    ModelDir md;
+    std::vector<char> raw;
+    if (!model_dir.empty()) md = load_model_dir(model_dir);
+    else {
+      std::ifstream tf(table, std::ios::binary);
+      raw.assign((std::istreambuf_iterator<char>(tf)), std::istreambuf_iterator<char>());
+      if (raw.empty() || raw.size() % (STB_DIM * sizeof(float))) { fprintf(stderr, "Error: bad table file\n"); return 1; }
+    }
+    const float *tab_E = model_dir.empty() ? reinterpret_cast<const float *>(raw.data()) : md.E.data();
+    const uint64_t tab_V = model_dir.empty() ? raw.size() / (STB_DIM * sizeof(float)) : md.V;
+    const bool tab_norm = model_dir.empty() ? true : md.normalize;
+    auto load = [&](Searcher &s) { s.load_table(tab_E, tab_V, tab_norm, md.weights.data(), md.weights.size(), md.mapping.data(), md.mapping.size()); };
+    // identity of this host's embedder, recorded in the store so its vectors are never mixed with another
+    // host's / model's: a model directory gets the Python host's fingerprint string, the
+    // synthetic forms (vocabulary file / bare tokenizer.json + raw table) their own
     char fp_buf[96];
-    {
+    if (!model_dir.empty()) snprintf(fp_buf, sizeof(fp_buf), "%s", md.fingerprint.c_str());
+    else {
       std::ifstream vf(tokenizer_json.empty() ? vocab : tokenizer_json, std::ios::binary);
       std::vector<char> vraw((std::istreambuf_iterator<char>(vf)), std::istreambuf_iterator<char>());
       const uint64_t hv = stb_fnv1a64(reinterpret_cast<const uint8_t *>(vraw.data()), vraw.size());
@@ -255,7 +280,7 @@ int main(int argc, char **argv) {
     if (in_workspace) {
       // cmds/search.rs:194-241: persisted line embeddings, only new/changed files are embedded
       Searcher s(0);
-      s.load_table(reinterpret_cast<const float *>(raw.data()), raw.size() / (STB_DIM * sizeof(float)), true);
+      load(s);
       auto ranked = search_with_workspace(
           files, s.encode_single(query, tok),
           [&](const std::vector<std::string> &lines) { return s.embed_lines(lines, tok, cfg.ignore_case); }, cfg, workspace_name,
@@ -270,7 +295,7 @@ int main(int argc, char **argv) {
       inputs.emplace_back(f, std::string((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>()));
     }
     Searcher s(0);
-    s.load_table(reinterpret_cast<const float *>(raw.data()), raw.size() / (STB_DIM * sizeof(float)), true);
+    load(s);
     for (const auto &in : inputs) s.add_document(in.first, in.second, tok, cfg.ignore_case);
     auto results = s.search_documents(s.encode_single(query, tok), cfg);
     if (json) printf("%s\n", search_output_json(results).c_str());

@@ -301,6 +301,11 @@ HfTokenizer::HfTokenizer(const std::string &path) {
   }
   if (tokens_.empty()) throw std::runtime_error("tokenizer.json: empty vocabulary");
   if (has_unk_ && unk_id_ >= tokens_.size()) throw std::runtime_error("tokenizer.json: unk_id outside the vocabulary");
+  if (const Json *ut = model.get("unk_token"); ut && ut->type == Json::Str) {      // token_to_id(unk_token): the last id carrying that string
+    for (size_t id = tokens_.size(); id-- > 0;)
+      if (tokens_[id] == ut->str) { drop_unk_ = true; drop_id_ = (uint32_t)id; break; }
+    if (!drop_unk_) throw std::runtime_error("tokenizer.json: unk_token \"" + ut->str + "\" is not in the vocabulary");
+  }
   min_score_ = *std::min_element(scores_.begin(), scores_.end());
   // byte trie; a token that occurs twice keeps the LAST id (tokenizers builds token_to_ids by insertion)
   std::unordered_map<uint64_t, uint32_t> edges;             // (node << 8 | byte) -> child, construction only
@@ -543,7 +548,7 @@ std::vector<uint32_t> HfTokenizer::encode_raw(const std::string &text) const {
 
 std::vector<uint32_t> HfTokenizer::encode(const std::string &text) const {
   std::vector<uint32_t> ids = encode_raw(text);
-  if (has_unk_) ids.erase(std::remove(ids.begin(), ids.end(), unk_id_), ids.end());    // encode_with_args drops unk ids
+  if (drop_unk_) ids.erase(std::remove(ids.begin(), ids.end(), drop_id_), ids.end());  // encode_with_args: ids.retain(|id| id != unk_token_id)
   return ids;
 }
 

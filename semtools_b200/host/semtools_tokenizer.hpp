@@ -37,7 +37,10 @@ namespace semtools {
 class HfTokenizer : public Tokenizer {
  public:
   explicit HfTokenizer(const std::string &tokenizer_json_path);
-  // ids of one line with unknown tokens DROPPED (model2vec's encode_with_args removes unk ids)
+  // ids of one line as encode_with_args prepares them: the id of the model's `unk_token` removed -- when the
+  // model section NAMES one (WordPiece / BPE style "unk_token": "<tok>"; model2vec-rs reads exactly that key,
+  // [UPSTREAM-MEMORY]).  A Unigram section carries `unk_id` instead, so -- as in the Python host and in
+  // model2vec itself -- nothing is dropped and an unknown character pools the unk row.
   std::vector<uint32_t> encode(const std::string &text) const override;
   // ids exactly as tokenizer.encode(text, add_special_tokens = false).ids
   std::vector<uint32_t> encode_raw(const std::string &text) const;
@@ -47,6 +50,7 @@ class HfTokenizer : public Tokenizer {
   size_t vocab_size() const { return tokens_.size(); }
   bool has_unk() const { return has_unk_; }
   uint32_t unk_id() const { return unk_id_; }
+  bool drops_unk() const { return drop_unk_; }
   // fnv1a64 of the file: part of the store's model fingerprint
   uint64_t fingerprint() const { return file_hash_; }
 
@@ -79,8 +83,10 @@ class HfTokenizer : public Tokenizer {
   std::vector<std::string> tokens_;
   std::vector<double> scores_;
   double min_score_ = 0.0;
-  bool has_unk_ = false;
+  bool has_unk_ = false;           // Unigram unk_id: what unknown characters are mapped to
   uint32_t unk_id_ = 0;
+  bool drop_unk_ = false;          // model.unk_token named and found: encode() removes drop_id_
+  uint32_t drop_id_ = 0;
   size_t median_len_ = 1;
   uint64_t file_hash_ = 0;
   // byte trie, flattened after construction: node n's children are child_byte_/child_node_

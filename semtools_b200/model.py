@@ -68,15 +68,21 @@ class StaticModel:
                 mapping = np.ascontiguousarray(st.get_tensor("mapping")).astype(np.uint32).reshape(-1)
         if emb.ndim != 2 or emb.shape[1] != capi.STB_DIM:
             raise ValueError(f"embedding table must be V x {capi.STB_DIM}, got {emb.shape}")
-        return cls(tokenizer, emb, weights, mapping, normalize, median, unk_id, ctx)
+        m = cls(tokenizer, emb, weights, mapping, normalize, median, unk_id, ctx)
+        with open(tok_path, "rb") as f:
+            m._tokenizer_file_hash = capi.fnv1a64(f.read())     # the C++ host hashes the same bytes (load_model_dir)
+        return m
 
     def fingerprint(self) -> str:
         """Identity of the embedder (tokenizer spec + table + pooling flags), recorded in the
         workspace store so vectors of different models / tokenizers never mix silently."""
-        tok = self.tokenizer.to_str().encode("utf-8") if hasattr(self.tokenizer, "to_str") else repr(self.tokenizer).encode()
-        e = np.ascontiguousarray(self.embeddings)
+        ht = getattr(self, "_tokenizer_file_hash", None)
+        if ht is None:                                           # built in memory (tests): hash the serialised spec
+            tok = self.tokenizer.to_str().encode("utf-8") if hasattr(self.tokenizer, "to_str") else repr(self.tokenizer).encode()
+            ht = capi.fnv1a64(tok)
+        e = np.ascontiguousarray(self.embeddings, dtype=np.float32)
         head = e.reshape(-1)[: 262144].tobytes()
-        h = capi.fnv1a64(tok) ^ (capi.fnv1a64(head) * 0x9E3779B97F4A7C15 & 0xFFFFFFFFFFFFFFFF)
+        h = ht ^ (capi.fnv1a64(head) * 0x9E3779B97F4A7C15 & 0xFFFFFFFFFFFFFFFF)
         return f"model2vec:{e.shape[0]}x{e.shape[1]}:n{int(self.normalize)}:{h:016x}"
 
     # -- tokenisation (host) --------------------------------------------------------------------

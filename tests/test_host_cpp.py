@@ -358,12 +358,26 @@ def test_cpp_unigram_tokenizer_matches_hf_tokenizers_id_for_id(binary, tmp_path,
     lens = sorted(len(t.encode("utf-8")) for t in tk.get_vocab(False).keys())
     assert out[0] == f"median_token_length {lens[len(lens) // 2]} vocab {tk.get_vocab_size()}"
     assert len(out) == len(lines) + 1
-    unk = 0
+    saw_unk = 0
     for line, got in zip(lines, out[1:]):
         want = tk.encode(line, add_special_tokens=False).ids
         raw, dropped = got.split("|")
         assert [int(x) for x in raw.split()] == want, (case, line)
-        assert [int(x) for x in dropped.split()] == [i for i in want if i != unk], (case, line)
+        # a Unigram model section names no `unk_token` (it has `unk_id`): encode_with_args drops nothing,
+        # exactly as the Python host (model.py: unk_token_id is None) -- the two hosts share one store
+        assert [int(x) for x in dropped.split()] == want, (case, line)
+        saw_unk += 0 in want
+    assert saw_unk > 20 or ascii_only
+    # a model section that NAMES its unk token: that id is removed (ids.retain(|id| id != unk_token_id))
+    j = json.loads(path.read_text(encoding="utf-8"))
+    j["model"]["unk_token"] = "<unk>"
+    named = tmp_path / "named_unk.json"
+    named.write_text(json.dumps(j), encoding="utf-8")
+    r = subprocess.run([binary, "--encode", str(named)], input=("\n".join(lines) + "\n").encode("utf-8"), capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    for line, got in zip(lines, r.stdout.decode().splitlines()[1:]):
+        want = tk.encode(line, add_special_tokens=False).ids
+        assert [int(x) for x in got.split("|")[1].split()] == [i for i in want if i != 0], (case, line)
     if ascii_only:      # non-ASCII text under NFKC is refused, not silently mis-normalised
         r = subprocess.run([binary, "--encode", str(path)], input="café\n".encode("utf-8"), capture_output=True)
         assert "ERROR" in r.stdout.decode() and "Python host" in r.stdout.decode()
@@ -538,3 +552,45 @@ def test_cpp_tokenizer_splits_added_tokens_like_hf(binary, tmp_path, scheme):
     path.write_text(json.dumps(j), encoding="utf-8")
     r = subprocess.run([binary, "--encode", str(path)], input=b"a\n", capture_output=True)
     assert r.returncode != 0 and b"single_word" in r.stderr
+
+
+@pytest.mark.parametrize("table_dtype", ["F32", "F16", "I8"])
+def test_cpp_model_directory_loader_equals_the_python_loader(binary, tmp_path, table_dtype):
+    """StaticModel::from_pretrained on a local directory (src/cmds/search.rs:123-128): the C++ host reads
+    tokenizer.json + model.safetensors (F32 / F16 / I8 table upcast to f32, optional weights and mapping) +
+    config.json itself.  Tensors, normalize flag and the store fingerprint must equal what the Python host
+    (model.py) loads from the same directory -- the two hosts then share one workspace."""
+    st = pytest.importorskip("safetensors.numpy")
+    from semtools_b200 import capi
+    from semtools_b200.model import StaticModel
+    rng = np.random.default_rng(12)
+    tk, tok_path, _ = _synthetic_unigram(tmp_path, seed=5, normalizer=None)
+    V = tk.get_vocab_size()
+    emb32 = (rng.standard_normal((V, 256)) * 0.1).astype(np.float32)
+    emb = {"F32": emb32, "F16": emb32.astype(np.float16), "I8": np.clip(np.round(emb32 * 400), -127, 127).astype(np.int8)}[table_dtype]
+    d = tmp_path / "model"
+    d.mkdir()
+    os.replace(tok_path, d / "tokenizer.json")
+    tensors = {"embeddings": emb}
+    if table_dtype != "F32":                                             # the newer model2vec layout: per-token weights + id mapping
+        tensors["weights"] = rng.uniform(0.1, 2.0, V).astype(np.float64 if table_dtype == "I8" else np.float32)
+        tensors["mapping"] = rng.permutation(V).astype(np.int64 if table_dtype == "I8" else np.int32)
+    st.save_file(tensors, str(d / "model.safetensors"))
+    (d / "config.json").write_text(json.dumps({"normalize": table_dtype != "F16", "hidden_dim": 256}))
+    r = subprocess.run([binary, "--model-info", str(d)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = json.loads(r.stdout)
+    m = StaticModel.from_pretrained(str(d))
+    h = lambda a: f"{capi.fnv1a64(np.ascontiguousarray(a).tobytes()):016x}"
+    assert got["V"] == V and got["normalize"] == m.normalize == (table_dtype != "F16")
+    assert got["table_fnv"] == h(m.embeddings) and m.embeddings.dtype == np.float32
+    if table_dtype == "F32":
+        assert got["n_weights"] == 0 and got["n_mapping"] == 0 and m.weights is None and m.mapping is None
+    else:
+        assert got["n_weights"] == V and got["weights_fnv"] == h(m.weights)
+        assert got["n_mapping"] == V and got["mapping_fnv"] == h(m.mapping)
+    assert got["fingerprint"] == m.fingerprint() and got["fingerprint"].startswith(f"model2vec:{V}x256:n")
+    # a directory without the table is an error, not a crash
+    os.remove(d / "model.safetensors")
+    r = subprocess.run([binary, "--model-info", str(d)], capture_output=True, text=True)
+    assert r.returncode == 1 and "model.safetensors" in r.stderr
