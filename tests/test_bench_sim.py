@@ -20,7 +20,15 @@ def _lines(stdout):
     return [json.loads(x) for x in stdout.strip().splitlines() if x.startswith("{")]
 
 
+def _free_port():
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 def _torchrun(n, port, extra, env=None):
+    port = _free_port()                                  # the fixed numbers below only label the cases
     e = dict(os.environ, STB_BENCH_ONE_GPU="1", **(env or {}))
     return subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
                            "--master-port", str(port), SIM, "--gpus", str(n)] + SMALL + extra,
