@@ -333,7 +333,9 @@ class Watchdog:
     def park(self, reason):
         """A non-zero rank whose section raised: the peers are inside a collective or a spin-wait and will
         run into their own deadline; stay alive until ours (torchrun kills the job if a rank dies)."""
-        print(f"[rank {self.rank}] {reason}; waiting for the phase deadline", file=sys.stderr, flush=True)
+        print(f"[rank {self.rank}] {reason}; leaving shortly", file=sys.stderr, flush=True)
+        with self.lock:                                        # no point in waiting out the whole budget: 10 s for rank 0 to print
+            self.deadline = min(self.deadline or float("inf"), time.monotonic() + 10.0)
         while True:
             time.sleep(1.0)
 
