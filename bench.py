@@ -491,6 +491,20 @@ def side_batch(E, corpus, rows, k, nq=1024, iters=5, make_xchg=None):
         # exchange together: its wait is bounded (STB_XCHG_TIMEOUT_CYCLES), a rank arriving later than that is "gone"
         corpus.search_batch_dev(q_dev.data_ptr(), nq, k, hits.data_ptr(), st.data_ptr())
         E.barrier()
+    fused_note = None
+    if xb is not None:
+        # probe: one fused exchange; if ANY rank saw a peer time out, every rank switches to the NCCL exchange
+        # (a timed-out exchange object is dead -- include/semtools_b200.h -- and the ranks must keep issuing
+        # the same calls)
+        xb.search_batch_dev(corpus, q_dev.data_ptr(), nq, k, merged.data_ptr(), st.data_ptr())
+        flag = torch.tensor([int(bool((st[:, 1] == 2).any()))], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if int(flag.item()):
+            xb.close()
+            xb = None
+            fused_note = "the fused peer-memory exchange timed out on at least one rank in its probe batch; measured with the NCCL exchange"
+            gathered = torch.zeros((world, nq, k, 2), dtype=torch.float64, device=dev)
+            st_all = torch.zeros((world, nq, 2), dtype=torch.int32, device=dev)
     fallbacks = []
 
     def one():
@@ -550,6 +564,8 @@ def side_batch(E, corpus, rows, k, nq=1024, iters=5, make_xchg=None):
         out["ranks_agree"] = bool(agree.item())
         out["exchange"] = ("fused: push + wait/merge kernels over NVLink peer memory (stb_search_batch_xchg_dev)" if xb is not None
                            else "nccl all_gather of nq x k hits + stb_hits_merge_batch_dev")
+        if fused_note:
+            out["note"] = fused_note
         # spot-check against the single-query fused path (exact by its own proof)
         chk = torch.zeros((k, 2), dtype=torch.float64, device=dev)
         same = True

@@ -5,7 +5,8 @@ of CPU tensors; the fused exchanges are played by gloo all-gathers, so a multi-r
 same sequence of bench.py calls, collectives and deadlines as the real thing.
 
 Fault injection for the deadline tests: FAKE_CAPI_STALL=<rank>:<method> makes that rank sleep forever
-inside the named Exchange / IvfPq method; FAKE_CAPI_RAISE=<rank>:<method> makes it raise StbError."""
+inside the named Exchange / IvfPq method; FAKE_CAPI_RAISE=<rank>:<method> makes it raise StbError;
+FAKE_CAPI_TIMEOUT=<rank>:search_batch_dev makes that rank report a peer time-out (proof flag 2)."""
 import ctypes
 import os
 import time
@@ -25,13 +26,16 @@ def _rank():
 
 
 def _fault(method):
-    for var, act in (("FAKE_CAPI_STALL", "stall"), ("FAKE_CAPI_RAISE", "raise")):
+    for var, act in (("FAKE_CAPI_STALL", "stall"), ("FAKE_CAPI_RAISE", "raise"), ("FAKE_CAPI_TIMEOUT", "timeout")):
         v = os.environ.get(var, "")
         if v and v.split(":")[0] == str(_rank()) and v.split(":")[1] == method:
             if act == "raise":
                 raise StbError(STB_ERR_STATE, f"injected failure in {method}")
+            if act == "timeout":
+                return True                                  # the caller reports "a peer never arrived"
             while True:
                 time.sleep(1.0)
+    return False
 
 
 def _view(ptr, shape, dtype):
@@ -212,7 +216,7 @@ class Exchange:
         _view(out_status_dev, (4,), np.uint32)[:] = [len(hits), 1, len(hits), 32 | (_TIERS[corpus._tier(top_k)] << 16)]
 
     def search_batch_dev(self, corpus, q_dev, nq, top_k, out_hits_dev, out_status_dev):
-        _fault("search_batch_dev")
+        timed_out = _fault("search_batch_dev")
         assert self.max_nq >= nq
         local = np.zeros((nq, top_k), dtype=HIT_DTYPE)
         st_local = np.zeros((nq, 2), dtype=np.uint32)
@@ -225,7 +229,7 @@ class Exchange:
         for i in range(nq):
             h = _merge([p[i] for p in parts], top_k)
             out[i] = _pad(h, top_k)
-            st[i] = [len(h), 1]
+            st[i] = [len(h), 2 if timed_out else 1]
         self.ctx.launches += 2
 
 

@@ -104,3 +104,15 @@ def test_shrink_line_keeps_the_contract_keys_and_the_limit():
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
     assert {"value", "unit", "cores", "kind", "sample"} <= set(line["cpu_baseline"])
     assert full["tier_stats"] and "tier_stats" in full                      # the input is not modified
+
+
+def test_a_timed_out_fused_exchange_makes_every_rank_switch_to_nccl():
+    """One rank reports a peer time-out in the probe batch of the sharded K2 section: the exchange object is
+    dead, all ranks agree (all-reduce) to measure with the NCCL exchange, and the section says so."""
+    r = _torchrun(2, 29545, ["--ivfpq-rows-per-gpu", "0"], env={"FAKE_CAPI_TIMEOUT": "1:search_batch_dev"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = _lines(r.stdout)
+    assert [d["side"] for d in out[:-1]] == ["config4_100M", "batch1024"]
+    b = out[1]
+    assert "error" not in b and b["exchange"].startswith("nccl") and "timed out" in b["note"] and b["ranks_agree"] is True
+    assert "side_sections_truncated" not in out[-1] and "batch1024_qps" in out[-1]["side"]
