@@ -301,7 +301,9 @@ int stb_search_xchg(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint
  * back to back, so every tail overlaps the next scan, and hits are written straight to pinned host
  * memory.  x == NULL: results are exactly stb_search's (an unproven query is re-run through it).
  * x != NULL: the sharded form of stb_search_xchg -- out_complete[i] = 0 marks a query some rank could
- * not prove (every rank sees the same flags).  out_complete may be NULL when x is NULL. */
+ * not prove (every rank sees the same flags).  out_complete may be NULL when x is NULL.
+ * Validation state: the x == NULL form is covered by the GPU suite; the x != NULL form is the same kernel
+ * stb_search_xchg launches, enqueued nq times, but has not yet run on a multi-GPU box. */
 int stb_search_many(stb_ctx *ctx, const stb_corpus *corpus, const float *q, uint32_t nq, uint32_t top_k,
                     stb_xchg *x, stb_hit *out_hits, uint32_t *out_n, uint8_t *out_complete);
 
