@@ -27,6 +27,7 @@ import argparse
 import json
 import os
 import subprocess
+import tempfile
 import sys
 import threading
 import time
@@ -298,6 +299,14 @@ class Watchdog:
         self.rank, self.emit = rank, emit
         self.deadline, self.label, self.budget = None, None, 0.0
         self.total_s, self.t_end = float(total_s), time.monotonic() + float(total_s)   # the whole run, whatever the phases do
+        # one node: a file every rank can see tells the others that one rank is leaving (same parent = the
+        # torchrun agent, so the name is unique to this job); no collective, no store traffic
+        self.flag = os.path.join(tempfile.gettempdir(), f"stb_bench_leave_{os.getppid()}_{os.environ.get('MASTER_PORT', '0')}")
+        if rank == 0:
+            try:
+                os.unlink(self.flag)
+            except OSError:
+                pass
         self.lock = threading.Lock()
         self.done = False
         t = threading.Thread(target=self._run, daemon=True)
@@ -319,6 +328,10 @@ class Watchdog:
                 return
             self.done = True
         print(f"[rank {self.rank}] leaving: {reason}", file=sys.stderr, flush=True)
+        try:
+            open(self.flag, "w").write(f"rank {self.rank}: {reason}\n")
+        except OSError:
+            pass
         if self.emit is None:                                  # nothing measured yet: an error, not a result
             if self.rank == 0:
                 print(json.dumps({"error": reason}), flush=True)
@@ -334,7 +347,11 @@ class Watchdog:
         """A non-zero rank whose section raised: the peers are inside a collective or a spin-wait and will
         run into their own deadline; stay alive until ours (torchrun kills the job if a rank dies)."""
         print(f"[rank {self.rank}] {reason}; leaving shortly", file=sys.stderr, flush=True)
-        with self.lock:                                        # no point in waiting out the whole budget: 10 s for rank 0 to print
+        try:
+            open(self.flag, "w").write(f"rank {self.rank}: {reason}\n")       # rank 0 prints the line when it sees this
+        except OSError:
+            pass
+        with self.lock:                                        # 10 s for rank 0 to print, then this rank goes too
             self.deadline = min(self.deadline or float("inf"), time.monotonic() + 10.0)
         while True:
             time.sleep(1.0)
@@ -348,6 +365,12 @@ class Watchdog:
                 self.fire(f"phase '{label}' exceeded its {budget:.0f} s deadline")
             if time.monotonic() > self.t_end:
                 self.fire(f"the run exceeded {self.total_s:.0f} s (phase '{label}')")
+            if os.path.exists(self.flag):
+                try:
+                    why = open(self.flag).read().strip()
+                except OSError:
+                    why = "another rank left"
+                self.fire(f"phase '{label}': {why}")
 
 
 def timed_queries(E, corpus, q_dev, k, steps, warm, xchg=None):

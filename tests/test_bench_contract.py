@@ -52,8 +52,13 @@ def test_synthetic_generators_are_deterministic():
     assert np.array_equal(q, bench.gen_queries(8)) and np.allclose(np.linalg.norm(q, axis=1), 1.0, atol=1e-5)
 
 
+_snippet_no = [0]
+
+
 def _run_snippet(code):
-    return subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=60)
+    _snippet_no[0] += 1                                   # the watchdog's leave-flag file is named after parent pid + port
+    env = dict(os.environ, MASTER_PORT=str(40000 + _snippet_no[0]))
+    return subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=60, env=env)
 
 
 def test_watchdog_prints_the_line_and_leaves_cleanly_when_a_phase_stalls():
