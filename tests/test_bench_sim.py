@@ -11,7 +11,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SIM = os.path.join(ROOT, "tests", "bench_sim.py")
-SMALL = ["--rows", "30000", "--steps", "5", "--warmup", "3", "--config4-rows", "40000", "--batch-queries", "32"]
+SMALL = ["--rows", "30000", "--steps", "5", "--warmup", "3", "--config4-rows", "40000", "--batch-queries", "32", "--clock-load-queries", "4"]
 CONTRACT_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
                  "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"}
 
