@@ -116,7 +116,7 @@ static int selftest() {
   return bad ? 1 : 0;
 }
 
-int main(int argc, char **argv) {
+static int real_main(int argc, char **argv) {
   std::string vocab, tokenizer_json, table, model_dir, query;
   std::vector<std::string> files;
   SearchConfig cfg;
@@ -305,4 +305,17 @@ int main(int argc, char **argv) {
     return 1;
   }
   return 0;
+}
+
+// nothing a bad input file can throw ends in std::terminate: every exit is a message + status
+int main(int argc, char **argv) {
+  try {
+    return real_main(argc, argv);
+  } catch (const std::exception &e) {
+    fprintf(stderr, "Error: %s\n", e.what());
+    return 1;
+  } catch (...) {
+    fprintf(stderr, "Error: unknown failure\n");
+    return 1;
+  }
 }

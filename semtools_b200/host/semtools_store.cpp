@@ -192,26 +192,42 @@ void Store::load() {
   Json j = Json::parse(read_file(meta));
   const Json *fmt = j.get("format");
   if (!fmt || fmt->str != "semtools_b200.flat.v1") throw std::runtime_error("unknown store format");
-  for (const auto &p : j.get("paths")->arr) { path_idx_[p.str] = (int32_t)paths_.size(); paths_.push_back(p.str); }
-  for (const auto &d : j.get("docs")->arr) {
+  // a damaged commit record is an error message, never undefined behaviour: every field is checked
+  auto corrupt = [&](const char *what) { return std::runtime_error("workspace store " + dir_ + ": store.json is corrupt (" + what + "); delete the directory to rebuild it"); };
+  auto field = [&](const Json &o, const char *key, Json::Type t) -> const Json & {
+    const Json *v = o.type == Json::Obj ? o.get(key) : nullptr;
+    if (!v || v->type != t) throw corrupt(key);
+    return *v;
+  };
+  for (const auto &p : field(j, "paths", Json::Arr).arr) {
+    if (p.type != Json::Str) throw corrupt("paths");
+    path_idx_[p.str] = (int32_t)paths_.size(); paths_.push_back(p.str);
+  }
+  for (const auto &d : field(j, "docs", Json::Arr).arr) {
     DocMeta m;
-    m.path = d.get("path")->str;
-    m.size_bytes = std::strtoull(d.get("size_bytes")->raw_num.c_str(), nullptr, 10);
-    m.mtime = std::strtoll(d.get("mtime")->raw_num.c_str(), nullptr, 10);
-    m.version = (uint32_t)d.get("_version")->num;
+    m.path = field(d, "path", Json::Str).str;
+    m.size_bytes = std::strtoull(field(d, "size_bytes", Json::Num).raw_num.c_str(), nullptr, 10);
+    m.mtime = std::strtoll(field(d, "mtime", Json::Num).raw_num.c_str(), nullptr, 10);
+    m.version = (uint32_t)field(d, "_version", Json::Num).num;
     docs_.push_back(m);
   }
-  if (const Json *g = j.get("gen")) gen_ = std::strtoull(g->raw_num.c_str(), nullptr, 10);
+  if (const Json *g = j.get("gen")) { if (g->type != Json::Num) throw corrupt("gen"); gen_ = std::strtoull(g->raw_num.c_str(), nullptr, 10); }
   if (const Json *f = j.get("files"); f && f->type == Json::Obj) {
-    if (const Json *r = f->get("rows")) rows_file_ = r->str;
-    if (const Json *e = f->get("emb")) emb_file_ = e->str;
+    auto file_name = [&](const char *key, std::string &dst) {
+      if (const Json *v = f->get(key)) {
+        if (v->type != Json::Str || v->str.empty() || v->str.find('/') != std::string::npos || v->str[0] == '.') throw corrupt("files");
+        dst = v->str;
+      }
+    };
+    file_name("rows", rows_file_);
+    file_name("emb", emb_file_);
   }
   if (const Json *m = j.get("model"); m && m->type == Json::Str) stored_model_ = m->str;
   const std::string rows_p = dir_ + "/" + rows_file_, emb_p = dir_ + "/" + emb_file_;
   const long long rs = file_size(rows_p), es = file_size(emb_p);
   const size_t n_rows_file = rs > 0 ? (size_t)rs / 8 : 0, n_emb_file = es > 0 ? (size_t)es / (LINE_EMBEDDING_SIZE * 4) : 0;
   size_t n = std::min(n_rows_file, n_emb_file);
-  if (const Json *r = j.get("rows")) n = (size_t)std::strtoull(r->raw_num.c_str(), nullptr, 10);
+  if (const Json *r = j.get("rows")) { if (r->type != Json::Num) throw corrupt("rows"); n = (size_t)std::strtoull(r->raw_num.c_str(), nullptr, 10); }
   if (n_rows_file < n || n_emb_file < n)
     throw std::runtime_error("workspace store " + dir_ + " is truncated: store.json commits " + std::to_string(n) + " rows, the row files hold " +
                              std::to_string(n_rows_file) + " / " + std::to_string(n_emb_file) + "; delete the directory to rebuild it");

@@ -65,7 +65,7 @@ static int store_selftest(const std::string &dir) {
   return 0;
 }
 
-int main(int argc, char **argv) {
+static int real_main(int argc, char **argv) {
   try {
     std::vector<std::string> a(argv + 1, argv + argc);
     bool json = false;
@@ -151,6 +151,19 @@ int main(int argc, char **argv) {
     return 2;
   } catch (const std::exception &e) {
     fprintf(stderr, "Error: %s\n", e.what());
+    return 1;
+  }
+}
+
+// nothing a bad input file can throw ends in std::terminate: every exit is a message + status
+int main(int argc, char **argv) {
+  try {
+    return real_main(argc, argv);
+  } catch (const std::exception &e) {
+    fprintf(stderr, "Error: %s\n", e.what());
+    return 1;
+  } catch (...) {
+    fprintf(stderr, "Error: unknown failure\n");
     return 1;
   }
 }

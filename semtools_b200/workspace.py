@@ -243,11 +243,27 @@ class Store:
             d = json.load(f)
         if d.get("format") != FORMAT:
             raise RuntimeError(f"unknown store format {d.get('format')!r}")
-        self._paths = list(d["paths"])
-        self._path_idx = {p: i for i, p in enumerate(self._paths)}
-        self._docs = {m["path"]: DocMeta(**m) for m in d["docs"]}
-        self._gen = int(d.get("gen", 0))
-        self._files = dict(d.get("files") or {"rows": "rows.i32", "emb": "line_embeddings.f32"})
+        try:                                     # a damaged commit record is a clear error, as in the C++ host
+            self._paths = list(d["paths"])
+            if not all(isinstance(p, str) for p in self._paths):
+                raise TypeError("paths")
+            self._path_idx = {p: i for i, p in enumerate(self._paths)}
+            self._docs = {}
+            for m in d["docs"]:
+                dm = DocMeta(**m)
+                if not isinstance(dm.path, str) or any(isinstance(v, bool) or not isinstance(v, int) for v in (dm.size_bytes, dm.mtime, dm._version)):
+                    raise TypeError("docs")
+                self._docs[dm.path] = dm
+            self._gen = int(d.get("gen", 0))
+            self._files = dict(d.get("files") or {"rows": "rows.i32", "emb": "line_embeddings.f32"})
+            for key in ("rows", "emb"):
+                name = self._files[key]
+                if not isinstance(name, str) or not name or "/" in name or name.startswith("."):
+                    raise ValueError("files")
+            if "rows" in d and (isinstance(d["rows"], bool) or not isinstance(d["rows"], int) or d["rows"] < 0):
+                raise ValueError("rows")
+        except (KeyError, TypeError, ValueError, AttributeError) as e:
+            raise RuntimeError(f"workspace store {self.dir}: store.json is corrupt ({e!r}); delete the directory to rebuild it") from e
         self.stored_model_fingerprint = d.get("model")
         rows_p, emb_p = os.path.join(self.dir, self._files["rows"]), os.path.join(self.dir, self._files["emb"])
         n_rows_file = os.path.getsize(rows_p) // 8 if os.path.exists(rows_p) else 0

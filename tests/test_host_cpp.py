@@ -594,3 +594,35 @@ def test_cpp_model_directory_loader_equals_the_python_loader(binary, tmp_path, t
     os.remove(d / "model.safetensors")
     r = subprocess.run([binary, "--model-info", str(d)], capture_output=True, text=True)
     assert r.returncode == 1 and "model.safetensors" in r.stderr
+
+
+def test_damaged_commit_records_are_errors_not_crashes(binary, tmp_path):
+    """A store.json that lost a key, has a field of the wrong type, a negative row count or a file name that
+    leaves the store directory must produce a clear error in BOTH hosts (found by fuzzing the loaders under
+    ASan / UBSan: the C++ loader used to dereference a missing key)."""
+    from semtools_b200.workspace import Store
+    d = tmp_path / "ws"
+    r = subprocess.run([WSBIN, "store-selftest", str(d)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    meta_p = d / "flat.b200" / "store.json"
+    good = json.loads(meta_p.read_text())
+    cases = []
+    for key in ("paths", "docs"):
+        j = dict(good); del j[key]; cases.append(j)
+        j = dict(good); j[key] = 7; cases.append(j)
+    j = json.loads(json.dumps(good)); del j["docs"][0]["mtime"]; cases.append(j)
+    j = json.loads(json.dumps(good)); j["docs"][0]["size_bytes"] = "big"; cases.append(j)
+    j = json.loads(json.dumps(good)); j["paths"][0] = None; cases.append(j)
+    j = dict(good); j["rows"] = -5; cases.append(j)
+    j = dict(good); j["rows"] = "many"; cases.append(j)
+    j = json.loads(json.dumps(good)); j["files"]["rows"] = "../../../etc/passwd"; cases.append(j)
+    j = json.loads(json.dumps(good)); j["files"]["emb"] = 3; cases.append(j)
+    for j in cases:
+        meta_p.write_text(json.dumps(j))
+        r = subprocess.run([WSBIN, "store-dump", str(d)], capture_output=True, text=True)
+        assert r.returncode == 1 and r.stderr.startswith("Error:"), (j.keys(), r.returncode, r.stderr[:200])
+        with pytest.raises(RuntimeError):
+            Store.open(str(d))
+    meta_p.write_text(json.dumps(good))                                 # and the intact record still loads
+    assert subprocess.run([WSBIN, "store-dump", str(d)], capture_output=True).returncode == 0
+    assert Store.open(str(d)).count_line_embeddings() == good["rows"]
