@@ -319,8 +319,12 @@ bool st_find(const Json &hdr, const std::string &blob, uint64_t base, const char
   if (!dt || !sh || !off || off->arr.size() != 2) throw std::runtime_error(std::string("model.safetensors: malformed entry for ") + name);
   t.dtype = dt->str;
   t.count = 1;
-  for (const auto &d : sh->arr) { t.shape.push_back((uint64_t)d.num); t.count *= (uint64_t)d.num; }
-  const uint64_t a = (uint64_t)off->arr[0].num, b = (uint64_t)off->arr[1].num;
+  for (const auto &d : sh->arr) {
+    const uint64_t dim = d.as_u64("a tensor dimension");
+    if (dim && t.count > (1ull << 40) / dim) throw std::runtime_error(std::string("model.safetensors: ") + name + " is implausibly large");
+    t.shape.push_back(dim); t.count *= dim;
+  }
+  const uint64_t a = off->arr[0].as_u64("a data offset"), b = off->arr[1].as_u64("a data offset");
   if (b < a || base + b > blob.size()) throw std::runtime_error(std::string("model.safetensors: data of ") + name + " lies outside the file");
   t.data = reinterpret_cast<const unsigned char *>(blob.data()) + base + a;
   t.bytes = b - a;
@@ -328,9 +332,9 @@ bool st_find(const Json &hdr, const std::string &blob, uint64_t base, const char
 }
 template <class T> T load_le(const unsigned char *p) { T v; memcpy(&v, p, sizeof(T)); return v; }
 void to_f32(const StTensor &t, const char *name, std::vector<float> &out) {
-  out.resize(t.count);
   const uint64_t w = t.dtype == "F32" ? 4 : t.dtype == "F16" ? 2 : t.dtype == "I8" ? 1 : t.dtype == "F64" ? 8 : 0;
   if (!w || t.bytes != t.count * w) throw std::runtime_error(std::string("model.safetensors: ") + name + " has dtype " + t.dtype + " / a size the host does not read");
+  out.resize(t.count);                               // only after the header's element count has been checked against the data it points at
   for (uint64_t i = 0; i < t.count; ++i) {
     const unsigned char *p = t.data + i * w;
     out[i] = w == 4 ? load_le<float>(p) : w == 2 ? half_to_float(load_le<uint16_t>(p)) : w == 1 ? (float)(int8_t)p[0] : (float)load_le<double>(p);

@@ -134,7 +134,7 @@ Workspace Workspace::open(const std::optional<std::string> &workspace_name) {
     const Json *n = j.get("name"), *r = j.get("root_dir"), *b = j.get("in_batch_size"), *o = j.get("oversample_factor");
     if (!n || !r || !b || !o || n->type != Json::Str || r->type != Json::Str) throw std::runtime_error("cfg");
     ws.config.name = n->str; ws.config.root_dir = r->str;
-    ws.config.in_batch_size = (size_t)b->num; ws.config.oversample_factor = (size_t)o->num;
+    ws.config.in_batch_size = (size_t)b->as_u64("in_batch_size"); ws.config.oversample_factor = (size_t)o->as_u64("oversample_factor");
   } catch (const std::exception &) {
     ws.config = WorkspaceConfig();
   }
@@ -208,7 +208,7 @@ void Store::load() {
     m.path = field(d, "path", Json::Str).str;
     m.size_bytes = std::strtoull(field(d, "size_bytes", Json::Num).raw_num.c_str(), nullptr, 10);
     m.mtime = std::strtoll(field(d, "mtime", Json::Num).raw_num.c_str(), nullptr, 10);
-    m.version = (uint32_t)field(d, "_version", Json::Num).num;
+    m.version = (uint32_t)field(d, "_version", Json::Num).as_u64("_version");
     docs_.push_back(m);
   }
   if (const Json *g = j.get("gen")) { if (g->type != Json::Num) throw corrupt("gen"); gen_ = std::strtoull(g->raw_num.c_str(), nullptr, 10); }

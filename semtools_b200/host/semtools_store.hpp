@@ -5,6 +5,7 @@
 // GPU's (stb_search with row ranges, STB_MODE_STORE_QUERY); nothing here computes a distance.
 #pragma once
 #include <cstdint>
+#include <stdexcept>
 #include <functional>
 #include <map>
 #include <optional>
@@ -142,6 +143,12 @@ struct Json {
   std::vector<Json> arr;
   std::vector<std::pair<std::string, Json>> obj;
   const Json *get(const std::string &key) const;
+  // the number as an unsigned integer; throws unless it is a non-negative whole number below 2^63
+  // (a double -> integer conversion out of range is undefined behaviour)
+  uint64_t as_u64(const char *what) const {
+    if (type != Num || !(num >= 0.0 && num < 9.2e18) || num != (double)(uint64_t)num) throw std::runtime_error(std::string("json: ") + what + " is not a non-negative integer");
+    return (uint64_t)num;
+  }
   static Json parse(const std::string &text);       // throws std::runtime_error
 };
 

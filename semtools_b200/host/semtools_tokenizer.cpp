@@ -291,7 +291,7 @@ HfTokenizer::HfTokenizer(const std::string &path) {
   const Json &model = need(j, "model", "the file");
   if (type_of(model) != "Unigram") throw std::runtime_error("tokenizer.json: model \"" + type_of(model) + "\" is not supported by the C++ host (Unigram only)");
   if (const Json *bf = model.get("byte_fallback"); bf && bf->b) throw std::runtime_error("tokenizer.json: Unigram byte_fallback is not supported by the C++ host");
-  if (const Json *u = model.get("unk_id"); u && u->type == Json::Num) { has_unk_ = true; unk_id_ = (uint32_t)u->num; }
+  if (const Json *u = model.get("unk_id"); u && u->type == Json::Num) { has_unk_ = true; unk_id_ = (uint32_t)std::min<uint64_t>(u->as_u64("unk_id"), 0xFFFFFFFFull); }
   const Json &vocab = need(model, "vocab", "Unigram model");
   tokens_.reserve(vocab.arr.size()); scores_.reserve(vocab.arr.size());
   for (const auto &e : vocab.arr) {
@@ -335,7 +335,7 @@ HfTokenizer::HfTokenizer(const std::string &path) {
     for (const auto &e : at->arr) {
       Added a;
       a.content = need(e, "content", "added token").str;
-      a.id = (uint32_t)need(e, "id", "added token").num;
+      a.id = (uint32_t)std::min<uint64_t>(need(e, "id", "added token").as_u64("an added token id"), 0xFFFFFFFFull);
       bool normalized = false;
       if (const Json *v = e.get("lstrip")) a.lstrip = v->b;
       if (const Json *v = e.get("rstrip")) a.rstrip = v->b;
