@@ -1049,7 +1049,9 @@ def run_ours(args):
                        "tier": tier, "tier_build_ms": float(f"{q8_build_ms:.4g}"),
                        "parallelism": f"row-shard x{world}" + (" ON ONE GPU (functional check, timings void)" if one_gpu else ""),
                        "exchange": exchange,
-                       "l2": "scanned copy >> 126 MB L2, no flush" if rows_per_gpu * TIER_BYTES[tier] > 4 * 126e6 else "WARNING scanned copy fits partly in L2"},
+                       # timing rule: inputs larger than L2 (every query streams the whole copy from HBM) or a flush
+                       "l2": (f"scanned copy {rows_per_gpu * TIER_BYTES[tier] / 1e6:.0f} MB = {rows_per_gpu * TIER_BYTES[tier] / 126e6:.1f}x the 126 MB L2, no flush"
+                              if rows_per_gpu * TIER_BYTES[tier] > 126e6 else "WARNING: the scanned copy fits in L2 and is not flushed")},
             "clocks": clocks,
             # e2e.value: one synchronous host call per query (stb_search / stb_search_xchg).  many16 (N=1): the same
             # queries through stb_search_many, 16 per call (one H2D, 16 kernels, one sync): what a host holding
