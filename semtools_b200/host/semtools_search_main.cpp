@@ -223,11 +223,14 @@ static int real_main(int argc, char **argv) {
     else if (!have_query) { query = a; have_query = true; }
     else files.push_back(a);
   }
+  if (model_dir.empty() && vocab.empty() && tokenizer_json.empty() && table.empty())
+    if (const char *e = getenv("SEMTOOLS_B200_MODEL_DIR"); e && *e) model_dir = e;              // as the Python CLI (__main__.py)
   if (!model_dir.empty() && vocab.empty() && tokenizer_json.empty() && table.empty()) tokenizer_json = model_dir + "/tokenizer.json";
   else if (!model_dir.empty()) { fprintf(stderr, "Error: --model replaces --tokenizer / --vocab / --table\n"); return 2; }
   if (!have_query || (vocab.empty() == tokenizer_json.empty()) || (table.empty() && model_dir.empty())) {
     fprintf(stderr, "usage: semtools_b200_search (--model DIR | (--tokenizer tokenizer.json | --vocab V) --table T) QUERY [FILES...] [-n N] [--top-k K] [-m D] [-i] [-j] [-w WORKSPACE]\n"
                     "  --model:     a local model2vec directory (tokenizer.json, model.safetensors, config.json), as StaticModel::from_pretrained reads it\n"
+                    "               (default: $SEMTOOLS_B200_MODEL_DIR, like the Python CLI)\n"
                     "  --tokenizer: the model's HF tokenizer.json (Unigram + Metaspace subset, see semtools_tokenizer.hpp)\n"
                     "  --vocab:     whitespace WordLevel vocabulary, one token per line (synthetic models)\n");
     return 2;
