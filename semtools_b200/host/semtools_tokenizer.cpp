@@ -66,6 +66,19 @@ inline uint8_t gcb_of(uint32_t cp) {
   if (cp >= 0xAC00 && cp <= 0xD7A3) return (cp - 0xAC00) % 28 == 0 ? GB_LV : GB_LVT;
   return gb_lookup(kGcbRanges, cp);
 }
+// all three properties of a code point in one byte: gcb | ext_pict << 4 | incb << 5; the BMP is a direct table
+// built once (function-local static: thread-safe), supplementary planes go through the range tables
+inline uint8_t gb_props_slow(uint32_t cp) {
+  return (uint8_t)(gcb_of(cp) | (gb_lookup(kExtPictRanges, cp) ? 0x10 : 0) | (gb_lookup(kInCbRanges, cp) << 5));
+}
+inline uint8_t gb_props(uint32_t cp) {
+  static const std::vector<uint8_t> bmp = [] {
+    std::vector<uint8_t> t(0x10000);
+    for (uint32_t c = 0; c < 0x10000; ++c) t[c] = gb_props_slow(c);
+    return t;
+  }();
+  return cp < 0x10000 ? bmp[cp] : gb_props_slow(cp);
+}
 // one scalar value at s[i]; malformed sequences yield the single byte as an (unassigned-looking) code point
 inline uint32_t decode_at(const std::string &s, size_t i, size_t *len) {
   const unsigned char c = (unsigned char)s[i];
@@ -109,9 +122,10 @@ std::vector<size_t> grapheme_ends(const std::string &s) {
   int prev = -1, ri_run = 0, ep_state = 0, incb_state = 0;   // ep: 1 = ExtPict Extend*, 2 = ... ZWJ; incb: 1 = Consonant [Extend|Linker]*, 2 = with a Linker
   while (i < s.size()) {
     const uint32_t cp = decode_at(s, i, &len);
-    const int c = gcb_of(cp);
-    const bool ep = gb_lookup(kExtPictRanges, cp) != 0;
-    const int incb = gb_lookup(kInCbRanges, cp);
+    const uint8_t props = gb_props(cp);
+    const int c = props & 0x0F;
+    const bool ep = (props & 0x10) != 0;
+    const int incb = props >> 5;
     if (prev >= 0) {
       bool brk;
       if (prev == GB_CR && c == GB_LF) brk = false;                                              // GB3
