@@ -59,3 +59,31 @@ def test_no_gpu_means_loud_failure_not_cpu_fallback():
         capi.Context(0)
     assert e.value.status == capi.STB_ERR_CUDA
     assert "no CPU path" in str(e.value)
+
+
+def test_header_is_plain_c_and_the_library_links_from_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/semtools_b200.h must compile as C99 (pedantic, no warnings)
+    and a C program must link against the shared library and call it (host-only entry points: no GPU here)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "use_abi.c"
+    src.write_text('#include <stdio.h>\n#include <string.h>\n#include "semtools_b200.h"\n'
+                   'int main(void) {\n'
+                   '  const char *s = "hello";\n'
+                   '  stb_hit h; h.distance = 0.5; h.row = 7;\n'
+                   '  printf("%d %llu %llu %d\\n", stb_version(), (unsigned long long)stb_fnv1a64((const uint8_t *)s, strlen(s)),\n'
+                   '         (unsigned long long)stb_line_id((const uint8_t *)"a.txt", 5, 3), (int)sizeof(h));\n'
+                   '  return 0;\n}\n')
+    exe = tmp_path / "use_abi"
+    lib_dir = os.path.dirname(capi.LIB_PATH)
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src),
+                        "-L", lib_dir, "-lsemtools_b200", f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    version, fnv, lid, hit_size = r.stdout.split()
+    assert int(version) == capi.lib().stb_version() and int(fnv) == capi.fnv1a64(b"hello") == 0xA430D84680AABD0B
+    assert int(lid) == capi.line_id("a.txt", 3) and int(hit_size) == 16
