@@ -500,7 +500,8 @@ void HfTokenizer::unigram(const std::string &s, std::vector<uint32_t> &out) cons
   const size_t size = s.size();
   if (size == 0) return;
   struct Node { uint32_t id = 0; double score = 0.0; int64_t starts_at = -1; };
-  std::vector<Node> best(size + 1);
+  static thread_local std::vector<Node> best;           // per-thread scratch: a piece is a few bytes, the allocation was the cost
+  best.assign(size + 1, Node());
   const double unk_score = min_score_ - 10.0;
   size_t at = 0;
   while (at < size) {
@@ -528,7 +529,8 @@ void HfTokenizer::unigram(const std::string &s, std::vector<uint32_t> &out) cons
     at += mblen;
   }
   // backtrack; consecutive unknown characters fuse into ONE unk token (fuse_unk)
-  std::vector<uint32_t> rev;
+  static thread_local std::vector<uint32_t> rev;
+  rev.clear();
   size_t ends = size;
   bool in_unk = false;
   while (ends > 0) {
@@ -553,7 +555,32 @@ std::vector<uint32_t> HfTokenizer::encode_raw(const std::string &text) const {
     for (const auto &part : sub) {
       if (part.id >= 0) { ids.push_back((uint32_t)part.id); continue; }
       if (part.text.empty()) continue;
-      pre_tokenize(part.text, pieces, seg.start == 0 && part.start == 0);   // Metaspace "first": only the split that starts the input
+      const bool origin = seg.start == 0 && part.start == 0;               // Metaspace "first": only the split that starts the input
+      if (pre_.size() == 1 && pre_[0].kind == P_METASPACE && pre_[0].split && !pre_[0].replacement.empty()) {
+        // the usual pipeline, without materialising the pieces: every space becomes the replacement and starts a piece
+        // that runs to the next one; a leading replacement is added per the prepend scheme (same result as pre_tokenize)
+        const PreStep &m = pre_[0];
+        const std::string &t = part.text, &rep = m.replacement;
+        static thread_local std::string piece;
+        const bool starts = t[0] == ' ' || t.compare(0, rep.size(), rep) == 0;
+        const bool prepend = !starts && (m.prepend == PREPEND_ALWAYS || (m.prepend == PREPEND_FIRST && origin));
+        piece.clear();
+        if (prepend) piece = rep;
+        size_t i = 0;
+        const size_t n = t.size();
+        while (i < n) {
+          const bool at_space = t[i] == ' ';
+          const bool at_rep = !at_space && t.compare(i, rep.size(), rep) == 0;
+          if (at_space || at_rep) {                                        // a delimiter: close the running piece, start the next with it
+            if (!piece.empty()) unigram(piece, ids);
+            piece = rep;
+            i += at_space ? 1 : rep.size();
+          } else piece.push_back(t[i++]);
+        }
+        if (!piece.empty()) unigram(piece, ids);
+        continue;
+      }
+      pre_tokenize(part.text, pieces, origin);
       for (const auto &p : pieces) unigram(p, ids);
     }
   }
