@@ -116,3 +116,23 @@ def test_a_timed_out_fused_exchange_makes_every_rank_switch_to_nccl():
     b = out[1]
     assert "error" not in b and b["exchange"].startswith("nccl") and "timed out" in b["note"] and b["ranks_agree"] is True
     assert "side_sections_truncated" not in out[-1] and "batch1024_qps" in out[-1]["side"]
+
+
+def test_the_stand_in_binding_has_the_real_binding_s_signatures():
+    """The simulation is only worth something if bench.py calls the stand-in exactly as it calls
+    semtools_b200.capi: every public method / function of tests/fake_capi.py must exist in the real binding
+    with the same parameter names in the same order."""
+    import inspect
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fake_capi as fake
+    from semtools_b200 import capi as real
+    for cname in ("Context", "Corpus", "Exchange", "IvfPq", "Table"):
+        fr, ff = getattr(real, cname), getattr(fake, cname)
+        for name, fn in inspect.getmembers(ff, predicate=inspect.isfunction):
+            if name.startswith("_") and name != "__init__":
+                continue
+            assert hasattr(fr, name), (cname, name)
+            assert list(inspect.signature(getattr(fr, name)).parameters) == list(inspect.signature(fn).parameters), (cname, name)
+    for name in ("embed", "embed_dev", "embed_status"):
+        assert list(inspect.signature(getattr(real, name)).parameters) == list(inspect.signature(getattr(fake, name)).parameters), name
+    assert fake.HIT_DTYPE is real.HIT_DTYPE and fake.StbError is real.StbError
