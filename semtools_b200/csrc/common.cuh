@@ -80,6 +80,7 @@ struct stb_ctx {
   unsigned long long *tickets;
   unsigned long long ticket_next[8];   // per slot: its value when the next launch using it starts
   unsigned long long topk_launches;    // picks the slot
+  bool ticket_ring;                    // set by the first overlapped launch; until then every launch uses slot 0
   float *q_dev;             // 256 f32 staging for host queries
   stb_hit *hits_dev;        // result hits (top-k path)
   size_t hits_cap;

@@ -1112,7 +1112,11 @@ static int stb_launch_topk_t(stb_ctx *ctx, const TopkArgs &a_in, bool overlapped
     const uint64_t single = std::min<uint64_t>(tiles, 2 * warps_total);
     a.scan.t_bulk = (tiles - single) / STB_TICKET_TILES;
     const uint64_t n_tickets = a.scan.t_bulk + (tiles - a.scan.t_bulk * STB_TICKET_TILES);
-    const int slot = (int)(ctx->topk_launches++ % STB_TICKET_SLOTS);     // at most ~3 grids are ever in flight
+    // one counter serves back-to-back launches (a grid starts drawing only after its predecessor's scan, the
+    // validated default); the ring is needed -- and used -- from the first overlapped launch on, when two
+    // consecutive scans co-run (at most ~3 grids are ever in flight)
+    if (overlapped) ctx->ticket_ring = true;
+    const int slot = ctx->ticket_ring ? (int)(ctx->topk_launches++ % STB_TICKET_SLOTS) : 0;
     a.scan.tickets = ctx->tickets + slot;
     a.scan.t_base = ctx->ticket_next[slot];
     ctx->ticket_next[slot] += n_tickets + warps_total;
